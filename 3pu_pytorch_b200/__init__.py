@@ -1,0 +1,15 @@
+"""3pu_pytorch_b200 -- B200-native (sm_100a) implementation of the 3PU patch-upsampling hot path.
+
+The directory name starts with a digit, so import it with
+    import importlib; pu3 = importlib.import_module("3pu_pytorch_b200")
+or put 3pu_pytorch_b200/shim on sys.path to get the reference's own module names
+(`sampling`, `losses`, `network.operations`, ...).
+
+Layout: csrc/ CUDA kernels + C ABI (include/pu3_b200.h) -> lib/libpu3_b200.so, loaded by _lib.py;
+sampling.py / losses.py mirror the reference's two pybind modules; operations.py, layers.py,
+upsampler.py, model_loss.py mirror network/*.py.  There is no CPU path.
+"""
+from . import _lib  # noqa: F401
+from . import sampling, losses, operations, model_loss  # noqa: F401
+
+__all__ = ["sampling", "losses", "operations", "model_loss"]

@@ -1,0 +1,98 @@
+"""ctypes binding of libpu3_b200.so (the C ABI declared in include/pu3_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or a call
+returns a non-zero status, a RuntimeError is raised.  The reference kills the
+process on a failed launch (sampling/sampling_cuda.cu:56-60) or ignores the
+status (network/model_loss.py:15); raising is the only behavioural change.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpu3_b200.so")
+ABI_VERSION = 1
+
+_c_int, _c_void_p, _c_size_t, _c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/pu3_b200.h (tests check this)
+SIGNATURES = {
+    "pu3_last_error": (ctypes.c_char_p, []),
+    "pu3_version": (_c_int, []),
+    "pu3_device_info": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "pu3_fps_f32": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "pu3_gather_fwd": (_c_int, [_c_int] * 5 + [_c_void_p] * 4),
+    "pu3_gather_bwd": (_c_int, [_c_int] * 5 + [_c_void_p] * 4),
+    "pu3_ball_query_f32": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "pu3_nmdist_fwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 7),
+    "pu3_nmdist_bwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 9),
+    "pu3_group_knn_workspace": (_c_size_t, [_c_int] * 7),
+    "pu3_group_knn_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
+    "pu3_group_gather_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 4),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"libpu3_b200.so not found at {LIB_PATH}: build it with `make -C {_HERE}/csrc` "
+                "(or __graft_entry__.build()); there is no CPU or PyTorch fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so is stale
+            fn.restype, fn.argtypes = res, args
+        if handle.pu3_version() != ABI_VERSION:
+            raise RuntimeError(f"libpu3_b200.so ABI {handle.pu3_version()} != expected {ABI_VERSION}: rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().pu3_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(t, name):
+    # same wording as the reference's CHECK_CUDA / CHECK_CONTIGUOUS (sampling/sampling.cpp:20-24)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def require_contiguous(t, name):
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+class on_device:
+    """Make the tensor's device current for the duration of a call (the reference has no device guard)."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False

@@ -1,0 +1,336 @@
+// Farthest point sampling, sm_100a.
+//
+// Replaces furthest_point_sampling_forward_kernel / furthest_sampling_cuda_forward
+// (sampling/sampling_cuda.cu:103-265 of the reference).
+//
+// The reference runs ONE CTA of <=512 threads per cloud; every one of the m-1 dependent rounds
+// re-reads the running distances (and every point past the first 512) from global memory and
+// ends in a log2(T)-step shared-memory tree with a __syncthreads per step.  FPS is a chain of
+// m-1 dependent arg-max rounds, so it is latency-bound: the design goal is the shortest round.
+//
+//   * the cloud lives ON CHIP for the whole kernel: each thread keeps its points' running
+//     distance (and, when they fit, the coordinates) in registers; a shared-memory copy of the
+//     coordinates serves the one winner lookup per round.  HBM is touched once.
+//   * a cloud too large for one SM is spread over a thread-block CLUSTER (2..16 CTAs); per round
+//     each CTA publishes its local winner into every peer's shared memory (DSMEM) and one
+//     barrier.cluster makes them visible.
+//   * the arg-max inside a CTA is two redux.sync per warp + ONE __syncthreads per round.
+//
+// Bit-exactness with the reference (indices are compared for equality):
+//   - distance: FMUL(dy,dy), FFMA(dx,dx,.), FFMA(dz,dz,.) like the reference SASS (sqdist3)
+//   - running distance t = fminf(d, t)                               (:144)
+//   - winner: largest t; among equal t the smallest (k mod T), then the smallest k, where
+//     T = 2^floor(log2 n) <= 512 is the reference's block size (cuda_utils.h:9-14).  That is what
+//     its per-thread strided scan (:133-150, first strictly greater) followed by its tree
+//     (:155-167, lower slot keeps ties) computes.  Here it is a lexicographic max on
+//     (t, -rank), rank = (k mod T) * ceil(n/T) + k / T.
+//   - deliberately NOT reproduced: the reference indexes temp rows by blockIdx.x (:131,146), which
+//     corrupts results for b > 32; every cloud owns its row here.
+#include "pu3_common.cuh"
+
+namespace pu3 {
+
+constexpr int FPS_MAX_CLUSTER = 16;
+
+// what a CTA publishes per round: 32 bytes
+struct __align__(16) FpsCand {
+    uint32_t dkey;  // float bits of the running distance (>= 0, so uint order == float order)
+    uint32_t rank;  // tie rank, smaller wins
+    int32_t k;      // point index
+    float x, y, z;
+    uint32_t pad0, pad1;
+};
+
+struct FpsSmem {
+    FpsCand cluster_slot[2][FPS_MAX_CLUSTER];  // [round parity][source CTA rank]
+    uint32_t warp_dkey[2][32];
+    uint32_t warp_rank[2][32];
+    int32_t warp_k[2][32];
+};
+
+// lexicographic arg-max over the full warp; returns true in exactly one lane (the winner)
+__device__ __forceinline__ bool warp_argmax(uint32_t dkey, uint32_t rank, uint32_t &dmax, uint32_t &rmin) {
+    dmax = __reduce_max_sync(0xffffffffu, dkey);
+    const uint32_t cand = (dkey == dmax) ? rank : 0xffffffffu;
+    rmin = __reduce_min_sync(0xffffffffu, cand);
+    return cand == rmin && rmin != 0xffffffffu;
+}
+
+// PPT points per thread; XYZ_REGS: coordinates in registers (else read from shared memory each round)
+template <int PPT, bool XYZ_REGS, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+fps_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__restrict__ temp,
+           int32_t *__restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FpsSmem &sm = *reinterpret_cast<FpsSmem *>(smem_raw);
+    float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem));
+
+    const uint32_t S = cluster_nctarank();
+    const uint32_t crank = cluster_ctarank();
+    const int cloud = blockIdx.x / S;
+    const int nthreads = blockDim.x;
+    const int GT = nthreads * S;                     // threads per cloud; a multiple of t_ref
+    const int g = crank * nthreads + threadIdx.x;    // this thread's id within the cloud
+    const int cap = nthreads * PPT;                  // points this CTA can hold
+    float *sy = sx + cap, *sz = sy + cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+
+    const float *p = xyz + (size_t)cloud * n * 3;
+    float *trow = temp ? temp + (size_t)cloud * n : nullptr;
+    int32_t *out = idx + (size_t)cloud * m;
+    const uint32_t rank_rows = (n + t_ref - 1) / t_ref;
+
+    // ---- load: thread owns points k = g + i*GT; local slot i*nthreads + tid -------------------
+    float px[XYZ_REGS ? PPT : 1], py[XYZ_REGS ? PPT : 1], pz[XYZ_REGS ? PPT : 1], t[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = g + i * GT;
+        float x = 0.f, y = 0.f, z = 0.f, tv = -1.f;  // tv < 0 marks "no point": never wins (real t >= 0)
+        if (k < n) {
+            x = __ldg(p + (size_t)k * 3 + 0);
+            y = __ldg(p + (size_t)k * 3 + 1);
+            z = __ldg(p + (size_t)k * 3 + 2);
+            tv = trow ? trow[k] : 1e10f;
+        }
+        const int slot = i * nthreads + threadIdx.x;
+        sx[slot] = x; sy[slot] = y; sz[slot] = z;
+        if (XYZ_REGS) { px[i] = x; py[i] = y; pz[i] = z; }
+        t[i] = tv;
+    }
+    if (g == 0) out[0] = 0;                                  // :115 first sample is point 0
+    float x1 = __ldg(p + 0), y1 = __ldg(p + 1), z1 = __ldg(p + 2);
+    __syncthreads();
+    if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem exists before remote stores
+
+    for (int j = 1; j < m; ++j) {
+        const int par = j & 1;
+        // ---- 1. update running distances, thread-local arg-max (first strictly greater) -------
+        float best = -1.f;
+        int besti = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            float x, y, z;
+            if (XYZ_REGS) { x = px[i]; y = py[i]; z = pz[i]; }
+            else { const int slot = i * nthreads + threadIdx.x; x = sx[slot]; y = sy[slot]; z = sz[slot]; }
+            const float d = sqdist3(x - x1, y - y1, z - z1);
+            // padding slots keep t = -1: fminf(d,-1) = -1
+            const float d2 = fminf(d, t[i]);
+            t[i] = d2;
+            if (d2 > best) { best = d2; besti = i; }
+        }
+        // ---- 2. warp arg-max ------------------------------------------------------------------
+        const int kbest = g + besti * GT;
+        const bool has = best >= 0.f;
+        const uint32_t dkey = has ? __float_as_uint(best) : 0u;
+        const uint32_t rank = has ? (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest / t_ref)
+                                  : 0xffffffffu;
+        uint32_t dmax, rmin;
+        if (warp_argmax(dkey, rank, dmax, rmin)) {
+            sm.warp_dkey[par][warp] = dmax;
+            sm.warp_rank[par][warp] = rmin;
+            sm.warp_k[par][warp] = kbest;
+        }
+        if (!__any_sync(0xffffffffu, has) && lane == 0) {  // warp without points
+            sm.warp_dkey[par][warp] = 0u;
+            sm.warp_rank[par][warp] = 0xffffffffu;
+            sm.warp_k[par][warp] = 0;
+        }
+        __syncthreads();
+        // ---- 3. CTA arg-max, redundantly in every warp (saves a second barrier) ---------------
+        const uint32_t wd = lane < nwarps ? sm.warp_dkey[par][lane] : 0u;
+        const uint32_t wr = lane < nwarps ? sm.warp_rank[par][lane] : 0xffffffffu;
+        const bool wwin = warp_argmax(wd, wr, dmax, rmin);
+        const uint32_t wsrc = __ffs(__ballot_sync(0xffffffffu, wwin)) - 1;  // 0xffffffff if nobody (empty CTA)
+        int kwin = 0;
+        bool cta_has = wsrc != 0xffffffffu;
+        if (cta_has) kwin = sm.warp_k[par][wsrc];
+
+        if (S == 1) {
+            const int slot = ((kwin / GT) * nthreads) + (kwin % GT);  // owner tid = kwin % GT when S == 1
+            x1 = sx[slot]; y1 = sy[slot]; z1 = sz[slot];
+            if (threadIdx.x == 0) out[j] = kwin;
+        } else {
+            // ---- 4. publish this CTA's winner to every CTA of the cluster, pick the global one --
+            if (warp == 0 && lane < (int)S) {
+                float wx = 0.f, wy = 0.f, wz = 0.f;
+                if (cta_has) {
+                    const int slot = (kwin / GT) * nthreads + ((kwin % GT) - (int)crank * nthreads);
+                    wx = sx[slot]; wy = sy[slot]; wz = sz[slot];
+                }
+                const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], lane);
+                st_cluster_v4(dst, cta_has ? dmax : 0u, cta_has ? rmin : 0xffffffffu, (uint32_t)kwin,
+                              __float_as_uint(wx));
+                st_cluster_v2(dst + 16, __float_as_uint(wy), __float_as_uint(wz));
+            }
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            const FpsCand *cs = sm.cluster_slot[par];
+            const uint32_t cd = lane < (int)S ? cs[lane].dkey : 0u;
+            const uint32_t cr = lane < (int)S ? cs[lane].rank : 0xffffffffu;
+            const bool cwin = warp_argmax(cd, cr, dmax, rmin);
+            const uint32_t csrc = __ffs(__ballot_sync(0xffffffffu, cwin)) - 1;
+            const FpsCand w = cs[csrc & (FPS_MAX_CLUSTER - 1)];
+            x1 = w.x; y1 = w.y; z1 = w.z;
+            if (g == 0) out[j] = w.k;
+        }
+    }
+    if (trow) {
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = g + i * GT;
+            if (k < n) trow[k] = t[i];
+        }
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }
+}
+
+// Any-size fallback: one CTA per cloud, running distances in global memory (workspace = temp or
+// a caller-invisible requirement that temp != NULL).  Only used when the cloud does not fit a
+// 16-CTA cluster (n > 262144).
+__global__ void __launch_bounds__(1024, 1)
+fps_fallback_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__restrict__ temp,
+                    int32_t *__restrict__ idx) {
+    __shared__ uint32_t s_d[2][32], s_r[2][32];
+    __shared__ int32_t s_k[2][32];
+    const int cloud = blockIdx.x;
+    const float *p = xyz + (size_t)cloud * n * 3;
+    float *trow = temp + (size_t)cloud * n;
+    int32_t *out = idx + (size_t)cloud * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t rank_rows = (n + t_ref - 1) / t_ref;
+    int old = 0;
+    if (threadIdx.x == 0) out[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const int par = j & 1;
+        const float x1 = __ldg(p + (size_t)old * 3), y1 = __ldg(p + (size_t)old * 3 + 1), z1 = __ldg(p + (size_t)old * 3 + 2);
+        float best = -1.f;
+        int kbest = 0;
+        // blockDim.x is a multiple of t_ref, so a thread's points share k mod t_ref
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const float d = sqdist3(__ldg(p + (size_t)k * 3) - x1, __ldg(p + (size_t)k * 3 + 1) - y1,
+                                    __ldg(p + (size_t)k * 3 + 2) - z1);
+            const float td = trow[k];
+            const float d2 = fminf(d, td);
+            if (d2 != td) trow[k] = d2;
+            if (d2 > best) { best = d2; kbest = k; }
+        }
+        const bool has = best >= 0.f;
+        const uint32_t dkey = has ? __float_as_uint(best) : 0u;
+        const uint32_t rank = has ? (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest / t_ref) : 0xffffffffu;
+        uint32_t dmax, rmin;
+        if (warp_argmax(dkey, rank, dmax, rmin)) { s_d[par][warp] = dmax; s_r[par][warp] = rmin; s_k[par][warp] = kbest; }
+        if (!__any_sync(0xffffffffu, has) && lane == 0) { s_d[par][warp] = 0u; s_r[par][warp] = 0xffffffffu; s_k[par][warp] = 0; }
+        __syncthreads();
+        const uint32_t wd = lane < nwarps ? s_d[par][lane] : 0u;
+        const uint32_t wr = lane < nwarps ? s_r[par][lane] : 0xffffffffu;
+        const bool wwin = warp_argmax(wd, wr, dmax, rmin);
+        const uint32_t wsrc = __ffs(__ballot_sync(0xffffffffu, wwin)) - 1;
+        old = wsrc != 0xffffffffu ? s_k[par][wsrc] : 0;
+        if (threadIdx.x == 0) out[j] = old;
+    }
+}
+
+static int floor_pow2(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+static int ceil_pow2(int v) {
+    int p = 1;
+    while (p < v) p *= 2;
+    return p;
+}
+
+// the reference's opt_n_threads (cuda_utils.h:9-14); n >= 1
+static int ref_block_size(int n) {
+    int t = floor_pow2(n);
+    return t > 512 ? 512 : t;
+}
+
+template <int PPT, bool XYZ_REGS, int MAX_THREADS>
+static int launch_fps(int b, int n, int m, int t_ref, int S, int threads, const float *xyz, float *temp,
+                      int32_t *idx, cudaStream_t stream) {
+    auto kern = fps_kernel<PPT, XYZ_REGS, MAX_THREADS>;
+    const size_t smem = sizeof(FpsSmem) + (size_t)threads * PPT * 3 * sizeof(float);
+    int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "fps: set max dynamic smem");
+    if (st) return st;
+    if (S > 8) {
+        st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                         "fps: allow cluster size 16");
+        if (st) return st;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * S));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, n, m, t_ref, xyz, temp, idx), "fps_kernel launch");
+}
+
+}  // namespace pu3
+
+using namespace pu3;
+
+// Test/tuning hook: force the cluster size (0 = heuristic).  Not part of the public header.
+static int g_fps_force_cluster = 0;
+extern "C" void pu3_fps_set_cluster(int s) { g_fps_force_cluster = s; }
+
+extern "C" int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
+                           pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && m >= 0, "fps: negative size b=%d n=%d m=%d", b, n, m);
+    if (b == 0 || m == 0) return PU3_OK;  // the reference kernel returns at once for m <= 0 (:106)
+    PU3_ARG_CHECK(n > 0, "fps: sampling %d points from an empty cloud", m);
+    PU3_ARG_CHECK(xyz && idx, "fps: null pointer");
+    cudaStream_t s = as_stream(stream);
+    const int t_ref = ref_block_size(n);
+    const int sms = device_info().sm_count;
+
+    // threads: power of two, a multiple of t_ref, about 4 points per thread for small clouds
+    int threads = ceil_pow2((n + 3) / 4);
+    if (threads < t_ref) threads = t_ref;
+    if (threads < 32) threads = 32;
+    if (threads > 1024) threads = 1024;
+
+    // cluster size: smallest power of two that brings the cloud down to <= 8 points per thread,
+    // limited by what keeps all clouds co-resident (b * S <= SM count) and by the portable limit
+    int S = 1;
+    if (g_fps_force_cluster > 0) {
+        S = g_fps_force_cluster;
+    } else {
+        int s_cap = floor_pow2(sms / b > 0 ? sms / b : 1);
+        if (s_cap > 8) s_cap = 8;
+        while (S < s_cap && (long long)S * threads * 8 < n) S *= 2;
+        // not enough with 8 points/thread: the shared-memory variants hold up to 32/thread at 512 threads
+        if ((long long)S * threads * 8 < n) {
+            S = 1;
+            while (S < 16 && (long long)S * 512 * 32 < n) S *= 2;
+        }
+    }
+    const long long per_cta_reg = (long long)threads * 8;
+    int st;
+    if ((long long)S * per_cta_reg >= n) {
+        const int ppt = (int)((n + (long long)S * threads - 1) / ((long long)S * threads));
+        if (ppt <= 1) st = launch_fps<1, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
+        else if (ppt <= 2) st = launch_fps<2, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
+        else if (ppt <= 4) st = launch_fps<4, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
+        else st = launch_fps<8, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
+    } else if ((long long)S * 512 * 32 >= n) {
+        const int ppt = (int)((n + (long long)S * 512 - 1) / ((long long)S * 512));
+        if (ppt <= 16) st = launch_fps<16, false, 512>(b, n, m, t_ref, S, 512, xyz, temp, idx, s);
+        else st = launch_fps<32, false, 512>(b, n, m, t_ref, S, 512, xyz, temp, idx, s);
+    } else {
+        PU3_ARG_CHECK(temp != nullptr, "fps: n=%d needs the temp buffer (clouds beyond 262144 points run from global memory)", n);
+        fps_fallback_kernel<<<b, 1024, 0, s>>>(n, m, t_ref, xyz, temp, idx);
+        st = cuda_status(cudaGetLastError(), "fps_fallback_kernel");
+    }
+    return st;
+}

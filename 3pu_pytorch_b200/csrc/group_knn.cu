@@ -1,0 +1,549 @@
+// k nearest neighbours + neighbour grouping, sm_100a.
+//
+// Replaces network.operations.group_knn / __batch_distance_matrix_general of the reference
+// (network/operations.py:151-216), which is a chain of PyTorch library calls with a blocking
+// device->host->device round trip in the middle:
+//     matmul + 2 broadcast adds  -> (B,M,N) distance matrix in HBM          (:158-161, :191)
+//     points.cpu().numpy(), np.unique per cloud, back to the device         (:192-204)
+//     topk(-D, k, sorted)         -> radix select + sort over the matrix    (:207)
+//     gather on an expanded view  -> (B,M,k,C), returned as a permuted view (:209-214)
+// Here the distance matrix never exists: distances are produced tile by tile from shared memory
+// and consumed by the selection in registers; duplicate detection runs on the device; the
+// neighbour features are written once, already in (B,C,M,k) order.
+//
+// Semantics kept from the reference:
+//   D = |q|^2 - 2 q.p + |p|^2 in fp32 ("expanded form", can be slightly negative)
+//   unique: every point equal (all channels) to an EARLIER point of its cloud gets max(D) added
+//           (np.unique keeps first occurrences; max over the reference's whole batch, here over
+//           `max_group` consecutive batch elements so that independent requests can share a launch)
+//   output sorted by ascending D; torch.topk leaves the order of equal distances unspecified,
+//   here equal distances are ordered by ascending point index.
+//
+// Kernels
+//   knn_dup_kernel       duplicate flags per point + "group has duplicates" flags
+//   knn_maxd_kernel      max(D) per group; exits at once when its group has no duplicates
+//   knn_small_kernel     k <= 64: one warp per query, candidates streamed from a shared-memory
+//                        tile, top-k kept sorted across the lanes of the warp
+//   knn_large_kernel     k  > 64: one CTA per query, keys in shared memory, radix select of the
+//                        k-th key, ordered compaction, bitonic sort of the k survivors
+#include "pu3_common.cuh"
+
+namespace pu3 {
+
+struct KnnArgs {
+    int b, c, m, n, k, p_div, max_group;
+    const float *query;   // (b,c,m)
+    const float *points;  // (b/p_div,c,n)
+    const uint8_t *dup;   // (b/p_div,n) or null
+    const int *group_any; // (groups) or null
+    const uint32_t *maxd; // (groups) ordered keys
+    float *knn;           // (b,c,m,k) or null
+    int64_t *idx64;       // (b,m,k) or null
+    int32_t *idx32;       // (b,m,k) or null
+    float *dist;          // (b,m,k) or null
+};
+
+// the reference's D = r_A - 2*m + r_B, evaluated left to right (operations.py:161)
+__device__ __forceinline__ float expanded_dist(float rq, float dot, float rp) {
+    return __fadd_rn(__fsub_rn(rq, __fmul_rn(2.0f, dot)), rp);
+}
+
+// --------------------------------------------------------------------------------------------
+// duplicates
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, int p_div, int max_group, int b,
+                                                     const float *__restrict__ points,
+                                                     uint8_t *__restrict__ dup, int *__restrict__ group_any) {
+    const int cloud = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float *p = points + (size_t)cloud * c * n;
+    const float v0 = p[j];
+    bool found = false;
+    for (int e = 0; e < j && !found; ++e) {
+        if (__ldg(p + e) != v0) continue;  // warp-uniform address: one broadcast load
+        bool same = true;
+        for (int ch = 1; ch < c && same; ++ch) same = p[(size_t)ch * n + e] == p[(size_t)ch * n + j];
+        found = same;
+    }
+    dup[(size_t)cloud * n + j] = found ? 1 : 0;
+    if (found) {
+        // every group that contains a batch element reading this cloud
+        const int b0 = cloud * p_div, b1 = min(b, (cloud + 1) * p_div) - 1;
+        for (int g = b0 / max_group; g <= b1 / max_group; ++g) group_any[g] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(128) knn_maxd_kernel(KnnArgs a, uint32_t *__restrict__ maxd) {
+    const int bi = blockIdx.y;
+    const int g = bi / a.max_group;
+    if (a.group_any[g] == 0) return;  // the common case: nothing to do
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t best = 0;
+    if (qi < a.m) {
+        const float *q = a.query + (size_t)bi * a.c * a.m;
+        const float *p = a.points + (size_t)(bi / a.p_div) * a.c * a.n;
+        float rq = 0.f;
+        for (int ch = 0; ch < a.c; ++ch) { const float v = q[(size_t)ch * a.m + qi]; rq = __fmaf_rn(v, v, rq); }
+        for (int j = 0; j < a.n; ++j) {
+            float dot = 0.f, rp = 0.f;
+            for (int ch = 0; ch < a.c; ++ch) {
+                const float pv = __ldg(p + (size_t)ch * a.n + j);
+                dot = __fmaf_rn(q[(size_t)ch * a.m + qi], pv, dot);
+                rp = __fmaf_rn(pv, pv, rp);
+            }
+            best = max(best, float_to_ordered(expanded_dist(rq, dot, rp)));
+        }
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(maxd + g, best);
+}
+
+// --------------------------------------------------------------------------------------------
+// k <= 64: warp per query
+// --------------------------------------------------------------------------------------------
+constexpr int KS_WARPS = 8;
+constexpr int KS_THREADS = KS_WARPS * 32;
+
+// Sorted top-k of a warp: position p = lane*E + e holds the p-th smallest (key, index).
+template <int E>
+struct WarpTopK {
+    uint32_t key[E];
+    int32_t id[E];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int e = 0; e < E; ++e) { key[e] = 0xffffffffu; id[e] = 0; }
+    }
+    // value at sorted position p, broadcast to the warp
+    __device__ __forceinline__ uint32_t key_at(int p) const {
+        uint32_t v = key[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e) if ((p % E) == e) v = key[e];
+        return __shfl_sync(0xffffffffu, v, p / E);
+    }
+    // insert (kd, ki) keeping order; equal keys stay in arrival (= index) order; the last of
+    // the 32*E positions falls off
+    __device__ __forceinline__ void insert(uint32_t kd, int32_t ki) {
+        const int lane = threadIdx.x & 31;
+        int ins = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) ins += __popc(__ballot_sync(0xffffffffu, key[e] <= kd));
+        const uint32_t up_k = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
+        const int32_t up_i = __shfl_up_sync(0xffffffffu, id[E - 1], 1);
+#pragma unroll
+        for (int e = E - 1; e >= 0; --e) {
+            const int p = lane * E + e;
+            const uint32_t prev_k = e == 0 ? up_k : key[e - 1];
+            const int32_t prev_i = e == 0 ? up_i : id[e - 1];
+            if (p > ins) { key[e] = prev_k; id[e] = prev_i; }
+            else if (p == ins) { key[e] = kd; id[e] = ki; }
+        }
+    }
+};
+
+// CT > 0: channel count known at compile time, query kept in registers.  CT == 0: generic.
+template <int CT, int E>
+__global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int tile_n, int q_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    const int C = CT > 0 ? CT : a.c;
+    float *sp = smem;                      // [C][tile_n] candidate tile, channel-major
+    float *srp = sp + (size_t)C * tile_n;  // [tile_n] squared norms
+    float *sq = srp + tile_n;              // [KS_WARPS][C] queries (generic path)
+
+    const int bi = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *qb = a.query + (size_t)bi * C * a.m;
+    const float *pb = a.points + (size_t)(bi / a.p_div) * C * a.n;
+    const int cloud = bi / a.p_div;
+    const bool penal = a.dup != nullptr && a.group_any[bi / a.max_group] != 0;
+    const float maxd = penal ? ordered_to_float(a.maxd[bi / a.max_group]) : 0.f;
+    const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
+
+    const int q_begin = blockIdx.x * q_per_cta;
+    const int q_end = min(a.m, q_begin + q_per_cta);
+    const int passes = (q_end - q_begin + KS_WARPS - 1) / KS_WARPS;
+
+    for (int pass = 0; pass < passes; ++pass) {
+        const int qi = q_begin + pass * KS_WARPS + warp;
+        const bool active = qi < q_end;  // warp-uniform
+        float qreg[CT > 0 ? CT : 1];
+        float rq = 0.f;
+        if (active) {
+            if (CT > 0) {
+#pragma unroll
+                for (int ch = 0; ch < (CT > 0 ? CT : 1); ++ch) {
+                    qreg[ch] = __ldg(qb + (size_t)ch * a.m + qi);
+                    rq = __fmaf_rn(qreg[ch], qreg[ch], rq);
+                }
+            } else {
+                for (int ch = lane; ch < C; ch += 32) sq[warp * C + ch] = __ldg(qb + (size_t)ch * a.m + qi);
+                __syncwarp();
+                for (int ch = 0; ch < C; ++ch) rq = __fmaf_rn(sq[warp * C + ch], sq[warp * C + ch], rq);
+            }
+        }
+        WarpTopK<E> top;
+        top.init();
+        uint32_t thr = 0xffffffffu;  // key at position k-1
+
+        for (int n0 = 0; n0 < a.n; n0 += tile_n) {
+            const int cnt = min(tile_n, a.n - n0);
+            // a cloud that fits one tile is staged once per CTA, not once per pass
+            if (n0 > 0 || pass == 0 || a.n > tile_n) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < cnt; t += KS_THREADS) {
+                    float r = 0.f;
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float v = __ldg(pb + (size_t)ch * a.n + n0 + t);
+                        sp[(size_t)ch * tile_n + t] = v;
+                        r = __fmaf_rn(v, v, r);
+                    }
+                    srp[t] = r;
+                }
+                __syncthreads();
+            }
+            if (!active) continue;
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int j = j0 + lane;
+                uint32_t key = 0xffffffffu;
+                if (j < cnt) {
+                    float dot = 0.f;
+                    if (CT > 0) {
+#pragma unroll
+                        for (int ch = 0; ch < (CT > 0 ? CT : 1); ++ch) dot = __fmaf_rn(qreg[ch], sp[ch * tile_n + j], dot);
+                    } else {
+                        for (int ch = 0; ch < C; ++ch) dot = __fmaf_rn(sq[warp * C + ch], sp[(size_t)ch * tile_n + j], dot);
+                    }
+                    float d = expanded_dist(rq, dot, srp[j]);
+                    if (penal && dupb[n0 + j]) d = __fadd_rn(d, maxd);  // D += max(D) * duplicated (:204)
+                    key = float_to_ordered(d);
+                }
+                unsigned pend = __ballot_sync(0xffffffffu, key < thr);
+                while (pend) {
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint32_t kd = __shfl_sync(0xffffffffu, key, src);
+                    if (kd < thr) {  // thr may have dropped since the ballot
+                        top.insert(kd, n0 + j0 + src);
+                        thr = top.key_at(a.k - 1);
+                    }
+                }
+            }
+        }
+        if (!active) continue;
+        // ---- outputs: position p = lane*E + e ----------------------------------------------
+        const size_t row = ((size_t)bi * a.m + qi) * a.k;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int p = lane * E + e;
+            if (p < a.k) {
+                if (a.idx64) a.idx64[row + p] = top.id[e];
+                if (a.idx32) a.idx32[row + p] = top.id[e];
+                if (a.dist) a.dist[row + p] = ordered_to_float(top.key[e]);
+            }
+        }
+        if (a.knn) {
+            for (int ch = 0; ch < C; ++ch) {
+                float *o = a.knn + (((size_t)bi * C + ch) * a.m + qi) * a.k;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int p = lane * E + e;
+                    if (p < a.k) o[p] = __ldg(pb + (size_t)ch * a.n + top.id[e]);
+                }
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// k > 64: CTA per query
+// --------------------------------------------------------------------------------------------
+constexpr int KL_THREADS = 256;
+
+__global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2, uint32_t *__restrict__ gkeys) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    // layout: sel[k2] u64 | hist[256] | misc[8] | keys[n] (unless gkeys)
+    unsigned long long *sel = reinterpret_cast<unsigned long long *>(raw);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sel + k2);
+    uint32_t *misc = hist + 256;
+    const int qi = blockIdx.x, bi = blockIdx.y;
+    uint32_t *keys = gkeys ? gkeys + ((size_t)bi * a.m + qi) * a.n : misc + 8;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.c;
+    const float *qb = a.query + (size_t)bi * C * a.m;
+    const float *pb = a.points + (size_t)(bi / a.p_div) * C * a.n;
+    const bool penal = a.dup != nullptr && a.group_any[bi / a.max_group] != 0;
+    const float maxd = penal ? ordered_to_float(a.maxd[bi / a.max_group]) : 0.f;
+    const uint8_t *dupb = penal ? a.dup + (size_t)(bi / a.p_div) * a.n : nullptr;
+
+    // ---- 1. keys --------------------------------------------------------------------------
+    float rq = 0.f;
+    for (int ch = 0; ch < C; ++ch) { const float v = __ldg(qb + (size_t)ch * a.m + qi); rq = __fmaf_rn(v, v, rq); }
+    for (int j = tid; j < a.n; j += KL_THREADS) {
+        float dot = 0.f, rp = 0.f;
+        for (int ch = 0; ch < C; ++ch) {
+            const float pv = __ldg(pb + (size_t)ch * a.n + j);
+            dot = __fmaf_rn(__ldg(qb + (size_t)ch * a.m + qi), pv, dot);
+            rp = __fmaf_rn(pv, pv, rp);
+        }
+        float d = expanded_dist(rq, dot, rp);
+        if (penal && dupb[j]) d = __fadd_rn(d, maxd);
+        keys[j] = float_to_ordered(d);
+    }
+    // ---- 2. radix select: key of rank k-1, MSB first, 8 bits per pass ------------------------
+    uint32_t prefix = 0, pmask = 0;
+    uint32_t want = a.k - 1;  // rank wanted among keys matching the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int j = tid; j < a.n; j += KL_THREADS) {
+            const uint32_t key = keys[j];
+            if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {  // 256 buckets: 8 per lane, exclusive scan
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { loc[i] = hist[lane * 8 + i]; sum += loc[i]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (want >= run && want < run + loc[i]) { misc[0] = lane * 8 + i; misc[1] = want - run; }
+                run += loc[i];
+            }
+        }
+        __syncthreads();
+        prefix |= misc[0] << shift;
+        pmask |= 255u << shift;
+        want = misc[1];
+        __syncthreads();
+    }
+    const uint32_t kth = prefix;         // key value at rank k-1
+    const uint32_t ties_wanted = want + 1;  // how many keys == kth belong to the top k (lowest indices)
+
+    // ---- 3. ordered compaction ------------------------------------------------------------
+    if (tid == 0) { misc[2] = 0; misc[3] = 0; }  // [2] slots used, [3] ties taken so far
+    for (int i = tid; i < k2; i += KL_THREADS) sel[i] = ~0ull;
+    __syncthreads();
+    for (int base = 0; base < a.n; base += KL_THREADS) {
+        const int j = base + tid;
+        const uint32_t key = j < a.n ? keys[j] : 0xffffffffu;
+        const bool less = j < a.n && key < kth;
+        const bool tie = j < a.n && key == kth;
+        // ties must be taken in index order: block-wide exclusive count of earlier ties
+        const unsigned tb = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) hist[warp] = __popc(tb);
+        __syncthreads();
+        uint32_t before = misc[3];
+        for (int w = 0; w < warp; ++w) before += hist[w];
+        before += __popc(tb & ((1u << lane) - 1u));
+        uint32_t total = 0;
+        for (int w = 0; w < KL_THREADS / 32; ++w) total += hist[w];
+        if (less || (tie && before < ties_wanted)) {
+            const uint32_t slot = atomicAdd(&misc[2], 1u);
+            sel[slot] = ((unsigned long long)key << 32) | (uint32_t)j;
+        }
+        __syncthreads();
+        if (tid == 0) misc[3] += total;
+        __syncthreads();
+    }
+    // ---- 4. bitonic sort of the packed (key,index) pairs, ascending ----------------------------
+    for (int size = 2; size <= k2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (k2 >> 1); t += KL_THREADS) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long x = sel[lo], y = sel[hi];
+                if ((x > y) == up) { sel[lo] = y; sel[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- 5. outputs ---------------------------------------------------------------------------
+    const size_t row = ((size_t)bi * a.m + qi) * a.k;
+    for (int p = tid; p < a.k; p += KL_THREADS) {
+        const unsigned long long v = sel[p];
+        const int32_t j = (int32_t)(uint32_t)v;
+        if (a.idx64) a.idx64[row + p] = j;
+        if (a.idx32) a.idx32[row + p] = j;
+        if (a.dist) a.dist[row + p] = ordered_to_float((uint32_t)(v >> 32));
+    }
+    if (a.knn) {
+        for (int ch = 0; ch < C; ++ch) {
+            float *o = a.knn + (((size_t)bi * C + ch) * a.m + qi) * a.k;
+            for (int p = tid; p < a.k; p += KL_THREADS) o[p] = __ldg(pb + (size_t)ch * a.n + (uint32_t)sel[p]);
+        }
+    }
+}
+
+// grad_points[b/p_div, c, idx[b,m,kk]] += grad_knn[b,c,m,kk]
+__global__ void __launch_bounds__(256) group_gather_bwd_kernel(int c, int m, int n, int k, int p_div, long long total,
+                                                              const float *__restrict__ grad_knn,
+                                                              const int64_t *__restrict__ idx,
+                                                              float *__restrict__ grad_points) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long mk = (long long)m * k;
+        const long long bc = t / mk;
+        const long long r = t - bc * mk;  // m*k offset
+        const long long bi = bc / c;
+        const int ch = (int)(bc - bi * c);
+        const int j = (int)idx[bi * mk + r];
+        atomicAdd(grad_points + ((bi / p_div) * c + ch) * (long long)n + j, grad_knn[t]);
+    }
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static int ceil_pow2_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct KnnPlan {
+    bool large;
+    int k2;
+    bool keys_global;
+    size_t smem;
+    int tile_n;
+    size_t off_dup, off_any, off_maxd, off_keys, total;
+    int groups;
+};
+
+static bool make_plan(int b, int c, int m, int n, int k, int p_div, int max_group, int unique, KnnPlan &pl) {
+    const int smem_cap = device_info().smem_optin;
+    pl.large = k > 64;
+    pl.k2 = 0; pl.keys_global = false; pl.tile_n = 0; pl.smem = 0;
+    if (pl.large) {
+        pl.k2 = ceil_pow2_i(k);
+        const size_t fixed = (size_t)pl.k2 * 8 + (256 + 8) * 4;
+        if (fixed > (size_t)smem_cap) return false;
+        pl.keys_global = fixed + (size_t)n * 4 > (size_t)smem_cap;
+        pl.smem = pl.keys_global ? fixed : fixed + (size_t)n * 4;
+    } else {
+        // ~48 KB candidate tile: several CTAs per SM; at least one warp-width of candidates
+        int tn = (int)((48 * 1024) / ((size_t)(c + 1) * 4));
+        tn = (tn / 32) * 32;
+        if (tn < 32) tn = 32;
+        const int n_up = ((n + 31) / 32) * 32;
+        if (tn > n_up) tn = n_up;
+        pl.tile_n = tn;
+        pl.smem = ((size_t)(c + 1) * tn + (size_t)KS_WARPS * c) * 4;
+        if (pl.smem > (size_t)smem_cap) return false;
+    }
+    const int clouds = (b + p_div - 1) / p_div;
+    pl.groups = (b + max_group - 1) / max_group;
+    size_t off = 0;
+    pl.off_any = off;  off += align256(unique ? (size_t)pl.groups * 4 : 0);
+    pl.off_maxd = off; off += align256(unique ? (size_t)pl.groups * 4 : 0);
+    pl.off_dup = off;  off += align256(unique ? (size_t)clouds * n : 0);
+    pl.off_keys = off; off += align256(pl.keys_global ? (size_t)b * m * n * 4 : 0);
+    pl.total = off;
+    return true;
+}
+
+}  // namespace pu3
+
+using namespace pu3;
+
+extern "C" size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique) {
+    if (b <= 0 || c <= 0 || m <= 0 || n <= 0 || k <= 0 || p_div <= 0) return 0;
+    KnnPlan pl;
+    // the group size does not change the byte count beyond the number of groups; size for max_group = 1
+    if (!make_plan(b, c, m, n, k, p_div, 1, unique, pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query,
+                                 const float *points, int unique, int max_group, float *knn, int64_t *idx64,
+                                 int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes,
+                                 pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && c > 0 && m >= 0 && n >= 0 && k >= 0, "group_knn: bad size b=%d c=%d m=%d n=%d k=%d", b, c, m, n, k);
+    PU3_ARG_CHECK(k <= n, "group_knn: points size must be greater or equal to k (n=%d, k=%d)", n, k);  // operations.py:186
+    if (b == 0 || m == 0 || k == 0) return PU3_OK;
+    PU3_ARG_CHECK(p_div >= 1 && b % p_div == 0, "group_knn: p_div=%d must divide b=%d", p_div, b);
+    PU3_ARG_CHECK(b <= 65535, "group_knn: b=%d exceeds 65535", b);
+    PU3_ARG_CHECK(query && points, "group_knn: null input pointer");
+    if (max_group <= 0 || max_group > b) max_group = b;
+    KnnPlan pl;
+    if (!make_plan(b, c, m, n, k, p_div, max_group, unique, pl)) {
+        set_error("group_knn: c=%d k=%d does not fit shared memory", c, k);
+        return PU3_E_UNSUPPORTED;
+    }
+    if (pl.total > 0) {
+        if (!workspace || workspace_bytes < pl.total) {
+            set_error("group_knn: workspace %zu bytes, need %zu", workspace_bytes, pl.total);
+            return PU3_E_WORKSPACE;
+        }
+        PU3_ARG_CHECK(((uintptr_t)workspace & 255) == 0, "group_knn: workspace must be 256-byte aligned");
+    }
+    cudaStream_t s = as_stream(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    KnnArgs a{b, c, m, n, k, p_div, max_group, query, points, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
+    if (unique) {
+        int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
+        uint32_t *maxd = reinterpret_cast<uint32_t *>(ws + pl.off_maxd);
+        uint8_t *dup = ws + pl.off_dup;
+        int st = cuda_status(cudaMemsetAsync(ws + pl.off_any, 0, pl.off_dup - pl.off_any, s), "group_knn: memset");
+        if (st) return st;
+        const int clouds = b / p_div;
+        knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, p_div, max_group, b, points, dup, group_any);
+        PU3_LAUNCH_CHECK("knn_dup_kernel");
+        a.dup = dup; a.group_any = group_any; a.maxd = maxd;
+        knn_maxd_kernel<<<dim3((m + 127) / 128, b), 128, 0, s>>>(a, maxd);
+        PU3_LAUNCH_CHECK("knn_maxd_kernel");
+    }
+    if (pl.large) {
+        PU3_ARG_CHECK(m <= 2147483647 / 1, "group_knn: m too large");
+        uint32_t *gkeys = pl.keys_global ? reinterpret_cast<uint32_t *>(ws + pl.off_keys) : nullptr;
+        int st = cuda_status(cudaFuncSetAttribute(knn_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+                             "group_knn: smem attr");
+        if (st) return st;
+        knn_large_kernel<<<dim3(m, b), KL_THREADS, pl.smem, s>>>(a, pl.k2, gkeys);
+        PU3_LAUNCH_CHECK("knn_large_kernel");
+        return PU3_OK;
+    }
+    // queries per CTA: enough CTAs to cover the chip twice, but never fewer than one pass of 8 warps
+    const int sms = device_info().sm_count;
+    int q_per_cta = m;
+    const long long want_ctas = 2LL * sms;
+    if ((long long)b < want_ctas) {
+        const int split = (int)((want_ctas + b - 1) / b);
+        q_per_cta = (m + split - 1) / split;
+        q_per_cta = ((q_per_cta + KS_WARPS - 1) / KS_WARPS) * KS_WARPS;
+    }
+    if (q_per_cta < KS_WARPS) q_per_cta = KS_WARPS;
+    dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
+    const int E = k <= 32 ? 1 : 2;
+#define PU3_KNN_LAUNCH(CT, EE)                                                                               \
+    do {                                                                                                      \
+        auto kern = knn_small_kernel<CT, EE>;                                                                 \
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem), \
+                             "group_knn: smem attr");                                                       \
+        if (st) return st;                                                                                    \
+        kern<<<grid, KS_THREADS, pl.smem, s>>>(a, pl.tile_n, q_per_cta);                                      \
+    } while (0)
+    if (c == 3 && E == 1) PU3_KNN_LAUNCH(3, 1);
+    else if (c == 3) PU3_KNN_LAUNCH(3, 2);
+    else if (c == 24 && E == 1) PU3_KNN_LAUNCH(24, 1);
+    else if (c == 24) PU3_KNN_LAUNCH(24, 2);
+    else if (E == 1) PU3_KNN_LAUNCH(0, 1);
+    else PU3_KNN_LAUNCH(0, 2);
+#undef PU3_KNN_LAUNCH
+    PU3_LAUNCH_CHECK("knn_small_kernel");
+    return PU3_OK;
+}
+
+extern "C" int pu3_group_gather_bwd_f32(int b, int c, int m, int n, int k, int p_div, const float *grad_knn,
+                                        const int64_t *idx64, float *grad_points, pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && c >= 0 && m >= 0 && n >= 0 && k >= 0 && p_div >= 1, "group_gather_bwd: bad size");
+    const long long total = (long long)b * c * m * k;
+    if (total == 0) return PU3_OK;
+    PU3_ARG_CHECK(grad_knn && idx64 && grad_points && n > 0, "group_gather_bwd: null pointer");
+    const long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_info().sm_count * 8;
+    group_gather_bwd_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(c, m, n, k, p_div, total,
+                                                                                              grad_knn, idx64, grad_points);
+    PU3_LAUNCH_CHECK("group_gather_bwd_kernel");
+    return PU3_OK;
+}

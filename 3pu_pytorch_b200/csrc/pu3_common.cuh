@@ -1,0 +1,91 @@
+// Shared device/host helpers of libpu3_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pu3_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpu3_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pu3 {
+
+// ---- host: status + error text -------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_status(cudaError_t e, const char *what);  // 0 or positive cudaError_t with text recorded
+
+#define PU3_ARG_CHECK(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::pu3::set_error(__VA_ARGS__);  \
+            return PU3_E_ARG;               \
+        }                                   \
+    } while (0)
+
+#define PU3_LAUNCH_CHECK(what)                                   \
+    do {                                                         \
+        int _st = ::pu3::cuda_status(cudaGetLastError(), what);  \
+        if (_st) return _st;                                     \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count;
+    int smem_optin;
+    int cc;
+};
+const DeviceInfo &device_info();  // cached per device
+
+static inline cudaStream_t as_stream(pu3_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device ---------------------------------------------------------------------------------
+// The reference's squared distance as its SASS evaluates it (nmdistance_cuda.cu:27-30,
+// sampling_cuda.cu:143): FMUL(dy,dy) -> FFMA(dx,dx,.) -> FFMA(dz,dz,.).  Spelled with
+// intrinsics so no compiler version can reassociate it.
+__device__ __forceinline__ float sqdist3(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Monotone map float -> uint32 (total order, -0 < +0, NaNs at the ends).
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// cluster helpers (inline PTX; cooperative_groups would do, this keeps the SASS visible)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_ptr` in CTA `rank` of this cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t map_to_cta(const void *local_smem_ptr, uint32_t rank) {
+    uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr)), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+}  // namespace pu3

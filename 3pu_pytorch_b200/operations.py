@@ -1,0 +1,194 @@
+"""Operator layer: same names, signatures and return conventions as the reference's
+network/operations.py (group_knn :165, gather_points :266, furthest_point_sample :303,
+normalize_point_batch :12), running on libpu3_b200's sm_100a kernels.
+
+CUDA tensors only.  A CPU tensor raises: this package has no CPU path by design (the CPU
+restatement lives in oracle/ and is test infrastructure).
+"""
+import torch
+
+from . import _lib
+from . import sampling
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensor required (3pu_pytorch_b200 has no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------------
+# normalize_point_batch
+# ------------------------------------------------------------------------------------------------
+def normalize_point_batch(pc, NCHW=True):
+    """operations.py:12-30.  Returns (normalised pc, centroid, furthest_distance)."""
+    point_axis, dim_axis = (2, 1) if NCHW else (1, 2)
+    centroid = torch.mean(pc, dim=point_axis, keepdim=True)
+    pc = pc - centroid
+    furthest_distance, _ = torch.max(
+        torch.sqrt(torch.sum(pc ** 2, dim=dim_axis, keepdim=True)), dim=point_axis, keepdim=True)
+    pc = pc / furthest_distance
+    return pc, centroid, furthest_distance
+
+
+# ------------------------------------------------------------------------------------------------
+# group_knn
+# ------------------------------------------------------------------------------------------------
+def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64):
+    """q (B,C,M), p (B/p_div,C,N) contiguous f32 on the same device -> (knn|None, idx, dist|None)."""
+    B, C, M = q.shape
+    Bp, _, N = p.shape
+    if Bp == 0 or B % Bp != 0:
+        raise RuntimeError(f"group_knn: points batch {Bp} must divide query batch {B}")
+    p_div = B // Bp
+    if N < k:
+        raise AssertionError("points size must be greater or equal to k")  # operations.py:186
+    dev = q.device
+    knn = torch.empty(B, C, M, k, dtype=torch.float32, device=dev) if want_knn else None
+    idx = torch.empty(B, M, k, dtype=idx_dtype, device=dev)
+    dist = torch.empty(B, M, k, dtype=torch.float32, device=dev) if want_dist else None
+    L = _lib.lib()
+    with _lib.on_device(q):
+        ws_bytes = L.pu3_group_knn_workspace(B, C, M, N, k, p_div, int(bool(unique)))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        idx64 = idx if idx_dtype == torch.int64 else None
+        idx32 = idx if idx_dtype == torch.int32 else None
+        _lib.check(L.pu3_group_knn_f32(B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
+                                       int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32),
+                                       _lib.ptr(dist), _lib.ptr(ws), ws_bytes, _lib.stream_of(q)), "group_knn")
+    return knn, idx, dist
+
+
+class GroupKNNFunction(torch.autograd.Function):
+    """Differentiable like the reference's composition: neighbours through torch.gather
+    (operations.py:209-211) and distances through the distance matrix (:158-161, :207)."""
+
+    @staticmethod
+    def forward(ctx, k, query, points, unique, max_group):
+        knn, idx, dist = _knn_raw(k, query, points, unique, max_group)
+        ctx.save_for_backward(query, points, idx)
+        ctx.mark_non_differentiable(idx)
+        return knn, idx, dist
+
+    @staticmethod
+    def backward(ctx, g_knn, _g_idx, g_dist):
+        query, points, idx = ctx.saved_tensors
+        B, C, M = query.shape
+        Bp, _, N = points.shape
+        k = idx.size(2)
+        p_div = B // Bp
+        g_query = None
+        g_scatter = g_knn.contiguous() if g_knn is not None else None
+        if g_dist is not None:
+            # d/dq D = 2 (q - p_j), d/dp_j D = -2 (q - p_j); the duplicate penalty is a constant
+            exp_idx = idx.unsqueeze(1).expand(-1, C, -1, -1).reshape(B, C, M * k)
+            src = points if p_div == 1 else points.repeat_interleave(p_div, dim=0)
+            nb = torch.gather(src, 2, exp_idx).view(B, C, M, k)
+            diff = 2.0 * g_dist.unsqueeze(1) * (query.unsqueeze(-1) - nb)
+            g_query = diff.sum(dim=-1)
+            g_scatter = -diff if g_scatter is None else g_scatter - diff
+        g_points = None
+        if g_scatter is not None and ctx.needs_input_grad[2]:
+            g_points = torch.zeros_like(points)
+            g_scatter = g_scatter.contiguous()
+            with _lib.on_device(points):
+                _lib.check(_lib.lib().pu3_group_gather_bwd_f32(B, C, M, N, k, p_div, _lib.ptr(g_scatter), _lib.ptr(idx),
+                                                               _lib.ptr(g_points), _lib.stream_of(points)),
+                           "group_knn backward")
+        if not ctx.needs_input_grad[1]:
+            g_query = None
+        return None, g_query, g_points, None, None
+
+
+def group_knn(k, query, points, unique=True, NCHW=True, max_group=None):
+    """operations.py:165-216.
+    :param k neighbourhood size; query BxCxM or BxMxC; points BxCxN or BxNxC
+    :param unique  duplicated points (all coordinates equal to an earlier point) are pushed to the back
+    :param NCHW    second dimension is the channel dimension
+    :param max_group (extension) number of consecutive batch elements the duplicate penalty max(D)
+                   is taken over; None = the whole batch, which is the reference's behaviour
+    :return neighbor_points BxCxMxk (NCHW) or BxMxkxC, index_batch BxMxk int64, distance_batch BxMxk ascending
+    `points` may have a batch that divides the query batch: element i then reads points[i // (B/Bp)]
+    (what the reference obtains with expand(), upsampler.py:319-323).
+    """
+    _need_cuda(query, "group_knn"); _need_cuda(points, "group_knn")
+    if query.dtype != torch.float32 or points.dtype != torch.float32:
+        raise RuntimeError("group_knn: float32 tensors required")
+    if NCHW:
+        q, p = query.contiguous(), points.contiguous()
+    else:
+        q, p = query.transpose(2, 1).contiguous(), points.transpose(2, 1).contiguous()
+    assert p.size(2) >= k, "points size must be greater or equal to k"
+    knn, idx, dist = GroupKNNFunction.apply(int(k), q, p, bool(unique), max_group)
+    if not NCHW:
+        knn = knn.permute(0, 2, 3, 1)
+    return knn, idx, dist
+
+
+# ------------------------------------------------------------------------------------------------
+# gather_points / furthest_point_sample
+# ------------------------------------------------------------------------------------------------
+class GatherFunction(torch.autograd.Function):
+    """operations.py:219-263."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        _need_cuda(features, "gather_points")
+        features = features.contiguous()
+        idx = idx.contiguous().to(dtype=torch.int32)
+        B, npoint = idx.size()
+        _, C, N = features.size()
+        output = torch.empty(B, C, npoint, dtype=features.dtype, device=features.device)
+        sampling.gather_forward(B, C, N, npoint, features, idx, output)
+        ctx.save_for_backward(idx)
+        ctx.C, ctx.N = C, N
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, = ctx.saved_tensors
+        B, npoint = idx.size()
+        grad_features = torch.zeros(B, ctx.C, ctx.N, dtype=grad_out.dtype, device=grad_out.device)
+        sampling.gather_backward(B, ctx.C, ctx.N, npoint, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+gather_points = GatherFunction.apply
+
+
+class FurthestPointSampling(torch.autograd.Function):
+    """operations.py:269-297.  xyz (B,N,3) -> idx (B,npoint) int32, not differentiable."""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        _need_cuda(xyz, "furthest_point_sample")
+        B, N, _ = xyz.size()
+        idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
+        # temp = None: "filled with 1e10, not written back" -- the reference allocates and fills a
+        # (B,N) buffer per call (operations.py:291) that nobody reads afterwards
+        with _lib.on_device(xyz):
+            _lib.check(_lib.lib().pu3_fps_f32(B, N, int(npoint), _lib.ptr(xyz), None, _lib.ptr(idx),
+                                              _lib.stream_of(xyz)), "furthest_point_sample")
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, grad_idx):
+        return None, None
+
+
+def furthest_point_sample(xyz, npoint, NCHW=True):
+    """operations.py:303-323.
+    :param xyz (B,3,N) or (B,N,3); npoint a constant
+    :return idx (B,npoint) int32 and the sampled points (B,3,npoint) or (B,npoint,3)
+    """
+    assert xyz.dim() == 3, "input for furthest sampling must be a 3D-tensor, but xyz.size() is {}".format(xyz.size())
+    if NCHW:
+        xyz = xyz.transpose(2, 1).contiguous()
+    assert xyz.size(2) == 3, "furthest sampling is implemented for 3D points"
+    if xyz.dtype != torch.float32:
+        raise RuntimeError("furthest_point_sample: float32 required")
+    idx = FurthestPointSampling.apply(xyz.contiguous(), npoint)
+    sampled_pc = gather_points(xyz.transpose(2, 1).contiguous(), idx)
+    if not NCHW:
+        sampled_pc = sampled_pc.transpose(2, 1).contiguous()
+    return idx, sampled_pc

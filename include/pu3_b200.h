@@ -1,0 +1,133 @@
+/*
+ * pu3_b200.h -- C ABI of the B200-native 3PU patch-upsampling hot path.
+ *
+ * One shared library (3pu_pytorch_b200/lib/libpu3_b200.so), plain pointers and
+ * sizes, no torch types.  Every pointer is a DEVICE pointer on the device that
+ * is current for the calling thread unless stated otherwise; every call only
+ * ENQUEUES work on `stream` (a cudaStream_t passed as void*, NULL = legacy
+ * default stream) and never synchronises, so all entry points can be captured
+ * in CUDA graphs.  Return value: 0 on success, otherwise a negative PU3_E_*
+ * code (argument error, nothing launched) or a positive cudaError_t; the text
+ * is available from pu3_last_error().  Nothing here ever calls exit(): the
+ * reference kills the process on a launch failure (sampling_cuda.cu:56-60,
+ * 259-263) or prints and carries on (nmdistance_cuda.cu:144-149).
+ *
+ * Section A replaces the reference's two pybind extension modules one entry
+ * point for one; section B is the part of the path the reference runs as
+ * PyTorch library calls (network/operations.py, layers.py, upsampler.py) and
+ * that this library runs as its own kernels.
+ */
+#ifndef PU3_B200_H
+#define PU3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *pu3_stream_t; /* cudaStream_t */
+
+#define PU3_OK 0
+#define PU3_E_ARG (-1)         /* bad size / null pointer / unsupported combination */
+#define PU3_E_WORKSPACE (-2)   /* workspace too small: call the *_workspace() query */
+#define PU3_E_UNSUPPORTED (-3) /* valid request this build cannot serve */
+
+const char *pu3_last_error(void); /* thread-local text of the last non-zero status */
+int pu3_version(void);            /* ABI version, bumped on any signature change */
+/* SM count, max opt-in shared memory per block and compute capability (major*10+minor) of the current device */
+int pu3_device_info(int *sm_count, int *smem_optin_bytes, int *cc);
+
+/* ------------------------------------------------------------------------------------------
+ * A. replacements of the reference's native entry points
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * Farthest point sampling.  Replaces sampling.furthest_sampling
+ * (sampling/sampling.cpp:26-35 -> furthest_sampling_cuda_forward,
+ * sampling/sampling_cuda.cu:103-265).
+ *   xyz  (b,n,3) f32 contiguous      idx (b,m) i32 out, idx[:,0] = 0
+ *   temp (b,n)   f32 in/out running min distance; the reference's caller fills it with 1e10
+ *        (network/operations.py:291).  NULL = "filled with 1e10, do not write back".
+ * Bit-exact with the reference kernel including its tie rule (lowest k mod T, then lowest k,
+ * T = 2^floor(log2 n) capped at 512) and its FMUL/FFMA distance; differs on purpose only where
+ * the reference is wrong: every batch element owns its temp row, so b > 32 is correct
+ * (the reference indexes temp by blockIdx.x, sampling_cuda.cu:131,146).
+ */
+int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, pu3_stream_t stream);
+
+/*
+ * Point gather, out[b,c,j] = points[b,c,idx[b,j]].  Replaces sampling.gather_forward
+ * (sampling/sampling.cpp:37-45, sampling_cuda.cu:26-62).  points (b,c,n), idx (b,m) i32, out (b,c,m).
+ * elem_bytes = 2, 4 or 8 (the reference dispatches half/float/double; a gather only moves bits).
+ */
+int pu3_gather_fwd(int b, int c, int n, int m, int elem_bytes, const void *points, const int32_t *idx,
+                   void *out, pu3_stream_t stream);
+
+/*
+ * Gather backward, grad_points[b,c,idx[b,j]] += grad_out[b,c,j] into a caller-zeroed buffer.
+ * Replaces sampling.gather_backward (sampling/sampling.cpp:47-53, sampling_cuda.cu:64-100).
+ * dtype: 0 = f32, 1 = f64, 2 = f16.  Atomic adds, summation order unspecified like the reference.
+ */
+int pu3_gather_bwd(int b, int c, int n, int m, int dtype, const void *grad_out, const int32_t *idx,
+                   void *grad_points, pu3_stream_t stream);
+
+/*
+ * Ball query.  Replaces sampling.ball_query (sampling/sampling.cpp:59-81, sampling_cuda.cu:267-314),
+ * which no reference Python calls; kept for surface completeness.  idx (b,m,nsample) i32 must arrive
+ * zero-filled (the reference allocates it with torch::zeros).
+ */
+int pu3_ball_query_f32(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                       const float *xyz, int32_t *idx, pu3_stream_t stream);
+
+/*
+ * Chamfer / nearest-neighbour distance, both directions.  Replaces losses.nmdistance_forward
+ * (losses/nmdistance.cpp:12-14 -> chamfer_cuda_forward, nmdistance_cuda.cu:11-153).
+ *   xyz1 (b,n,3), xyz2 (b,m,3) f32;  dist1,idx1 (b,n);  dist2,idx2 (b,m); idx = lowest index at the minimum.
+ * Bit-exact with the reference kernel (same FMUL/FFMA order).
+ */
+int pu3_nmdist_fwd_f32(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
+                       float *dist2, int32_t *idx1, int32_t *idx2, pu3_stream_t stream);
+
+/*
+ * Chamfer backward into caller-zeroed gradxyz1 (b,n,3), gradxyz2 (b,m,3).  Replaces
+ * losses.nmdistance_backward (losses/nmdistance.cpp:17-21, nmdistance_cuda.cu:154-194).
+ */
+int pu3_nmdist_bwd_f32(int b, int n, int m, const float *xyz1, const float *xyz2, float *gradxyz1,
+                       float *gradxyz2, const float *graddist1, const float *graddist2,
+                       const int32_t *idx1, const int32_t *idx2, pu3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B. the PyTorch-level part of the path, as kernels
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * k nearest neighbours + neighbour grouping.  Replaces network.operations.group_knn
+ * (network/operations.py:151-216: matmul distance matrix, CPU np.unique round trip, topk, gather).
+ *   query  (b,c,m) f32, points (b/p_div,c,n) f32 -- channel-major ("NCHW"); batch element i reads
+ *          points[i / p_div] (p_div > 1 = the reference's expand() of the previous level, upsampler.py:319-323)
+ *   k <= n; distances are the reference's expanded form |q|^2 - 2 q.p + |p|^2 in f32
+ *   unique != 0: every point that equals an earlier point of its cloud in all c channels gets
+ *          max(D) added, max taken over groups of `max_group` consecutive batch elements
+ *          (the reference takes it over its whole batch: max_group = b; operations.py:204)
+ *   outputs, each may be NULL: knn (b,c,m,k) f32 contiguous; idx64 (b,m,k) i64; idx32 (b,m,k) i32;
+ *          dist (b,m,k) f32, ascending; ties are ordered by ascending point index.
+ *   workspace: pu3_group_knn_workspace() bytes, 256-byte aligned.
+ */
+size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique);
+int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query, const float *points,
+                      int unique, int max_group, float *knn, int64_t *idx64, int32_t *idx32, float *dist,
+                      void *workspace, size_t workspace_bytes, pu3_stream_t stream);
+
+/*
+ * Backward of the neighbour gather of group_knn: grad_points[b/p_div, c, idx[b,m,kk]] += grad_knn[b,c,m,kk]
+ * into a caller-zeroed (b/p_div,c,n) buffer (autograd of torch.gather, operations.py:209-211).
+ */
+int pu3_group_gather_bwd_f32(int b, int c, int m, int n, int k, int p_div, const float *grad_knn,
+                             const int64_t *idx64, float *grad_points, pu3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PU3_B200_H */

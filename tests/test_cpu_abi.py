@@ -1,0 +1,46 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pu3_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pu3_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for must in ("pu3_fps_f32", "pu3_gather_fwd", "pu3_gather_bwd", "pu3_nmdist_fwd_f32", "pu3_nmdist_bwd_f32",
+                 "pu3_group_knn_f32", "pu3_ball_query_f32"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(pu3):
+    handle = ctypes.CDLL(pu3._lib.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(handle, name), f"{name} declared in include/pu3_b200.h but not exported"
+    assert set(_declared_symbols()) == set(pu3._lib.SIGNATURES), "binding table and header disagree"
+    assert handle.pu3_version() == pu3._lib.ABI_VERSION
+
+
+def test_argument_errors_do_not_need_a_gpu(pu3):
+    L = pu3._lib.lib()
+    assert L.pu3_fps_f32(1, 0, 3, None, None, None, None) == -1
+    assert b"empty cloud" in L.pu3_last_error()
+    assert L.pu3_gather_fwd(1, 1, 4, 2, 3, 1, 1, 1, None) == -1  # elem_bytes 3
+    assert L.pu3_group_knn_f32(1, 3, 4, 2, 5, 1, 1, 1, 0, 0, None, None, None, None, None, 0, None) == -1  # k > n
+    assert b"greater or equal to k" in L.pu3_last_error()
+
+
+def test_cpu_tensors_are_refused(pu3):
+    import torch
+    with pytest.raises(RuntimeError):
+        pu3.operations.group_knn(3, torch.rand(1, 3, 8), torch.rand(1, 3, 8))
+    with pytest.raises(RuntimeError):
+        pu3.operations.furthest_point_sample(torch.rand(1, 3, 8), 2)

@@ -1,0 +1,138 @@
+"""GPU parity of group_knn (the reference runs it as PyTorch library calls + a CPU np.unique round trip,
+network/operations.py:165-216) against the CPU oracle restatement oracle/ref_net.group_knn.
+
+Indices: exact wherever the float64 distance gap between the two candidates exceeds the fp32 rounding of
+the expanded-form distance (tests/util.knn_gap_check); neighbour features: bit-exact copies of
+points[idx]; distances: within that same rounding, ascending."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_net
+from tests.util import knn_gap_check, bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(pu3, cuda, k, q, p, unique, penalty_dups=False, max_group=None):
+    rk, ri, rd = ref_net.group_knn(k, q, p.expand(q.size(0), -1, -1) if p.size(0) != q.size(0) else p,
+                                   unique=unique, NCHW=True)
+    nb, idx, dist = pu3.operations.group_knn(k, q.to(cuda), p.to(cuda), unique=unique, NCHW=True, max_group=max_group)
+    assert nb.shape == rk.shape and idx.dtype == torch.int64 and idx.shape == ri.shape
+    penalty = None
+    if unique and penalty_dups:
+        pe = p.expand(q.size(0), -1, -1) if p.size(0) != q.size(0) else p
+        dmask = ref_net.duplicate_mask(pe.transpose(1, 2).contiguous()).double()
+        D = ref_net.pairwise_sqdist_expanded(q.transpose(1, 2).contiguous(), pe.transpose(1, 2).contiguous())
+        penalty = float(D.max()) * dmask
+    ndiff = knn_gap_check(q, p, idx, dist, ri, k, penalty=penalty)
+    # neighbour features are exact copies of the selected points
+    pe = p if p.size(0) == q.size(0) else p.repeat_interleave(q.size(0) // p.size(0), dim=0)
+    B, C, M = q.shape
+    exp = torch.gather(pe, 2, idx.cpu().view(B, 1, M * k).expand(-1, C, -1)).view(B, C, M, k)
+    assert bits_equal(nb.cpu().numpy(), exp.numpy())
+    return ndiff, idx.numel()
+
+
+@pytest.mark.parametrize("b,c,n,k", [(4, 24, 312, 33), (2, 24, 312, 17), (3, 3, 700, 5), (2, 3, 2496, 2),
+                                     (1, 3, 6240, 5), (2, 7, 100, 64), (2, 24, 40, 33), (1, 3, 33, 33)])
+def test_self_knn_small_k(pu3, cuda, b, c, n, k):
+    g = torch.Generator().manual_seed(b * 100 + n + k)
+    x = torch.rand(b, c, n, generator=g)
+    ndiff, total = _check(pu3, cuda, k, x, x, unique=True)
+    assert ndiff <= max(4, total // 2000), (ndiff, total)  # near-ties are rare on random data
+
+
+@pytest.mark.parametrize("b,m,n,k", [(2, 5, 3000, 312), (2, 1, 4992, 2496), (3, 1, 624, 312), (1, 48, 5000, 312),
+                                     (1, 2, 300, 300), (1, 3, 24960, 312), (2, 4, 1000, 65), (1, 2, 9000, 4992)])
+def test_patch_extraction_large_k(pu3, cuda, b, m, n, k):
+    g = torch.Generator().manual_seed(m * 10 + n + k)
+    p = torch.rand(b, 3, n, generator=g)
+    seeds = p[:, :, torch.randperm(n, generator=g)[:m]].contiguous()
+    ndiff, total = _check(pu3, cuda, k, seeds, p, unique=False)
+    assert ndiff <= max(4, total // 2000), (ndiff, total)
+
+
+def test_query_differs_from_points_with_shared_cloud(pu3, cuda):
+    # inter-level skip connection: 10 patches of 312 queries against ONE previous-level cloud
+    # (the reference expand()s it, upsampler.py:319-323); here the points batch divides the query batch
+    g = torch.Generator().manual_seed(4)
+    prev = torch.rand(2, 3, 3120, generator=g)
+    q = torch.rand(20, 3, 312, generator=g)
+    _check(pu3, cuda, 5, q, prev, unique=True)
+
+
+def test_duplicates_are_pushed_back(pu3, cuda):
+    g = torch.Generator().manual_seed(8)
+    p = torch.rand(3, 3, 200, generator=g)
+    p[0, :, 50] = p[0, :, 10]; p[0, :, 51] = p[0, :, 10]; p[1, :, 199] = p[1, :, 0]; p[2, :, 7] = p[2, :, 3]
+    q = p[:, :, :64].contiguous()
+    _check(pu3, cuda, 8, q, p, unique=True, penalty_dups=True)
+    nb, idx, dist = pu3.operations.group_knn(200, q.to(cuda), p.to(cuda), unique=True)
+    # with k == n every duplicate must sit at the very end of its row, after all first occurrences
+    assert set(idx[0, 0, -2:].tolist()) == {50, 51} and int(idx[1, 0, -1]) == 199 and int(idx[2, 0, -1]) == 7
+    # unique=False keeps them where their distance puts them: point 10's row has 10, 50, 51 in index order first
+    _, idx2, d2 = pu3.operations.group_knn(3, q.to(cuda), p.to(cuda), unique=False)
+    assert idx2[0, 10].tolist() == [10, 50, 51]
+
+
+def test_duplicate_penalty_group_scope(pu3, cuda):
+    # max(D) is taken over the whole batch in the reference (operations.py:204); max_group narrows it
+    g = torch.Generator().manual_seed(9)
+    p = torch.rand(4, 3, 100, generator=g)
+    p[1] *= 10.0  # cloud 1 has by far the largest distances
+    p[0, :, 5] = p[0, :, 2]
+    pc = p.to(cuda)
+    _, _, d_all = pu3.operations.group_knn(100, pc, pc, unique=True)
+    _, _, d_own = pu3.operations.group_knn(100, pc, pc, unique=True, max_group=1)
+    D = ref_net.pairwise_sqdist_expanded(p.transpose(1, 2).contiguous(), p.transpose(1, 2).contiguous())
+    add_all = float(D.max()); add_own = float(D[0].max())
+    assert abs(float(d_all[0, 0, -1]) - (float(D[0, 0, 5]) + add_all)) <= 1e-4 * add_all
+    assert abs(float(d_own[0, 0, -1]) - (float(D[0, 0, 5]) + add_own)) <= 1e-4 * add_own
+
+
+def test_nhwc_layout_and_errors(pu3, cuda):
+    g = torch.Generator().manual_seed(1)
+    p = torch.rand(2, 150, 3, generator=g); q = torch.rand(2, 9, 3, generator=g)
+    rk, ri, rd = ref_net.group_knn(6, q, p, unique=True, NCHW=False)
+    nb, idx, dist = pu3.operations.group_knn(6, q.to(cuda), p.to(cuda), unique=True, NCHW=False)
+    assert nb.shape == (2, 9, 6, 3) and rk.shape == nb.shape
+    knn_gap_check(q.transpose(1, 2).contiguous(), p.transpose(1, 2).contiguous(), idx, dist, ri, 6)
+    exp = torch.gather(p.unsqueeze(1).expand(-1, 9, -1, -1), 2, idx.cpu().unsqueeze(-1).expand(-1, -1, -1, 3))
+    assert bits_equal(nb.contiguous().cpu().numpy(), exp.contiguous().numpy())
+    with pytest.raises(AssertionError, match="greater or equal to k"):
+        pu3.operations.group_knn(200, q.to(cuda), p.to(cuda), NCHW=False)
+    with pytest.raises(RuntimeError, match="CUDA tensor required"):
+        pu3.operations.group_knn(3, q, p, NCHW=False)
+
+
+def test_group_knn_backward_matches_oracle_autograd(pu3, cuda):
+    g = torch.Generator().manual_seed(12)
+    p0 = torch.rand(2, 6, 80, generator=g); q0 = torch.rand(2, 6, 30, generator=g)
+    w_nb = torch.randn(2, 6, 30, 7, generator=g); w_d = torch.randn(2, 30, 7, generator=g)
+
+    def run(fn, dev):
+        p = p0.clone().to(dev).requires_grad_(); q = q0.clone().to(dev).requires_grad_()
+        nb, idx, d = fn(7, q, p, unique=True, NCHW=True)
+        ((nb * w_nb.to(dev)).sum() + (d * w_d.to(dev)).sum()).backward()
+        return p.grad.cpu(), q.grad.cpu(), idx.cpu()
+
+    gp_ref, gq_ref, i_ref = run(ref_net.group_knn, "cpu")
+    gp, gq, i = run(pu3.operations.group_knn, cuda)
+    assert torch.equal(i, i_ref)
+    torch.testing.assert_close(gp, gp_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gq, gq_ref, rtol=1e-5, atol=1e-5)
+
+
+def test_chamfer_loss_module(pu3, cuda):
+    g = torch.Generator().manual_seed(3)
+    a0 = torch.rand(4, 3, 624, generator=g); b0 = torch.rand(4, 3, 624, generator=g)
+    for thr in (None, 2.0):
+        a = a0.clone().requires_grad_()
+        want = ref_net.chamfer_loss(a, b0, threshold=thr)
+        want.backward()
+        ac = a0.clone().to(cuda).requires_grad_()
+        got = pu3.model_loss.ChamferLoss(threshold=thr)(ac, b0.to(cuda))
+        got.backward()
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-6, atol=1e-8)
+        torch.testing.assert_close(ac.grad.cpu(), a.grad, rtol=1e-5, atol=1e-8)

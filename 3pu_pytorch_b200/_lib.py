@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpu3_b200.so")
 ABI_VERSION = 1
 
 _c_int, _c_void_p, _c_size_t, _c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float
+_c_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes); must list every symbol of include/pu3_b200.h (tests check this)
 SIGNATURES = {
@@ -30,6 +31,11 @@ SIGNATURES = {
     "pu3_group_knn_workspace": (_c_size_t, [_c_int] * 7),
     "pu3_group_knn_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "pu3_group_gather_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 4),
+    "pu3_pointwise_conv_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p, _c_ll,
+                                                         _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_void_p]),
+    "pu3_expand_code_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "pu3_edgeconv_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
+                         [_c_void_p, _c_ll, _c_void_p]),
 }
 
 _lib = None

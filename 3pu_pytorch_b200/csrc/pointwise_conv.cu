@@ -1,0 +1,175 @@
+// 1x1 convolution over points (per-point MLP layer), fp32, sm_100a.
+//
+// Replaces the nn.Conv1d / nn.Conv2d 1x1 layers of the reference (network/layers.py:115-204 used at
+// network/upsampler.py:209-230,288-369), which run as cuDNN/cuBLAS library calls plus separate bias /
+// ReLU / cat kernels.  Here one kernel computes
+//     Y[b, co, p] = act( sum_ci W[co,ci] * X[b, ci, p] + bias[co] )  (+ residual R[b, co, p / rdiv])
+// reading X from and writing Y into CHANNEL SLICES of larger (B, Ctot, N) buffers (pointer + batch
+// stride), so the dense concatenations of Level.forward (torch.cat at upsampler.py:293,299,305,311)
+// cost nothing: every layer writes its output where the next layer expects it.
+//
+// fp32 FFMA on purpose: the tolerance of the path is 1e-5 relative, which rules out TF32/BF16 tensor
+// core inputs (hard parts).  It is a register-tiled SGEMM: the CTA tile is
+// TM output channels x TN points, each thread owns 8x8 (or RM x 8) accumulators, K (= Cin) is streamed
+// through shared memory in chunks of KC.  Columns are the flattened (batch, point) index, so tiles
+// are full even when N (312) is not a multiple of the tile width.
+#include "pu3_common.cuh"
+
+namespace pu3 {
+
+constexpr int PW_KC = 16;
+
+struct PwArgs {
+    int b, n, cin, cout;
+    const float *x; long long x_bstride;   // X[b] = x + b*x_bstride, channel stride n
+    const float *w;                        // (cout, cin) row-major
+    const float *bias;                     // (cout) or null
+    float *y; long long y_bstride;
+    const float *res; long long res_bstride; int res_n, res_div;  // optional residual (b, cout, res_n), column p / res_div
+    int relu;
+};
+
+// TM = RM * TY output channels, TN = 8 * TX columns, threads = TX * TY
+template <int RM, int TY, int TX>
+__global__ void __launch_bounds__(TX * TY) pointwise_conv_kernel(PwArgs a) {
+    constexpr int TM = RM * TY, TN = 8 * TX, NT = TX * TY;
+    __shared__ __align__(16) float Ws[PW_KC][TM + 4];
+    __shared__ __align__(16) float Xs[PW_KC][TN];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long cols = (long long)a.b * a.n;
+    const long long col0 = (long long)blockIdx.x * TN;
+    const int co0 = blockIdx.y * TM;
+
+    // column bookkeeping for the loads: thread loads column (tid % TN) for rows tid / TN, ...
+    float acc[RM][8];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < a.cin; k0 += PW_KC) {
+        // ---- stage W chunk (transposed: Ws[k][co]) and X chunk ---------------------------------
+        for (int t = threadIdx.x; t < PW_KC * TM; t += NT) {
+            const int k = t % PW_KC, co = t / PW_KC;  // consecutive threads walk k: contiguous in W rows
+            const int gk = k0 + k, gco = co0 + co;
+            Ws[k][co] = (gk < a.cin && gco < a.cout) ? __ldg(a.w + (size_t)gco * a.cin + gk) : 0.f;
+        }
+        for (int t = threadIdx.x; t < PW_KC * TN; t += NT) {
+            const int c = t % TN, k = t / TN;
+            const long long col = col0 + c;
+            const int gk = k0 + k;
+            float v = 0.f;
+            if (col < cols && gk < a.cin) {
+                const long long bi = col / a.n;
+                const int p = (int)(col - bi * a.n);
+                v = __ldg(a.x + bi * a.x_bstride + (size_t)gk * a.n + p);
+            }
+            Xs[k][c] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PW_KC; ++k) {
+            float wv[RM], xv[8];
+#pragma unroll
+            for (int i = 0; i < RM; i += 4) {
+                if (RM - i >= 4) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(&Ws[k][ty * RM + i]);
+                    wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+                } else {
+#pragma unroll
+                    for (int r = i; r < RM; ++r) wv[r] = Ws[k][ty * RM + r];
+                }
+            }
+            const float4 x0 = *reinterpret_cast<const float4 *>(&Xs[k][tx * 8]);
+            const float4 x1 = *reinterpret_cast<const float4 *>(&Xs[k][tx * 8 + 4]);
+            xv[0] = x0.x; xv[1] = x0.y; xv[2] = x0.z; xv[3] = x0.w;
+            xv[4] = x1.x; xv[5] = x1.y; xv[6] = x1.z; xv[7] = x1.w;
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(wv[i], xv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: bias, residual, ReLU, store ---------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int co = co0 + ty * RM + i;
+        if (co >= a.cout) continue;
+        const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long col = col0 + tx * 8 + j;
+            if (col >= cols) continue;
+            const long long bi = col / a.n;
+            const int p = (int)(col - bi * a.n);
+            float v = acc[i][j] + bv;
+            if (a.relu) v = fmaxf(v, 0.f);
+            if (a.res) v += __ldg(a.res + bi * a.res_bstride + (size_t)co * a.res_n + p / a.res_div);
+            a.y[bi * a.y_bstride + (size_t)co * a.n + p] = v;
+        }
+    }
+}
+
+// Feature expansion of the up-sampling head (upsampler.py:349-366): the reference replicates every point's
+// 264 features r times, appends one code channel and runs the 265->128 convolution on the (B,265,N*r) tensor.
+// The replicas share W[:, :264] . x, so that product is computed once per point (pre, (B,cout,N)) and this
+// kernel only adds the code column:  Y[b,co,p*r+j] = relu(pre[b,co,p] + wcode[co] * code[j]).
+__global__ void __launch_bounds__(256) expand_code_kernel(int b, int cout, int n, int r, const float *__restrict__ pre,
+                                                         const float *__restrict__ w, int w_stride, int code_col,
+                                                         const float *__restrict__ code, float *__restrict__ y) {
+    const long long total = (long long)b * cout * n * r;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % r);
+        const long long q = t / r;           // (b*cout + co)*n + p
+        const int co = (int)((q / n) % cout);
+        const float v = __fmaf_rn(__ldg(w + (size_t)co * w_stride + code_col), __ldg(code + j), __ldg(pre + q));
+        y[t] = fmaxf(v, 0.f);
+    }
+}
+
+}  // namespace pu3
+
+using namespace pu3;
+
+extern "C" int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
+                                      const float *w, const float *bias, float *y, long long y_bstride,
+                                      const float *res, long long res_bstride, int res_n, int res_div, int relu,
+                                      pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0 && cout > 0, "pointwise_conv: bad size b=%d n=%d cin=%d cout=%d", b, n, cin, cout);
+    if (b == 0 || n == 0) return PU3_OK;
+    PU3_ARG_CHECK(x && w && y, "pointwise_conv: null pointer");
+    PU3_ARG_CHECK(!res || (res_div >= 1 && res_n >= 1), "pointwise_conv: bad residual description");
+    PwArgs a{b, n, cin, cout, x, x_bstride, w, bias, y, y_bstride, res, res_bstride, res_n, res_div > 0 ? res_div : 1, relu};
+    const long long cols = (long long)b * n;
+    cudaStream_t s = as_stream(stream);
+    if (cout <= 4) {          // 64 -> 3 regressor: 4 x 256-column tiles, 32 threads
+        dim3 grid((unsigned)((cols + 255) / 256), (cout + 3) / 4);
+        pointwise_conv_kernel<4, 1, 32><<<grid, 32, 0, s>>>(a);
+    } else if (cout <= 24) {  // 3->24, 84/144/204 -> 24: 24 x 256 tile, 96 threads
+        dim3 grid((unsigned)((cols + 255) / 256), (cout + 23) / 24);
+        pointwise_conv_kernel<8, 3, 32><<<grid, 96, 0, s>>>(a);
+    } else if (cout <= 64) {  // 128 -> 64: 64 x 256 tile
+        dim3 grid((unsigned)((cols + 255) / 256), (cout + 63) / 64);
+        pointwise_conv_kernel<8, 8, 32><<<grid, 256, 0, s>>>(a);
+    } else {                  // 264/128 -> 128: 128 x 128 tile
+        dim3 grid((unsigned)((cols + 127) / 128), (cout + 127) / 128);
+        pointwise_conv_kernel<8, 16, 16><<<grid, 256, 0, s>>>(a);
+    }
+    PU3_LAUNCH_CHECK("pointwise_conv_kernel");
+    return PU3_OK;
+}
+
+extern "C" int pu3_expand_code_f32(int b, int cout, int n, int r, const float *pre, const float *w, int w_stride,
+                                   int code_col, const float *code, float *y, pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && cout > 0 && n >= 0 && r > 0, "expand_code: bad size");
+    const long long total = (long long)b * cout * n * r;
+    if (total == 0) return PU3_OK;
+    PU3_ARG_CHECK(pre && w && code && y, "expand_code: null pointer");
+    const long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_info().sm_count * 16;
+    expand_code_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(b, cout, n, r, pre, w, w_stride,
+                                                                                         code_col, code, y);
+    PU3_LAUNCH_CHECK("expand_code_kernel");
+    return PU3_OK;
+}

@@ -1,0 +1,111 @@
+"""Python front-ends of the fused compute kernels (1x1 convolutions, DenseEdgeConv, expansion head).
+
+Forward passes run on libpu3_b200.  Gradients: when autograd is recording and an input or weight
+requires grad, the same mathematics is evaluated through differentiable operators (group_knn's own
+backward + torch autograd for the small dense algebra) so that training is correct today; the
+hand-written backward kernels replace that branch kernel by kernel ("backward").
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .operations import group_knn, _knn_raw
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _check_f32_cuda(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError(f"{name}: float32 CUDA tensor required (3pu_pytorch_b200 has no CPU fallback)")
+
+
+def conv_into(x, w, b, out, relu=False, residual=None, res_div=1):
+    """out[:, :, :] = act(W x + b) (+ residual[..., p // res_div]) with x (B,Cin,N) and out (B,Cout,N) possibly
+    channel slices of larger contiguous buffers (stride(1) == N, stride(2) == 1)."""
+    B, Cin, N = x.shape
+    Cout = out.shape[1]
+    assert x.stride(2) == 1 and x.stride(1) == N and out.stride(2) == 1 and out.stride(1) == N
+    w2 = w.reshape(Cout, Cin)
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    rp, rbs, rn = None, 0, 1
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape[0] == B and residual.shape[1] == Cout
+        rp, rbs, rn = residual.data_ptr(), residual.stride(0), residual.shape[2]
+    with _lib.on_device(x):
+        _lib.check(_lib.lib().pu3_pointwise_conv_f32(B, N, Cin, Cout, x.data_ptr(), x.stride(0) if B > 1 else Cin * N,
+                                                     w2.data_ptr(), _lib.ptr(b), out.data_ptr(),
+                                                     out.stride(0) if B > 1 else Cout * N, rp, rbs, rn, res_div,
+                                                     int(relu), _lib.stream_of(x)), "pointwise_conv")
+    return out
+
+
+def pointwise_conv(x, weight, bias, relu=False):
+    """1x1 Conv1d/Conv2d (+ReLU) on (B,C,N) or (B,C,N,1) input: layers.py:115-204 with kernel size 1."""
+    _check_f32_cuda(x, "pointwise_conv")
+    if _needs_grad(x, weight, bias):
+        y = F.conv2d(x, weight, bias) if weight.dim() == 4 else F.conv1d(x, weight, bias)
+        return F.relu(y) if relu else y
+    shape = x.shape
+    x3 = x.reshape(shape[0], shape[1], -1).contiguous()
+    out = torch.empty(shape[0], weight.shape[0], x3.shape[2], dtype=torch.float32, device=x.device)
+    conv_into(x3, weight, bias, out, relu=relu)
+    return out.reshape(shape[0], weight.shape[0], *shape[2:])
+
+
+def edgeconv_into(x, idx32, idx_off, k, weights, biases, out):
+    """out (B,60,N) slice <- fused DenseEdgeConv of x (B,24,N) slice with neighbours idx32[..., idx_off:idx_off+k]."""
+    B, C, N = x.shape
+    assert C == 24 and out.shape[1] == 60 and idx32.dtype == torch.int32 and idx32.is_contiguous()
+    assert x.stride(2) == 1 and x.stride(1) == N and out.stride(2) == 1 and out.stride(1) == N
+    w = [wi.reshape(wi.shape[0], wi.shape[1]).contiguous() for wi in weights]
+    with _lib.on_device(x):
+        _lib.check(_lib.lib().pu3_edgeconv_f32(B, N, k, x.data_ptr(), x.stride(0) if B > 1 else C * N, idx32.data_ptr(),
+                                               idx32.shape[2], idx_off, w[0].data_ptr(), biases[0].data_ptr(),
+                                               w[1].data_ptr(), biases[1].data_ptr(), w[2].data_ptr(),
+                                               biases[2].data_ptr(), out.data_ptr(),
+                                               out.stride(0) if B > 1 else 60 * N, _lib.stream_of(x)), "edgeconv")
+    return out
+
+
+def _edgeconv_supported(x, weights):
+    return (x.shape[1] == 24 and len(weights) == 3 and tuple(weights[0].shape[:2]) == (12, 48)
+            and tuple(weights[1].shape[:2]) == (12, 36) and tuple(weights[2].shape[:2]) == (12, 48))
+
+
+def dense_edge_conv(x, weights, biases, k, idx=None, max_group=None):
+    """DenseEdgeConv.forward (layers.py:44-64).  x (B,C,N) -> (y (B,C+n*growth,N), idx (B,N,k) int64)."""
+    _check_f32_cuda(x, "DenseEdgeConv")
+    n_layers = len(weights)
+    if _needs_grad(x, *weights, *biases) or not _edgeconv_supported(x, weights):
+        # differentiable composition (same operators as the reference, group_knn on our kernels)
+        if idx is None:
+            knn_point, idx, _ = group_knn(k + 1, x, x, unique=True, max_group=max_group)
+            idx = idx[:, :, 1:]
+            knn_point = knn_point[:, :, :, 1:]
+        else:
+            B, C, N = x.shape
+            knn_point = torch.gather(x.unsqueeze(2).expand(-1, -1, N, -1), 3, idx.unsqueeze(1).expand(-1, C, -1, -1))
+        center = x.unsqueeze(-1).expand_as(knn_point)
+        y = torch.cat([center, knn_point - center], dim=1)
+        for i in range(n_layers):
+            h = F.conv2d(y, weights[i], biases[i])
+            if i == 0:
+                y = torch.cat([F.relu(h), x.unsqueeze(-1).expand(-1, -1, -1, k)], dim=1)
+            elif i == n_layers - 1:
+                y = torch.cat([h, y], dim=1)
+            else:
+                y = torch.cat([F.relu(h), y], dim=1)
+        return y.max(dim=-1)[0], idx
+    xc = x.contiguous()
+    B, C, N = xc.shape
+    if idx is None:
+        _, idx32, _ = _knn_raw(k + 1, xc, xc, True, max_group, want_knn=False, want_dist=False, idx_dtype=torch.int32)
+        off = 1
+    else:
+        idx32, off = idx.to(torch.int32).contiguous(), 0
+    out = torch.empty(B, 60, N, dtype=torch.float32, device=x.device)
+    edgeconv_into(xc, idx32, off, k, weights, biases, out)
+    return out, idx32[:, :, off:off + k].long()

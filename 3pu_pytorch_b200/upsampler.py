@@ -1,0 +1,365 @@
+"""Network mirrors of the reference's network/upsampler.py: Net (:9-189) and Level (:192-374).
+
+Same constructor arguments, module/parameter names (state_dict keys `levels.level_{l}....`, SURVEY.md
+appendix A) and the same results, on libpu3_b200 kernels.  What differs from the reference:
+  * eval-mode Net.forward accepts a BATCH of input patches.  The reference asserts batch_size == 1 past
+    level 1 (upsampler.py:61) and main.py loops over patches (main.py:237-244); here the B patches run
+    together and every one of them gets exactly the result of its own B=1 call.
+  * Level.forward writes every layer's output straight into its slot of one (B,264,N) feature buffer
+    instead of torch.cat-ing (upsampler.py:293,299,305,311), and the neighbourhood tensors of
+    DenseEdgeConv never exist (fused kernel).
+AdaptiveLevel (:377-512, never instantiated) and the phase == "vis" debug branches are not provided.
+"""
+from collections import OrderedDict
+from math import log, sqrt
+
+import torch
+
+from . import fused, layers, operations
+
+
+class Level(torch.nn.Module):
+    """3PU per-level network (upsampler.py:192-374)."""
+
+    def __init__(self, dense_n=3, growth_rate=12, knn=16, fm_knn=5, step_ratio=2):
+        super(Level, self).__init__()
+        self.dense_n = dense_n
+        self.fm_knn = fm_knn
+        self.step_ratio = step_ratio
+        self.knn = knn
+        self.growth_rate = growth_rate
+        if step_ratio < 4:
+            self.code = self.gen_1d_grid(step_ratio).unsqueeze(0).detach()      # 1 x 1 x r
+        else:
+            expansion_ratio = round(sqrt(step_ratio)) ** 2
+            self.code = self.gen_grid(expansion_ratio).unsqueeze(0).detach()    # 1 x 2 x r
+        self._code_dev = {}
+
+        comp = 24 + growth_rate * dense_n                                       # channels a dense block adds
+        self.layer0 = layers.Conv2d(3, 24, [1, 1], activation=None)
+        self.layer1 = layers.DenseEdgeConv(24, growth_rate=growth_rate, n=dense_n, k=knn)
+        in_channels = 24 + comp
+        self.layer2_prep = layers.Conv1d(in_channels, 24, 1, activation="relu")
+        self.layer2 = layers.DenseEdgeConv(24, growth_rate=growth_rate, n=dense_n, k=knn)
+        in_channels += comp
+        self.layer3_prep = layers.Conv1d(in_channels, 24, 1, activation="relu")
+        self.layer3 = layers.DenseEdgeConv(24, growth_rate=growth_rate, n=dense_n, k=knn)
+        in_channels += comp
+        self.layer4_prep = layers.Conv1d(in_channels, 24, 1, activation="relu")
+        self.layer4 = layers.DenseEdgeConv(24, growth_rate=growth_rate, n=dense_n, k=knn)
+        in_channels += comp
+        self.feat_channels = in_channels
+        self.up_layer = torch.nn.Sequential(OrderedDict([
+            ("up_layer1", layers.Conv2d(in_channels + self.code.size(1), 128, 1, activation="relu")),
+            ("up_layer2", layers.Conv2d(128, 128, 1, activation="relu")), ]))
+        self.fc_layer1 = layers.Conv2d(128, 64, 1, activation="relu")
+        self.fc_layer2 = layers.Conv2d(64, 3, 1, activation=None)
+
+    # ---- helpers kept from the reference ---------------------------------------------------------
+    def exponential_distance(self, points, knnIdx_points):
+        """upsampler.py:232-250: squared distance to the k neighbours and exp(-d / (h/2)), h = mean_N(min_K d)."""
+        if points.dim() == 3:
+            points = points.unsqueeze(dim=-1)
+        distance = torch.sum((points - knnIdx_points) ** 2, dim=1, keepdim=True).detach()
+        h = torch.mean(torch.min(distance, dim=-1, keepdim=True)[0], dim=-2, keepdim=True)
+        weight = torch.exp(-distance / (h / 2)).detach()
+        return distance, weight
+
+    def gen_grid(self, grid_size):
+        """output [2, grid_size x grid_size] (upsampler.py:252-262)"""
+        x = torch.linspace(-0.2, 0.2, grid_size, dtype=torch.float32)
+        x, y = torch.meshgrid(x, x, indexing="ij")
+        return torch.stack([x, y], dim=0).view([2, grid_size * grid_size])
+
+    def gen_1d_grid(self, num_grid_point):
+        """output [1, num_grid_point] (upsampler.py:264-270)"""
+        return torch.linspace(-0.2, 0.2, num_grid_point).view(1, num_grid_point)
+
+    def _code_on(self, device):
+        c = self._code_dev.get(device)
+        if c is None:
+            c = self.code.to(device=device, dtype=torch.float32).contiguous()
+            self._code_dev[device] = c
+        return c
+
+    # ---- forward ---------------------------------------------------------------------------------------
+    def _fast_path_ok(self, xyz_normalized):
+        # gradients wanted (training mode, or an input that requires grad): differentiable composition instead
+        wants_grad = torch.is_grad_enabled() and (self.training or xyz_normalized.requires_grad)
+        return (xyz_normalized.is_cuda and xyz_normalized.dtype == torch.float32 and self.dense_n == 3
+                and self.growth_rate == 12 and self.code.size(1) == 1 and not wants_grad)
+
+    def _features_fused(self, xyz_normalized, group):
+        """layer0 + 4 dense blocks into one (B,264,N) buffer; channel order [y4, y3, y2, y1, x0]."""
+        B, _, N = xyz_normalized.shape
+        C = self.feat_channels
+        feat = torch.empty(B, C, N, dtype=torch.float32, device=xyz_normalized.device)
+        # h: the 24-channel input of the current dense block (contiguous: kNN and edge-conv read it)
+        h = torch.empty(B, 24, N, dtype=torch.float32, device=feat.device)
+        fused.conv_into(xyz_normalized.contiguous(), self.layer0.conv.weight, self.layer0.conv.bias, h)
+        feat[:, C - 24:].copy_(h)
+        lo = C - 24
+        for li, (prep, block) in enumerate(((None, self.layer1), (self.layer2_prep, self.layer2),
+                                            (self.layer3_prep, self.layer3), (self.layer4_prep, self.layer4))):
+            if prep is not None:
+                fused.conv_into(feat[:, lo:], prep.conv.weight, prep.conv.bias, h, relu=True)
+            src = h
+            _, idx32, _ = operations._knn_raw(block.k + 1, src, src, True, group, want_knn=False, want_dist=False,
+                                              idx_dtype=torch.int32)
+            fused.edgeconv_into(src, idx32, 1, block.k, [m.weight for m in block.mlps], [m.bias for m in block.mlps],
+                                feat[:, lo - 60:lo])
+            lo -= 60
+        return feat
+
+    def _skip_connection(self, x, xyz, previous_level4, group):
+        """upsampler.py:317-347: bilateral (spatial x feature) interpolation of the previous level's features."""
+        previous_xyz, previous_feat = previous_level4
+        B, _, N = xyz.shape
+        Bp = previous_xyz.shape[0]
+        knnIdx_points, knnIdx_idx, _ = operations.group_knn(self.fm_knn, xyz, previous_xyz, unique=True, NCHW=True,
+                                                            max_group=group)
+        if Bp == B:
+            pf = previous_feat.unsqueeze(2).expand(-1, -1, N, -1)
+            knnIdx_feats = torch.gather(pf, 3, knnIdx_idx.unsqueeze(1).expand(-1, pf.size(1), -1, -1))
+        else:
+            # previous level shared by B/Bp consecutive patches (the reference expand()s it, :319-323)
+            p_div = B // Bp
+            Cp, Mp = previous_feat.shape[1], previous_feat.shape[2]
+            flat = previous_feat.permute(1, 0, 2).reshape(Cp, Bp * Mp)
+            offs = (torch.arange(B, device=xyz.device) // p_div * Mp).view(B, 1, 1)
+            g = flat[:, (knnIdx_idx + offs).reshape(-1)]                       # Cp, B*N*K
+            knnIdx_feats = g.view(Cp, B, N, self.fm_knn).permute(1, 0, 2, 3)
+        _, s_average_weight = self.exponential_distance(xyz, knnIdx_points)
+        _, f_average_weight = self.exponential_distance(x, knnIdx_feats)
+        average_weight = s_average_weight * f_average_weight
+        average_weight = average_weight / torch.sum(average_weight + 1e-5, dim=-1, keepdim=True)
+        knnIdx_feats = torch.sum(average_weight * knnIdx_feats, dim=-1)
+        return 0.2 * knnIdx_feats + x
+
+    def _head_fused(self, x, xyz_normalized):
+        """upsampler.py:349-372 without materialising the (B,265,N*r) replicated tensor."""
+        B, C, N = x.shape
+        r = self.code.size(2)
+        dev = x.device
+        w1 = self.up_layer.up_layer1.conv.weight.reshape(128, C + 1)
+        pre = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
+        fused.conv_into(x.contiguous(), w1[:, :C].contiguous(), self.up_layer.up_layer1.conv.bias, pre)
+        h1 = torch.empty(B, 128, N * r, dtype=torch.float32, device=dev)
+        code = self._code_on(dev)
+        w1c = w1.contiguous()
+        with fused._lib.on_device(x):
+            fused._lib.check(fused._lib.lib().pu3_expand_code_f32(B, 128, N, r, pre.data_ptr(), w1c.data_ptr(), C + 1, C,
+                                                                 code.data_ptr(), h1.data_ptr(), fused._lib.stream_of(x)),
+                             "expand_code")
+        h2 = torch.empty_like(h1)
+        fused.conv_into(h1, self.up_layer.up_layer2.conv.weight, self.up_layer.up_layer2.conv.bias, h2, relu=True)
+        h3 = torch.empty(B, 64, N * r, dtype=torch.float32, device=dev)
+        fused.conv_into(h2, self.fc_layer1.conv.weight, self.fc_layer1.conv.bias, h3, relu=True)
+        out = torch.empty(B, 3, N * r, dtype=torch.float32, device=dev)
+        fused.conv_into(h3, self.fc_layer2.conv.weight, self.fc_layer2.conv.bias, out, residual=xyz_normalized.contiguous(),
+                        res_div=r)
+        return out
+
+    def forward(self, xyz, xyz_normalized, previous_level4=None, group=None, **kwargs):
+        """
+        :param xyz Bx3xN input xyz, unnormalized; xyz_normalized Bx3xN; previous_level4 (Bx3xM, BxCxM) of the
+               previous level (its batch may divide B: shared by consecutive patches)
+        :param group (extension) patches per independent request, scope of group_knn's duplicate penalty
+        :return xyz Bx3xNr (normalised frame), features BxCxN of the input points
+        """
+        if kwargs.get("phase") == "vis":
+            raise NotImplementedError("phase='vis' (debug visualisation, upsampler.py:285-314) is out of scope")
+        batch_size, _, num_point = xyz_normalized.size()
+        fast = self._fast_path_ok(xyz_normalized)
+        if fast:
+            x = self._features_fused(xyz_normalized, group)
+        else:
+            x = self.layer0(xyz_normalized.unsqueeze(dim=-1)).squeeze(dim=-1)
+            y, _ = self.layer1(x)
+            x = torch.cat([y, x], dim=1)
+            y, _ = self.layer2(self.layer2_prep(x))
+            x = torch.cat([y, x], dim=1)
+            y, _ = self.layer3(self.layer3_prep(x))
+            x = torch.cat([y, x], dim=1)
+            y, _ = self.layer4(self.layer4_prep(x))
+            x = torch.cat([y, x], dim=1)
+
+        if previous_level4 is not None and self.fm_knn > 0:
+            x = self._skip_connection(x, xyz, previous_level4, group)
+
+        point_features = x
+        if fast:
+            return self._head_fused(x, xyz_normalized), point_features
+
+        _, code_length, ratio = self.code.size()
+        code = self._code_on(x.device).repeat(x.size(0), 1, num_point)
+        x = x.unsqueeze(-1).expand(-1, -1, -1, ratio)
+        x = torch.reshape(x, [batch_size, x.size(1), num_point * ratio]).contiguous()
+        x = torch.cat([x, code], dim=1).unsqueeze(-1)
+        x = self.up_layer(x)
+        x = self.fc_layer1(x)
+        x = self.fc_layer2(x).squeeze(-1)
+        x = x + torch.reshape(xyz_normalized.unsqueeze(3).repeat([1, 1, 1, ratio]), [batch_size, 3, num_point * ratio])
+        return x, point_features
+
+
+class Net(torch.nn.Module):
+    """3PU inter-level plus skip connection and dense layers (upsampler.py:9-189)."""
+
+    def __init__(self, max_up_ratio=16, step_ratio=2, knn=16, growth_rate=12,
+                 dense_n=3, max_num_point=312, fm_knn=3, **kwargs):
+        super(Net, self).__init__()
+        self.max_up_ratio = max_up_ratio
+        self.step_ratio = step_ratio
+        self.knn = knn
+        self.growth_rate = growth_rate
+        self.dense_n = dense_n
+        self.fm_knn = fm_knn   # stored but, as in the reference (:25-26), not forwarded: Level's default 5 applies
+        self.num_levels = int(log(max_up_ratio, step_ratio))
+        self.levels = torch.nn.ModuleDict()
+        self.max_num_point = max_num_point
+        for l in range(1, self.num_levels + 1):
+            self.levels['level_%d' % l] = Level(dense_n=dense_n, growth_rate=growth_rate, knn=knn, step_ratio=step_ratio)
+        if self.training:
+            for m in self.modules():
+                if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv1d)):
+                    torch.nn.init.xavier_uniform_(m.weight)
+                    torch.nn.init.zeros_(m.bias)
+
+    # ---- patch extraction (upsampler.py:39-105) ------------------------------------------------------
+    def _train_patches(self, batch_xyz, k, gt_xyz, gt_k, seed_idx=None):
+        batch_size, _, num_point = batch_xyz.size()
+        if seed_idx is None:
+            seed_idx = torch.randint(low=0, high=num_point, size=[batch_size, 1], dtype=torch.int32,
+                                     device=batch_xyz.device)
+        seeds = operations.gather_points(batch_xyz, seed_idx)                   # B x 3 x 1
+        patches, _, _ = operations.group_knn(k, seeds, batch_xyz, unique=False, NCHW=True)
+        patches = torch.cat(torch.unbind(patches, dim=2), dim=0)
+        if gt_xyz is not None and gt_k is not None:
+            gt_xyz, _, _ = operations.group_knn(gt_k, seeds, gt_xyz, unique=False)
+            gt_xyz = torch.cat(torch.unbind(gt_xyz, dim=2), dim=0)
+        else:
+            gt_xyz = None
+        return patches, gt_xyz
+
+    def _eval_outlier_mask(self, batch_xyz):
+        """:63-73: a point is kept when its nearest-neighbour distance is < 5x the cloud's mean."""
+        _, _, closest_d = operations.group_knn(2, batch_xyz, batch_xyz, unique=False, NCHW=True)
+        closest_d = closest_d[:, :, 1]
+        return closest_d < (5 * torch.mean(closest_d, dim=1, keepdim=True))
+
+    def _eval_tiles(self, batch_xyz, k):
+        """Seeds by FPS, int(N/k*5) overlapping kNN tiles per cloud (:76-86).  batch_xyz (B,3,N) already
+        filtered -> tiles (B*P,3,k') with the P tiles of a cloud consecutive, and P."""
+        B, _, num_point = batch_xyz.shape
+        patch_num = int(num_point / k * 5)
+        _, seeds = operations.furthest_point_sample(batch_xyz, patch_num)
+        k = min(k, num_point)
+        tiles, _, _ = operations.group_knn(k, seeds, batch_xyz, unique=False, NCHW=True)   # B,3,P,k
+        return tiles.permute(0, 2, 1, 3).reshape(B * patch_num, 3, k), patch_num
+
+    def extract_xyz_feature_patch(self, batch_xyz, k, gt_xyz=None, gt_k=None):
+        """upsampler.py:39-105 (reference signature; eval expects batch 1 like the reference)."""
+        if self.training:
+            return self._train_patches(batch_xyz, k, gt_xyz, gt_k)
+        assert batch_xyz.size(0) == 1
+        mask = self._eval_outlier_mask(batch_xyz)
+        batch_xyz = torch.masked_select(batch_xyz, mask.unsqueeze(1).expand_as(batch_xyz)).view(1, 3, -1)
+        tiles, _ = self._eval_tiles(batch_xyz, k)
+        return tiles, None
+
+    # ---- one eval level past the first, for a batch of clouds that share N' -----------------------
+    def _eval_level(self, level, xyz, old_xyz, old_features, max_num_point, num_output_point, **kwargs):
+        B = xyz.shape[0]
+        if xyz.size(-1) > max_num_point:
+            patch_xyz, P = self._eval_tiles(xyz, max_num_point)
+        else:
+            patch_xyz, P = xyz, 1
+        patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+        new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), group=P, **kwargs)
+        new_xyz = new_xyz * radius + centroid
+        if P != 1:
+            # merge the P tiles of every cloud along the point axis (:149-155) and resample (:156-159)
+            def merge(t):
+                C, n = t.shape[1], t.shape[2]
+                return t.view(B, P, C, n).permute(0, 2, 1, 3).reshape(B, C, P * n)
+            new_xyz, patch_xyz, features = merge(new_xyz), merge(patch_xyz), merge(features)
+            _, new_xyz = operations.furthest_point_sample(new_xyz, num_output_point)
+        return new_xyz, patch_xyz, features
+
+    def forward(self, xyz, ratio=None, gt=None, seed_idx_per_level=None, **kwargs):
+        """
+        :param xyz Bx3xN; ratio upscaling factor; gt Bx3x(max_up_ratio*N) (training)
+        :param seed_idx_per_level (extension, training) {level: (B,1) int32} to fix the random zoom seeds
+        :return xyz Bx3x(ratio*N) (eval) or (xyz, gt) zoomed patches (training)
+        """
+        ratio = ratio or self.max_up_ratio
+        if self.training:
+            assert gt is not None
+        batch_size, _, num_point = xyz.size()
+        num_levels = int(log(ratio, self.step_ratio))
+        max_num_point = min(num_point, self.max_num_point)
+
+        for l in range(1, num_levels + 1):
+            curr_ratio = self.step_ratio ** l
+            level = self.levels['level_%d' % l]
+            if l == 1:
+                old_xyz = xyz
+                # eval: every cloud is its own request (duplicate-penalty scope 1); training: the whole batch
+                xyz, features = level(xyz, xyz, previous_level4=None, group=None if self.training else 1, **kwargs)
+                old_features = features
+                continue
+            if self.training:
+                if xyz.size(-1) > max_num_point:
+                    gt_k = max_num_point * ratio // curr_ratio * self.step_ratio
+                    sidx = None if seed_idx_per_level is None else seed_idx_per_level.get(l)
+                    patch_xyz, gt = self._train_patches(xyz, max_num_point, gt, gt_k, seed_idx=sidx)
+                else:
+                    patch_xyz = xyz
+                patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+                xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), **kwargs)
+                xyz = xyz * radius + centroid
+                old_xyz, old_features = patch_xyz, features
+                continue
+            # ---- eval: every cloud is an independent request (the reference handles one per call) ----
+            num_output_point = num_point * curr_ratio
+            if xyz.size(-1) > max_num_point:
+                mask = self._eval_outlier_mask(xyz)
+                counts = mask.sum(dim=1).tolist()                           # the one host sync per level
+            else:
+                mask, counts = None, [xyz.size(-1)] * batch_size
+            if all(c == xyz.size(-1) for c in counts):
+                xyz, old_xyz, old_features = self._eval_level(level, xyz, old_xyz, old_features, max_num_point,
+                                                              num_output_point, **kwargs)
+            else:
+                outs = []
+                for i in range(batch_size):
+                    xi = torch.masked_select(xyz[i:i + 1], mask[i:i + 1].unsqueeze(1).expand(-1, 3, -1)).view(1, 3, -1)
+                    outs.append(self._eval_level(level, xi, old_xyz[i:i + 1], old_features[i:i + 1], max_num_point,
+                                                 num_output_point, **kwargs))
+                xyz = torch.cat([o[0] for o in outs], dim=0)
+                # tile counts differ between clouds: pad-free batching of the next level needs equal sizes
+                sizes = {o[1].shape[2] for o in outs}
+                if len(sizes) != 1:
+                    return self._finish_ragged(outs, l, num_levels, num_point, max_num_point, **kwargs)
+                old_xyz = torch.cat([o[1] for o in outs], dim=0)
+                old_features = torch.cat([o[2] for o in outs], dim=0)
+
+        if self.training:
+            return xyz, gt
+        return xyz
+
+    def _finish_ragged(self, outs, l_done, num_levels, num_point, max_num_point, **kwargs):
+        """Clouds whose outlier filter removed different numbers of points carry previous-level clouds of
+        different sizes; finish each of them on its own (still on the GPU kernels)."""
+        results = []
+        for xyz, old_xyz, old_features in outs:
+            for l in range(l_done + 1, num_levels + 1):
+                level = self.levels['level_%d' % l]
+                if xyz.size(-1) > max_num_point:
+                    mask = self._eval_outlier_mask(xyz)
+                    xyz = torch.masked_select(xyz, mask.unsqueeze(1).expand_as(xyz)).view(1, 3, -1)
+                xyz, old_xyz, old_features = self._eval_level(level, xyz, old_xyz, old_features, max_num_point,
+                                                              num_point * self.step_ratio ** l, **kwargs)
+            results.append(xyz)
+        return torch.cat(results, dim=0)

@@ -127,6 +127,37 @@ int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float 
 int pu3_group_gather_bwd_f32(int b, int c, int m, int n, int k, int p_div, const float *grad_knn,
                              const int64_t *idx64, float *grad_points, pu3_stream_t stream);
 
+/*
+ * 1x1 convolution over points: Y[b,co,p] = act(sum_ci W[co,ci] X[b,ci,p] + bias[co]) (+ R[b,co,p/res_div]).
+ * Replaces the nn.Conv1d/nn.Conv2d 1x1 layers of the reference (network/layers.py:115-204; used at
+ * network/upsampler.py:209-230) including their bias, ReLU and the torch.cat that follows them: X and Y are
+ * channel slices of larger (B,Ctot,N) buffers, addressed as base pointer + batch stride (elements), channel
+ * stride n.  w (cout,cin) row-major as in the state_dict, bias may be NULL, relu != 0 applies max(.,0) before
+ * the optional residual res (b,cout,res_n), read at column p / res_div (upsampler.py:371-372).  fp32 FFMA.
+ */
+int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *w,
+                           const float *bias, float *y, long long y_bstride, const float *res,
+                           long long res_bstride, int res_n, int res_div, int relu, pu3_stream_t stream);
+
+/*
+ * Code column of the feature-expansion layer (network/upsampler.py:349-366):
+ * Y[b,co,p*r+j] = relu(pre[b,co,p] + w[co*w_stride + code_col] * code[j]) with pre = W[:, :code_col] x + bias
+ * computed once per point by pu3_pointwise_conv_f32; y is (b,cout,n*r) contiguous.
+ */
+int pu3_expand_code_f32(int b, int cout, int n, int r, const float *pre, const float *w, int w_stride, int code_col,
+                        const float *code, float *y, pu3_stream_t stream);
+
+/*
+ * Fused DenseEdgeConv forward for the reference configuration (24 input channels, growth 12, 3 layers):
+ * replaces network/layers.py:22-64 (neighbour gather, edge feature [c, n-c], three 1x1 convolutions with dense
+ * concatenation, max over the k edges).  x (b,24,n) slice (batch stride x_bstride), idx (b,n,idx_stride) i32 of which
+ * entries [idx_off, idx_off+k) are the neighbours (idx_off = 1 drops rank 0, layers.py:34-35), weights as in
+ * the state_dict (w0 (12,48), w1 (12,36), w2 (12,48)), y (b,60,n) slice = [max h2, max h1, max h0, x].
+ */
+int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx, int idx_stride,
+                     int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
+                     const float *w2, const float *b2, float *y, long long y_bstride, pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,3 +42,23 @@ def knn_gap_check(query, points, idx, dist, ref_idx, k, penalty=None, tol=4e-6):
     assert bool(((dist.double() - d_mine).abs() <= eps).all()), "reported distances off"
     assert bool((dist[..., 1:] >= dist[..., :-1]).all()), "distances not ascending"
     return int(differ.sum())
+
+
+def assert_close_frac(got, want, rtol=1e-5, atol=1e-6, frac=1.0, what=""):
+    """|got-want| <= atol + rtol*|want| for at least `frac` of the elements (frac < 1 only where a discrete
+    choice upstream -- a kNN near-tie -- may legitimately differ; the caller says why)."""
+    got = torch.as_tensor(got).detach().cpu().double()
+    want = torch.as_tensor(want).detach().cpu().double()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    ok = (got - want).abs() <= atol + rtol * want.abs()
+    share = ok.double().mean().item()
+    worst = ((got - want).abs() / (atol + rtol * want.abs())).max().item()
+    assert share >= frac, f"{what}: only {share:.6f} of elements within tolerance (need {frac}), worst ratio {worst:.3g}"
+    return share
+
+
+def cloud_match_fraction(a, b, tol):
+    """a, b (3,N) point clouds: share of points of a that have a point of b within tol (and vice versa), min of both."""
+    a = torch.as_tensor(a).double().t(); b = torch.as_tensor(b).double().t()
+    d = torch.cdist(a, b)
+    return min((d.min(dim=1)[0] <= tol).double().mean().item(), (d.min(dim=0)[0] <= tol).double().mean().item())

@@ -65,6 +65,70 @@ def check(status, what):
         raise RuntimeError(f"{what} failed (status {status}): {msg}")
 
 
+# kernels enqueued per entry point (for the launch count bench.py reports); memsets are not kernels
+KERNELS_PER_CALL = {
+    "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
+    "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
+    "pu3_edgeconv_f32": 1,
+    "pu3_group_knn_f32": 1,  # + 2 (duplicate flags, max D) when unique: added by the caller
+}
+
+
+class Profiler:
+    """Per-entry-point CUDA-event timing on the launching stream + launch counter (bench.py, tests).
+    Events are recorded only while a Profiler is installed; the cost is two cudaEventRecord per call."""
+
+    def __init__(self, timing=True):
+        self.timing = timing
+        self.launches = 0
+        self.calls = {}
+        self._events = {}
+
+    def add(self, name, nkernels, e0, e1):
+        self.launches += nkernels
+        self.calls[name] = self.calls.get(name, 0) + 1
+        if e0 is not None:
+            self._events.setdefault(name, []).append((e0, e1))
+
+    def summary(self):
+        """{name: (calls, total_ms)} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, n in self.calls.items():
+            ms = sum(a.elapsed_time(b) for a, b in self._events.get(name, []))
+            out[name] = (n, ms)
+        return out
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    prev, _profiler = _profiler, p
+    return prev
+
+
+def launch(name, tensor, *args, extra_kernels=0, tag=None):
+    """Call entry point `name` with `args` (+ the current stream of `tensor`'s device appended), on that device,
+    and raise on a non-zero status."""
+    fn = getattr(lib(), name)
+    with on_device(tensor):
+        stream = torch.cuda.current_stream(tensor.device)
+        prof = _profiler
+        if prof is not None and prof.timing:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            status = fn(*args, stream.cuda_stream)
+            e1.record(stream)
+        else:
+            e0 = e1 = None
+            status = fn(*args, stream.cuda_stream)
+    if status != 0:
+        check(status, name)
+    if prof is not None:
+        prof.add(tag or name, KERNELS_PER_CALL.get(name, 1) + extra_kernels, e0, e1)
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()

@@ -21,6 +21,18 @@ def _check_f32_cuda(t, name):
         raise RuntimeError(f"{name}: float32 CUDA tensor required (3pu_pytorch_b200 has no CPU fallback)")
 
 
+def conv1x1_autograd(x, weight, bias):
+    """Differentiable 1x1 convolution as an fp32 matmul.  NOT F.conv2d: cuDNN convolutions run with TF32
+    inputs by default (torch.backends.cudnn.allow_tf32), whose 5e-4 relative rounding breaks the 1e-5
+    tolerance of this path; torch.matmul stays in full fp32 unless the user opts in."""
+    shape = x.shape
+    w2 = weight.reshape(weight.shape[0], weight.shape[1])
+    y = torch.matmul(w2, x.reshape(shape[0], shape[1], -1))
+    if bias is not None:
+        y = y + bias.view(1, -1, 1)
+    return y.reshape(shape[0], weight.shape[0], *shape[2:])
+
+
 def conv_into(x, w, b, out, relu=False, residual=None, res_div=1):
     """out[:, :, :] = act(W x + b) (+ residual[..., p // res_div]) with x (B,Cin,N) and out (B,Cout,N) possibly
     channel slices of larger contiguous buffers (stride(1) == N, stride(2) == 1)."""
@@ -34,11 +46,10 @@ def conv_into(x, w, b, out, relu=False, residual=None, res_div=1):
     if residual is not None:
         assert residual.is_contiguous() and residual.shape[0] == B and residual.shape[1] == Cout
         rp, rbs, rn = residual.data_ptr(), residual.stride(0), residual.shape[2]
-    with _lib.on_device(x):
-        _lib.check(_lib.lib().pu3_pointwise_conv_f32(B, N, Cin, Cout, x.data_ptr(), x.stride(0) if B > 1 else Cin * N,
+    _lib.launch("pu3_pointwise_conv_f32", x, B, N, Cin, Cout, x.data_ptr(), x.stride(0) if B > 1 else Cin * N,
                                                      w2.data_ptr(), _lib.ptr(b), out.data_ptr(),
                                                      out.stride(0) if B > 1 else Cout * N, rp, rbs, rn, res_div,
-                                                     int(relu), _lib.stream_of(x)), "pointwise_conv")
+                                                     int(relu))
     return out
 
 
@@ -46,7 +57,7 @@ def pointwise_conv(x, weight, bias, relu=False):
     """1x1 Conv1d/Conv2d (+ReLU) on (B,C,N) or (B,C,N,1) input: layers.py:115-204 with kernel size 1."""
     _check_f32_cuda(x, "pointwise_conv")
     if _needs_grad(x, weight, bias):
-        y = F.conv2d(x, weight, bias) if weight.dim() == 4 else F.conv1d(x, weight, bias)
+        y = conv1x1_autograd(x, weight, bias)
         return F.relu(y) if relu else y
     shape = x.shape
     x3 = x.reshape(shape[0], shape[1], -1).contiguous()
@@ -61,12 +72,11 @@ def edgeconv_into(x, idx32, idx_off, k, weights, biases, out):
     assert C == 24 and out.shape[1] == 60 and idx32.dtype == torch.int32 and idx32.is_contiguous()
     assert x.stride(2) == 1 and x.stride(1) == N and out.stride(2) == 1 and out.stride(1) == N
     w = [wi.reshape(wi.shape[0], wi.shape[1]).contiguous() for wi in weights]
-    with _lib.on_device(x):
-        _lib.check(_lib.lib().pu3_edgeconv_f32(B, N, k, x.data_ptr(), x.stride(0) if B > 1 else C * N, idx32.data_ptr(),
+    _lib.launch("pu3_edgeconv_f32", x, B, N, k, x.data_ptr(), x.stride(0) if B > 1 else C * N, idx32.data_ptr(),
                                                idx32.shape[2], idx_off, w[0].data_ptr(), biases[0].data_ptr(),
                                                w[1].data_ptr(), biases[1].data_ptr(), w[2].data_ptr(),
                                                biases[2].data_ptr(), out.data_ptr(),
-                                               out.stride(0) if B > 1 else 60 * N, _lib.stream_of(x)), "edgeconv")
+                                               out.stride(0) if B > 1 else 60 * N)
     return out
 
 
@@ -91,7 +101,7 @@ def dense_edge_conv(x, weights, biases, k, idx=None, max_group=None):
         center = x.unsqueeze(-1).expand_as(knn_point)
         y = torch.cat([center, knn_point - center], dim=1)
         for i in range(n_layers):
-            h = F.conv2d(y, weights[i], biases[i])
+            h = conv1x1_autograd(y, weights[i], biases[i])
             if i == 0:
                 y = torch.cat([F.relu(h), x.unsqueeze(-1).expand(-1, -1, -1, k)], dim=1)
             elif i == n_layers - 1:

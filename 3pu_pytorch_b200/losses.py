@@ -25,9 +25,8 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2):
             raise RuntimeError(f"nmdistance_forward: {nm} has the wrong dtype or size")
     if xyz2.size(0) != b:
         raise RuntimeError("nmdistance_forward: batch sizes differ")
-    with _lib.on_device(xyz1):
-        _lib.check(_lib.lib().pu3_nmdist_fwd_f32(b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist1), _lib.ptr(dist2),
-                                                 _lib.ptr(idx1), _lib.ptr(idx2), _lib.stream_of(xyz1)), "nmdistance_forward")
+    _lib.launch("pu3_nmdist_fwd_f32", xyz1, b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist1), _lib.ptr(dist2),
+                                                 _lib.ptr(idx1), _lib.ptr(idx2))
     return 1
 
 
@@ -43,8 +42,7 @@ def nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, id
         _lib.require_cuda(t, nm); _lib.require_contiguous(t, nm)
         if t.dtype != dt or t.numel() != cnt:
             raise RuntimeError(f"nmdistance_backward: {nm} has the wrong dtype or size")
-    with _lib.on_device(xyz1):
-        _lib.check(_lib.lib().pu3_nmdist_bwd_f32(b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(gradxyz1),
+    _lib.launch("pu3_nmdist_bwd_f32", xyz1, b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(gradxyz1),
                                                  _lib.ptr(gradxyz2), _lib.ptr(graddist1), _lib.ptr(graddist2),
-                                                 _lib.ptr(idx1), _lib.ptr(idx2), _lib.stream_of(xyz1)), "nmdistance_backward")
+                                                 _lib.ptr(idx1), _lib.ptr(idx2))
     return 1

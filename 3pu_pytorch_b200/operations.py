@@ -46,15 +46,15 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
     knn = torch.empty(B, C, M, k, dtype=torch.float32, device=dev) if want_knn else None
     idx = torch.empty(B, M, k, dtype=idx_dtype, device=dev)
     dist = torch.empty(B, M, k, dtype=torch.float32, device=dev) if want_dist else None
-    L = _lib.lib()
-    with _lib.on_device(q):
-        ws_bytes = L.pu3_group_knn_workspace(B, C, M, N, k, p_div, int(bool(unique)))
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        idx64 = idx if idx_dtype == torch.int64 else None
-        idx32 = idx if idx_dtype == torch.int32 else None
-        _lib.check(L.pu3_group_knn_f32(B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
-                                       int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32),
-                                       _lib.ptr(dist), _lib.ptr(ws), ws_bytes, _lib.stream_of(q)), "group_knn")
+    ws_bytes = _lib.lib().pu3_group_knn_workspace(B, C, M, N, k, p_div, int(bool(unique)))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    idx64 = idx if idx_dtype == torch.int64 else None
+    idx32 = idx if idx_dtype == torch.int32 else None
+    # stream goes last in the C signature, after (workspace, workspace_bytes)
+    _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
+                int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32), _lib.ptr(dist), _lib.ptr(ws),
+                ws_bytes, extra_kernels=2 if unique else 0,
+                tag="pu3_group_knn_f32[k<=64]" if k <= 64 else "pu3_group_knn_f32[k>64]")
     return knn, idx, dist
 
 
@@ -90,10 +90,8 @@ class GroupKNNFunction(torch.autograd.Function):
         if g_scatter is not None and ctx.needs_input_grad[2]:
             g_points = torch.zeros_like(points)
             g_scatter = g_scatter.contiguous()
-            with _lib.on_device(points):
-                _lib.check(_lib.lib().pu3_group_gather_bwd_f32(B, C, M, N, k, p_div, _lib.ptr(g_scatter), _lib.ptr(idx),
-                                                               _lib.ptr(g_points), _lib.stream_of(points)),
-                           "group_knn backward")
+            _lib.launch("pu3_group_gather_bwd_f32", points, B, C, M, N, k, p_div, _lib.ptr(g_scatter), _lib.ptr(idx),
+                        _lib.ptr(g_points))
         if not ctx.needs_input_grad[1]:
             g_query = None
         return None, g_query, g_points, None, None
@@ -165,9 +163,7 @@ class FurthestPointSampling(torch.autograd.Function):
         idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
         # temp = None: "filled with 1e10, not written back" -- the reference allocates and fills a
         # (B,N) buffer per call (operations.py:291) that nobody reads afterwards
-        with _lib.on_device(xyz):
-            _lib.check(_lib.lib().pu3_fps_f32(B, N, int(npoint), _lib.ptr(xyz), None, _lib.ptr(idx),
-                                              _lib.stream_of(xyz)), "furthest_point_sample")
+        _lib.launch("pu3_fps_f32", xyz, B, N, int(npoint), _lib.ptr(xyz), None, _lib.ptr(idx))
         ctx.mark_non_differentiable(idx)
         return idx
 

@@ -23,9 +23,7 @@ def furthest_sampling(b, n, m, input, temp, idx):
         raise RuntimeError("furthest_sampling expects float32 input/temp and int32 idx")
     if input.numel() != b * n * 3 or temp.numel() != b * n or idx.numel() != b * m:
         raise RuntimeError("furthest_sampling: tensor sizes do not match (b, n, m)")
-    with _lib.on_device(input):
-        _lib.check(_lib.lib().pu3_fps_f32(b, n, m, _lib.ptr(input), _lib.ptr(temp), _lib.ptr(idx),
-                                          _lib.stream_of(input)), "furthest_sampling")
+    _lib.launch("pu3_fps_f32", input, b, n, m, _lib.ptr(input), _lib.ptr(temp), _lib.ptr(idx))
     return idx
 
 
@@ -38,9 +36,8 @@ def gather_forward(b, c, n, npoints, points, idx, out):
         raise RuntimeError("gather_forward expects half/float/double points and int32 idx")
     if points.numel() != b * c * n or idx.numel() != b * npoints or out.numel() != b * c * npoints:
         raise RuntimeError("gather_forward: tensor sizes do not match (b, c, n, npoints)")
-    with _lib.on_device(points):
-        _lib.check(_lib.lib().pu3_gather_fwd(b, c, n, npoints, _ELEM[points.dtype], _lib.ptr(points), _lib.ptr(idx),
-                                             _lib.ptr(out), _lib.stream_of(points)), "gather_forward")
+    _lib.launch("pu3_gather_fwd", points, b, c, n, npoints, _ELEM[points.dtype], _lib.ptr(points), _lib.ptr(idx),
+                                             _lib.ptr(out))
     return out
 
 
@@ -52,10 +49,8 @@ def gather_backward(b, c, n, npoints, grad_out, idx, grad_points):
         raise RuntimeError("gather_backward expects half/float/double grads and int32 idx")
     if grad_out.numel() != b * c * npoints or idx.numel() != b * npoints or grad_points.numel() != b * c * n:
         raise RuntimeError("gather_backward: tensor sizes do not match (b, c, n, npoints)")
-    with _lib.on_device(grad_out):
-        _lib.check(_lib.lib().pu3_gather_bwd(b, c, n, npoints, _BWD_DTYPE[grad_out.dtype], _lib.ptr(grad_out),
-                                             _lib.ptr(idx), _lib.ptr(grad_points), _lib.stream_of(grad_out)),
-                   "gather_backward")
+    _lib.launch("pu3_gather_bwd", grad_out, b, c, n, npoints, _BWD_DTYPE[grad_out.dtype], _lib.ptr(grad_out),
+                                             _lib.ptr(idx), _lib.ptr(grad_points))
     return grad_points
 
 
@@ -66,8 +61,6 @@ def ball_query(query, xyz, radius, nsample):
     if query.dtype != torch.float32 or xyz.dtype != torch.float32:
         raise RuntimeError("ball_query expects float32")
     idx = torch.zeros(query.size(0), query.size(1), nsample, dtype=torch.int32, device=query.device)
-    with _lib.on_device(query):
-        _lib.check(_lib.lib().pu3_ball_query_f32(xyz.size(0), xyz.size(1), query.size(1), float(radius), int(nsample),
-                                                 _lib.ptr(query), _lib.ptr(xyz), _lib.ptr(idx), _lib.stream_of(query)),
-                   "ball_query")
+    _lib.launch("pu3_ball_query_f32", query, xyz.size(0), xyz.size(1), query.size(1), float(radius), int(nsample),
+                                                 _lib.ptr(query), _lib.ptr(xyz), _lib.ptr(idx))
     return idx

@@ -147,10 +147,8 @@ class Level(torch.nn.Module):
         h1 = torch.empty(B, 128, N * r, dtype=torch.float32, device=dev)
         code = self._code_on(dev)
         w1c = w1.contiguous()
-        with fused._lib.on_device(x):
-            fused._lib.check(fused._lib.lib().pu3_expand_code_f32(B, 128, N, r, pre.data_ptr(), w1c.data_ptr(), C + 1, C,
-                                                                 code.data_ptr(), h1.data_ptr(), fused._lib.stream_of(x)),
-                             "expand_code")
+        fused._lib.launch("pu3_expand_code_f32", x, B, 128, N, r, pre.data_ptr(), w1c.data_ptr(), C + 1, C,
+                                                                 code.data_ptr(), h1.data_ptr())
         h2 = torch.empty_like(h1)
         fused.conv_into(h1, self.up_layer.up_layer2.conv.weight, self.up_layer.up_layer2.conv.bias, h2, relu=True)
         h3 = torch.empty(B, 64, N * r, dtype=torch.float32, device=dev)

@@ -23,6 +23,7 @@ SIGNATURES = {
     "pu3_version": (_c_int, []),
     "pu3_device_info": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "pu3_fps_f32": (_c_int, [_c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "pu3_fps_ragged_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 6),
     "pu3_gather_fwd": (_c_int, [_c_int] * 5 + [_c_void_p] * 4),
     "pu3_gather_bwd": (_c_int, [_c_int] * 5 + [_c_void_p] * 4),
     "pu3_ball_query_f32": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
@@ -30,6 +31,7 @@ SIGNATURES = {
     "pu3_nmdist_bwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 9),
     "pu3_group_knn_workspace": (_c_size_t, [_c_int] * 7),
     "pu3_group_knn_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
+    "pu3_group_knn_ragged_f32": (_c_int, [_c_int] * 7 + [_c_void_p] * 6 + [_c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "pu3_group_gather_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 4),
     "pu3_pointwise_conv_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p, _c_ll,
                                                          _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_void_p]),
@@ -70,7 +72,8 @@ KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
     "pu3_edgeconv_f32": 1,
-    "pu3_group_knn_f32": 1,  # + 2 (duplicate flags, max D) when unique: added by the caller
+    "pu3_fps_ragged_f32": 1,
+    "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique
 }
 
 

@@ -59,8 +59,8 @@ __device__ __forceinline__ bool warp_argmax(uint32_t dkey, uint32_t rank, uint32
 // PPT points per thread; XYZ_REGS: coordinates in registers (else read from shared memory each round)
 template <int PPT, bool XYZ_REGS, int MAX_THREADS>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-fps_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__restrict__ temp,
-           int32_t *__restrict__ idx) {
+fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const int32_t *__restrict__ m_arr,
+           const float *__restrict__ xyz, float *__restrict__ temp, int32_t *__restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FpsSmem &sm = *reinterpret_cast<FpsSmem *>(smem_raw);
     float *sx = reinterpret_cast<float *>(smem_raw + sizeof(FpsSmem));
@@ -68,6 +68,10 @@ fps_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__rest
     const uint32_t S = cluster_nctarank();
     const uint32_t crank = cluster_ctarank();
     const int cloud = blockIdx.x / S;
+    // ragged batches: every cloud may have its own point / sample count (rows are n_stride / m_stride apart)
+    const int n = n_arr ? min(__ldg(n_arr + cloud), n_stride) : n_stride;
+    const int m = m_arr ? min(__ldg(m_arr + cloud), m_stride) : m_stride;
+    const int t_ref = n > 0 ? min(512, 1 << (31 - __clz(n))) : 1;  // the reference's block size for THIS cloud
     const int nthreads = blockDim.x;
     const int GT = nthreads * S;                     // threads per cloud; a multiple of t_ref
     const int g = crank * nthreads + threadIdx.x;    // this thread's id within the cloud
@@ -75,9 +79,9 @@ fps_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__rest
     float *sy = sx + cap, *sz = sy + cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
 
-    const float *p = xyz + (size_t)cloud * n * 3;
-    float *trow = temp ? temp + (size_t)cloud * n : nullptr;
-    int32_t *out = idx + (size_t)cloud * m;
+    const float *p = xyz + (size_t)cloud * n_stride * 3;
+    float *trow = temp ? temp + (size_t)cloud * n_stride : nullptr;
+    int32_t *out = idx + (size_t)cloud * m_stride;
     const uint32_t rank_rows = (n + t_ref - 1) / t_ref;
 
     // ---- load: thread owns points k = g + i*GT; local slot i*nthreads + tid -------------------
@@ -97,8 +101,9 @@ fps_kernel(int n, int m, int t_ref, const float *__restrict__ xyz, float *__rest
         if (XYZ_REGS) { px[i] = x; py[i] = y; pz[i] = z; }
         t[i] = tv;
     }
-    if (g == 0) out[0] = 0;                                  // :115 first sample is point 0
-    float x1 = __ldg(p + 0), y1 = __ldg(p + 1), z1 = __ldg(p + 2);
+    if (g == 0 && m > 0) out[0] = 0;                         // :115 first sample is point 0
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (n > 0) { x1 = __ldg(p + 0); y1 = __ldg(p + 1); z1 = __ldg(p + 2); }
     __syncthreads();
     if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem exists before remote stores
 
@@ -249,8 +254,8 @@ static int ref_block_size(int n) {
 }
 
 template <int PPT, bool XYZ_REGS, int MAX_THREADS>
-static int launch_fps(int b, int n, int m, int t_ref, int S, int threads, const float *xyz, float *temp,
-                      int32_t *idx, cudaStream_t stream) {
+static int launch_fps(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, int S, int threads,
+                      const float *xyz, float *temp, int32_t *idx, cudaStream_t stream) {
     auto kern = fps_kernel<PPT, XYZ_REGS, MAX_THREADS>;
     const size_t smem = sizeof(FpsSmem) + (size_t)threads * PPT * 3 * sizeof(float);
     int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -273,7 +278,7 @@ static int launch_fps(int b, int n, int m, int t_ref, int S, int threads, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cuda_status(cudaLaunchKernelEx(&cfg, kern, n, m, t_ref, xyz, temp, idx), "fps_kernel launch");
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, n, m, n_arr, m_arr, xyz, temp, idx), "fps_kernel launch");
 }
 
 }  // namespace pu3
@@ -284,8 +289,21 @@ using namespace pu3;
 static int g_fps_force_cluster = 0;
 extern "C" void pu3_fps_set_cluster(int s) { g_fps_force_cluster = s; }
 
+static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, const float *xyz, float *temp,
+                        int32_t *idx, pu3_stream_t stream);
+
 extern "C" int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
                            pu3_stream_t stream) {
+    return fps_dispatch(b, n, m, nullptr, nullptr, xyz, temp, idx, stream);
+}
+
+extern "C" int pu3_fps_ragged_f32(int b, int n_stride, int m_stride, const int32_t *n_arr, const int32_t *m_arr,
+                                  const float *xyz, float *temp, int32_t *idx, pu3_stream_t stream) {
+    return fps_dispatch(b, n_stride, m_stride, n_arr, m_arr, xyz, temp, idx, stream);
+}
+
+static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, const float *xyz, float *temp,
+                        int32_t *idx, pu3_stream_t stream) {
     PU3_ARG_CHECK(b >= 0 && n >= 0 && m >= 0, "fps: negative size b=%d n=%d m=%d", b, n, m);
     if (b == 0 || m == 0) return PU3_OK;  // the reference kernel returns at once for m <= 0 (:106)
     PU3_ARG_CHECK(n > 0, "fps: sampling %d points from an empty cloud", m);
@@ -319,15 +337,16 @@ extern "C" int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, i
     int st;
     if ((long long)S * per_cta_reg >= n) {
         const int ppt = (int)((n + (long long)S * threads - 1) / ((long long)S * threads));
-        if (ppt <= 1) st = launch_fps<1, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
-        else if (ppt <= 2) st = launch_fps<2, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
-        else if (ppt <= 4) st = launch_fps<4, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
-        else st = launch_fps<8, true, 1024>(b, n, m, t_ref, S, threads, xyz, temp, idx, s);
+        if (ppt <= 1) st = launch_fps<1, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
+        else if (ppt <= 2) st = launch_fps<2, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
+        else if (ppt <= 4) st = launch_fps<4, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
+        else st = launch_fps<8, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
     } else if ((long long)S * 512 * 32 >= n) {
         const int ppt = (int)((n + (long long)S * 512 - 1) / ((long long)S * 512));
-        if (ppt <= 16) st = launch_fps<16, false, 512>(b, n, m, t_ref, S, 512, xyz, temp, idx, s);
-        else st = launch_fps<32, false, 512>(b, n, m, t_ref, S, 512, xyz, temp, idx, s);
+        if (ppt <= 16) st = launch_fps<16, false, 512>(b, n, m, n_arr, m_arr, S, 512, xyz, temp, idx, s);
+        else st = launch_fps<32, false, 512>(b, n, m, n_arr, m_arr, S, 512, xyz, temp, idx, s);
     } else {
+        PU3_ARG_CHECK(n_arr == nullptr && m_arr == nullptr, "fps: ragged batches beyond 262144 points per cloud are not supported");
         PU3_ARG_CHECK(temp != nullptr, "fps: n=%d needs the temp buffer (clouds beyond 262144 points run from global memory)", n);
         fps_fallback_kernel<<<b, 1024, 0, s>>>(n, m, t_ref, xyz, temp, idx);
         st = cuda_status(cudaGetLastError(), "fps_fallback_kernel");

@@ -32,6 +32,9 @@ namespace pu3 {
 
 struct KnnArgs {
     int b, c, m, n, k, p_div, max_group;
+    // ragged batches (all optional): cloud read by a batch element, duplicate-penalty group of a batch element,
+    // valid points per cloud (<= n), valid queries per batch element (<= m); n and m stay the row strides
+    const int32_t *owner, *group_of, *n_arr, *m_arr;
     const float *query;   // (b,c,m)
     const float *points;  // (b/p_div,c,n)
     const uint8_t *dup;   // (b/p_div,n) or null
@@ -43,6 +46,11 @@ struct KnnArgs {
     float *dist;          // (b,m,k) or null
 };
 
+__device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.owner ? __ldg(a.owner + bi) : bi / a.p_div; }
+__device__ __forceinline__ int knn_group(const KnnArgs &a, int bi) { return a.group_of ? __ldg(a.group_of + bi) : bi / a.max_group; }
+__device__ __forceinline__ int knn_n(const KnnArgs &a, int cloud) { return a.n_arr ? min(a.n, __ldg(a.n_arr + cloud)) : a.n; }
+__device__ __forceinline__ int knn_m(const KnnArgs &a, int bi) { return a.m_arr ? min(a.m, __ldg(a.m_arr + bi)) : a.m; }
+
 // the reference's D = r_A - 2*m + r_B, evaluated left to right (operations.py:161)
 __device__ __forceinline__ float expanded_dist(float rq, float dot, float rp) {
     return __fadd_rn(__fsub_rn(rq, __fmul_rn(2.0f, dot)), rp);
@@ -51,12 +59,13 @@ __device__ __forceinline__ float expanded_dist(float rq, float dot, float rp) {
 // --------------------------------------------------------------------------------------------
 // duplicates
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, int p_div, int max_group, int b,
+__global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, const int32_t *__restrict__ n_arr,
                                                      const float *__restrict__ points,
-                                                     uint8_t *__restrict__ dup, int *__restrict__ group_any) {
+                                                     uint8_t *__restrict__ dup, int *__restrict__ cloud_any) {
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    const int nv = n_arr ? min(n, __ldg(n_arr + cloud)) : n;
+    if (j >= nv) return;
     const float *p = points + (size_t)cloud * c * n;
     const float v0 = p[j];
     bool found = false;
@@ -67,25 +76,30 @@ __global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, int p_div, i
         found = same;
     }
     dup[(size_t)cloud * n + j] = found ? 1 : 0;
-    if (found) {
-        // every group that contains a batch element reading this cloud
-        const int b0 = cloud * p_div, b1 = min(b, (cloud + 1) * p_div) - 1;
-        for (int g = b0 / max_group; g <= b1 / max_group; ++g) group_any[g] = 1;
-    }
+    if (found) cloud_any[cloud] = 1;
+}
+
+// a group needs max(D) as soon as one of its batch elements reads a cloud with duplicates
+__global__ void __launch_bounds__(256) knn_groupflag_kernel(KnnArgs a, const int *__restrict__ cloud_any,
+                                                           int *__restrict__ group_any) {
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi < a.b && cloud_any[knn_cloud(a, bi)]) group_any[knn_group(a, bi)] = 1;
 }
 
 __global__ void __launch_bounds__(128) knn_maxd_kernel(KnnArgs a, uint32_t *__restrict__ maxd) {
     const int bi = blockIdx.y;
-    const int g = bi / a.max_group;
+    const int g = knn_group(a, bi);
     if (a.group_any[g] == 0) return;  // the common case: nothing to do
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t best = 0;
-    if (qi < a.m) {
+    const int cloud = knn_cloud(a, bi);
+    const int nv = knn_n(a, cloud);
+    if (qi < knn_m(a, bi)) {
         const float *q = a.query + (size_t)bi * a.c * a.m;
-        const float *p = a.points + (size_t)(bi / a.p_div) * a.c * a.n;
+        const float *p = a.points + (size_t)cloud * a.c * a.n;
         float rq = 0.f;
         for (int ch = 0; ch < a.c; ++ch) { const float v = q[(size_t)ch * a.m + qi]; rq = __fmaf_rn(v, v, rq); }
-        for (int j = 0; j < a.n; ++j) {
+        for (int j = 0; j < nv; ++j) {
             float dot = 0.f, rp = 0.f;
             for (int ch = 0; ch < a.c; ++ch) {
                 const float pv = __ldg(p + (size_t)ch * a.n + j);
@@ -152,15 +166,18 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
 
     const int bi = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = knn_cloud(a, bi);
+    const int grp = knn_group(a, bi);
+    const int nv = knn_n(a, cloud);          // valid candidates of this cloud
     const float *qb = a.query + (size_t)bi * C * a.m;
-    const float *pb = a.points + (size_t)(bi / a.p_div) * C * a.n;
-    const int cloud = bi / a.p_div;
-    const bool penal = a.dup != nullptr && a.group_any[bi / a.max_group] != 0;
-    const float maxd = penal ? ordered_to_float(a.maxd[bi / a.max_group]) : 0.f;
+    const float *pb = a.points + (size_t)cloud * C * a.n;
+    const bool penal = a.dup != nullptr && a.group_any[grp] != 0;
+    const float maxd = penal ? ordered_to_float(a.maxd[grp]) : 0.f;
     const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
 
     const int q_begin = blockIdx.x * q_per_cta;
-    const int q_end = min(a.m, q_begin + q_per_cta);
+    const int q_end = min(knn_m(a, bi), q_begin + q_per_cta);
+    if (q_begin >= q_end) return;            // block-uniform
     const int passes = (q_end - q_begin + KS_WARPS - 1) / KS_WARPS;
 
     for (int pass = 0; pass < passes; ++pass) {
@@ -185,10 +202,10 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
         top.init();
         uint32_t thr = 0xffffffffu;  // key at position k-1
 
-        for (int n0 = 0; n0 < a.n; n0 += tile_n) {
-            const int cnt = min(tile_n, a.n - n0);
+        for (int n0 = 0; n0 < nv; n0 += tile_n) {
+            const int cnt = min(tile_n, nv - n0);
             // a cloud that fits one tile is staged once per CTA, not once per pass
-            if (n0 > 0 || pass == 0 || a.n > tile_n) {
+            if (n0 > 0 || pass == 0 || nv > tile_n) {
                 __syncthreads();
                 for (int t = threadIdx.x; t < cnt; t += KS_THREADS) {
                     float r = 0.f;
@@ -266,20 +283,26 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + k2);
     uint32_t *misc = hist + 256;
     const int qi = blockIdx.x, bi = blockIdx.y;
+    if (qi >= knn_m(a, bi)) return;          // ragged: this batch element has fewer queries (block-uniform)
     uint32_t *keys = gkeys ? gkeys + ((size_t)bi * a.m + qi) * a.n : misc + 8;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.c;
+    const int cloud = knn_cloud(a, bi);
+    const int grp = knn_group(a, bi);
+    const int nv = knn_n(a, cloud);
+    const int kv = min(a.k, nv);             // a ragged cloud may hold fewer than k points: the tail stays unwritten
     const float *qb = a.query + (size_t)bi * C * a.m;
-    const float *pb = a.points + (size_t)(bi / a.p_div) * C * a.n;
-    const bool penal = a.dup != nullptr && a.group_any[bi / a.max_group] != 0;
-    const float maxd = penal ? ordered_to_float(a.maxd[bi / a.max_group]) : 0.f;
-    const uint8_t *dupb = penal ? a.dup + (size_t)(bi / a.p_div) * a.n : nullptr;
+    const float *pb = a.points + (size_t)cloud * C * a.n;
+    const bool penal = a.dup != nullptr && a.group_any[grp] != 0;
+    const float maxd = penal ? ordered_to_float(a.maxd[grp]) : 0.f;
+    const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
+    if (kv <= 0) return;
 
     // ---- 1. keys --------------------------------------------------------------------------
     float rq = 0.f;
     for (int ch = 0; ch < C; ++ch) { const float v = __ldg(qb + (size_t)ch * a.m + qi); rq = __fmaf_rn(v, v, rq); }
-    for (int j = tid; j < a.n; j += KL_THREADS) {
+    for (int j = tid; j < nv; j += KL_THREADS) {
         float dot = 0.f, rp = 0.f;
         for (int ch = 0; ch < C; ++ch) {
             const float pv = __ldg(pb + (size_t)ch * a.n + j);
@@ -292,11 +315,11 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     }
     // ---- 2. radix select: key of rank k-1, MSB first, 8 bits per pass ------------------------
     uint32_t prefix = 0, pmask = 0;
-    uint32_t want = a.k - 1;  // rank wanted among keys matching the prefix
+    uint32_t want = kv - 1;  // rank wanted among keys matching the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
         hist[tid] = 0;
         __syncthreads();
-        for (int j = tid; j < a.n; j += KL_THREADS) {
+        for (int j = tid; j < nv; j += KL_THREADS) {
             const uint32_t key = keys[j];
             if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
@@ -328,11 +351,11 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     if (tid == 0) { misc[2] = 0; misc[3] = 0; }  // [2] slots used, [3] ties taken so far
     for (int i = tid; i < k2; i += KL_THREADS) sel[i] = ~0ull;
     __syncthreads();
-    for (int base = 0; base < a.n; base += KL_THREADS) {
+    for (int base = 0; base < nv; base += KL_THREADS) {
         const int j = base + tid;
-        const uint32_t key = j < a.n ? keys[j] : 0xffffffffu;
-        const bool less = j < a.n && key < kth;
-        const bool tie = j < a.n && key == kth;
+        const uint32_t key = j < nv ? keys[j] : 0xffffffffu;
+        const bool less = j < nv && key < kth;
+        const bool tie = j < nv && key == kth;
         // ties must be taken in index order: block-wide exclusive count of earlier ties
         const unsigned tb = __ballot_sync(0xffffffffu, tie);
         if (lane == 0) hist[warp] = __popc(tb);
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     }
     // ---- 5. outputs ---------------------------------------------------------------------------
     const size_t row = ((size_t)bi * a.m + qi) * a.k;
-    for (int p = tid; p < a.k; p += KL_THREADS) {
+    for (int p = tid; p < kv; p += KL_THREADS) {
         const unsigned long long v = sel[p];
         const int32_t j = (int32_t)(uint32_t)v;
         if (a.idx64) a.idx64[row + p] = j;
@@ -375,7 +398,7 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     if (a.knn) {
         for (int ch = 0; ch < C; ++ch) {
             float *o = a.knn + (((size_t)bi * C + ch) * a.m + qi) * a.k;
-            for (int p = tid; p < a.k; p += KL_THREADS) o[p] = __ldg(pb + (size_t)ch * a.n + (uint32_t)sel[p]);
+            for (int p = tid; p < kv; p += KL_THREADS) o[p] = __ldg(pb + (size_t)ch * a.n + (uint32_t)sel[p]);
         }
     }
 }
@@ -406,11 +429,11 @@ struct KnnPlan {
     bool keys_global;
     size_t smem;
     int tile_n;
-    size_t off_dup, off_any, off_maxd, off_keys, total;
+    size_t off_dup, off_any, off_cany, off_maxd, off_keys, total;
     int groups;
 };
 
-static bool make_plan(int b, int c, int m, int n, int k, int p_div, int max_group, int unique, KnnPlan &pl) {
+static bool make_plan(int b, int c, int m, int n, int k, int clouds, int groups, int unique, KnnPlan &pl) {
     const int smem_cap = device_info().smem_optin;
     pl.large = k > 64;
     pl.k2 = 0; pl.keys_global = false; pl.tile_n = 0; pl.smem = 0;
@@ -431,10 +454,10 @@ static bool make_plan(int b, int c, int m, int n, int k, int p_div, int max_grou
         pl.smem = ((size_t)(c + 1) * tn + (size_t)KS_WARPS * c) * 4;
         if (pl.smem > (size_t)smem_cap) return false;
     }
-    const int clouds = (b + p_div - 1) / p_div;
-    pl.groups = (b + max_group - 1) / max_group;
+    pl.groups = groups;
     size_t off = 0;
     pl.off_any = off;  off += align256(unique ? (size_t)pl.groups * 4 : 0);
+    pl.off_cany = off; off += align256(unique ? (size_t)clouds * 4 : 0);
     pl.off_maxd = off; off += align256(unique ? (size_t)pl.groups * 4 : 0);
     pl.off_dup = off;  off += align256(unique ? (size_t)clouds * n : 0);
     pl.off_keys = off; off += align256(pl.keys_global ? (size_t)b * m * n * 4 : 0);
@@ -449,24 +472,54 @@ using namespace pu3;
 extern "C" size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique) {
     if (b <= 0 || c <= 0 || m <= 0 || n <= 0 || k <= 0 || p_div <= 0) return 0;
     KnnPlan pl;
-    // the group size does not change the byte count beyond the number of groups; size for max_group = 1
-    if (!make_plan(b, c, m, n, k, p_div, 1, unique, pl)) return 0;
+    // upper bound for every grouping: one cloud and one group per batch element
+    (void)p_div;
+    if (!make_plan(b, c, m, n, k, b, b, unique, pl)) return 0;
     return pl.total;
 }
+
+static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clouds, int groups, const int32_t *owner,
+                          const int32_t *group_of, const int32_t *n_arr, const int32_t *m_arr, const float *query,
+                          const float *points, int unique, int max_group, float *knn, int64_t *idx64,
+                          int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
 
 extern "C" int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query,
                                  const float *points, int unique, int max_group, float *knn, int64_t *idx64,
                                  int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes,
                                  pu3_stream_t stream) {
+    if (b > 0 && p_div >= 1 && b % p_div == 0) {
+        if (max_group <= 0 || max_group > b) max_group = b;
+        return group_knn_impl(b, c, m, n, k, p_div, b / p_div, (b + max_group - 1) / max_group, nullptr, nullptr, nullptr,
+                              nullptr, query, points, unique, max_group, knn, idx64, idx32, dist, workspace,
+                              workspace_bytes, stream);
+    }
+    return group_knn_impl(b, c, m, n, k, p_div, 0, 0, nullptr, nullptr, nullptr, nullptr, query, points, unique, max_group,
+                          knn, idx64, idx32, dist, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pu3_group_knn_ragged_f32(int b, int c, int m, int n, int k, int clouds, int groups, const int32_t *owner,
+                                        const int32_t *group_of, const int32_t *n_arr, const int32_t *m_arr,
+                                        const float *query, const float *points, int unique, float *knn,
+                                        int64_t *idx64, int32_t *idx32, float *dist, void *workspace,
+                                        size_t workspace_bytes, pu3_stream_t stream) {
+    PU3_ARG_CHECK(owner && group_of, "group_knn_ragged: owner and group_of are required");
+    PU3_ARG_CHECK(clouds > 0 && groups > 0 && clouds <= 65535, "group_knn_ragged: clouds=%d groups=%d", clouds, groups);
+    return group_knn_impl(b, c, m, n, k, 1, clouds, groups, owner, group_of, n_arr, m_arr, query, points, unique, 1, knn,
+                          idx64, idx32, dist, workspace, workspace_bytes, stream);
+}
+
+static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clouds, int groups, const int32_t *owner,
+                          const int32_t *group_of, const int32_t *n_arr, const int32_t *m_arr, const float *query,
+                          const float *points, int unique, int max_group, float *knn, int64_t *idx64,
+                          int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes, pu3_stream_t stream) {
     PU3_ARG_CHECK(b >= 0 && c > 0 && m >= 0 && n >= 0 && k >= 0, "group_knn: bad size b=%d c=%d m=%d n=%d k=%d", b, c, m, n, k);
     PU3_ARG_CHECK(k <= n, "group_knn: points size must be greater or equal to k (n=%d, k=%d)", n, k);  // operations.py:186
     if (b == 0 || m == 0 || k == 0) return PU3_OK;
     PU3_ARG_CHECK(p_div >= 1 && b % p_div == 0, "group_knn: p_div=%d must divide b=%d", p_div, b);
     PU3_ARG_CHECK(b <= 65535, "group_knn: b=%d exceeds 65535", b);
     PU3_ARG_CHECK(query && points, "group_knn: null input pointer");
-    if (max_group <= 0 || max_group > b) max_group = b;
     KnnPlan pl;
-    if (!make_plan(b, c, m, n, k, p_div, max_group, unique, pl)) {
+    if (!make_plan(b, c, m, n, k, clouds, groups, unique, pl)) {
         set_error("group_knn: c=%d k=%d does not fit shared memory", c, k);
         return PU3_E_UNSUPPORTED;
     }
@@ -479,16 +532,19 @@ extern "C" int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, c
     }
     cudaStream_t s = as_stream(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    KnnArgs a{b, c, m, n, k, p_div, max_group, query, points, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
+    KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
+              query, points, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
     if (unique) {
         int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
+        int *cloud_any = reinterpret_cast<int *>(ws + pl.off_cany);
         uint32_t *maxd = reinterpret_cast<uint32_t *>(ws + pl.off_maxd);
         uint8_t *dup = ws + pl.off_dup;
         int st = cuda_status(cudaMemsetAsync(ws + pl.off_any, 0, pl.off_dup - pl.off_any, s), "group_knn: memset");
         if (st) return st;
-        const int clouds = b / p_div;
-        knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, p_div, max_group, b, points, dup, group_any);
+        knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
         PU3_LAUNCH_CHECK("knn_dup_kernel");
+        knn_groupflag_kernel<<<(b + 255) / 256, 256, 0, s>>>(a, cloud_any, group_any);
+        PU3_LAUNCH_CHECK("knn_groupflag_kernel");
         a.dup = dup; a.group_any = group_any; a.maxd = maxd;
         knn_maxd_kernel<<<dim3((m + 127) / 128, b), 128, 0, s>>>(a, maxd);
         PU3_LAUNCH_CHECK("knn_maxd_kernel");

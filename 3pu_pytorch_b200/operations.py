@@ -33,10 +33,36 @@ def normalize_point_batch(pc, NCHW=True):
 # ------------------------------------------------------------------------------------------------
 # group_knn
 # ------------------------------------------------------------------------------------------------
-def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64):
-    """q (B,C,M), p (B/p_div,C,N) contiguous f32 on the same device -> (knn|None, idx, dist|None)."""
+class Ragged:
+    """Description of a ragged batch for group_knn (batched eval): batch element i reads cloud owner[i], which
+    holds n_arr[owner[i]] valid points; it has m_arr[i] valid queries and belongs to duplicate-penalty group
+    group_of[i].  All tensors int32 on the device; n_arr / m_arr may be None (= full rows)."""
+
+    def __init__(self, owner, group_of, groups, n_arr=None, m_arr=None):
+        self.owner, self.group_of, self.groups, self.n_arr, self.m_arr = owner, group_of, int(groups), n_arr, m_arr
+
+
+def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64, ragged=None):
+    """q (B,C,M), p (B/p_div,C,N) contiguous f32 on the same device -> (knn|None, idx, dist|None).
+    With `ragged`, p is (clouds,C,N) and the mapping comes from the Ragged description; outputs of invalid
+    rows / columns are zero."""
     B, C, M = q.shape
     Bp, _, N = p.shape
+    if ragged is not None:
+        dev = q.device
+        alloc = torch.zeros
+        knn = alloc(B, C, M, k, dtype=torch.float32, device=dev) if want_knn else None
+        idx = alloc(B, M, k, dtype=idx_dtype, device=dev)
+        dist = alloc(B, M, k, dtype=torch.float32, device=dev) if want_dist else None
+        ws_bytes = _lib.lib().pu3_group_knn_workspace(B, C, M, N, k, 1, int(bool(unique)))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _lib.launch("pu3_group_knn_ragged_f32", q, B, C, M, N, k, Bp, ragged.groups, _lib.ptr(ragged.owner),
+                    _lib.ptr(ragged.group_of), _lib.ptr(ragged.n_arr), _lib.ptr(ragged.m_arr), _lib.ptr(q), _lib.ptr(p),
+                    int(bool(unique)), _lib.ptr(knn), _lib.ptr(idx if idx_dtype == torch.int64 else None),
+                    _lib.ptr(idx if idx_dtype == torch.int32 else None), _lib.ptr(dist), _lib.ptr(ws), ws_bytes,
+                    extra_kernels=3 if unique else 0,
+                    tag="pu3_group_knn_f32[k<=64]" if k <= 64 else "pu3_group_knn_f32[k>64]")
+        return knn, idx, dist
     if Bp == 0 or B % Bp != 0:
         raise RuntimeError(f"group_knn: points batch {Bp} must divide query batch {B}")
     p_div = B // Bp
@@ -53,7 +79,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
     # stream goes last in the C signature, after (workspace, workspace_bytes)
     _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
                 int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32), _lib.ptr(dist), _lib.ptr(ws),
-                ws_bytes, extra_kernels=2 if unique else 0,
+                ws_bytes, extra_kernels=3 if unique else 0,
                 tag="pu3_group_knn_f32[k<=64]" if k <= 64 else "pu3_group_knn_f32[k>64]")
     return knn, idx, dist
 
@@ -188,3 +214,16 @@ def furthest_point_sample(xyz, npoint, NCHW=True):
     if not NCHW:
         sampled_pc = sampled_pc.transpose(2, 1).contiguous()
     return idx, sampled_pc
+
+
+def furthest_point_sample_ragged(xyz, n_arr, m_arr, m_max):
+    """Batched FPS over clouds of different sizes (batched eval): xyz (B,3,Nmax) with n_arr[i] valid leading
+    points, m_arr[i] <= m_max samples wanted (None = m_max everywhere).  Returns idx (B,m_max) int32 (zeros past
+    m_arr[i]) and the gathered points (B,3,m_max).  Every cloud gets what furthest_point_sample gives it alone."""
+    _need_cuda(xyz, "furthest_point_sample_ragged")
+    B, _, N = xyz.shape
+    pts = xyz.transpose(2, 1).contiguous()
+    idx = torch.zeros(B, m_max, dtype=torch.int32, device=xyz.device)
+    _lib.launch("pu3_fps_ragged_f32", pts, B, N, int(m_max), _lib.ptr(n_arr), _lib.ptr(m_arr), _lib.ptr(pts), None,
+                _lib.ptr(idx), tag="pu3_fps_f32")
+    return idx, gather_points(xyz.contiguous(), idx)

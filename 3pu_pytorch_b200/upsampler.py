@@ -89,9 +89,13 @@ class Level(torch.nn.Module):
         return (xyz_normalized.is_cuda and xyz_normalized.dtype == torch.float32 and self.dense_n == 3
                 and self.growth_rate == 12 and self.code.size(1) == 1 and not wants_grad)
 
-    def _features_fused(self, xyz_normalized, group):
+    def _features_fused(self, xyz_normalized, group, ragged=None):
         """layer0 + 4 dense blocks into one (B,264,N) buffer; channel order [y4, y3, y2, y1, x0]."""
         B, _, N = xyz_normalized.shape
+        self_ragged = None
+        if ragged is not None:   # every patch is its own cloud; the duplicate-penalty group is its request
+            me = torch.arange(B, dtype=torch.int32, device=xyz_normalized.device)
+            self_ragged = operations.Ragged(me, ragged.owner, ragged.groups)
         C = self.feat_channels
         feat = torch.empty(B, C, N, dtype=torch.float32, device=xyz_normalized.device)
         # h: the 24-channel input of the current dense block (contiguous: kNN and edge-conv read it)
@@ -105,20 +109,32 @@ class Level(torch.nn.Module):
                 fused.conv_into(feat[:, lo:], prep.conv.weight, prep.conv.bias, h, relu=True)
             src = h
             _, idx32, _ = operations._knn_raw(block.k + 1, src, src, True, group, want_knn=False, want_dist=False,
-                                              idx_dtype=torch.int32)
+                                              idx_dtype=torch.int32, ragged=self_ragged)
             fused.edgeconv_into(src, idx32, 1, block.k, [m.weight for m in block.mlps], [m.bias for m in block.mlps],
                                 feat[:, lo - 60:lo])
             lo -= 60
         return feat
 
-    def _skip_connection(self, x, xyz, previous_level4, group):
+    def _skip_connection(self, x, xyz, previous_level4, group, ragged=None):
         """upsampler.py:317-347: bilateral (spatial x feature) interpolation of the previous level's features."""
         previous_xyz, previous_feat = previous_level4
         B, _, N = xyz.shape
         Bp = previous_xyz.shape[0]
-        knnIdx_points, knnIdx_idx, _ = operations.group_knn(self.fm_knn, xyz, previous_xyz, unique=True, NCHW=True,
-                                                            max_group=group)
-        if Bp == B:
+        if ragged is not None:
+            # patch i reads the previous-level cloud of its request owner[i], which holds n_arr[owner[i]] points
+            knnIdx_points, knnIdx_idx, _ = operations._knn_raw(self.fm_knn, xyz.contiguous(), previous_xyz.contiguous(),
+                                                               True, None, want_dist=False, ragged=ragged)
+            Cp, Mp = previous_feat.shape[1], previous_feat.shape[2]
+            flat = previous_feat.permute(1, 0, 2).reshape(Cp, Bp * Mp)
+            offs = (ragged.owner.long() * Mp).view(B, 1, 1)
+            g = flat[:, (knnIdx_idx + offs).reshape(-1)]
+            knnIdx_feats = g.view(Cp, B, N, self.fm_knn).permute(1, 0, 2, 3)
+        else:
+            knnIdx_points, knnIdx_idx, _ = operations.group_knn(self.fm_knn, xyz, previous_xyz, unique=True, NCHW=True,
+                                                                max_group=group)
+        if ragged is not None:
+            pass
+        elif Bp == B:
             pf = previous_feat.unsqueeze(2).expand(-1, -1, N, -1)
             knnIdx_feats = torch.gather(pf, 3, knnIdx_idx.unsqueeze(1).expand(-1, pf.size(1), -1, -1))
         else:
@@ -158,19 +174,23 @@ class Level(torch.nn.Module):
                         res_div=r)
         return out
 
-    def forward(self, xyz, xyz_normalized, previous_level4=None, group=None, **kwargs):
+    def forward(self, xyz, xyz_normalized, previous_level4=None, group=None, ragged=None, **kwargs):
         """
         :param xyz Bx3xN input xyz, unnormalized; xyz_normalized Bx3xN; previous_level4 (Bx3xM, BxCxM) of the
                previous level (its batch may divide B: shared by consecutive patches)
         :param group (extension) patches per independent request, scope of group_knn's duplicate penalty
+        :param ragged (extension, eval) operations.Ragged: request of every patch + valid size of every request's
+               previous-level cloud, for requests with different numbers of patches
         :return xyz Bx3xNr (normalised frame), features BxCxN of the input points
         """
         if kwargs.get("phase") == "vis":
             raise NotImplementedError("phase='vis' (debug visualisation, upsampler.py:285-314) is out of scope")
         batch_size, _, num_point = xyz_normalized.size()
         fast = self._fast_path_ok(xyz_normalized)
+        if ragged is not None and not fast:
+            raise RuntimeError("ragged batches are an eval-mode (no-grad, CUDA fp32) feature")
         if fast:
-            x = self._features_fused(xyz_normalized, group)
+            x = self._features_fused(xyz_normalized, group, ragged)
         else:
             x = self.layer0(xyz_normalized.unsqueeze(dim=-1)).squeeze(dim=-1)
             y, _ = self.layer1(x)
@@ -183,7 +203,7 @@ class Level(torch.nn.Module):
             x = torch.cat([y, x], dim=1)
 
         if previous_level4 is not None and self.fm_knn > 0:
-            x = self._skip_connection(x, xyz, previous_level4, group)
+            x = self._skip_connection(x, xyz, previous_level4, group, ragged)
 
         point_features = x
         if fast:
@@ -247,14 +267,13 @@ class Net(torch.nn.Module):
         return closest_d < (5 * torch.mean(closest_d, dim=1, keepdim=True))
 
     def _eval_tiles(self, batch_xyz, k):
-        """Seeds by FPS, int(N/k*5) overlapping kNN tiles per cloud (:76-86).  batch_xyz (B,3,N) already
-        filtered -> tiles (B*P,3,k') with the P tiles of a cloud consecutive, and P."""
-        B, _, num_point = batch_xyz.shape
+        """Seeds by FPS, int(N/k*5) overlapping kNN tiles (:76-86) of ONE filtered cloud (1,3,N') -> (P,3,k'), P."""
+        num_point = batch_xyz.shape[2]
         patch_num = int(num_point / k * 5)
         _, seeds = operations.furthest_point_sample(batch_xyz, patch_num)
         k = min(k, num_point)
-        tiles, _, _ = operations.group_knn(k, seeds, batch_xyz, unique=False, NCHW=True)   # B,3,P,k
-        return tiles.permute(0, 2, 1, 3).reshape(B * patch_num, 3, k), patch_num
+        tiles, _, _ = operations.group_knn(k, seeds, batch_xyz, unique=False, NCHW=True)   # 1,3,P,k
+        return torch.cat(torch.unbind(tiles, dim=2), dim=0), patch_num
 
     def extract_xyz_feature_patch(self, batch_xyz, k, gt_xyz=None, gt_k=None):
         """upsampler.py:39-105 (reference signature; eval expects batch 1 like the reference)."""
@@ -266,24 +285,77 @@ class Net(torch.nn.Module):
         tiles, _ = self._eval_tiles(batch_xyz, k)
         return tiles, None
 
-    # ---- one eval level past the first, for a batch of clouds that share N' -----------------------
-    def _eval_level(self, level, xyz, old_xyz, old_features, max_num_point, num_output_point, **kwargs):
-        B = xyz.shape[0]
+    # ---- eval levels past the first ------------------------------------------------------------------
+    def _eval_level_single(self, level, xyz, old_xyz, old_features, max_num_point, num_output_point, **kwargs):
+        """One request (batch 1) exactly as the reference walks it (upsampler.py:128-159); used when a filtered
+        cloud is smaller than a tile, which changes the tile size itself."""
         if xyz.size(-1) > max_num_point:
+            mask = self._eval_outlier_mask(xyz)
+            xyz = torch.masked_select(xyz, mask.unsqueeze(1).expand_as(xyz)).view(1, 3, -1)
             patch_xyz, P = self._eval_tiles(xyz, max_num_point)
         else:
             patch_xyz, P = xyz, 1
         patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
         new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), group=P, **kwargs)
         new_xyz = new_xyz * radius + centroid
-        if P != 1:
-            # merge the P tiles of every cloud along the point axis (:149-155) and resample (:156-159)
-            def merge(t):
-                C, n = t.shape[1], t.shape[2]
-                return t.view(B, P, C, n).permute(0, 2, 1, 3).reshape(B, C, P * n)
-            new_xyz, patch_xyz, features = merge(new_xyz), merge(patch_xyz), merge(features)
+        if patch_xyz.shape[0] != 1:
+            new_xyz = torch.cat(torch.split(new_xyz, 1, dim=0), dim=2)
+            patch_xyz = torch.cat(torch.split(patch_xyz, 1, dim=0), dim=2)
+            features = torch.cat(torch.split(features, 1, dim=0), dim=2)
             _, new_xyz = operations.furthest_point_sample(new_xyz, num_output_point)
         return new_xyz, patch_xyz, features
+
+    def _eval_level_batched(self, level, xyz, old_xyz, old_features, old_n, max_num_point, num_output_point,
+                            keep_features, **kwargs):
+        """All requests of the batch together.  xyz (B,3,N) uniform; old_xyz (B,3,No) / old_features (B,264,No)
+        padded, old_n (B,) int32 valid sizes.  The outlier filter leaves request b with N'_b points and
+        int(N'_b/312*5) tiles, so tiles are processed as ONE flat list with an owner per tile.
+        Returns (xyz (B,3,num_output_point), new old_xyz, new old_features, new old_n) or None when a filtered
+        cloud is smaller than a tile (caller falls back to per-request processing)."""
+        B, _, N = xyz.shape
+        dev = xyz.device
+        k = max_num_point
+        mask = self._eval_outlier_mask(xyz)                                          # (B,N)
+        counts = mask.sum(dim=1)
+        counts_h = counts.tolist()                                                   # the one host sync of the level
+        if min(counts_h) < k:
+            return None
+        # compact every cloud to its kept points, order preserved (what masked_select does, :72-73)
+        order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
+        xyz_c = torch.gather(xyz, 2, order.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+        n_arr = counts.to(torch.int32)
+        P_h = [int(c / k * 5) for c in counts_h]                                     # :76
+        Pmax = max(P_h)
+        p_arr = torch.tensor(P_h, dtype=torch.int32, device=dev)
+        req = torch.arange(B, dtype=torch.int32, device=dev)
+        # seeds (:78) and tiles (:83)
+        _, seeds = operations.furthest_point_sample_ragged(xyz_c, n_arr, p_arr, Pmax)  # (B,3,Pmax)
+        tiles, _, _ = operations._knn_raw(k, seeds, xyz_c, False, None, want_dist=False,
+                                          ragged=operations.Ragged(req, req, B, n_arr=n_arr, m_arr=p_arr))
+        # flat list of the valid tiles, request-major (the reference's torch.cat(torch.unbind(., 2), 0), :85)
+        owner_h = [b for b in range(B) for _ in range(P_h[b])]
+        slot_h = [b * Pmax + p for b in range(B) for p in range(P_h[b])]
+        owner = torch.tensor(owner_h, dtype=torch.int32, device=dev)
+        slot = torch.tensor(slot_h, dtype=torch.int64, device=dev)
+        patch_xyz = tiles.permute(0, 2, 1, 3).reshape(B * Pmax, 3, k)[slot].contiguous()   # (T,3,k)
+        patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+        ragged = operations.Ragged(owner, owner, B, n_arr=old_n)
+        new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged, **kwargs)
+        new_xyz = new_xyz * radius + centroid                                        # (T,3,k*r)
+
+        def merge(t):
+            """(T,C,n) tiles -> (B,C,Pmax*n): the tiles of a request side by side (:149-155), zero padded"""
+            C, n = t.shape[1], t.shape[2]
+            buf = torch.zeros(B * Pmax, C, n, dtype=t.dtype, device=dev)
+            buf[slot] = t
+            return buf.view(B, Pmax, C, n).permute(0, 2, 1, 3).reshape(B, C, Pmax * n)
+
+        merged = merge(new_xyz)
+        r = new_xyz.shape[2] // k
+        _, out_xyz = operations.furthest_point_sample_ragged(merged, p_arr * (k * r), None, num_output_point)  # :158
+        if keep_features:
+            return out_xyz, merge(patch_xyz), merge(features), p_arr * k
+        return out_xyz, None, None, None
 
     def forward(self, xyz, ratio=None, gt=None, seed_idx_per_level=None, **kwargs):
         """
@@ -297,67 +369,56 @@ class Net(torch.nn.Module):
         batch_size, _, num_point = xyz.size()
         num_levels = int(log(ratio, self.step_ratio))
         max_num_point = min(num_point, self.max_num_point)
+        if not self.training:
+            return self._forward_eval(xyz, num_levels, num_point, max_num_point, **kwargs)
 
         for l in range(1, num_levels + 1):
             curr_ratio = self.step_ratio ** l
             level = self.levels['level_%d' % l]
             if l == 1:
                 old_xyz = xyz
-                # eval: every cloud is its own request (duplicate-penalty scope 1); training: the whole batch
-                xyz, features = level(xyz, xyz, previous_level4=None, group=None if self.training else 1, **kwargs)
+                xyz, features = level(xyz, xyz, previous_level4=None, **kwargs)
                 old_features = features
                 continue
-            if self.training:
-                if xyz.size(-1) > max_num_point:
-                    gt_k = max_num_point * ratio // curr_ratio * self.step_ratio
-                    sidx = None if seed_idx_per_level is None else seed_idx_per_level.get(l)
-                    patch_xyz, gt = self._train_patches(xyz, max_num_point, gt, gt_k, seed_idx=sidx)
-                else:
-                    patch_xyz = xyz
-                patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
-                xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), **kwargs)
-                xyz = xyz * radius + centroid
-                old_xyz, old_features = patch_xyz, features
-                continue
-            # ---- eval: every cloud is an independent request (the reference handles one per call) ----
-            num_output_point = num_point * curr_ratio
             if xyz.size(-1) > max_num_point:
-                mask = self._eval_outlier_mask(xyz)
-                counts = mask.sum(dim=1).tolist()                           # the one host sync per level
+                gt_k = max_num_point * ratio // curr_ratio * self.step_ratio
+                sidx = None if seed_idx_per_level is None else seed_idx_per_level.get(l)
+                patch_xyz, gt = self._train_patches(xyz, max_num_point, gt, gt_k, seed_idx=sidx)
             else:
-                mask, counts = None, [xyz.size(-1)] * batch_size
-            if all(c == xyz.size(-1) for c in counts):
-                xyz, old_xyz, old_features = self._eval_level(level, xyz, old_xyz, old_features, max_num_point,
-                                                              num_output_point, **kwargs)
-            else:
-                outs = []
-                for i in range(batch_size):
-                    xi = torch.masked_select(xyz[i:i + 1], mask[i:i + 1].unsqueeze(1).expand(-1, 3, -1)).view(1, 3, -1)
-                    outs.append(self._eval_level(level, xi, old_xyz[i:i + 1], old_features[i:i + 1], max_num_point,
-                                                 num_output_point, **kwargs))
-                xyz = torch.cat([o[0] for o in outs], dim=0)
-                # tile counts differ between clouds: pad-free batching of the next level needs equal sizes
-                sizes = {o[1].shape[2] for o in outs}
-                if len(sizes) != 1:
-                    return self._finish_ragged(outs, l, num_levels, num_point, max_num_point, **kwargs)
-                old_xyz = torch.cat([o[1] for o in outs], dim=0)
-                old_features = torch.cat([o[2] for o in outs], dim=0)
+                patch_xyz = xyz
+            patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+            xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), **kwargs)
+            xyz = xyz * radius + centroid
+            old_xyz, old_features = patch_xyz, features
+        return xyz, gt
 
-        if self.training:
-            return xyz, gt
+    def _forward_eval(self, xyz, num_levels, num_point, max_num_point, **kwargs):
+        """Eval: every cloud of the batch is an independent request (the reference takes one per call)."""
+        B = xyz.shape[0]
+        dev = xyz.device
+        level = self.levels['level_1']
+        old_xyz = xyz
+        xyz, old_features = level(xyz, xyz, previous_level4=None, group=1, **kwargs)    # duplicate-penalty scope: 1 cloud
+        old_n = torch.full((B,), old_xyz.shape[2], dtype=torch.int32, device=dev)
+        for l in range(2, num_levels + 1):
+            level = self.levels['level_%d' % l]
+            num_output_point = num_point * self.step_ratio ** l
+            res = None
+            if xyz.size(-1) > max_num_point and xyz.is_cuda:
+                res = self._eval_level_batched(level, xyz, old_xyz, old_features, old_n, max_num_point, num_output_point,
+                                               keep_features=l < num_levels, **kwargs)
+            if res is not None:
+                xyz, old_xyz, old_features, old_n = res
+                continue
+            # per-request processing (a filtered cloud smaller than one tile, or nothing to tile)
+            old_n_h = old_n.tolist()
+            outs = [self._eval_level_single(level, xyz[i:i + 1], old_xyz[i:i + 1, :, :old_n_h[i]].contiguous(),
+                                            old_features[i:i + 1, :, :old_n_h[i]].contiguous(), max_num_point,
+                                            num_output_point, **kwargs) for i in range(B)]
+            xyz = torch.cat([o[0] for o in outs], dim=0)
+            old_n = torch.tensor([o[1].shape[2] for o in outs], dtype=torch.int32, device=dev)
+            nmax = int(old_n.max())
+            pad = lambda t: torch.nn.functional.pad(t, (0, nmax - t.shape[2]))
+            old_xyz = torch.cat([pad(o[1]) for o in outs], dim=0)
+            old_features = torch.cat([pad(o[2]) for o in outs], dim=0)
         return xyz
-
-    def _finish_ragged(self, outs, l_done, num_levels, num_point, max_num_point, **kwargs):
-        """Clouds whose outlier filter removed different numbers of points carry previous-level clouds of
-        different sizes; finish each of them on its own (still on the GPU kernels)."""
-        results = []
-        for xyz, old_xyz, old_features in outs:
-            for l in range(l_done + 1, num_levels + 1):
-                level = self.levels['level_%d' % l]
-                if xyz.size(-1) > max_num_point:
-                    mask = self._eval_outlier_mask(xyz)
-                    xyz = torch.masked_select(xyz, mask.unsqueeze(1).expand_as(xyz)).view(1, 3, -1)
-                xyz, old_xyz, old_features = self._eval_level(level, xyz, old_xyz, old_features, max_num_point,
-                                                              num_point * self.step_ratio ** l, **kwargs)
-            results.append(xyz)
-        return torch.cat(results, dim=0)

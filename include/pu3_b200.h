@@ -58,6 +58,16 @@ int pu3_device_info(int *sm_count, int *smem_optin_bytes, int *cc);
 int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, pu3_stream_t stream);
 
 /*
+ * Ragged batch of clouds for the batched eval path: cloud i has n_arr[i] <= n_stride points and wants
+ * m_arr[i] <= m_stride samples (either array may be NULL = the stride); rows of xyz / temp / idx are
+ * n_stride / m_stride apart and entries past a cloud's own counts are neither read nor written.  Each cloud
+ * gets exactly the result pu3_fps_f32 would give for it alone (the tie rule uses the cloud's own n).
+ * n_arr / m_arr are DEVICE arrays of b int32.
+ */
+int pu3_fps_ragged_f32(int b, int n_stride, int m_stride, const int32_t *n_arr, const int32_t *m_arr,
+                       const float *xyz, float *temp, int32_t *idx, pu3_stream_t stream);
+
+/*
  * Point gather, out[b,c,j] = points[b,c,idx[b,j]].  Replaces sampling.gather_forward
  * (sampling/sampling.cpp:37-45, sampling_cuda.cu:26-62).  points (b,c,n), idx (b,m) i32, out (b,c,m).
  * elem_bytes = 2, 4 or 8 (the reference dispatches half/float/double; a gather only moves bits).
@@ -119,6 +129,20 @@ size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int
 int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query, const float *points,
                       int unique, int max_group, float *knn, int64_t *idx64, int32_t *idx32, float *dist,
                       void *workspace, size_t workspace_bytes, pu3_stream_t stream);
+
+/*
+ * group_knn over a ragged batch (batched eval, where the outlier filter of network/upsampler.py:63-73 leaves
+ * every cloud its own size): batch element i reads cloud owner[i] (clouds clouds of n_arr[c] <= n valid points,
+ * row stride n), has m_arr[i] <= m valid queries, and belongs to duplicate-penalty group group_of[i]
+ * (0 <= group_of[i] < groups).  n_arr / m_arr may be NULL.  Rows of batch elements / queries past the valid
+ * counts are not written; when a cloud holds fewer than k points only its first n_arr[c] result columns are.
+ * All index arrays are DEVICE int32.  Workspace as for pu3_group_knn_f32.
+ */
+int pu3_group_knn_ragged_f32(int b, int c, int m, int n, int k, int clouds, int groups, const int32_t *owner,
+                             const int32_t *group_of, const int32_t *n_arr, const int32_t *m_arr,
+                             const float *query, const float *points, int unique, float *knn, int64_t *idx64,
+                             int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes,
+                             pu3_stream_t stream);
 
 /*
  * Backward of the neighbour gather of group_knn: grad_points[b/p_div, c, idx[b,m,kk]] += grad_knn[b,c,m,kk]

@@ -134,3 +134,35 @@ def test_chamfer_loss_module(pu3, cuda):
         got.backward()
         torch.testing.assert_close(got.cpu(), want, rtol=1e-6, atol=1e-8)
         torch.testing.assert_close(ac.grad.cpu(), a.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_ragged_batch_equals_per_element_calls(pu3, cuda):
+    """Batched eval: tiles of different requests in one launch, every request with its own cloud size."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [900, 400, 1300]
+    nmax = max(sizes)
+    clouds = torch.full((3, 3, nmax), 50.0)
+    for i, n in enumerate(sizes):
+        clouds[i, :, :n] = torch.rand(3, n, generator=g)
+    owner = torch.tensor([0, 0, 1, 2, 2, 2, 2], dtype=torch.int32)
+    q = torch.rand(7, 3, 100, generator=g)
+    R = pu3.operations.Ragged(owner.to(cuda), owner.to(cuda), 3, n_arr=torch.tensor(sizes, dtype=torch.int32, device=cuda))
+    for k in (5, 200):
+        nb, idx, dist = pu3.operations._knn_raw(k, q.to(cuda), clouds.to(cuda), True, None, ragged=R)
+        for i in range(7):
+            c = int(owner[i]); n = sizes[c]
+            nb1, idx1, dist1 = pu3.operations.group_knn(k, q[i:i + 1].to(cuda), clouds[c:c + 1, :, :n].contiguous().to(cuda),
+                                                        unique=True)
+            assert torch.equal(idx[i:i + 1], idx1) and torch.equal(nb[i:i + 1], nb1) and torch.equal(dist[i:i + 1], dist1)
+    # ragged query counts (seeds per request) with k > 64
+    m_arr = torch.tensor([3, 1, 2], dtype=torch.int32, device=cuda)
+    req = torch.arange(3, dtype=torch.int32, device=cuda)
+    seeds = clouds[:, :, :3].contiguous()
+    R2 = pu3.operations.Ragged(req, req, 3, n_arr=torch.tensor(sizes, dtype=torch.int32, device=cuda), m_arr=m_arr)
+    nb, idx, _ = pu3.operations._knn_raw(312, seeds.to(cuda), clouds.to(cuda), False, None, ragged=R2)
+    for i in range(3):
+        n = sizes[i]; m = int(m_arr[i])
+        nb1, idx1, _ = pu3.operations.group_knn(312, seeds[i:i + 1, :, :m].contiguous().to(cuda),
+                                                clouds[i:i + 1, :, :n].contiguous().to(cuda), unique=False)
+        assert torch.equal(idx[i:i + 1, :m], idx1) and torch.equal(nb[i:i + 1, :, :m], nb1)
+        assert int(idx[i, m:].abs().sum()) == 0

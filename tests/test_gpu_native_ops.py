@@ -236,3 +236,28 @@ def test_errors_raise_not_exit(pu3, cuda):
                                     torch.zeros(1, 2, dtype=torch.int32, device=cuda), torch.zeros(1, 3, 2, device=cuda))
     with pytest.raises(RuntimeError, match="empty cloud"):
         pu3._lib.check(pu3._lib.lib().pu3_fps_f32(1, 0, 3, None, None, None, None), "fps")
+
+
+# ------------------------------------------------------------------------------------------- ragged batches
+def test_fps_ragged_equals_per_cloud_calls(pu3, cuda):
+    rng = np.random.default_rng(41)
+    sizes = [700, 312, 6240, 513, 2000]
+    wants = [64, 10, 300, 64, 1]
+    nmax, mmax = max(sizes), max(wants)
+    x = np.zeros((len(sizes), nmax, 3), np.float32)
+    for i, n in enumerate(sizes):
+        x[i, :n] = _cloud(rng, 1, n, dup_frac=0.05)[0]
+        x[i, n:] = 1e6  # padding must never be looked at
+    xt = torch.from_numpy(x).to(cuda).transpose(1, 2).contiguous()  # (B,3,Nmax)
+    n_arr = torch.tensor(sizes, dtype=torch.int32, device=cuda)
+    m_arr = torch.tensor(wants, dtype=torch.int32, device=cuda)
+    idx, pts = pu3.operations.furthest_point_sample_ragged(xt, n_arr, m_arr, mmax)
+    for i, (n, m) in enumerate(zip(sizes, wants)):
+        want = c_oracle.fps(x[i:i + 1, :n], m)[0]
+        assert np.array_equal(idx[i, :m].cpu().numpy(), want), i
+        assert int(idx[i, m:].abs().sum()) == 0
+        assert bits_equal(pts[i, :, :m].cpu().numpy(), np.ascontiguousarray(x[i, want].T))
+    # more samples than points (a request whose tiles cover fewer points than the level must output)
+    idx2, _ = pu3.operations.furthest_point_sample_ragged(xt, n_arr, None, 400)
+    for i in (1, 3):
+        assert np.array_equal(idx2[i].cpu().numpy(), c_oracle.fps(x[i:i + 1, :sizes[i]], 400)[0])

@@ -38,7 +38,8 @@ struct KnnArgs {
     const float *query;   // (b,c,m)
     const float *points;  // (b/p_div,c,n)
     const uint8_t *dup;   // (b/p_div,n) or null
-    const int *group_any; // (groups) or null
+    const int *cloud_dups; // (clouds) number of duplicate points per cloud, or null
+    const int *group_any; // (groups) or null: group needs the exact max(D) penalty
     const uint32_t *maxd; // (groups) ordered keys
     float *knn;           // (b,c,m,k) or null
     int64_t *idx64;       // (b,m,k) or null
@@ -50,6 +51,18 @@ __device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.ow
 __device__ __forceinline__ int knn_group(const KnnArgs &a, int bi) { return a.group_of ? __ldg(a.group_of + bi) : bi / a.max_group; }
 __device__ __forceinline__ int knn_n(const KnnArgs &a, int cloud) { return a.n_arr ? min(a.n, __ldg(a.n_arr + cloud)) : a.n; }
 __device__ __forceinline__ int knn_m(const KnnArgs &a, int bi) { return a.m_arr ? min(a.m, __ldg(a.m_arr + bi)) : a.m; }
+
+// Duplicate handling of one batch element (operations.py:192-204).  The reference adds max(D) to every
+// duplicate candidate, which sorts ALL duplicates after ALL first occurrences (max(D) >= any D).  So:
+//   mode 0  no duplicates in the cloud: nothing to do
+//   mode 1  the cloud has at least k first occurrences: duplicates can never be selected -> skip them
+//           (no max(D) pass at all; the merged previous-level clouds of the eval path are full of duplicates)
+//   mode 2  fewer than k first occurrences: exact penalty, max(D) computed by knn_maxd_kernel for the group
+__device__ __forceinline__ int knn_dup_mode(const KnnArgs &a, int cloud, int grp) {
+    if (a.dup == nullptr) return 0;
+    if (a.group_any[grp] != 0) return 2;
+    return a.cloud_dups[cloud] > 0 ? 1 : 0;
+}
 
 // the reference's D = r_A - 2*m + r_B, evaluated left to right (operations.py:161)
 __device__ __forceinline__ float expanded_dist(float rq, float dot, float rp) {
@@ -76,14 +89,18 @@ __global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, const int32_
         found = same;
     }
     dup[(size_t)cloud * n + j] = found ? 1 : 0;
-    if (found) cloud_any[cloud] = 1;
+    if (found) atomicAdd(cloud_any + cloud, 1);   // number of duplicates of the cloud
 }
 
 // a group needs max(D) as soon as one of its batch elements reads a cloud with duplicates
 __global__ void __launch_bounds__(256) knn_groupflag_kernel(KnnArgs a, const int *__restrict__ cloud_any,
                                                            int *__restrict__ group_any) {
     const int bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi < a.b && cloud_any[knn_cloud(a, bi)]) group_any[knn_group(a, bi)] = 1;
+    if (bi >= a.b) return;
+    const int cloud = knn_cloud(a, bi);
+    const int dups = cloud_any[cloud];
+    // the exact max(D) penalty is needed only when the k nearest cannot be filled with first occurrences
+    if (dups > 0 && knn_n(a, cloud) - dups < a.k) group_any[knn_group(a, bi)] = 1;
 }
 
 __global__ void __launch_bounds__(128) knn_maxd_kernel(KnnArgs a, uint32_t *__restrict__ maxd) {
@@ -171,8 +188,9 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
     const int nv = knn_n(a, cloud);          // valid candidates of this cloud
     const float *qb = a.query + (size_t)bi * C * a.m;
     const float *pb = a.points + (size_t)cloud * C * a.n;
-    const bool penal = a.dup != nullptr && a.group_any[grp] != 0;
-    const float maxd = penal ? ordered_to_float(a.maxd[grp]) : 0.f;
+    const int dmode = knn_dup_mode(a, cloud, grp);
+    const bool penal = dmode != 0;
+    const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
     const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
 
     const int q_begin = blockIdx.x * q_per_cta;
@@ -231,8 +249,9 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
                         for (int ch = 0; ch < C; ++ch) dot = __fmaf_rn(sq[warp * C + ch], sp[(size_t)ch * tile_n + j], dot);
                     }
                     float d = expanded_dist(rq, dot, srp[j]);
-                    if (penal && dupb[n0 + j]) d = __fadd_rn(d, maxd);  // D += max(D) * duplicated (:204)
-                    key = float_to_ordered(d);
+                    const bool isdup = penal && dupb[n0 + j];
+                    if (isdup) d = __fadd_rn(d, maxd);  // D += max(D) * duplicated (:204)
+                    key = (isdup && dmode == 1) ? 0xffffffffu : float_to_ordered(d);
                 }
                 unsigned pend = __ballot_sync(0xffffffffu, key < thr);
                 while (pend) {
@@ -271,6 +290,307 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
     }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// k <= 64, n <= 320: the feature-space kNN of DenseEdgeConv (layers.py:33: 24 channels, 312 points, k+1 = 33)
+// --------------------------------------------------------------------------------------------
+// One CTA per cloud.  Queries are processed in blocks of KF_QB:
+//   phase 1  the KF_QB x n block of distances as a register-tiled (4 queries x 4 candidates per thread)
+//            product from the shared-memory copy of the cloud, stored as ordered keys in shared memory
+//   phase 2  one warp per query: every lane takes the 10 keys of its column stripe, sorts them in registers
+//            (29-comparator network on packed (key,stripe) words), writes the sorted keys back over its own
+//            slots of the row and the warp pops the global minimum k times: redux.min on the key, redux.min on
+//            the index among the lanes that hold that key, the winning lane advances its list head.
+// Cost per query is independent of the data (the streaming-insertion kernel above degrades to one insertion per
+// candidate on sorted input) and about 4x lower at k = 33.
+constexpr int KF_QB = 64;       // queries per block
+constexpr int KF_NMAX = 320;    // candidates per cloud (10 per lane)
+constexpr int KF_S = KF_NMAX / 32;
+constexpr int KF_THREADS = 256;
+
+__device__ __forceinline__ void cex(unsigned long long &a, unsigned long long &b) {
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(KF_THREADS) knn_feat_kernel(KnnArgs a) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const int C = CT > 0 ? CT : a.c;
+    float *sx = reinterpret_cast<float *>(raw);                        // [C][KF_NMAX] cloud, channel-major, zero padded
+    float *snorm = sx + (size_t)C * KF_NMAX;                           // [KF_NMAX]
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(snorm + KF_NMAX);   // [KF_QB][KF_NMAX]
+    unsigned long long *sout = reinterpret_cast<unsigned long long *>(skeys + KF_QB * KF_NMAX);   // [8 warps][64]
+
+    const int bi = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = knn_cloud(a, bi), grp = knn_group(a, bi);
+    const int nv = knn_n(a, cloud), mv = knn_m(a, bi);
+    const float *qb = a.query + (size_t)bi * C * a.m;
+    const float *pb = a.points + (size_t)cloud * C * a.n;
+    const bool self = (qb == pb) && (a.m == a.n);                      // DenseEdgeConv: queries are the cloud itself
+    const int dmode = knn_dup_mode(a, cloud, grp);
+    const bool penal = dmode != 0;
+    const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
+    const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
+
+    for (int t = tid; t < C * KF_NMAX; t += KF_THREADS) {
+        const int ch = t / KF_NMAX, j = t - ch * KF_NMAX;
+        sx[t] = j < nv ? __ldg(pb + (size_t)ch * a.n + j) : 0.f;
+    }
+    __syncthreads();
+    for (int j = tid; j < KF_NMAX; j += KF_THREADS) {
+        float r = 0.f;
+        for (int ch = 0; ch < C; ++ch) r = __fmaf_rn(sx[ch * KF_NMAX + j], sx[ch * KF_NMAX + j], r);
+        snorm[j] = r;
+    }
+    __syncthreads();
+
+    for (int q0 = 0; q0 < mv; q0 += KF_QB) {
+        // ---- phase 1: keys of queries [q0, q0+KF_QB) x candidates [0, KF_NMAX) ----------------------
+        // 16 query groups x 80 candidate groups of 4x4; thread t walks tiles t, t+256, ...
+        for (int tile = tid; tile < (KF_QB / 4) * (KF_NMAX / 4); tile += KF_THREADS) {
+            const int qg = tile / (KF_NMAX / 4), jg = tile - qg * (KF_NMAX / 4);
+            const int ql = qg * 4, j0 = jg * 4;
+            float acc[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+            float rq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (self) {
+#pragma unroll 4
+                for (int ch = 0; ch < C; ++ch) {
+                    const int qq = q0 + ql;   // < KF_NMAX because n <= KF_NMAX and q0 + KF_QB may overrun: clamp below
+                    float qv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) qv[u] = (qq + u) < KF_NMAX ? sx[ch * KF_NMAX + qq + u] : 0.f;
+                    const float4 pv = *reinterpret_cast<const float4 *>(&sx[ch * KF_NMAX + j0]);
+                    const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(qv[u], pj[v], acc[u][v]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rq[u] = (q0 + ql + u) < KF_NMAX ? snorm[q0 + ql + u] : 0.f;
+            } else {
+                for (int ch = 0; ch < C; ++ch) {
+                    float qv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int qi = q0 + ql + u;
+                        qv[u] = qi < mv ? __ldg(qb + (size_t)ch * a.m + qi) : 0.f;
+                        rq[u] = __fmaf_rn(qv[u], qv[u], rq[u]);
+                    }
+                    const float4 pv = *reinterpret_cast<const float4 *>(&sx[ch * KF_NMAX + j0]);
+                    const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(qv[u], pj[v], acc[u][v]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t kk[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int j = j0 + v;
+                    float d = expanded_dist(rq[u], acc[u][v], snorm[j]);
+                    const bool isdup = penal && j < nv && dupb[j];
+                    if (isdup) d = __fadd_rn(d, maxd);
+                    kk[v] = (j < nv && !(isdup && dmode == 1)) ? float_to_ordered(d) : 0xffffffffu;
+                }
+                *reinterpret_cast<uint4 *>(&skeys[(ql + u) * KF_NMAX + j0]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: selection, one warp per query ----------------------------------------------------
+        unsigned long long *myout = sout + warp * 64;
+        for (int ql = warp; ql < KF_QB; ql += 8) {
+            const int qi = q0 + ql;
+            if (qi >= mv) break;  // warp-uniform
+            uint32_t *krow = skeys + ql * KF_NMAX;
+            // packed (key, stripe): a candidate's index is stripe*32 + lane, so 4 bits identify it inside the lane
+            unsigned long long v[KF_S];
+#pragma unroll
+            for (int s = 0; s < KF_S; ++s) v[s] = ((unsigned long long)krow[s * 32 + lane] << 32) | (uint32_t)s;
+            // optimal 29-comparator sorting network for 10 inputs
+            cex(v[4], v[9]); cex(v[3], v[8]); cex(v[2], v[7]); cex(v[1], v[6]); cex(v[0], v[5]);
+            cex(v[1], v[4]); cex(v[6], v[9]); cex(v[0], v[3]); cex(v[5], v[8]);
+            cex(v[0], v[2]); cex(v[3], v[6]); cex(v[7], v[9]);
+            cex(v[0], v[1]); cex(v[2], v[4]); cex(v[5], v[7]); cex(v[8], v[9]);
+            cex(v[1], v[2]); cex(v[4], v[6]); cex(v[7], v[8]); cex(v[3], v[5]);
+            cex(v[2], v[5]); cex(v[6], v[8]); cex(v[1], v[3]); cex(v[4], v[7]);
+            cex(v[2], v[3]); cex(v[6], v[7]);
+            cex(v[3], v[4]); cex(v[5], v[6]);
+            cex(v[4], v[5]);
+            // the sorted keys go back into the lane's own 10 slots of the row, the stripe order into one register
+            unsigned long long perm = 0;
+#pragma unroll
+            for (int s = 0; s < KF_S; ++s) {
+                perm |= (v[s] & 15ull) << (4 * s);
+                if (s > 0) krow[s * 32 + lane] = (uint32_t)(v[s] >> 32);
+            }
+            uint32_t hk = (uint32_t)(v[0] >> 32);
+            int h = 1;
+            for (int r = 0; r < a.k; ++r) {
+                const uint32_t hj = (uint32_t)(perm & 15ull) * 32u + lane;
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
+                const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
+                if (hk == kmin && hj == jmin) {       // exactly one lane (indices are unique)
+                    myout[r] = ((unsigned long long)hk << 32) | hj;
+                    hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
+                    perm >>= 4;
+                    ++h;
+                }
+            }
+            __syncwarp();
+            // ---- outputs -------------------------------------------------------------------------------
+            const size_t row = ((size_t)bi * a.m + qi) * a.k;
+            for (int p = lane; p < a.k; p += 32) {
+                const unsigned long long o = myout[p];
+                const int32_t j = (int32_t)(uint32_t)o;
+                if (a.idx32) a.idx32[row + p] = j;
+                if (a.idx64) a.idx64[row + p] = j;
+                if (a.dist) a.dist[row + p] = ordered_to_float((uint32_t)(o >> 32));
+            }
+            if (a.knn) {
+                for (int ch = 0; ch < C; ++ch) {
+                    float *o = a.knn + (((size_t)bi * C + ch) * a.m + qi) * a.k;
+                    for (int p = lane; p < a.k; p += 32) o[p] = sx[ch * KF_NMAX + (uint32_t)myout[p]];
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+
+// --------------------------------------------------------------------------------------------
+// k <= 8, 3 channels: the xyz-space searches (inter-level skip k = 5, upsampler.py:325; outlier filter k = 2, :63)
+// --------------------------------------------------------------------------------------------
+// Many candidates (up to 6240 per query at level 4), tiny k: one THREAD per query keeps its k best in
+// registers as a sorted list; candidates stream through shared memory as (x, y, z, |p|^2) so that the inner
+// loop is one broadcast LDS.128 + 5 FP32 ops + one compare per pair, shared by KT_QPT queries per thread.
+// An insertion (rare after the first few hundred candidates: ~k ln(n/k) per query) is a short bubble pass.
+constexpr int KT_KMAX = 8;
+constexpr int KT_THREADS = 128;
+constexpr int KT_QPT = 2;
+constexpr int KT_TILE = 1024;   // candidates per shared-memory tile (16 KB)
+
+template <int KK>
+__global__ void __launch_bounds__(KT_THREADS) knn_thread_kernel(KnnArgs a) {
+    __shared__ float4 tile[KT_TILE];
+    __shared__ int tidx[KT_TILE];
+    __shared__ uint8_t tdup[KT_TILE];
+    __shared__ int wtot[KT_THREADS / 32];
+    const int bi = blockIdx.y;
+    const int cloud = knn_cloud(a, bi), grp = knn_group(a, bi);
+    const int nv = knn_n(a, cloud), mv = knn_m(a, bi);
+    const int q0 = blockIdx.x * (KT_THREADS * KT_QPT);
+    if (q0 >= mv) return;  // block-uniform
+    const float *qb = a.query + (size_t)bi * 3 * a.m;
+    const float *pb = a.points + (size_t)cloud * 3 * a.n;
+    const int dmode = knn_dup_mode(a, cloud, grp);
+    const bool penal = dmode != 0;
+    const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
+    const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
+
+    float qx[KT_QPT], qy[KT_QPT], qz[KT_QPT], rq[KT_QPT];
+    float bd[KT_QPT][KK];
+    int bj[KT_QPT][KK];
+#pragma unroll
+    for (int r = 0; r < KT_QPT; ++r) {
+        const int qi = min(q0 + r * KT_THREADS + (int)threadIdx.x, mv - 1);
+        qx[r] = __ldg(qb + qi); qy[r] = __ldg(qb + a.m + qi); qz[r] = __ldg(qb + 2 * (size_t)a.m + qi);
+        rq[r] = __fmaf_rn(qz[r], qz[r], __fmaf_rn(qy[r], qy[r], __fmul_rn(qx[r], qx[r])));  // same chain as the other kernels: fma over ch 0,1,2 from 0
+#pragma unroll
+        for (int e = 0; e < KK; ++e) { bd[r][e] = __int_as_float(0x7f800000); bj[r][e] = 0; }
+    }
+    for (int n0 = 0; n0 < nv; n0 += KT_TILE) {
+        const int src = min(KT_TILE, nv - n0);
+        __syncthreads();
+        int cnt;
+        if (dmode == 1) {
+            // stage only first occurrences, in index order (ordered compaction: ballot prefix inside the warp,
+            // warp totals through shared memory).  In the merged previous-level clouds ~4 of 5 points are duplicates.
+            int base = 0;
+            for (int c0 = 0; c0 < src; c0 += KT_THREADS) {
+                const int t = c0 + threadIdx.x;
+                const bool keep = t < src && dupb[n0 + t] == 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = __popc(bal);
+                __syncthreads();
+                int off = base;
+                for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += wtot[w];
+                int total = 0;
+                for (int w = 0; w < KT_THREADS / 32; ++w) total += wtot[w];
+                if (keep) {
+                    const int slot = off + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                    const float x = __ldg(pb + n0 + t), y = __ldg(pb + a.n + n0 + t), z = __ldg(pb + 2 * (size_t)a.n + n0 + t);
+                    tile[slot] = make_float4(x, y, z, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+                    tidx[slot] = n0 + t;
+                }
+                base += total;
+                __syncthreads();
+            }
+            cnt = base;
+        } else {
+            for (int t = threadIdx.x; t < src; t += KT_THREADS) {
+                const float x = __ldg(pb + n0 + t), y = __ldg(pb + a.n + n0 + t), z = __ldg(pb + 2 * (size_t)a.n + n0 + t);
+                tile[t] = make_float4(x, y, z, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+                tidx[t] = n0 + t;
+                if (dmode == 2) tdup[t] = dupb[n0 + t];
+            }
+            cnt = src;
+            __syncthreads();
+        }
+#pragma unroll 2
+        for (int j = 0; j < cnt; ++j) {
+            const float4 p = tile[j];
+            const bool dp = dmode == 2 && tdup[j];
+#pragma unroll
+            for (int r = 0; r < KT_QPT; ++r) {
+                const float dot = __fmaf_rn(qz[r], p.z, __fmaf_rn(qy[r], p.y, __fmul_rn(qx[r], p.x)));
+                float d = expanded_dist(rq[r], dot, p.w);
+                if (dp) d = __fadd_rn(d, maxd);
+                if (d < bd[r][KK - 1]) {           // strict: an equal distance with a larger index stays behind
+                    bd[r][KK - 1] = d; bj[r][KK - 1] = tidx[j];
+#pragma unroll
+                    for (int e = KK - 1; e > 0; --e) {
+                        if (bd[r][e] < bd[r][e - 1]) {
+                            const float td = bd[r][e]; bd[r][e] = bd[r][e - 1]; bd[r][e - 1] = td;
+                            const int tj = bj[r][e]; bj[r][e] = bj[r][e - 1]; bj[r][e - 1] = tj;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KT_QPT; ++r) {
+        const int qi = q0 + r * KT_THREADS + threadIdx.x;
+        if (qi >= mv) continue;
+        const size_t row = ((size_t)bi * a.m + qi) * a.k;
+#pragma unroll
+        for (int e = 0; e < KK; ++e) {
+            if (e < a.k) {
+                if (a.idx64) a.idx64[row + e] = bj[r][e];
+                if (a.idx32) a.idx32[row + e] = bj[r][e];
+                if (a.dist) a.dist[row + e] = bd[r][e];
+                if (a.knn) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        a.knn[(((size_t)bi * 3 + ch) * a.m + qi) * a.k + e] = __ldg(pb + (size_t)ch * a.n + bj[r][e]);
+                }
+            }
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // k > 64: CTA per query
 // --------------------------------------------------------------------------------------------
@@ -294,8 +614,9 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
     const int kv = min(a.k, nv);             // a ragged cloud may hold fewer than k points: the tail stays unwritten
     const float *qb = a.query + (size_t)bi * C * a.m;
     const float *pb = a.points + (size_t)cloud * C * a.n;
-    const bool penal = a.dup != nullptr && a.group_any[grp] != 0;
-    const float maxd = penal ? ordered_to_float(a.maxd[grp]) : 0.f;
+    const int dmode = knn_dup_mode(a, cloud, grp);
+    const bool penal = dmode != 0;
+    const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
     const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
     if (kv <= 0) return;
 
@@ -310,8 +631,9 @@ __global__ void __launch_bounds__(KL_THREADS) knn_large_kernel(KnnArgs a, int k2
             rp = __fmaf_rn(pv, pv, rp);
         }
         float d = expanded_dist(rq, dot, rp);
-        if (penal && dupb[j]) d = __fadd_rn(d, maxd);
-        keys[j] = float_to_ordered(d);
+        const bool isdup = penal && dupb[j];
+        if (isdup) d = __fadd_rn(d, maxd);
+        keys[j] = (isdup && dmode == 1) ? 0xffffffffu : float_to_ordered(d);
     }
     // ---- 2. radix select: key of rank k-1, MSB first, 8 bits per pass ------------------------
     uint32_t prefix = 0, pmask = 0;
@@ -469,6 +791,10 @@ static bool make_plan(int b, int c, int m, int n, int k, int clouds, int groups,
 
 using namespace pu3;
 
+// Test hook: force the streaming-insertion kernel for k <= 64 even when the cloud fits the tiled kernel.
+static int g_knn_force_stream = 0;
+extern "C" void pu3_knn_force_stream(int on) { g_knn_force_stream = on; }
+
 extern "C" size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique) {
     if (b <= 0 || c <= 0 || m <= 0 || n <= 0 || k <= 0 || p_div <= 0) return 0;
     KnnPlan pl;
@@ -533,7 +859,7 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
     cudaStream_t s = as_stream(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
-              query, points, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
+              query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
     if (unique) {
         int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
         int *cloud_any = reinterpret_cast<int *>(ws + pl.off_cany);
@@ -545,7 +871,7 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         PU3_LAUNCH_CHECK("knn_dup_kernel");
         knn_groupflag_kernel<<<(b + 255) / 256, 256, 0, s>>>(a, cloud_any, group_any);
         PU3_LAUNCH_CHECK("knn_groupflag_kernel");
-        a.dup = dup; a.group_any = group_any; a.maxd = maxd;
+        a.dup = dup; a.cloud_dups = cloud_any; a.group_any = group_any; a.maxd = maxd;
         knn_maxd_kernel<<<dim3((m + 127) / 128, b), 128, 0, s>>>(a, maxd);
         PU3_LAUNCH_CHECK("knn_maxd_kernel");
     }
@@ -558,6 +884,31 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         knn_large_kernel<<<dim3(m, b), KL_THREADS, pl.smem, s>>>(a, pl.k2, gkeys);
         PU3_LAUNCH_CHECK("knn_large_kernel");
         return PU3_OK;
+    }
+    if (c == 3 && k <= KT_KMAX && g_knn_force_stream == 0) {
+        dim3 grid((m + KT_THREADS * KT_QPT - 1) / (KT_THREADS * KT_QPT), b);
+        if (k <= 2) knn_thread_kernel<2><<<grid, KT_THREADS, 0, s>>>(a);
+        else if (k <= 5) knn_thread_kernel<5><<<grid, KT_THREADS, 0, s>>>(a);
+        else knn_thread_kernel<8><<<grid, KT_THREADS, 0, s>>>(a);
+        PU3_LAUNCH_CHECK("knn_thread_kernel");
+        return PU3_OK;
+    }
+    if (n <= KF_NMAX && g_knn_force_stream == 0) {
+        const size_t smem = ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4 + 8 * 64 * 8;
+        if (smem <= (size_t)device_info().smem_optin) {
+            int st;
+            if (c == 24) {
+                st = cuda_status(cudaFuncSetAttribute(knn_feat_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "group_knn: smem attr");
+                if (st) return st;
+                knn_feat_kernel<24><<<b, KF_THREADS, smem, s>>>(a);
+            } else {
+                st = cuda_status(cudaFuncSetAttribute(knn_feat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "group_knn: smem attr");
+                if (st) return st;
+                knn_feat_kernel<0><<<b, KF_THREADS, smem, s>>>(a);
+            }
+            PU3_LAUNCH_CHECK("knn_feat_kernel");
+            return PU3_OK;
+        }
     }
     // queries per CTA: enough CTAs to cover the chip twice, but never fewer than one pass of 8 warps
     const int sms = device_info().sm_count;

@@ -61,7 +61,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
                     int(bool(unique)), _lib.ptr(knn), _lib.ptr(idx if idx_dtype == torch.int64 else None),
                     _lib.ptr(idx if idx_dtype == torch.int32 else None), _lib.ptr(dist), _lib.ptr(ws), ws_bytes,
                     extra_kernels=3 if unique else 0,
-                    tag="pu3_group_knn_f32[k<=64]" if k <= 64 else "pu3_group_knn_f32[k>64]")
+                    tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")
         return knn, idx, dist
     if Bp == 0 or B % Bp != 0:
         raise RuntimeError(f"group_knn: points batch {Bp} must divide query batch {B}")
@@ -80,7 +80,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
     _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
                 int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32), _lib.ptr(dist), _lib.ptr(ws),
                 ws_bytes, extra_kernels=3 if unique else 0,
-                tag="pu3_group_knn_f32[k<=64]" if k <= 64 else "pu3_group_knn_f32[k>64]")
+                tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")
     return knn, idx, dist
 
 

@@ -83,6 +83,10 @@ def _algorithmic_bytes(name, calls):
     P_lv = [1, 10, 20, 40]                       # tiles per input patch at levels 1..4
     rows = [B_PATCHES * p for p in P_lv]         # batch elements per level call
     N, K = NUM_POINT, KNN
+    if name.startswith("pu3_group_knn_f32[c=24"):
+        # feature kNN (16 calls): read x (24ch) once, write idx32 (k+1)
+        tot = sum(4 * (b * 24 * N * 4 + b * N * (K + 1) * 4) for b in rows)
+        return tot / max(calls, 1)
     if name == "pu3_group_knn_f32[k<=64]":
         # feature kNN (16 calls): read x (24ch) once for queries and once as candidates, write idx32 (k+1)
         tot = sum(4 * (b * 24 * N * 4 * 2 + b * N * (K + 1) * 4) for b in rows)

@@ -166,3 +166,30 @@ def test_ragged_batch_equals_per_element_calls(pu3, cuda):
                                                 clouds[i:i + 1, :, :n].contiguous().to(cuda), unique=False)
         assert torch.equal(idx[i:i + 1, :m], idx1) and torch.equal(nb[i:i + 1, :, :m], nb1)
         assert int(idx[i, m:].abs().sum()) == 0
+
+
+def test_tiled_and_streaming_kernels_agree(pu3, cuda):
+    """k <= 64 has two kernels (tiled sort+pop for clouds of <= 320 points, streaming insertion otherwise):
+    identical results, including tie order and the duplicate penalty."""
+    import ctypes
+    g = torch.Generator().manual_seed(33)
+    x = torch.rand(5, 24, 312, generator=g)
+    x[0, :, 100] = x[0, :, 7]; x[3, :, 311] = x[3, :, 0]
+    q = torch.rand(5, 24, 40, generator=g)
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    outs = []
+    for force in (0, 1):
+        lib.pu3_knn_force_stream(force)
+        try:
+            outs.append((pu3.operations.group_knn(33, x.to(cuda), x.to(cuda), unique=True),
+                         pu3.operations.group_knn(9, q.to(cuda), x.to(cuda), unique=True),
+                         pu3.operations.group_knn(64, x[:, :3, :70].contiguous().to(cuda), x[:, :3, :70].contiguous().to(cuda), unique=False),
+                         # thread-per-query kernel (3 channels, k <= 8) against the streaming kernel
+                         pu3.operations.group_knn(5, q[:, :3].contiguous().to(cuda), x[:, :3].contiguous().to(cuda), unique=True),
+                         pu3.operations.group_knn(2, x[:, :3].contiguous().to(cuda), x[:, :3].contiguous().to(cuda), unique=False),
+                         pu3.operations.group_knn(8, x[:, :3].contiguous().to(cuda), x[:, :3].contiguous().to(cuda), unique=True)))
+        finally:
+            lib.pu3_knn_force_stream(0)
+    for a, b in zip(outs[0], outs[1]):
+        for ta, tb in zip(a, b):
+            assert torch.equal(ta, tb)

@@ -115,6 +115,20 @@ class Level(torch.nn.Module):
             lo -= 60
         return feat
 
+    def _skip_connection_fused(self, x, xyz, previous_level4, group, ragged=None):
+        """The same computation as _skip_connection in one kernel (csrc/skip.cu), x (T,C,N) updated in place.
+        previous_level4 = (prev_xyz (clouds,3,No) channel-major, prev_feat (clouds,No,C) POINT-major)."""
+        previous_xyz, previous_feat_pm = previous_level4
+        T, C, N = x.shape
+        clouds, No, _ = previous_feat_pm.shape
+        _, idx, _ = operations._knn_raw(self.fm_knn, xyz.contiguous(), previous_xyz.contiguous(), True, group,
+                                        want_knn=False, want_dist=False, ragged=ragged)
+        owner = ragged.owner if ragged is not None else None
+        fused._lib.launch("pu3_skip_fuse_f32", x, T, N, C, self.fm_knn, 1 if ragged is not None else T // clouds, No,
+                          x.data_ptr(), xyz.contiguous().data_ptr(), idx.data_ptr(), previous_xyz.data_ptr(),
+                          previous_feat_pm.data_ptr(), fused._lib.ptr(owner))
+        return x
+
     def _skip_connection(self, x, xyz, previous_level4, group, ragged=None):
         """upsampler.py:317-347: bilateral (spatial x feature) interpolation of the previous level's features."""
         previous_xyz, previous_feat = previous_level4
@@ -174,11 +188,13 @@ class Level(torch.nn.Module):
                         res_div=r)
         return out
 
-    def forward(self, xyz, xyz_normalized, previous_level4=None, group=None, ragged=None, **kwargs):
+    def forward(self, xyz, xyz_normalized, previous_level4=None, group=None, ragged=None, prev_point_major=False,
+                **kwargs):
         """
         :param xyz Bx3xN input xyz, unnormalized; xyz_normalized Bx3xN; previous_level4 (Bx3xM, BxCxM) of the
                previous level (its batch may divide B: shared by consecutive patches)
         :param group (extension) patches per independent request, scope of group_knn's duplicate penalty
+        :param prev_point_major (extension, eval) previous_level4[1] is laid out (clouds, M, C) instead of (B, C, M)
         :param ragged (extension, eval) operations.Ragged: request of every patch + valid size of every request's
                previous-level cloud, for requests with different numbers of patches
         :return xyz Bx3xNr (normalised frame), features BxCxN of the input points
@@ -203,7 +219,12 @@ class Level(torch.nn.Module):
             x = torch.cat([y, x], dim=1)
 
         if previous_level4 is not None and self.fm_knn > 0:
-            x = self._skip_connection(x, xyz, previous_level4, group, ragged)
+            if prev_point_major:
+                if not fast:
+                    raise RuntimeError("point-major previous features are an eval-mode (no-grad, CUDA fp32) feature")
+                x = self._skip_connection_fused(x, xyz, previous_level4, group, ragged)
+            else:
+                x = self._skip_connection(x, xyz, previous_level4, group, ragged)
 
         point_features = x
         if fast:
@@ -340,7 +361,8 @@ class Net(torch.nn.Module):
         patch_xyz = tiles.permute(0, 2, 1, 3).reshape(B * Pmax, 3, k)[slot].contiguous()   # (T,3,k)
         patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
         ragged = operations.Ragged(owner, owner, B, n_arr=old_n)
-        new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged, **kwargs)
+        new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged,
+                                  prev_point_major=True, **kwargs)
         new_xyz = new_xyz * radius + centroid                                        # (T,3,k*r)
 
         def merge(t):
@@ -354,7 +376,12 @@ class Net(torch.nn.Module):
         r = new_xyz.shape[2] // k
         _, out_xyz = operations.furthest_point_sample_ragged(merged, p_arr * (k * r), None, num_output_point)  # :158
         if keep_features:
-            return out_xyz, merge(patch_xyz), merge(features), p_arr * k
+            # the next level gathers whole feature rows: hand the features over point-major, tiles side by side
+            Cf = features.shape[1]
+            feat_pm = torch.zeros(B, Pmax * k, Cf, dtype=torch.float32, device=dev)
+            fused._lib.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(),
+                              slot.data_ptr(), feat_pm.data_ptr())
+            return out_xyz, merge(patch_xyz), feat_pm, p_arr * k
         return out_xyz, None, None, None
 
     def forward(self, xyz, ratio=None, gt=None, seed_idx_per_level=None, **kwargs):
@@ -400,6 +427,12 @@ class Net(torch.nn.Module):
         old_xyz = xyz
         xyz, old_features = level(xyz, xyz, previous_level4=None, group=1, **kwargs)    # duplicate-penalty scope: 1 cloud
         old_n = torch.full((B,), old_xyz.shape[2], dtype=torch.int32, device=dev)
+        point_major = xyz.is_cuda and num_levels > 1
+        if point_major:    # (B,C,N) -> (B,N,C): the layout the fused skip connection gathers from
+            pm = torch.empty(B, old_features.shape[2], old_features.shape[1], dtype=torch.float32, device=dev)
+            fused._lib.launch("pu3_to_point_major_f32", old_features, B, old_features.shape[1], old_features.shape[2],
+                              old_features.contiguous().data_ptr(), None, pm.data_ptr())
+            old_features = pm
         for l in range(2, num_levels + 1):
             level = self.levels['level_%d' % l]
             num_output_point = num_point * self.step_ratio ** l
@@ -412,6 +445,8 @@ class Net(torch.nn.Module):
                 continue
             # per-request processing (a filtered cloud smaller than one tile, or nothing to tile)
             old_n_h = old_n.tolist()
+            if point_major:
+                old_features, point_major = old_features.transpose(1, 2), False    # (B,C,M) view for this path
             outs = [self._eval_level_single(level, xyz[i:i + 1], old_xyz[i:i + 1, :, :old_n_h[i]].contiguous(),
                                             old_features[i:i + 1, :, :old_n_h[i]].contiguous(), max_num_point,
                                             num_output_point, **kwargs) for i in range(B)]
@@ -421,4 +456,6 @@ class Net(torch.nn.Module):
             pad = lambda t: torch.nn.functional.pad(t, (0, nmax - t.shape[2]))
             old_xyz = torch.cat([pad(o[1]) for o in outs], dim=0)
             old_features = torch.cat([pad(o[2]) for o in outs], dim=0)
+            if xyz.is_cuda and num_levels > 1:   # restore the invariant: previous features travel point-major
+                old_features, point_major = old_features.transpose(1, 2).contiguous(), True
         return xyz

@@ -182,6 +182,24 @@ int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, c
                      int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
                      const float *w2, const float *b2, float *y, long long y_bstride, pu3_stream_t stream);
 
+/*
+ * Inter-level skip connection, fused (network/upsampler.py:317-347 and exponential_distance :232-250):
+ * for each of t patches of n points, given the k nearest previous-level points idx (t,n,k) i64 (from
+ * pu3_group_knn*), x (t,c,n) is updated in place:  x += 0.2 * sum_k w_k * prev_feat[idx_k],
+ * w = ws*wf / sum_k(ws*wf + 1e-5), ws/wf the exponential spatial/feature weights with the per-patch bandwidths
+ * h = mean_n(min_k d).  prev_xyz (clouds,3,no) channel-major; prev_feat_pm (clouds,no,c) POINT-major (see
+ * pu3_to_point_major_f32); patch i reads cloud owner[i] (or i / p_div when owner is NULL).
+ */
+int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
+                      const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, pu3_stream_t stream);
+
+/*
+ * Layout change for the features handed to the next level: in (t,c,n) channel-major ->
+ * out[(slot[t]*n + i)*c + ch] = in[t][ch][i]  (slot NULL = identity), i.e. tiles placed side by side along the
+ * point axis of a point-major (rows,c) buffer (the merge of network/upsampler.py:149-155 for the features).
+ */
+int pu3_to_point_major_f32(int t, int c, int n, const float *in, const int64_t *slot, float *out, pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,3 +202,47 @@ def test_net_train_forward_backward_against_oracle(pu3, cuda, params):
     gname = "levels.level_1.layer0.conv.weight"
     got_g = dict(net.named_parameters())[gname].grad
     assert_close_frac(got_g, P[gname].grad, rtol=2e-2, atol=1e-4, frac=0.9, what="first-layer weight grad")
+
+
+def test_fused_skip_connection_matches_composition(pu3, cuda, params):
+    """csrc/skip.cu against the operator-by-operator skip connection (itself checked against the oracle above),
+    on a ragged batch: 5 tiles belonging to 2 requests whose previous-level clouds have different sizes."""
+    net = _net(pu3, params, cuda).eval()
+    level = net.levels["level_3"]
+    g = torch.Generator().manual_seed(23)
+    sizes = [936, 624]
+    prev_xyz = torch.zeros(2, 3, 936); prev_feat = torch.zeros(2, 264, 936)
+    for i, n in enumerate(sizes):
+        base = torch.rand(3, n // 3, generator=g)
+        prev_xyz[i, :, :n] = base.repeat(1, 3) + (torch.arange(n) >= n // 3).float() * 0.0   # exact duplicates (overlapping tiles)
+        prev_feat[i, :, :n] = torch.randn(264, n, generator=g)
+    xyz = torch.rand(5, 3, 312, generator=g)
+    x = torch.randn(5, 264, 312, generator=g)
+    owner = torch.tensor([0, 0, 0, 1, 1], dtype=torch.int32, device=cuda)
+    R = pu3.operations.Ragged(owner, owner, 2, n_arr=torch.tensor(sizes, dtype=torch.int32, device=cuda))
+    with torch.no_grad():
+        want = level._skip_connection(x.to(cuda), xyz.to(cuda), (prev_xyz.to(cuda), prev_feat.to(cuda)), None, R)
+        got = level._skip_connection_fused(x.to(cuda).clone(), xyz.to(cuda),
+                                           (prev_xyz.to(cuda), prev_feat.to(cuda).transpose(1, 2).contiguous()), None, R)
+    assert_close_frac(got, want, rtol=1e-5, atol=2e-6, what="fused skip connection")
+    # and the oracle itself, request by request (the reference expand()s one previous cloud per call)
+    for lo, hi, c in ((0, 3, 0), (3, 5, 1)):
+        n = sizes[c]
+        nb_xyz, nb_idx, _ = ref_net.group_knn(5, xyz[lo:hi], prev_xyz[c:c + 1, :, :n].expand(hi - lo, -1, -1), unique=True)
+        pf = prev_feat[c:c + 1, :, :n].expand(hi - lo, -1, -1).unsqueeze(2).expand(-1, -1, 312, -1)
+        nb_feat = torch.gather(pf, 3, nb_idx.unsqueeze(1).expand(-1, 264, -1, -1))
+        _, ws = ref_net.exponential_distance(xyz[lo:hi], nb_xyz)
+        _, wf = ref_net.exponential_distance(x[lo:hi], nb_feat)
+        w = ws * wf
+        w = w / torch.sum(w + 1e-5, dim=-1, keepdim=True)
+        ref = 0.2 * torch.sum(w * nb_feat, dim=-1) + x[lo:hi]
+        assert_close_frac(got[lo:hi], ref, rtol=1e-5, atol=2e-6, frac=0.999, what="fused skip connection vs oracle")
+
+
+def test_to_point_major(pu3, cuda):
+    x = torch.randn(3, 70, 45, device=cuda)
+    slot = torch.tensor([2, 0, 5], dtype=torch.int64, device=cuda)
+    out = torch.zeros(6 * 45, 70, device=cuda)
+    pu3._lib.launch("pu3_to_point_major_f32", x, 3, 70, 45, x.data_ptr(), slot.data_ptr(), out.data_ptr())
+    for t, sl in enumerate(slot.tolist()):
+        assert torch.equal(out[sl * 45:(sl + 1) * 45], x[t].t())

@@ -46,6 +46,8 @@ struct FpsSmem {
     uint32_t warp_dkey[2][32];
     uint32_t warp_rank[2][32];
     int32_t warp_k[2][32];
+    float win[2][4];                           // [round parity] coordinates of the round's winner
+    uint64_t mbar[2];                          // [round parity] "all S candidates of the round have landed"
 };
 
 // lexicographic arg-max over the full warp; returns true in exactly one lane (the winner)
@@ -104,8 +106,13 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     if (g == 0 && m > 0) out[0] = 0;                         // :115 first sample is point 0
     float x1 = 0.f, y1 = 0.f, z1 = 0.f;
     if (n > 0) { x1 = __ldg(p + 0); y1 = __ldg(p + 1); z1 = __ldg(p + 2); }
+    if (S > 1 && threadIdx.x == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        mbar_fence_init_cluster();
+    }
     __syncthreads();
-    if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem exists before remote stores
+    if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem + barriers exist before remote stores
 
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
@@ -123,61 +130,70 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             t[i] = d2;
             if (d2 > best) { best = d2; besti = i; }
         }
-        // ---- 2. warp arg-max ------------------------------------------------------------------
-        const int kbest = g + besti * GT;
-        const bool has = best >= 0.f;
-        const uint32_t dkey = has ? __float_as_uint(best) : 0u;
-        const uint32_t rank = has ? (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest / t_ref)
-                                  : 0xffffffffu;
-        uint32_t dmax, rmin;
-        if (warp_argmax(dkey, rank, dmax, rmin)) {
-            sm.warp_dkey[par][warp] = dmax;
-            sm.warp_rank[par][warp] = rmin;
+        // ---- 2. warp arg-max: one lane per warp publishes (distance, tie rank, index) ------------
+        // The round is issue-bound, so everything after this point is done by ONE warp per CTA; the other
+        // warps only pay two barriers.
+        const uint32_t dkey = best >= 0.f ? __float_as_uint(best) : 0u;
+        const uint32_t dmax_w = __reduce_max_sync(0xffffffffu, dkey);
+        uint32_t rank = 0xffffffffu;
+        int kbest = 0;
+        if (dkey == dmax_w && best >= 0.f) {     // rank only where it can matter
+            kbest = g + besti * GT;
+            rank = (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest / t_ref);
+        }
+        const uint32_t rmin_w = __reduce_min_sync(0xffffffffu, rank);
+        if (rank == rmin_w && (rmin_w != 0xffffffffu || lane == 0)) {   // the winner, or lane 0 of an empty warp
+            sm.warp_dkey[par][warp] = dmax_w;
+            sm.warp_rank[par][warp] = rmin_w;
             sm.warp_k[par][warp] = kbest;
         }
-        if (!__any_sync(0xffffffffu, has) && lane == 0) {  // warp without points
-            sm.warp_dkey[par][warp] = 0u;
-            sm.warp_rank[par][warp] = 0xffffffffu;
-            sm.warp_k[par][warp] = 0;
+        __syncthreads();
+        // ---- 3. leader warp: CTA arg-max, cluster exchange ----------------------------------------
+        if (warp == 0) {
+            const uint32_t wd = lane < nwarps ? sm.warp_dkey[par][lane] : 0u;
+            const uint32_t wr = lane < nwarps ? sm.warp_rank[par][lane] : 0xffffffffu;
+            uint32_t dmax, rmin;
+            const bool wwin = warp_argmax(wd, wr, dmax, rmin);
+            const uint32_t wsrc = __ffs(__ballot_sync(0xffffffffu, wwin)) - 1;  // 0xffffffff: CTA without points
+            const bool cta_has = wsrc != 0xffffffffu;
+            const int kwin = cta_has ? sm.warp_k[par][wsrc & 31] : 0;
+            float wx = 0.f, wy = 0.f, wz = 0.f;
+            if (cta_has) {
+                const int slot = (kwin / GT) * nthreads + ((kwin % GT) - (int)crank * nthreads);
+                wx = sx[slot]; wy = sy[slot]; wz = sz[slot];
+            }
+            if (S == 1) {
+                if (lane == 0) {
+                    sm.win[par][0] = wx; sm.win[par][1] = wy; sm.win[par][2] = wz;
+                    out[j] = kwin;
+                }
+            } else {
+                // Leader-to-leader exchange: every leader posts its candidate (32 B) into every CTA's slot with
+                // an async DSMEM store that completes on the RECEIVER's mbarrier; each leader then waits for
+                // S x 32 bytes on its own barrier.  No cluster-wide barrier: the other warps never leave the CTA.
+                if (lane == 0) mbar_arrive_expect_tx(&sm.mbar[par], S * 32u);
+                if (lane < (int)S) {
+                    const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], lane);
+                    const uint32_t rbar = map_to_cta(&sm.mbar[par], lane);
+                    st_async_v4(dst, rbar, cta_has ? dmax : 0u, cta_has ? rmin : 0xffffffffu, (uint32_t)kwin, __float_as_uint(wx));
+                    st_async_v4(dst + 16, rbar, __float_as_uint(wy), __float_as_uint(wz), 0u, 0u);
+                }
+                mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);  // phase = earlier uses of this buffer
+                const FpsCand *cs = sm.cluster_slot[par];
+                const uint32_t cd = lane < (int)S ? cs[lane].dkey : 0u;
+                const uint32_t cr = lane < (int)S ? cs[lane].rank : 0xffffffffu;
+                uint32_t dmax, rmin;
+                const bool cwin = warp_argmax(cd, cr, dmax, rmin);
+                const uint32_t csrc = __ffs(__ballot_sync(0xffffffffu, cwin)) - 1;
+                if (lane == 0) {
+                    const FpsCand w = cs[csrc & (FPS_MAX_CLUSTER - 1)];
+                    sm.win[par][0] = w.x; sm.win[par][1] = w.y; sm.win[par][2] = w.z;
+                    if (crank == 0) out[j] = w.k;
+                }
+            }
         }
         __syncthreads();
-        // ---- 3. CTA arg-max, redundantly in every warp (saves a second barrier) ---------------
-        const uint32_t wd = lane < nwarps ? sm.warp_dkey[par][lane] : 0u;
-        const uint32_t wr = lane < nwarps ? sm.warp_rank[par][lane] : 0xffffffffu;
-        const bool wwin = warp_argmax(wd, wr, dmax, rmin);
-        const uint32_t wsrc = __ffs(__ballot_sync(0xffffffffu, wwin)) - 1;  // 0xffffffff if nobody (empty CTA)
-        int kwin = 0;
-        bool cta_has = wsrc != 0xffffffffu;
-        if (cta_has) kwin = sm.warp_k[par][wsrc];
-
-        if (S == 1) {
-            const int slot = ((kwin / GT) * nthreads) + (kwin % GT);  // owner tid = kwin % GT when S == 1
-            x1 = sx[slot]; y1 = sy[slot]; z1 = sz[slot];
-            if (threadIdx.x == 0) out[j] = kwin;
-        } else {
-            // ---- 4. publish this CTA's winner to every CTA of the cluster, pick the global one --
-            if (warp == 0 && lane < (int)S) {
-                float wx = 0.f, wy = 0.f, wz = 0.f;
-                if (cta_has) {
-                    const int slot = (kwin / GT) * nthreads + ((kwin % GT) - (int)crank * nthreads);
-                    wx = sx[slot]; wy = sy[slot]; wz = sz[slot];
-                }
-                const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], lane);
-                st_cluster_v4(dst, cta_has ? dmax : 0u, cta_has ? rmin : 0xffffffffu, (uint32_t)kwin,
-                              __float_as_uint(wx));
-                st_cluster_v2(dst + 16, __float_as_uint(wy), __float_as_uint(wz));
-            }
-            cluster_arrive_release();
-            cluster_wait_acquire();
-            const FpsCand *cs = sm.cluster_slot[par];
-            const uint32_t cd = lane < (int)S ? cs[lane].dkey : 0u;
-            const uint32_t cr = lane < (int)S ? cs[lane].rank : 0xffffffffu;
-            const bool cwin = warp_argmax(cd, cr, dmax, rmin);
-            const uint32_t csrc = __ffs(__ballot_sync(0xffffffffu, cwin)) - 1;
-            const FpsCand w = cs[csrc & (FPS_MAX_CLUSTER - 1)];
-            x1 = w.x; y1 = w.y; z1 = w.z;
-            if (g == 0) out[j] = w.k;
-        }
+        x1 = sm.win[par][0]; y1 = sm.win[par][1]; z1 = sm.win[par][2];
     }
     if (trow) {
 #pragma unroll
@@ -312,37 +328,52 @@ static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t
     const int t_ref = ref_block_size(n);
     const int sms = device_info().sm_count;
 
-    // threads: power of two, a multiple of t_ref, about 4 points per thread for small clouds
-    int threads = ceil_pow2((n + 3) / 4);
-    if (threads < t_ref) threads = t_ref;
-    if (threads < 32) threads = 32;
-    if (threads > 1024) threads = 1024;
-
-    // cluster size: smallest power of two that brings the cloud down to <= 8 points per thread,
-    // limited by what keeps all clouds co-resident (b * S <= SM count) and by the portable limit
-    int S = 1;
-    if (g_fps_force_cluster > 0) {
-        S = g_fps_force_cluster;
-    } else {
-        int s_cap = floor_pow2(sms / b > 0 ? sms / b : 1);
-        if (s_cap > 8) s_cap = 8;
-        while (S < s_cap && (long long)S * threads * 8 < n) S *= 2;
-        // not enough with 8 points/thread: the shared-memory variants hold up to 32/thread at 512 threads
-        if ((long long)S * threads * 8 < n) {
-            S = 1;
-            while (S < 16 && (long long)S * 512 * 32 < n) S *= 2;
+    // Launch shape.  A round costs every warp (10 instructions per point + ~35 of reduction) issue slots plus
+    // ~450 cycles of cluster barrier when the cloud is spread over S > 1 CTAs; pick the (threads, S) with the
+    // smallest modelled round among the shapes that (a) keep S*threads a multiple of the reference block size
+    // (tie rule), (b) hold the cloud in <= 8 points per thread, (c) keep all clouds co-resident (b*S <= SMs).
+    int s_cap = floor_pow2(sms / b > 0 ? sms / b : 1);
+    if (s_cap > 8) s_cap = 8;
+    int threads = 0, S = 1, ppt = 0;
+    long long best_cost = -1;
+    static const int kThreads[] = {1024, 896, 768, 640, 512, 384, 256, 128, 64, 32};
+    for (int cs = 1; cs <= s_cap; cs *= 2) {
+        if (g_fps_force_cluster > 0 && cs != g_fps_force_cluster) continue;
+        for (int th : kThreads) {
+            const long long gt = (long long)cs * th;
+            if (gt % t_ref != 0) continue;
+            const long long p = (n + gt - 1) / gt;
+            if (p > 8) continue;
+            const long long cost = (long long)(th / 32) * (p * 10 + 35) / 4 + (cs > 1 ? 450 : 0) + 80;
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; threads = th; S = cs; ppt = (int)p; }
         }
     }
-    const long long per_cta_reg = (long long)threads * 8;
+    if (g_fps_force_cluster > 0 && threads == 0) {   // forced cluster size (tests): any shape that fits
+        S = g_fps_force_cluster;
+        for (int th : kThreads) {
+            const long long gt = (long long)S * th;
+            if (gt % t_ref == 0 && (n + gt - 1) / gt <= 8) { threads = th; ppt = (int)((n + gt - 1) / gt); break; }
+        }
+    }
     int st;
-    if ((long long)S * per_cta_reg >= n) {
-        const int ppt = (int)((n + (long long)S * threads - 1) / ((long long)S * threads));
-        if (ppt <= 1) st = launch_fps<1, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
-        else if (ppt <= 2) st = launch_fps<2, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
-        else if (ppt <= 4) st = launch_fps<4, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
-        else st = launch_fps<8, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s);
-    } else if ((long long)S * 512 * 32 >= n) {
-        const int ppt = (int)((n + (long long)S * 512 - 1) / ((long long)S * 512));
+    if (threads > 0) {
+        switch (ppt) {
+            case 1: st = launch_fps<1, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 2: st = launch_fps<2, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 3: st = launch_fps<3, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 4: st = launch_fps<4, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 5: st = launch_fps<5, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 6: st = launch_fps<6, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            case 7: st = launch_fps<7, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            default: st = launch_fps<8, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+        }
+        return st;
+    }
+    // does not fit 8 points per thread in the allowed cluster: shared-memory coordinate variants, up to 32 per thread
+    S = 1;
+    while (S < 16 && (long long)S * 512 * 32 < n) S *= 2;
+    if ((long long)S * 512 * 32 >= n) {
+        ppt = (int)((n + (long long)S * 512 - 1) / ((long long)S * 512));
         if (ppt <= 16) st = launch_fps<16, false, 512>(b, n, m, n_arr, m_arr, S, 512, xyz, temp, idx, s);
         else st = launch_fps<32, false, 512>(b, n, m, n_arr, m_arr, S, 512, xyz, temp, idx, s);
     } else {

@@ -88,4 +88,32 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_
     asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
+// ---- mbarrier + async DSMEM stores (leader-to-leader exchange without a cluster-wide barrier) ----------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init_cluster() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {   // try_wait suspends the thread in hardware for a bounded time, so this is not a hot spin
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+// 16-byte store into a peer CTA's shared memory that signals `bytes written` on that peer's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar) : "memory");
+}
+
 }  // namespace pu3

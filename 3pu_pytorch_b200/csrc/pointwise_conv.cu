@@ -111,6 +111,146 @@ __global__ void __launch_bounds__(TX * TY) pointwise_conv_kernel(PwArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fast path: n % 4 == 0, 16-byte aligned slices.  Double-buffered shared memory (one barrier per K chunk),
+// global->register prefetch of the next chunk under the FMAs of the current one, conflict-free 128-bit
+// fragment loads (a thread's 8 columns are two groups of 4, TN/2 apart), FFMA2 inner product.
+// ------------------------------------------------------------------------------------------------------
+template <int RM, int TY, int TX>
+__global__ void __launch_bounds__(TX * TY) pointwise_conv_fast_kernel(PwArgs a) {
+    constexpr int TM = RM * TY, TN = 8 * TX, NT = TX * TY, KC = PW_KC;
+    constexpr int WV = (TM * KC / 4 + NT - 1) / NT;      // float4 of W per thread per chunk
+    constexpr int XV = (KC * TN / 4 + NT - 1) / NT;      // float4 of X per thread per chunk
+    __shared__ __align__(16) float Ws[2][KC][TM + 4];
+    __shared__ __align__(16) float Xs[2][KC][TN];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const long long cols = (long long)a.b * a.n;
+    const long long col0 = (long long)blockIdx.x * TN;
+    const int co0 = blockIdx.y * TM;
+    const bool w_vec = (a.cin % 4) == 0;
+
+    f32x2 acc[RM][4];                                    // [row][column pair]: pairs (0,1)(2,3) | (4,5)(6,7)
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+
+    // the (batch, point) of this thread's X loads: float4 index v -> row k = v / (TN/4), column group c4 = v % (TN/4)
+    float4 xr[XV], wr[WV];
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < XV; ++q) {
+            const int v = threadIdx.x + q * NT;
+            const int k = v / (TN / 4), c4 = v % (TN / 4);
+            const long long col = col0 + c4 * 4;
+            const int gk = k0 + k;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < KC * TN / 4 && col < cols && gk < a.cin) {
+                const long long bi = col / a.n;
+                const int p = (int)(col - bi * a.n);     // n % 4 == 0: the 4 columns share the batch element
+                val = __ldg(reinterpret_cast<const float4 *>(a.x + bi * a.x_bstride + (size_t)gk * a.n + p));
+            }
+            xr[q] = val;
+        }
+#pragma unroll
+        for (int q = 0; q < WV; ++q) {
+            const int v = threadIdx.x + q * NT;
+            const int co = v / (KC / 4), k4 = v % (KC / 4);
+            const int gco = co0 + co, gk = k0 + k4 * 4;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < TM * KC / 4 && gco < a.cout) {
+                const float *src = a.w + (size_t)gco * a.cin + gk;
+                if (w_vec && gk + 3 < a.cin) val = __ldg(reinterpret_cast<const float4 *>(src));
+                else {
+                    if (gk < a.cin) val.x = __ldg(src);
+                    if (gk + 1 < a.cin) val.y = __ldg(src + 1);
+                    if (gk + 2 < a.cin) val.z = __ldg(src + 2);
+                    if (gk + 3 < a.cin) val.w = __ldg(src + 3);
+                }
+            }
+            wr[q] = val;
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < XV; ++q) {
+            const int v = threadIdx.x + q * NT;
+            if (v < KC * TN / 4) *reinterpret_cast<float4 *>(&Xs[buf][v / (TN / 4)][(v % (TN / 4)) * 4]) = xr[q];
+        }
+#pragma unroll
+        for (int q = 0; q < WV; ++q) {
+            const int v = threadIdx.x + q * NT;
+            if (v < TM * KC / 4) {
+                const int co = v / (KC / 4), k = (v % (KC / 4)) * 4;
+                Ws[buf][k][co] = wr[q].x; Ws[buf][k + 1][co] = wr[q].y; Ws[buf][k + 2][co] = wr[q].z; Ws[buf][k + 3][co] = wr[q].w;
+            }
+        }
+    };
+
+    const int nchunks = (a.cin + KC - 1) / KC;
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) load_chunk((ch + 1) * KC);   // in flight during the FMAs below
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const float4 xa = *reinterpret_cast<const float4 *>(&Xs[buf][k][tx * 4]);
+            const float4 xb = *reinterpret_cast<const float4 *>(&Xs[buf][k][TN / 2 + tx * 4]);
+            const f32x2 x01 = pack2(xa.x, xa.y), x23 = pack2(xa.z, xa.w), x45 = pack2(xb.x, xb.y), x67 = pack2(xb.z, xb.w);
+            float wv[RM];
+            if constexpr (RM % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < RM; i += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(&Ws[buf][k][ty * RM + i]);
+                    wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RM; ++i) wv[i] = Ws[buf][k][ty * RM + i];
+            }
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                const f32x2 ww = pack2(wv[i], wv[i]);
+                acc[i][0] = fma2(ww, x01, acc[i][0]);
+                acc[i][1] = fma2(ww, x23, acc[i][1]);
+                acc[i][2] = fma2(ww, x45, acc[i][2]);
+                acc[i][3] = fma2(ww, x67, acc[i][3]);
+            }
+        }
+        if (ch + 1 < nchunks) {
+            store_chunk(buf ^ 1);     // the other buffer: nobody reads it during this chunk
+            __syncthreads();
+        }
+    }
+    // ---- epilogue: bias, ReLU, residual, 128-bit stores --------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int co = co0 + ty * RM + i;
+        if (co >= a.cout) continue;
+        const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long col = col0 + h * (TN / 2) + tx * 4;
+            if (col >= cols) continue;
+            const long long bi = col / a.n;
+            const int p = (int)(col - bi * a.n);
+            float v[4];
+            unpack2(acc[i][h * 2], v[0], v[1]);
+            unpack2(acc[i][h * 2 + 1], v[2], v[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] += bv;
+                if (a.relu) v[j] = fmaxf(v[j], 0.f);
+                if (a.res) v[j] += __ldg(a.res + bi * a.res_bstride + (size_t)co * a.res_n + (p + j) / a.res_div);
+            }
+            *reinterpret_cast<float4 *>(a.y + bi * a.y_bstride + (size_t)co * a.n + p) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 // Feature expansion of the up-sampling head (upsampler.py:349-366): the reference replicates every point's
 // 264 features r times, appends one code channel and runs the 265->128 convolution on the (B,265,N*r) tensor.
 // The replicas share W[:, :264] . x, so that product is computed once per point (pre, (B,cout,N)) and this
@@ -132,6 +272,11 @@ __global__ void __launch_bounds__(256) expand_code_kernel(int b, int cout, int n
 
 using namespace pu3;
 
+// Test hook: force the generic (unaligned-safe) kernel.
+static int g_pw_force_generic = 0;
+extern "C" void pu3_pointwise_force_generic(int on) { g_pw_force_generic = on; }
+#define RM4_OK(cout) true
+
 extern "C" int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
                                       const float *w, const float *bias, float *y, long long y_bstride,
                                       const float *res, long long res_bstride, int res_n, int res_div, int relu,
@@ -143,6 +288,25 @@ extern "C" int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const flo
     PwArgs a{b, n, cin, cout, x, x_bstride, w, bias, y, y_bstride, res, res_bstride, res_n, res_div > 0 ? res_div : 1, relu};
     const long long cols = (long long)b * n;
     cudaStream_t s = as_stream(stream);
+    const bool aligned = (n % 4 == 0) && (x_bstride % 4 == 0) && (y_bstride % 4 == 0) &&
+                         (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && g_pw_force_generic == 0;
+    if (aligned && RM4_OK(cout)) {
+        if (cout <= 4) {
+            dim3 grid((unsigned)((cols + 255) / 256), 1);
+            pointwise_conv_fast_kernel<1, 4, 32><<<grid, 128, 0, s>>>(a);
+        } else if (cout <= 24) {
+            dim3 grid((unsigned)((cols + 255) / 256), (cout + 23) / 24);
+            pointwise_conv_fast_kernel<8, 3, 32><<<grid, 96, 0, s>>>(a);
+        } else if (cout <= 64) {
+            dim3 grid((unsigned)((cols + 127) / 128), (cout + 63) / 64);
+            pointwise_conv_fast_kernel<8, 8, 16><<<grid, 128, 0, s>>>(a);
+        } else {
+            dim3 grid((unsigned)((cols + 127) / 128), (cout + 127) / 128);
+            pointwise_conv_fast_kernel<8, 16, 16><<<grid, 256, 0, s>>>(a);
+        }
+        PU3_LAUNCH_CHECK("pointwise_conv_fast_kernel");
+        return PU3_OK;
+    }
     if (cout <= 4) {          // 64 -> 3 regressor: 4 x 256-column tiles, 32 threads
         dim3 grid((unsigned)((cols + 255) / 256), (cout + 3) / 4);
         pointwise_conv_kernel<4, 1, 32><<<grid, 32, 0, s>>>(a);

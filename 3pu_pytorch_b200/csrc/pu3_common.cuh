@@ -88,6 +88,25 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_
     asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
+// ---- packed fp32 (sm_100a FFMA2): two IEEE round-to-nearest FMAs per issued instruction ---------------
+// B200 issues scalar FFMA at full rate, but kernels that also have to issue the shared-memory loads of their
+// operands are issue-bound (profiles/r1_microbench_ffma.md); FFMA2 halves the FMA issue cost.  Results are
+// bit-identical to two scalar fmaf().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // ---- mbarrier + async DSMEM stores (leader-to-leader exchange without a cluster-wide barrier) ----------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");

@@ -246,3 +246,25 @@ def test_to_point_major(pu3, cuda):
     pu3._lib.launch("pu3_to_point_major_f32", x, 3, 70, 45, x.data_ptr(), slot.data_ptr(), out.data_ptr())
     for t, sl in enumerate(slot.tolist()):
         assert torch.equal(out[sl * 45:(sl + 1) * 45], x[t].t())
+
+
+def test_pointwise_conv_fast_and_generic_kernels_agree(pu3, cuda):
+    """Aligned inputs take the double-buffered FFMA2 kernel, everything else the generic one: same numbers
+    (both accumulate over input channels in ascending order with fused multiply-adds)."""
+    import ctypes
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    g = torch.Generator().manual_seed(77)
+    for b, n, cin, cout, relu in [(3, 312, 84, 24, True), (2, 624, 264, 128, False), (2, 624, 128, 64, True),
+                                  (2, 624, 64, 3, False), (5, 312, 3, 24, False), (1, 8, 17, 130, True)]:
+        x = torch.randn(b, cin, n, generator=g).to(cuda); w = (torch.randn(cout, cin, generator=g) * 0.2).to(cuda)
+        bias = torch.randn(cout, generator=g).to(cuda)
+        outs = []
+        for force in (0, 1):
+            lib.pu3_pointwise_force_generic(force)
+            try:
+                o = torch.empty(b, cout, n, device=cuda)
+                pu3.fused.conv_into(x, w, bias, o, relu=relu)
+                outs.append(o)
+            finally:
+                lib.pu3_pointwise_force_generic(0)
+        assert torch.equal(outs[0], outs[1]), (b, n, cin, cout)

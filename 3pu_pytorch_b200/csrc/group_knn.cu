@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
 // k <= 64, n <= 320: the feature-space kNN of DenseEdgeConv (layers.py:33: 24 channels, 312 points, k+1 = 33)
 // --------------------------------------------------------------------------------------------
 // One CTA per cloud.  Queries are processed in blocks of KF_QB:
-//   phase 1  the KF_QB x n block of distances as a register-tiled (4 queries x 4 candidates per thread)
+//   phase 1  the KF_QB x n block of distances as a register-tiled (8 queries x 5 candidates per thread, FFMA2)
 //            product from the shared-memory copy of the cloud, stored as ordered keys in shared memory
 //   phase 2  one warp per query: every lane takes the 10 keys of its column stripe, sorts them in registers
 //            (29-comparator network on packed (key,stripe) words), writes the sorted keys back over its own
@@ -303,24 +303,27 @@ __global__ void __launch_bounds__(KS_THREADS) knn_small_kernel(KnnArgs a, int ti
 //            the index among the lanes that hold that key, the winning lane advances its list head.
 // Cost per query is independent of the data (the streaming-insertion kernel above degrades to one insertion per
 // candidate on sorted input) and about 4x lower at k = 33.
-constexpr int KF_QB = 64;       // queries per block
+constexpr int KF_QB = 32;       // queries per block
 constexpr int KF_NMAX = 320;    // candidates per cloud (10 per lane)
 constexpr int KF_S = KF_NMAX / 32;
 constexpr int KF_THREADS = 256;
+#ifndef KF_MINB
+#define KF_MINB 3
+#endif
+constexpr int KF_JG = 64;       // candidate groups: thread tile = 8 queries x 5 candidates (jg, jg+64, ..., jg+256)
 
 __device__ __forceinline__ void cex(unsigned long long &a, unsigned long long &b) {
     const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
     a = lo; b = hi;
 }
 
-template <int CT>
-__global__ void __launch_bounds__(KF_THREADS) knn_feat_kernel(KnnArgs a) {
+template <int CT, bool HOT>
+__global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a) {
     extern __shared__ __align__(16) unsigned char raw[];
     const int C = CT > 0 ? CT : a.c;
     float *sx = reinterpret_cast<float *>(raw);                        // [C][KF_NMAX] cloud, channel-major, zero padded
     float *snorm = sx + (size_t)C * KF_NMAX;                           // [KF_NMAX]
     uint32_t *skeys = reinterpret_cast<uint32_t *>(snorm + KF_NMAX);   // [KF_QB][KF_NMAX]
-    unsigned long long *sout = reinterpret_cast<unsigned long long *>(skeys + KF_QB * KF_NMAX);   // [8 warps][64]
 
     const int bi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -346,69 +349,78 @@ __global__ void __launch_bounds__(KF_THREADS) knn_feat_kernel(KnnArgs a) {
     }
     __syncthreads();
 
+    const int qg = tid / KF_JG, jg = tid % KF_JG;    // 4 query groups of 8 x 64 candidate groups of 5
     for (int q0 = 0; q0 < mv; q0 += KF_QB) {
-        // ---- phase 1: keys of queries [q0, q0+KF_QB) x candidates [0, KF_NMAX) ----------------------
-        // 16 query groups x 80 candidate groups of 4x4; thread t walks tiles t, t+256, ...
-        for (int tile = tid; tile < (KF_QB / 4) * (KF_NMAX / 4); tile += KF_THREADS) {
-            const int qg = tile / (KF_NMAX / 4), jg = tile - qg * (KF_NMAX / 4);
-            const int ql = qg * 4, j0 = jg * 4;
-            float acc[4][4];
+        // ---- phase 1: keys of queries [q0, q0+32) x candidates [0, 320): one 8x5 tile per thread, FFMA2 -------
+        {
+            const int ql = qg * 8;
+            f32x2 acc[4][5];                          // [query pair][candidate]
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
-            float rq[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int v = 0; v < 5; ++v) acc[u][v] = 0ull;
+            float rq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rq[u] = 0.f;
             if (self) {
+                const int qq = q0 + ql;               // multiple of 8, qq + 7 < KF_NMAX (q0 < n <= 320, q0 % 32 == 0)
 #pragma unroll 4
                 for (int ch = 0; ch < C; ++ch) {
-                    const int qq = q0 + ql;   // < KF_NMAX because n <= KF_NMAX and q0 + KF_QB may overrun: clamp below
-                    float qv[4];
+                    const float *row = sx + ch * KF_NMAX;
+                    const float4 qa = *reinterpret_cast<const float4 *>(row + qq);
+                    const float4 qc = *reinterpret_cast<const float4 *>(row + qq + 4);
+                    const f32x2 q01 = pack2(qa.x, qa.y), q23 = pack2(qa.z, qa.w), q45 = pack2(qc.x, qc.y), q67 = pack2(qc.z, qc.w);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qv[u] = (qq + u) < KF_NMAX ? sx[ch * KF_NMAX + qq + u] : 0.f;
-                    const float4 pv = *reinterpret_cast<const float4 *>(&sx[ch * KF_NMAX + j0]);
-                    const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(qv[u], pj[v], acc[u][v]);
+                    for (int v = 0; v < 5; ++v) {
+                        const float pv = row[jg + v * KF_JG];
+                        const f32x2 pp = pack2(pv, pv);
+                        acc[0][v] = fma2(q01, pp, acc[0][v]); acc[1][v] = fma2(q23, pp, acc[1][v]);
+                        acc[2][v] = fma2(q45, pp, acc[2][v]); acc[3][v] = fma2(q67, pp, acc[3][v]);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) rq[u] = (q0 + ql + u) < KF_NMAX ? snorm[q0 + ql + u] : 0.f;
+                for (int u = 0; u < 8; ++u) rq[u] = snorm[qq + u];
             } else {
                 for (int ch = 0; ch < C; ++ch) {
-                    float qv[4];
+                    const float *row = sx + ch * KF_NMAX;
+                    float qv[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int qi = q0 + ql + u;
                         qv[u] = qi < mv ? __ldg(qb + (size_t)ch * a.m + qi) : 0.f;
                         rq[u] = __fmaf_rn(qv[u], qv[u], rq[u]);
                     }
-                    const float4 pv = *reinterpret_cast<const float4 *>(&sx[ch * KF_NMAX + j0]);
-                    const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
+                    const f32x2 q01 = pack2(qv[0], qv[1]), q23 = pack2(qv[2], qv[3]), q45 = pack2(qv[4], qv[5]), q67 = pack2(qv[6], qv[7]);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) acc[u][v] = __fmaf_rn(qv[u], pj[v], acc[u][v]);
+                    for (int v = 0; v < 5; ++v) {
+                        const float pv = row[jg + v * KF_JG];
+                        const f32x2 pp = pack2(pv, pv);
+                        acc[0][v] = fma2(q01, pp, acc[0][v]); acc[1][v] = fma2(q23, pp, acc[1][v]);
+                        acc[2][v] = fma2(q45, pp, acc[2][v]); acc[3][v] = fma2(q67, pp, acc[3][v]);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t kk[4];
+            for (int v = 0; v < 5; ++v) {
+                const int j = jg + v * KF_JG;
+                const float rp = snorm[j];
+                const bool live = j < nv;
+                const bool isdup = penal && live && dupb[j];
+                const bool drop = !live || (isdup && dmode == 1);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int j = j0 + v;
-                    float d = expanded_dist(rq[u], acc[u][v], snorm[j]);
-                    const bool isdup = penal && j < nv && dupb[j];
-                    if (isdup) d = __fadd_rn(d, maxd);
-                    kk[v] = (j < nv && !(isdup && dmode == 1)) ? float_to_ordered(d) : 0xffffffffu;
+                for (int u = 0; u < 4; ++u) {
+                    float d0, d1;
+                    unpack2(acc[u][v], d0, d1);
+                    float e0 = expanded_dist(rq[2 * u], d0, rp), e1 = expanded_dist(rq[2 * u + 1], d1, rp);
+                    if (isdup) { e0 = __fadd_rn(e0, maxd); e1 = __fadd_rn(e1, maxd); }
+                    skeys[(ql + 2 * u) * KF_NMAX + j] = drop ? 0xffffffffu : float_to_ordered(e0);
+                    skeys[(ql + 2 * u + 1) * KF_NMAX + j] = drop ? 0xffffffffu : float_to_ordered(e1);
                 }
-                *reinterpret_cast<uint4 *>(&skeys[(ql + u) * KF_NMAX + j0]) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
             }
         }
         __syncthreads();
         // ---- phase 2: selection, one warp per query ----------------------------------------------------
-        unsigned long long *myout = sout + warp * 64;
-        for (int ql = warp; ql < KF_QB; ql += 8) {
+        for (int ql = warp; ql < KF_QB; ql += KF_THREADS / 32) {
             const int qi = q0 + ql;
             if (qi >= mv) break;  // warp-uniform
             uint32_t *krow = skeys + ql * KF_NMAX;
@@ -426,48 +438,62 @@ __global__ void __launch_bounds__(KF_THREADS) knn_feat_kernel(KnnArgs a) {
             cex(v[2], v[3]); cex(v[6], v[7]);
             cex(v[3], v[4]); cex(v[5], v[6]);
             cex(v[4], v[5]);
-            // the sorted keys go back into the lane's own 10 slots of the row, the stripe order into one register
-            unsigned long long perm = 0;
+            // the sorted keys go back into the lane's own 10 slots of the row, the stripe order into two registers
+            uint32_t perm_lo = 0, perm_hi = 0;
 #pragma unroll
             for (int s = 0; s < KF_S; ++s) {
-                perm |= (v[s] & 15ull) << (4 * s);
+                const uint32_t tag = (uint32_t)v[s] & 15u;
+                if (s < 8) perm_lo |= tag << (4 * s); else perm_hi |= tag << (4 * (s - 8));
                 if (s > 0) krow[s * 32 + lane] = (uint32_t)(v[s] >> 32);
             }
             uint32_t hk = (uint32_t)(v[0] >> 32);
+            uint32_t hj = (perm_lo & 15u) * 32u + lane;
             int h = 1;
-            for (int r = 0; r < a.k; ++r) {
-                const uint32_t hj = (uint32_t)(perm & 15ull) * 32u + lane;
-                const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
-                const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
-                if (hk == kmin && hj == jmin) {       // exactly one lane (indices are unique)
-                    myout[r] = ((unsigned long long)hk << 32) | hj;
-                    hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
-                    perm >>= 4;
-                    ++h;
-                }
-            }
-            __syncwarp();
-            // ---- outputs -------------------------------------------------------------------------------
             const size_t row = ((size_t)bi * a.m + qi) * a.k;
-            for (int p = lane; p < a.k; p += 32) {
-                const unsigned long long o = myout[p];
-                const int32_t j = (int32_t)(uint32_t)o;
-                if (a.idx32) a.idx32[row + p] = j;
-                if (a.idx64) a.idx64[row + p] = j;
-                if (a.dist) a.dist[row + p] = ordered_to_float((uint32_t)(o >> 32));
-            }
-            if (a.knn) {
-                for (int ch = 0; ch < C; ++ch) {
-                    float *o = a.knn + (((size_t)bi * C + ch) * a.m + qi) * a.k;
-                    for (int p = lane; p < a.k; p += 32) o[p] = sx[ch * KF_NMAX + (uint32_t)myout[p]];
+            if (HOT) {
+                // only int32 indices wanted (the fused DenseEdgeConv path): the loop body is kept minimal; winners
+                // are staged as 16-bit indices in stripe 0 of the row (free: those heads live in registers)
+                uint16_t *stage = reinterpret_cast<uint16_t *>(krow);
+                __syncwarp();
+                for (int r = 0; r < a.k; ++r) {
+                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
+                    const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
+                    if (hj == jmin && hk == kmin) {       // exactly one lane (indices are unique)
+                        stage[r] = (uint16_t)hj;
+                        hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
+                        perm_lo = __funnelshift_r(perm_lo, perm_hi, 4);
+                        perm_hi >>= 4;
+                        hj = (perm_lo & 15u) * 32u + lane;
+                        ++h;
+                    }
+                }
+                __syncwarp();
+                int32_t *o = a.idx32 + row;
+                for (int r = lane; r < a.k; r += 32) o[r] = stage[r];
+                __syncwarp();
+            } else {
+                for (int r = 0; r < a.k; ++r) {
+                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
+                    const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
+                    if (hj == jmin && hk == kmin) {
+                        if (a.idx32) a.idx32[row + r] = (int32_t)hj;
+                        if (a.idx64) a.idx64[row + r] = (int64_t)hj;
+                        if (a.dist) a.dist[row + r] = ordered_to_float(hk);
+                        if (a.knn)
+                            for (int ch = 0; ch < C; ++ch)
+                                a.knn[(((size_t)bi * C + ch) * a.m + qi) * a.k + r] = sx[ch * KF_NMAX + hj];
+                        hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
+                        perm_lo = __funnelshift_r(perm_lo, perm_hi, 4);
+                        perm_hi >>= 4;
+                        hj = (perm_lo & 15u) * 32u + lane;
+                        ++h;
+                    }
                 }
             }
-            __syncwarp();
         }
         __syncthreads();
     }
 }
-
 
 // --------------------------------------------------------------------------------------------
 // k <= 8, 3 channels: the xyz-space searches (inter-level skip k = 5, upsampler.py:325; outlier filter k = 2, :63)
@@ -894,18 +920,22 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         return PU3_OK;
     }
     if (n <= KF_NMAX && g_knn_force_stream == 0) {
-        const size_t smem = ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4 + 8 * 64 * 8;
+        const size_t smem = ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4;
         if (smem <= (size_t)device_info().smem_optin) {
-            int st;
-            if (c == 24) {
-                st = cuda_status(cudaFuncSetAttribute(knn_feat_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "group_knn: smem attr");
-                if (st) return st;
-                knn_feat_kernel<24><<<b, KF_THREADS, smem, s>>>(a);
-            } else {
-                st = cuda_status(cudaFuncSetAttribute(knn_feat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "group_knn: smem attr");
-                if (st) return st;
-                knn_feat_kernel<0><<<b, KF_THREADS, smem, s>>>(a);
-            }
+            const bool hot = idx32 && !idx64 && !dist && !knn;
+#define PU3_KF_LAUNCH(CTV, HOTV)                                                                                        \
+    do {                                                                                                                \
+        auto kern = knn_feat_kernel<CTV, HOTV>;                                                                          \
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),        \
+                             "group_knn: smem attr");                                                                   \
+        if (st) return st;                                                                                              \
+        kern<<<b, KF_THREADS, smem, s>>>(a);                                                                            \
+    } while (0)
+            if (c == 24 && hot) PU3_KF_LAUNCH(24, true);
+            else if (c == 24) PU3_KF_LAUNCH(24, false);
+            else if (hot) PU3_KF_LAUNCH(0, true);
+            else PU3_KF_LAUNCH(0, false);
+#undef PU3_KF_LAUNCH
             PU3_LAUNCH_CHECK("knn_feat_kernel");
             return PU3_OK;
         }

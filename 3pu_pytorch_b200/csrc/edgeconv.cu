@@ -205,9 +205,229 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edgeconv_kernel(int n, int k, i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fast kernel (k <= 32, the cloud fits shared memory).  Differences to edgeconv_kernel above, all driven by the
+// round-1 profile (fp32-issue bound, FMA pipe 20 % busy, 1 CTA/SM, 21 M shared-memory bank conflicts):
+//   * 2 edges per lane (a half-warp of 16 lanes owns one point): every broadcast LDS.128 of 4 weights feeds
+//     8 FMAs, issued as 4 FFMA2 -> the FMA pipe, not instruction issue, is the limiter
+//   * neighbour rows are fetched as 6 LDS.128 from a 28-float row stride (conflict-free quarter-warp phases)
+//     instead of 24 scalar LDS
+//   * the max over the 32 edges goes through shared memory (36 STS + ~60 LDS/FMNMX per warp) instead of a
+//     5-step shuffle butterfly on 36 values
+//   * <= 128 registers: 2 CTAs per SM
+// ------------------------------------------------------------------------------------------------------
+constexpr int EF_XS = 28;            // row stride of a point in shared memory (floats): 7 quads, odd -> conflict free
+constexpr int EF_RS = 20;            // row stride of the reduction scratch (16 lanes + pad)
+constexpr int EF_PS = 36 * EF_RS;    // per-point scratch; 720 % 32 == 16 keeps the two half-warps on disjoint banks
+
+struct EfSmemW {
+    float w0b[EC_C][EC_G];
+    float w1a[EC_G][EC_G];
+    float w2a[EC_G][EC_G];
+    float w2b[EC_G][EC_G];
+    float wp[EC_C][36];
+    float bp[36];
+};
+
+__device__ __forceinline__ void ef_layer(f32x2 (&h)[6], const float *wrow, float x) {
+    const float4 a = *reinterpret_cast<const float4 *>(wrow);
+    const float4 b = *reinterpret_cast<const float4 *>(wrow + 4);
+    const float4 c = *reinterpret_cast<const float4 *>(wrow + 8);
+    const f32x2 xx = pack2(x, x);
+    h[0] = fma2(pack2(a.x, a.y), xx, h[0]); h[1] = fma2(pack2(a.z, a.w), xx, h[1]);
+    h[2] = fma2(pack2(b.x, b.y), xx, h[2]); h[3] = fma2(pack2(b.z, b.w), xx, h[3]);
+    h[4] = fma2(pack2(c.x, c.y), xx, h[4]); h[5] = fma2(pack2(c.z, c.w), xx, h[5]);
+}
+// two edges share the weight loads
+__device__ __forceinline__ void ef_layer2(f32x2 (&ha)[6], f32x2 (&hb)[6], const float *wrow, float xa, float xb) {
+    const float4 a = *reinterpret_cast<const float4 *>(wrow);
+    const float4 b = *reinterpret_cast<const float4 *>(wrow + 4);
+    const float4 c = *reinterpret_cast<const float4 *>(wrow + 8);
+    const f32x2 w0 = pack2(a.x, a.y), w1 = pack2(a.z, a.w), w2 = pack2(b.x, b.y), w3 = pack2(b.z, b.w),
+                w4 = pack2(c.x, c.y), w5 = pack2(c.z, c.w);
+    const f32x2 xxa = pack2(xa, xa), xxb = pack2(xb, xb);
+    ha[0] = fma2(w0, xxa, ha[0]); ha[1] = fma2(w1, xxa, ha[1]); ha[2] = fma2(w2, xxa, ha[2]);
+    ha[3] = fma2(w3, xxa, ha[3]); ha[4] = fma2(w4, xxa, ha[4]); ha[5] = fma2(w5, xxa, ha[5]);
+    hb[0] = fma2(w0, xxb, hb[0]); hb[1] = fma2(w1, xxb, hb[1]); hb[2] = fma2(w2, xxb, hb[2]);
+    hb[3] = fma2(w3, xxb, hb[3]); hb[4] = fma2(w4, xxb, hb[4]); hb[5] = fma2(w5, xxb, hb[5]);
+}
+
+__global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, int k, int pts_per_cta,
+                                                                         const float *__restrict__ x, long long x_bstride,
+                                                                         const int32_t *__restrict__ idx, int idx_stride,
+                                                                         int idx_off, EcWeights W, float *__restrict__ y,
+                                                                         long long y_bstride) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    EfSmemW &sw = *reinterpret_cast<EfSmemW *>(raw);
+    float *s_out = reinterpret_cast<float *>(raw + sizeof(EfSmemW));   // [EC_OUT][EC_PT+1]
+    float *s_a = s_out + EC_OUT * (EC_PT + 1);                           // [EC_WARPS][2][36]
+    float *s_red = s_a + EC_WARPS * 2 * 36;                              // [EC_WARPS][2][EF_PS]
+    float *xs = s_red + EC_WARPS * 2 * EF_PS;                            // [n][EF_XS]
+
+    const int bi = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hl = lane & 15, hp = lane >> 4;
+    const float *xb = x + bi * x_bstride;
+    float *yb = y + bi * y_bstride;
+    const int32_t *ib = idx + (size_t)bi * n * idx_stride;
+
+    for (int t = threadIdx.x; t < EC_C * EC_G; t += blockDim.x) {
+        const int in = t / EC_G, o = t % EC_G;
+        sw.w0b[in][o] = __ldg(W.w0 + o * 48 + 24 + in);
+    }
+    for (int t = threadIdx.x; t < EC_G * EC_G; t += blockDim.x) {
+        const int in = t / EC_G, o = t % EC_G;
+        sw.w1a[in][o] = __ldg(W.w1 + o * 36 + in);
+        sw.w2a[in][o] = __ldg(W.w2 + o * 48 + in);
+        sw.w2b[in][o] = __ldg(W.w2 + o * 48 + 12 + in);
+    }
+    for (int t = threadIdx.x; t < EC_C * 36; t += blockDim.x) {
+        const int in = t / 36, o = t % 36;
+        float v;
+        if (o < 12) v = __ldg(W.w0 + o * 48 + in);
+        else if (o < 24) v = __ldg(W.w1 + (o - 12) * 36 + 12 + in);
+        else v = __ldg(W.w2 + (o - 24) * 48 + 24 + in);
+        sw.wp[in][o] = v;
+    }
+    if (threadIdx.x < 36) {
+        const int o = threadIdx.x;
+        sw.bp[o] = o < 12 ? __ldg(W.b0 + o) : (o < 24 ? __ldg(W.b1 + o - 12) : __ldg(W.b2 + o - 24));
+    }
+    for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) {
+        const int c = t / n, p = t - c * n;
+        xs[p * EF_XS + c] = __ldg(xb + (size_t)c * n + p);
+    }
+    __syncthreads();
+
+    const int p_begin = blockIdx.x * pts_per_cta;
+    const int p_end = min(n, p_begin + pts_per_cta);
+    float *wa = s_a + (warp * 2 + hp) * 36;
+    float *wred = s_red + (size_t)(warp * 2 + hp) * EF_PS;
+
+    for (int t0 = p_begin; t0 < p_end; t0 += EC_PT) {
+        const int tcnt = min(EC_PT, p_end - t0);
+        for (int lp0 = warp * 2; lp0 < tcnt; lp0 += EC_WARPS * 2) {
+            const int lp = lp0 + hp;
+            const bool pvalid = lp < tcnt;                 // the second point of the pair may not exist
+            const int i = pvalid ? t0 + lp : t0 + lp0;
+            const float *ci = xs + i * EF_XS;
+            // ---- per-point terms A0|A1|A2 (36 values) by the 16 lanes of the half-warp -------------------
+            {
+                float a0 = sw.bp[hl], a1 = sw.bp[16 + hl], a2 = hl < 4 ? sw.bp[32 + hl] : 0.f;
+#pragma unroll
+                for (int ch = 0; ch < EC_C; ++ch) {
+                    const float cv = ci[ch];
+                    a0 = __fmaf_rn(sw.wp[ch][hl], cv, a0);
+                    a1 = __fmaf_rn(sw.wp[ch][16 + hl], cv, a1);
+                    if (hl < 4) a2 = __fmaf_rn(sw.wp[ch][32 + hl], cv, a2);
+                }
+                __syncwarp();
+                wa[hl] = a0; wa[16 + hl] = a1;
+                if (hl < 4) wa[32 + hl] = a2;
+                __syncwarp();
+            }
+            // ---- the lane's two edges -------------------------------------------------------------------------
+            const int ea = hl, eb = 16 + hl;
+            const bool va = ea < k, vb = eb < k;
+            const int ja = va ? __ldg(ib + (size_t)i * idx_stride + idx_off + ea) : i;
+            const int jb = vb ? __ldg(ib + (size_t)i * idx_stride + idx_off + eb) : i;
+            const float *na = xs + ja * EF_XS, *nb = xs + jb * EF_XS;
+            f32x2 h0a[6], h0b[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) h0a[q] = h0b[q] = pack2(wa[2 * q], wa[2 * q + 1]);
+#pragma unroll
+            for (int c4 = 0; c4 < EC_C; c4 += 4) {
+                const float4 cc = *reinterpret_cast<const float4 *>(ci + c4);
+                const float4 fa = *reinterpret_cast<const float4 *>(na + c4);
+                const float4 fb = *reinterpret_cast<const float4 *>(nb + c4);
+                ef_layer2(h0a, h0b, &sw.w0b[c4 + 0][0], fa.x - cc.x, fb.x - cc.x);   // edge feature n - c (layers.py:41)
+                ef_layer2(h0a, h0b, &sw.w0b[c4 + 1][0], fa.y - cc.y, fb.y - cc.y);
+                ef_layer2(h0a, h0b, &sw.w0b[c4 + 2][0], fa.z - cc.z, fb.z - cc.z);
+                ef_layer2(h0a, h0b, &sw.w0b[c4 + 3][0], fa.w - cc.w, fb.w - cc.w);
+            }
+            float r0a[EC_G], r0b[EC_G];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                unpack2(h0a[q], r0a[2 * q], r0a[2 * q + 1]);
+                unpack2(h0b[q], r0b[2 * q], r0b[2 * q + 1]);
+            }
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) { r0a[o] = fmaxf(r0a[o], 0.f); r0b[o] = fmaxf(r0b[o], 0.f); }
+            f32x2 h1a[6], h1b[6], h2a[6], h2b[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                h1a[q] = h1b[q] = pack2(wa[12 + 2 * q], wa[12 + 2 * q + 1]);
+                h2a[q] = h2b[q] = pack2(wa[24 + 2 * q], wa[24 + 2 * q + 1]);
+            }
+#pragma unroll
+            for (int in = 0; in < EC_G; ++in) {
+                ef_layer2(h1a, h1b, &sw.w1a[in][0], r0a[in], r0b[in]);
+                ef_layer2(h2a, h2b, &sw.w2b[in][0], r0a[in], r0b[in]);
+            }
+            float m[36];   // max over the lane's two edges: [h2 | h1 | h0]
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) {
+                const float xa = va ? r0a[o] : -INFINITY, xb2 = vb ? r0b[o] : -INFINITY;
+                m[24 + o] = fmaxf(xa, xb2);
+            }
+            {
+                float r1a[EC_G], r1b[EC_G];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    unpack2(h1a[q], r1a[2 * q], r1a[2 * q + 1]);
+                    unpack2(h1b[q], r1b[2 * q], r1b[2 * q + 1]);
+                }
+#pragma unroll
+                for (int o = 0; o < EC_G; ++o) { r1a[o] = fmaxf(r1a[o], 0.f); r1b[o] = fmaxf(r1b[o], 0.f); }
+#pragma unroll
+                for (int in = 0; in < EC_G; ++in) ef_layer2(h2a, h2b, &sw.w2a[in][0], r1a[in], r1b[in]);
+#pragma unroll
+                for (int o = 0; o < EC_G; ++o) m[12 + o] = fmaxf(va ? r1a[o] : -INFINITY, vb ? r1b[o] : -INFINITY);
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                float a0, a1, b0, b1;
+                unpack2(h2a[q], a0, a1);
+                unpack2(h2b[q], b0, b1);
+                m[2 * q] = fmaxf(va ? a0 : -INFINITY, vb ? b0 : -INFINITY);
+                m[2 * q + 1] = fmaxf(va ? a1 : -INFINITY, vb ? b1 : -INFINITY);
+            }
+            // ---- max over the 16 lanes of the point through shared memory -------------------------------------------
+            __syncwarp();
+#pragma unroll
+            for (int o = 0; o < 36; ++o) wred[o * EF_RS + hl] = m[o];
+            __syncwarp();
+            const float *wbase = s_red + (size_t)(warp * 2) * EF_PS;
+            for (int o = lane; o < 72; o += 32) {
+                const int pp = o / 36, ch = o - pp * 36;
+                const float *rrow = wbase + (size_t)pp * EF_PS + ch * EF_RS;
+                const float4 v0 = *reinterpret_cast<const float4 *>(rrow), v1 = *reinterpret_cast<const float4 *>(rrow + 4);
+                const float4 v2 = *reinterpret_cast<const float4 *>(rrow + 8), v3 = *reinterpret_cast<const float4 *>(rrow + 12);
+                const float mx = fmaxf(fmaxf(fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w)), fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w))),
+                                       fmaxf(fmaxf(fmaxf(v2.x, v2.y), fmaxf(v2.z, v2.w)), fmaxf(fmaxf(v3.x, v3.y), fmaxf(v3.z, v3.w))));
+                if (lp0 + pp < tcnt) s_out[ch * (EC_PT + 1) + lp0 + pp] = mx;   // rows 0..35 = [h2, h1, h0] already in output order
+            }
+            if (pvalid) {
+                for (int ch = hl; ch < EC_C; ch += 16) s_out[(36 + ch) * (EC_PT + 1) + lp] = ci[ch];
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < EC_OUT * EC_PT; t += blockDim.x) {
+            const int ch = t / EC_PT, lp = t % EC_PT;
+            if (lp < tcnt) yb[(size_t)ch * n + t0 + lp] = s_out[ch * (EC_PT + 1) + lp];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace pu3
 
 using namespace pu3;
+
+// Test hook: force the generic kernel.
+static int g_ec_force_generic = 0;
+extern "C" void pu3_edgeconv_force_generic(int on) { g_ec_force_generic = on; }
 
 extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
                                 int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
@@ -234,6 +454,14 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     dim3 grid((n + pts - 1) / pts, b);
     cudaStream_t s = as_stream(stream);
     int st;
+    const size_t fast_smem = sizeof(EfSmemW) + (size_t)(EC_OUT * (EC_PT + 1) + EC_WARPS * 2 * 36 + EC_WARPS * 2 * EF_PS + (size_t)n * EF_XS) * sizeof(float);
+    if (k <= 32 && fast_smem <= 110 * 1024 && g_ec_force_generic == 0) {
+        st = cuda_status(cudaFuncSetAttribute(edgeconv_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem), "edgeconv: smem attr");
+        if (st) return st;
+        edgeconv_fast_kernel<<<grid, EC_WARPS * 32, fast_smem, s>>>(n, k, pts, x, x_bstride, idx, idx_stride, idx_off, W, y, y_bstride);
+        PU3_LAUNCH_CHECK("edgeconv_fast_kernel");
+        return PU3_OK;
+    }
     if (in_smem) {
         st = cuda_status(cudaFuncSetAttribute(edgeconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "edgeconv: smem attr");
         if (st) return st;

@@ -268,3 +268,25 @@ def test_pointwise_conv_fast_and_generic_kernels_agree(pu3, cuda):
             finally:
                 lib.pu3_pointwise_force_generic(0)
         assert torch.equal(outs[0], outs[1]), (b, n, cin, cout)
+
+
+def test_edgeconv_fast_and_generic_kernels_agree(pu3, cuda, params):
+    """k <= 32 takes the FFMA2 two-edges-per-lane kernel; it accumulates in the same order as the generic one."""
+    import ctypes
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    g = torch.Generator().manual_seed(5)
+    pre = "levels.level_3.layer2"
+    ws = [params[f"{pre}.mlps.{i}.weight"].to(cuda) for i in range(3)]
+    bs = [params[f"{pre}.mlps.{i}.bias"].to(cuda) for i in range(3)]
+    for b, n, k in [(3, 312, 32), (2, 100, 16), (1, 45, 31), (4, 312, 5)]:
+        x = torch.randn(b, 24, n, generator=g).to(cuda)
+        idx = torch.stack([torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(n)]) for _ in range(b)]).to(cuda)
+        outs = []
+        for force in (0, 1):
+            lib.pu3_edgeconv_force_generic(force)
+            try:
+                with torch.no_grad():
+                    outs.append(pu3.fused.dense_edge_conv(x, ws, bs, k, idx=idx)[0])
+            finally:
+                lib.pu3_edgeconv_force_generic(0)
+        assert torch.equal(outs[0], outs[1]), (b, n, k)

@@ -200,6 +200,16 @@ int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, c
  */
 int pu3_to_point_major_f32(int t, int c, int n, const float *in, const int64_t *slot, float *out, pu3_stream_t stream);
 
+/*
+ * Train-step tail on one flat buffer (model.py:63-65 of the reference: clip_grad_value_(params, clip) followed by
+ * Adam.step()): g = clamp(grad * grad_scale, -clip, clip) (clip <= 0: no clipping), then the Adam update with
+ * torch.optim.Adam's formulas (no weight decay, no amsgrad); step = 1 for the first update.  grad_scale = 1/world
+ * turns an all-reduce(sum) into the DDP mean.
+ */
+int pu3_clip_adam_f32(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                      float grad_scale, float clip, float lr, float beta1, float beta2, float eps, int step,
+                      pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

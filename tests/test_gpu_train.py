@@ -1,0 +1,58 @@
+"""GPU: train-step tail (fused clip + Adam on the flat buffer) and the Model wrapper against torch / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_net
+from tests.util import assert_close_frac
+
+pytestmark = pytest.mark.gpu
+
+
+def test_flat_adam_matches_torch_adam_with_value_clipping(pu3, cuda):
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Conv1d(3, 16, 1), torch.nn.ReLU(), torch.nn.Conv1d(16, 3, 1)).to(cuda)
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    opt_b = torch.optim.Adam(b.parameters(), lr=5e-4, betas=(0.9, 0.999))
+    opt_a = pu3.dist.FlatAdam(a, lr=5e-4, betas=(0.9, 0.999), clip_value=1.0)
+    g = torch.Generator().manual_seed(1)
+    for step in range(5):
+        x = (torch.randn(4, 3, 50, generator=g) * 30).to(cuda)   # large inputs: the clipping is active
+        opt_a.zero_grad(); opt_b.zero_grad()
+        a(x).square().mean().backward()
+        b(x).square().mean().backward()
+        torch.nn.utils.clip_grad_value_(b.parameters(), 1)
+        opt_a.step(); opt_b.step()
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-7)
+
+
+def test_model_optimize_matches_oracle_step(pu3, cuda):
+    """Two train steps of the Model wrapper (model.py:53-66 order) against the oracle network + torch Adam."""
+    levels, ratio, B = 2, 2, 2   # up_ratio 2 of a 4x network: weight log2(4/2) = 1
+    P0 = {k: v for k, v in ref_net.make_params(4, seed=3).items() if int(k.split(".")[1].split("_")[1]) <= levels}
+    Pr = {k: v.clone().requires_grad_() for k, v in P0.items()}
+    opt_r = torch.optim.Adam(list(Pr.values()), lr=5e-4, betas=(0.9, 0.999))
+    net = pu3.Net(max_up_ratio=4, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5)
+    net.load_state_dict(P0, strict=True)
+    net = net.to(cuda)
+    model = pu3.Model(net, "train", lr_init=5e-4)
+    g = torch.Generator().manual_seed(4)
+    for step in range(2):
+        x = torch.rand(B, 3, 312, generator=g); gt = torch.rand(B, 3, 624, generator=g)
+        opt_r.zero_grad()
+        pr, gr = ref_net.net_forward(Pr, x, ratio=ratio, gt=gt, training=True, max_up_ratio=4, knn=16)
+        loss_r = ref_net.chamfer_loss(pr, gr) * 1.0
+        loss_r.backward()
+        torch.nn.utils.clip_grad_value_(list(Pr.values()), 1)
+        opt_r.step()
+        model.set_input(x.to(cuda), ratio, label_pc=gt.to(cuda))
+        loss = model.optimize()
+        assert abs(float(loss) - float(loss_r)) <= 1e-4 * abs(float(loss_r))
+    assert model.step == 2 and abs(model.error_log["cd_loss_x2"] - float(loss_r)) < 0.5
+    got = dict(net.named_parameters())
+    for name in ("levels.level_1.fc_layer2.conv.weight", "levels.level_1.layer1.mlps.0.weight", "levels.level_1.layer0.conv.bias"):
+        # Adam's first steps are +-lr per weight: compare the UPDATE, which is what the gradients drive
+        du = got[name].detach().cpu() - P0[name]; dr = Pr[name].detach() - P0[name]
+        assert_close_frac(du, dr, rtol=5e-2, atol=2e-5, frac=0.97, what=name)

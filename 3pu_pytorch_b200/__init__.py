@@ -10,9 +10,9 @@ sampling.py / losses.py mirror the reference's two pybind modules; operations.py
 upsampler.py, model_loss.py mirror network/*.py.  There is no CPU path.
 """
 from . import _lib  # noqa: F401
-from . import sampling, losses, operations, model_loss, fused, layers, upsampler, dist, model  # noqa: F401
+from . import sampling, losses, operations, model_loss, fused, layers, upsampler, dist, model, pipeline  # noqa: F401
 from .model import Model  # noqa: F401
 from .upsampler import Net, Level  # noqa: F401
 from .model_loss import ChamferLoss  # noqa: F401
 
-__all__ = ["sampling", "losses", "operations", "model_loss", "fused", "layers", "upsampler", "dist", "model", "Net", "Level", "ChamferLoss", "Model"]
+__all__ = ["sampling", "losses", "operations", "model_loss", "fused", "layers", "upsampler", "dist", "model", "pipeline", "Net", "Level", "ChamferLoss", "Model"]

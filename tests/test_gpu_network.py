@@ -290,3 +290,47 @@ def test_edgeconv_fast_and_generic_kernels_agree(pu3, cuda, params):
             finally:
                 lib.pu3_edgeconv_force_generic(0)
         assert torch.equal(outs[0], outs[1]), (b, n, k)
+
+
+def test_reference_import_names_resolve_through_the_shim(pu3, cuda):
+    """What `main.py` of the reference imports (main.py:12-17, operations.py:2-6, model_loss.py:2) resolves to this
+    package when 3pu_pytorch_b200/shim is first on sys.path."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, sampling, losses, faiss\n"
+            "from network import operations\n"
+            "from network.upsampler import Net\n"
+            "from network.model_loss import ChamferLoss\n"
+            "from network.layers import Conv1d, Conv2d, DenseEdgeConv\n"
+            "net = Net(max_up_ratio=4, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5).cuda().eval()\n"
+            "x = operations.normalize_point_batch(torch.rand(2, 3, 312).cuda())[0]\n"
+            "with torch.no_grad(): y = net.forward(x, ratio=4)\n"
+            "idx, pts = operations.furthest_point_sample(y, 100)\n"
+            "print(tuple(y.shape), tuple(pts.shape), sampling.furthest_sampling.__module__)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "3pu_pytorch_b200", "shim"), root]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "(2, 3, 1248) (2, 3, 100) 3pu_pytorch_b200.sampling" in out.stdout
+
+
+def test_whole_shape_pipeline_against_oracle(pu3, cuda, params):
+    """BASELINE config 5 at reduced size: FPS seeds -> kNN patches -> batched upsample -> merge -> FPS."""
+    levels, ratio, n_shape = 2, 4, 1000
+    net = _net(pu3, params, cuda, levels=levels).eval()
+    P = {k: v for k, v in params.items() if int(k.split(".")[1].split("_")[1]) <= levels}
+    g = torch.Generator().manual_seed(31)
+    pc = ref_net.normalize_point_batch(torch.rand(1, 3, n_shape, generator=g))[0]
+    got = pu3.pipeline.upsample_shape(net, pc.to(cuda), num_point=312, patch_num_ratio=3, up_ratio=ratio).cpu()
+    # the reference's loop (main.py:225-246, 375-380), on the oracle
+    num_patches = int(n_shape / 312 * 3)
+    _, seeds = ref_net.furthest_point_sample(pc, num_patches)
+    patches, _, _ = ref_net.group_knn(312, seeds, pc)
+    ups = []
+    with torch.no_grad():
+        for k in range(num_patches):
+            patch, c, r = ref_net.normalize_point_batch(patches[:, :, k, :])
+            ups.append(ref_net.net_forward(P, patch, ratio=ratio, max_up_ratio=ratio) * r + c)
+    pred = torch.cat(ups, dim=-1)
+    _, want = ref_net.furthest_point_sample(pred, n_shape * ratio)
+    assert got.shape == want.shape == (1, 3, n_shape * ratio)
+    assert cloud_match_fraction(got[0], want[0], tol=1e-4) > 0.95

@@ -92,6 +92,45 @@ __global__ void __launch_bounds__(256) knn_dup_kernel(int c, int n, const int32_
     if (found) atomicAdd(cloud_any + cloud, 1);   // number of duplicates of the cloud
 }
 
+
+// Clouds of <= 1024 points (every feature-space search): one CTA per cloud, a 32-bit hash of each point's
+// channels in shared memory, candidates compared hash first.  Comparing channel 0 first (kernel above) is
+// useless on post-ReLU features, where a third of the values are exactly 0.
+constexpr int KD_MAXN = 1024;
+__global__ void __launch_bounds__(256) knn_dup_small_kernel(int c, int n, const int32_t *__restrict__ n_arr,
+                                                           const float *__restrict__ points,
+                                                           uint8_t *__restrict__ dup, int *__restrict__ cloud_any) {
+    __shared__ uint32_t hsh[KD_MAXN];
+    const int cloud = blockIdx.x;
+    const int nv = n_arr ? min(n, __ldg(n_arr + cloud)) : n;
+    const float *p = points + (size_t)cloud * c * n;
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        uint32_t h = 2166136261u;
+        for (int ch = 0; ch < c; ++ch) {
+            uint32_t u = __float_as_uint(__ldg(p + (size_t)ch * n + j));
+            if ((u << 1) == 0u) u = 0u;                  // -0.0 == +0.0 (np.unique compares values)
+            h = (h ^ u) * 16777619u;
+            h ^= h >> 15;
+        }
+        hsh[j] = h;
+    }
+    __syncthreads();
+    int found_any = 0;
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        const uint32_t hj = hsh[j];
+        bool found = false;
+        for (int e = 0; e < j && !found; ++e) {
+            if (hsh[e] != hj) continue;
+            bool same = true;
+            for (int ch = 0; ch < c && same; ++ch) same = p[(size_t)ch * n + e] == p[(size_t)ch * n + j];
+            found = same;
+        }
+        dup[(size_t)cloud * n + j] = found ? 1 : 0;
+        found_any += found ? 1 : 0;
+    }
+    if (found_any) atomicAdd(cloud_any + cloud, found_any);
+}
+
 // a group needs max(D) as soon as one of its batch elements reads a cloud with duplicates
 __global__ void __launch_bounds__(256) knn_groupflag_kernel(KnnArgs a, const int *__restrict__ cloud_any,
                                                            int *__restrict__ group_any) {
@@ -893,7 +932,8 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         uint8_t *dup = ws + pl.off_dup;
         int st = cuda_status(cudaMemsetAsync(ws + pl.off_any, 0, pl.off_dup - pl.off_any, s), "group_knn: memset");
         if (st) return st;
-        knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
+        if (n <= KD_MAXN) knn_dup_small_kernel<<<clouds, 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
+        else knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
         PU3_LAUNCH_CHECK("knn_dup_kernel");
         knn_groupflag_kernel<<<(b + 255) / 256, 256, 0, s>>>(a, cloud_any, group_any);
         PU3_LAUNCH_CHECK("knn_groupflag_kernel");

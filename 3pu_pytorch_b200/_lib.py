@@ -39,9 +39,24 @@ SIGNATURES = {
     "pu3_skip_fuse_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 7),
     "pu3_to_point_major_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
     "pu3_clip_adam_f32": (_c_int, [_c_ll] + [_c_void_p] * 4 + [_c_float] * 6 + [_c_int, _c_void_p]),
+    "pu3_level_workspace": (_c_size_t, [_c_int] * 8),
+    "pu3_level_forward_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                       _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "pu3_iota_i32": (_c_int, [_c_int, _c_void_p, _c_void_p]),
     "pu3_edgeconv_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
                          [_c_void_p, _c_ll, _c_void_p]),
 }
+
+class LevelWeights(ctypes.Structure):
+    """pu3_level_weights of include/pu3_b200.h"""
+    _fields_ = [("layer0_w", _c_void_p), ("layer0_b", _c_void_p),
+                ("ec_w", (_c_void_p * 3) * 4), ("ec_b", (_c_void_p * 3) * 4),
+                ("prep_w", _c_void_p * 3), ("prep_b", _c_void_p * 3),
+                ("up1_w", _c_void_p), ("up1_w_feat", _c_void_p), ("up1_b", _c_void_p),
+                ("up2_w", _c_void_p), ("up2_b", _c_void_p), ("fc1_w", _c_void_p), ("fc1_b", _c_void_p),
+                ("fc2_w", _c_void_p), ("fc2_b", _c_void_p), ("code", _c_void_p),
+                ("r", _c_int), ("knn", _c_int), ("fm_knn", _c_int), ("reserved", _c_int)]
+
 
 _lib = None
 
@@ -74,7 +89,9 @@ def check(status, what):
 KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
-    "pu3_edgeconv_f32": 1,
+    "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
+    # layer0 + 4 x (kNN + edge-conv) + 3 preps + 5 head kernels; + 4 x 3 duplicate kernels; skip adds 2 + 3, iota 1
+    "pu3_level_forward_f32": 29,
     "pu3_fps_ragged_f32": 1,
     "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique
 }
@@ -96,12 +113,29 @@ class Profiler:
         if e0 is not None:
             self._events.setdefault(name, []).append((e0, e1))
 
+    ENGINE_TAGS = ["pu3_pointwise_conv_f32", "pu3_group_knn_f32[c=24,k=33,n<=312]", "pu3_edgeconv_f32",
+                   "pu3_group_knn_f32[c=3,k=5,skip]", "pu3_skip_fuse_f32", "pu3_expand_code_f32", "misc"]
+
     def summary(self):
-        """{name: (calls, total_ms)} -- call after torch.cuda.synchronize()."""
+        """{name: (calls, total_ms)} -- call after torch.cuda.synchronize().  Kernels launched inside the level
+        engine are reported under their own families (timed by the engine's event pairs), not under the engine."""
         out = {}
         for name, n in self.calls.items():
             ms = sum(a.elapsed_time(b) for a, b in self._events.get(name, []))
             out[name] = (n, ms)
+        if self.timing:
+            n = len(self.ENGINE_TAGS)
+            ms = (ctypes.c_float * n)(); calls = (ctypes.c_int * n)()
+            h = ctypes.CDLL(LIB_PATH)
+            h.pu3_prof_collect(ms, calls, n)
+            inner = 0.0
+            for i, name in enumerate(self.ENGINE_TAGS):
+                if calls[i]:
+                    c0, m0 = out.get(name, (0, 0.0))
+                    out[name] = (c0 + calls[i], m0 + ms[i]); inner += ms[i]
+            if "pu3_level_forward_f32" in out and inner > 0:
+                c0, m0 = out.pop("pu3_level_forward_f32")
+                out["pu3_level_forward_f32[engine: gaps between its kernels]"] = (c0, max(m0 - inner, 0.0))
         return out
 
 
@@ -111,6 +145,7 @@ _profiler = None
 def set_profiler(p):
     global _profiler
     prev, _profiler = _profiler, p
+    ctypes.CDLL(LIB_PATH).pu3_prof_enable(1 if (p is not None and p.timing) else 0)
     return prev
 
 

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "pu3_common.cuh"
 
 namespace pu3 {
@@ -42,7 +45,48 @@ const DeviceInfo &device_info() {
     return info[dev];
 }
 
+// ---- optional per-kernel-family timing inside composite entry points (level engine) -------------------------
+// bench.py times kernels live with CUDA events; the engine launches ~35 kernels per call, so it records its own
+// event pairs (only while enabled: two cudaEventRecord per sub-launch) and hands the sums back by tag.
+struct ProfRec { int tag; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+int prof_begin(int tag, cudaStream_t s) {
+    if (!g_prof_on) return -1;
+    ProfRec r; r.tag = tag;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+    cudaEventRecord(r.e0, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
+}
+void prof_end(int id, cudaStream_t s) {
+    if (id < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (id < (int)g_prof.size()) cudaEventRecord(g_prof[id].e1, s);
+}
+
 }  // namespace pu3
+
+extern "C" void pu3_prof_enable(int on) { pu3::g_prof_on = on != 0; }
+// Adds the elapsed milliseconds / launch counts of everything recorded since the last call to ms[tag], calls[tag]
+// (tags >= ntags are dropped); synchronises on the recorded events.  Returns the number of records consumed.
+extern "C" int pu3_prof_collect(float *ms, int *calls, int ntags) {
+    std::lock_guard<std::mutex> lk(pu3::g_prof_mu);
+    int n = 0;
+    for (auto &r : pu3::g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess &&
+            r.tag >= 0 && r.tag < ntags) { ms[r.tag] += t; calls[r.tag] += 1; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+        ++n;
+    }
+    pu3::g_prof.clear();
+    (void)cudaGetLastError();
+    return n;
+}
 
 extern "C" const char *pu3_last_error(void) { return pu3::g_err; }
 extern "C" int pu3_version(void) { return 1; }

@@ -43,10 +43,7 @@ struct __align__(16) FpsCand {
 
 struct FpsSmem {
     FpsCand cluster_slot[2][FPS_MAX_CLUSTER];  // [round parity][source CTA rank]
-    uint32_t warp_dkey[2][32];
-    uint32_t warp_rank[2][32];
-    int32_t warp_k[2][32];
-    float win[2][4];                           // [round parity] coordinates of the round's winner
+    FpsCand warp_slot[2][32];                  // [round parity][warp]: the warp's winner, coordinates included
     uint64_t mbar[2];                          // [round parity] "all S candidates of the round have landed"
 };
 
@@ -130,9 +127,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             t[i] = d2;
             if (d2 > best) { best = d2; besti = i; }
         }
-        // ---- 2. warp arg-max: one lane per warp publishes (distance, tie rank, index) ------------
-        // The round is issue-bound, so everything after this point is done by ONE warp per CTA; the other
-        // warps only pay two barriers.
+        // ---- 2. warp arg-max: the winning lane publishes (distance, tie rank, index, coordinates) ----------
         const uint32_t dkey = best >= 0.f ? __float_as_uint(best) : 0u;
         const uint32_t dmax_w = __reduce_max_sync(0xffffffffu, dkey);
         uint32_t rank = 0xffffffffu;
@@ -143,57 +138,67 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
         }
         const uint32_t rmin_w = __reduce_min_sync(0xffffffffu, rank);
         if (rank == rmin_w && (rmin_w != 0xffffffffu || lane == 0)) {   // the winner, or lane 0 of an empty warp
-            sm.warp_dkey[par][warp] = dmax_w;
-            sm.warp_rank[par][warp] = rmin_w;
-            sm.warp_k[par][warp] = kbest;
+            const int slot = besti * nthreads + threadIdx.x;            // coordinates from the smem copy: no dynamic
+            uint4 lo, hi;                                               // register indexing, and off the leader's path
+            lo.x = dmax_w; lo.y = rmin_w; lo.z = (uint32_t)kbest; lo.w = __float_as_uint(sx[slot]);
+            hi.x = __float_as_uint(sy[slot]); hi.y = __float_as_uint(sz[slot]); hi.z = 0u; hi.w = 0u;
+            uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
+            dst[0] = lo; dst[1] = hi;
         }
-        __syncthreads();
-        // ---- 3. leader warp: CTA arg-max, cluster exchange ----------------------------------------
-        if (warp == 0) {
-            const uint32_t wd = lane < nwarps ? sm.warp_dkey[par][lane] : 0u;
-            const uint32_t wr = lane < nwarps ? sm.warp_rank[par][lane] : 0xffffffffu;
+        __syncthreads();                          // the only CTA-wide barrier of the round
+        if (S == 1) {
+            // ---- 3a. one CTA per cloud: every warp reduces the warp slots itself (no second barrier) -------
+            uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+            if (lane < nwarps) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.warp_slot[par][lane]);
+                lo = src[0]; hi = src[1];
+            }
             uint32_t dmax, rmin;
-            const bool wwin = warp_argmax(wd, wr, dmax, rmin);
-            const uint32_t wsrc = __ffs(__ballot_sync(0xffffffffu, wwin)) - 1;  // 0xffffffff: CTA without points
-            const bool cta_has = wsrc != 0xffffffffu;
-            const int kwin = cta_has ? sm.warp_k[par][wsrc & 31] : 0;
-            float wx = 0.f, wy = 0.f, wz = 0.f;
-            if (cta_has) {
-                const int slot = (kwin / GT) * nthreads + ((kwin % GT) - (int)crank * nthreads);
-                wx = sx[slot]; wy = sy[slot]; wz = sz[slot];
-            }
-            if (S == 1) {
-                if (lane == 0) {
-                    sm.win[par][0] = wx; sm.win[par][1] = wy; sm.win[par][2] = wz;
-                    out[j] = kwin;
+            const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
+            const int wsrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
+            x1 = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, wsrc));
+            y1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, wsrc));
+            z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, wsrc));
+            const int kw = (int)__shfl_sync(0xffffffffu, lo.z, wsrc);
+            if (threadIdx.x == 0) out[j] = kw;
+        } else {
+            // ---- 3b. leader warp: CTA winner -> every peer's slot by async DSMEM stores that complete on the
+            //          receiver's mbarrier.  No cluster-wide barrier; the other warps go straight to the wait.
+            if (warp == 0) {
+                uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+                if (lane < nwarps) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&sm.warp_slot[par][lane]);
+                    lo = src[0]; hi = src[1];
                 }
-            } else {
-                // Leader-to-leader exchange: every leader posts its candidate (32 B) into every CTA's slot with
-                // an async DSMEM store that completes on the RECEIVER's mbarrier; each leader then waits for
-                // S x 32 bytes on its own barrier.  No cluster-wide barrier: the other warps never leave the CTA.
-                if (lane == 0) mbar_arrive_expect_tx(&sm.mbar[par], S * 32u);
-                if (lane < (int)S) {
-                    const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], lane);
-                    const uint32_t rbar = map_to_cta(&sm.mbar[par], lane);
-                    st_async_v4(dst, rbar, cta_has ? dmax : 0u, cta_has ? rmin : 0xffffffffu, (uint32_t)kwin, __float_as_uint(wx));
-                    st_async_v4(dst + 16, rbar, __float_as_uint(wy), __float_as_uint(wz), 0u, 0u);
-                }
-                mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);  // phase = earlier uses of this buffer
-                const FpsCand *cs = sm.cluster_slot[par];
-                const uint32_t cd = lane < (int)S ? cs[lane].dkey : 0u;
-                const uint32_t cr = lane < (int)S ? cs[lane].rank : 0xffffffffu;
                 uint32_t dmax, rmin;
-                const bool cwin = warp_argmax(cd, cr, dmax, rmin);
-                const uint32_t csrc = __ffs(__ballot_sync(0xffffffffu, cwin)) - 1;
-                if (lane == 0) {
-                    const FpsCand w = cs[csrc & (FPS_MAX_CLUSTER - 1)];
-                    sm.win[par][0] = w.x; sm.win[par][1] = w.y; sm.win[par][2] = w.z;
-                    if (crank == 0) out[j] = w.k;
+                const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
+                const unsigned wb = __ballot_sync(0xffffffffu, win);
+                if (wb == 0u ? lane == 0 : win) {      // the winning lane holds the candidate in registers
+                    mbar_arrive_expect_tx(&sm.mbar[par], S * 32u);
+                    for (uint32_t r = 0; r < S; ++r) {
+                        const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], r);
+                        const uint32_t rbar = map_to_cta(&sm.mbar[par], r);
+                        st_async_v4(dst, rbar, lo.x, lo.y, lo.z, lo.w);
+                        st_async_v4(dst + 16, rbar, hi.x, hi.y, 0u, 0u);
+                    }
                 }
             }
+            // ---- 4. every warp: wait for the S candidates, reduce them, take the winner's coordinates ----------
+            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);   // phase = earlier uses of this buffer
+            uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+            if (lane < (int)S) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][lane]);
+                lo = src[0]; hi = src[1];
+            }
+            uint32_t dmax, rmin;
+            const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
+            const int csrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
+            x1 = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, csrc));
+            y1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, csrc));
+            z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, csrc));
+            const int kw = (int)__shfl_sync(0xffffffffu, lo.z, csrc);
+            if (g == 0) out[j] = kw;
         }
-        __syncthreads();
-        x1 = sm.win[par][0]; y1 = sm.win[par][1]; z1 = sm.win[par][2];
     }
     if (trow) {
 #pragma unroll
@@ -303,7 +308,9 @@ using namespace pu3;
 
 // Test/tuning hook: force the cluster size (0 = heuristic).  Not part of the public header.
 static int g_fps_force_cluster = 0;
+static int g_fps_force_threads = 0;
 extern "C" void pu3_fps_set_cluster(int s) { g_fps_force_cluster = s; }
+extern "C" void pu3_fps_set_threads(int t) { g_fps_force_threads = t; }   // tuning hook (profiles/tune_fps.py)
 
 static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, const float *xyz, float *temp,
                         int32_t *idx, pu3_stream_t stream);
@@ -328,45 +335,66 @@ static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t
     const int t_ref = ref_block_size(n);
     const int sms = device_info().sm_count;
 
-    // Launch shape.  A round costs every warp (10 instructions per point + ~35 of reduction) issue slots plus
-    // ~450 cycles of cluster barrier when the cloud is spread over S > 1 CTAs; pick the (threads, S) with the
+    // Launch shape.  A round costs every warp (10 instructions per point + ~45 of reduction / hand-shake) issue
+    // slots, plus ~350 cycles of DSMEM exchange when the cloud is spread over S > 1 CTAs.  Few fat warps beat many
+    // thin ones (the per-warp overhead is paid by every warp): pick the (threads, S, points per thread) with the
     // smallest modelled round among the shapes that (a) keep S*threads a multiple of the reference block size
-    // (tie rule), (b) hold the cloud in <= 8 points per thread, (c) keep all clouds co-resident (b*S <= SMs).
-    int s_cap = floor_pow2(sms / b > 0 ? sms / b : 1);
+    // (tie rule), (b) hold the cloud in registers (<= 24 points per thread, fewer at high thread counts),
+    // (c) keep all clouds co-resident (b*S <= SMs).
+    // Two CTAs of DIFFERENT clouds per SM let one cloud's serial phase (reduction + exchange, issue slots idle)
+    // overlap the other's point loop, so the cluster may be twice as wide as "one CTA per SM" allows, provided
+    // two CTAs fit an SM (threads <= 512 and 2 * threads * registers <= 64 K).
+    int s_cap = floor_pow2((2 * sms) / b > 0 ? (2 * sms) / b : 1);
     if (s_cap > 8) s_cap = 8;
     int threads = 0, S = 1, ppt = 0;
     long long best_cost = -1;
     static const int kThreads[] = {1024, 896, 768, 640, 512, 384, 256, 128, 64, 32};
+    static const int kPpt[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24};
+    auto ppt_slot = [&](long long need, int th) -> int {   // smallest instantiated points-per-thread >= need that fits the registers
+        for (int v : kPpt) {
+            if (v < need) continue;
+            if (v > 8 && th > 512) return 0;
+            if (v > 16 && th > 384) return 0;
+            return v;
+        }
+        return 0;
+    };
     for (int cs = 1; cs <= s_cap; cs *= 2) {
         if (g_fps_force_cluster > 0 && cs != g_fps_force_cluster) continue;
+        const bool two_per_sm = (long long)b * cs > sms;
         for (int th : kThreads) {
+            if (g_fps_force_threads > 0 && th != g_fps_force_threads) continue;
             const long long gt = (long long)cs * th;
             if (gt % t_ref != 0) continue;
-            const long long p = (n + gt - 1) / gt;
-            if (p > 8) continue;
-            const long long cost = (long long)(th / 32) * (p * 10 + 35) / 4 + (cs > 1 ? 450 : 0) + 80;
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; threads = th; S = cs; ppt = (int)p; }
+            const int p = ppt_slot((n + gt - 1) / gt, th);
+            if (p == 0) continue;
+            if (two_per_sm && (th > 512 || (long long)2 * th * (4 * p + 40) > 65536)) continue;
+            const long long issue = (long long)(th / 32) * (p * 10 + 45) / 4;
+            const long long lat = cs > 1 ? 1100 : 600;
+            const long long cost = two_per_sm ? (2 * issue > issue + lat ? 2 * issue : issue + lat) + 100 : issue + lat;
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; threads = th; S = cs; ppt = p; }
         }
     }
     if (g_fps_force_cluster > 0 && threads == 0) {   // forced cluster size (tests): any shape that fits
         S = g_fps_force_cluster;
         for (int th : kThreads) {
             const long long gt = (long long)S * th;
-            if (gt % t_ref == 0 && (n + gt - 1) / gt <= 8) { threads = th; ppt = (int)((n + gt - 1) / gt); break; }
+            if (gt % t_ref != 0) continue;
+            const int p = ppt_slot((n + gt - 1) / gt, th);
+            if (p) { threads = th; ppt = p; break; }
         }
     }
     int st;
     if (threads > 0) {
+#define PU3_FPS_CASE(P, MT) case P: st = launch_fps<P, true, MT>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
         switch (ppt) {
-            case 1: st = launch_fps<1, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 2: st = launch_fps<2, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 3: st = launch_fps<3, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 4: st = launch_fps<4, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 5: st = launch_fps<5, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 6: st = launch_fps<6, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            case 7: st = launch_fps<7, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
-            default: st = launch_fps<8, true, 1024>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, s); break;
+            PU3_FPS_CASE(1, 1024) PU3_FPS_CASE(2, 1024) PU3_FPS_CASE(3, 1024) PU3_FPS_CASE(4, 1024)
+            PU3_FPS_CASE(5, 1024) PU3_FPS_CASE(6, 1024) PU3_FPS_CASE(7, 1024) PU3_FPS_CASE(8, 1024)
+            PU3_FPS_CASE(10, 512) PU3_FPS_CASE(12, 512) PU3_FPS_CASE(14, 512) PU3_FPS_CASE(16, 512)
+            PU3_FPS_CASE(20, 384) PU3_FPS_CASE(24, 384)
+            default: set_error("fps: internal: no kernel for %d points per thread", ppt); return PU3_E_UNSUPPORTED;
         }
+#undef PU3_FPS_CASE
         return st;
     }
     // does not fit 8 points per thread in the allowed cluster: shared-memory coordinate variants, up to 32 per thread

@@ -21,6 +21,8 @@ from . import fused, layers, operations
 class Level(torch.nn.Module):
     """3PU per-level network (upsampler.py:192-374)."""
 
+    use_engine = True    # eval fast path through the C++ level engine (False: one Python call per kernel, for profiling)
+
     def __init__(self, dense_n=3, growth_rate=12, knn=16, fm_knn=5, step_ratio=2):
         super(Level, self).__init__()
         self.dense_n = dense_n
@@ -88,6 +90,79 @@ class Level(torch.nn.Module):
         wants_grad = torch.is_grad_enabled() and (self.training or xyz_normalized.requires_grad)
         return (xyz_normalized.is_cuda and xyz_normalized.dtype == torch.float32 and self.dense_n == 3
                 and self.growth_rate == 12 and self.code.size(1) == 1 and not wants_grad)
+
+    # ---- level engine: one C call for the whole forward (csrc/level.cu) --------------------------------------
+    def _engine_weights(self, device):
+        """ctypes pu3_level_weights for the current parameter storage (rebuilt when a parameter moved or changed)."""
+        params = [self.layer0.conv.weight, self.layer0.conv.bias]
+        for blk in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for m in blk.mlps:
+                params += [m.weight, m.bias]
+        for prep in (self.layer2_prep, self.layer3_prep, self.layer4_prep):
+            params += [prep.conv.weight, prep.conv.bias]
+        up1, up2 = self.up_layer.up_layer1.conv, self.up_layer.up_layer2.conv
+        params += [up1.weight, up1.bias, up2.weight, up2.bias, self.fc_layer1.conv.weight, self.fc_layer1.conv.bias,
+                   self.fc_layer2.conv.weight, self.fc_layer2.conv.bias]
+        key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
+        cached = self.__dict__.get("_engine_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        if not all(p.is_contiguous() and p.device == device and p.dtype == torch.float32 for p in params):
+            raise RuntimeError("Level parameters must be contiguous float32 tensors on the input's device")
+        W = fused._lib.LevelWeights()
+        it = iter(params)
+        W.layer0_w, W.layer0_b = next(it).data_ptr(), next(it).data_ptr()
+        for bi in range(4):
+            for li in range(3):
+                W.ec_w[bi][li], W.ec_b[bi][li] = next(it).data_ptr(), next(it).data_ptr()
+        for pi in range(3):
+            W.prep_w[pi], W.prep_b[pi] = next(it).data_ptr(), next(it).data_ptr()
+        C = self.feat_channels
+        up1_feat = up1.weight.detach().reshape(128, C + 1)[:, :C].contiguous()     # without the code column
+        code = self._code_on(device)
+        W.up1_w, W.up1_w_feat, W.up1_b = up1.weight.data_ptr(), up1_feat.data_ptr(), up1.bias.data_ptr()
+        W.up2_w, W.up2_b = up2.weight.data_ptr(), up2.bias.data_ptr()
+        W.fc1_w, W.fc1_b = self.fc_layer1.conv.weight.data_ptr(), self.fc_layer1.conv.bias.data_ptr()
+        W.fc2_w, W.fc2_b = self.fc_layer2.conv.weight.data_ptr(), self.fc_layer2.conv.bias.data_ptr()
+        W.code = code.data_ptr()
+        W.r, W.knn, W.fm_knn, W.reserved = int(self.code.size(2)), int(self.knn), int(self.fm_knn), 0
+        self.__dict__["_engine_cache"] = (key, W, up1_feat, code)       # keep the derived tensors alive
+        return W
+
+    def _engine_ok(self):
+        return (self.feat_channels == 264 and all(b.k == self.knn for b in (self.layer1, self.layer2, self.layer3, self.layer4))
+                and self.up_layer.up_layer1.conv.weight.shape[1] == 265)
+
+    def _forward_engine(self, xyz, xyz_normalized, previous_level4, group, ragged):
+        import ctypes
+        T, _, N = xyz_normalized.shape
+        dev = xyz_normalized.device
+        W = self._engine_weights(dev)
+        r = W.r
+        xn = xyz_normalized.contiguous()
+        has_prev = previous_level4 is not None and self.fm_knn > 0
+        if has_prev:
+            prev_xyz, prev_feat_pm = previous_level4
+            prev_xyz, prev_feat_pm = prev_xyz.contiguous(), prev_feat_pm.contiguous()
+            clouds, No = prev_feat_pm.shape[0], prev_feat_pm.shape[1]
+            xyz_c = xyz.contiguous()
+        else:
+            prev_xyz = prev_feat_pm = xyz_c = None
+            clouds, No = 0, 0
+        owner = ragged.owner if ragged is not None else None
+        groups = ragged.groups if ragged is not None else 0
+        prev_n = ragged.n_arr if (ragged is not None and has_prev) else None
+        L = fused._lib.lib()
+        ws_bytes = L.pu3_level_workspace(T, N, r, W.knn, W.fm_knn, max(clouds, 1), max(No, 1), int(has_prev))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        feat = torch.empty(T, 264, N, dtype=torch.float32, device=dev)
+        out = torch.empty(T, 3, N * r, dtype=torch.float32, device=dev)
+        extra = 12 + (6 if has_prev else 0) + (1 if owner is not None else 0)
+        fused._lib.launch("pu3_level_forward_f32", xn, ctypes.addressof(W), T, N, fused._lib.ptr(xyz_c), xn.data_ptr(),
+                          fused._lib.ptr(owner), int(groups), int(group or T), fused._lib.ptr(prev_xyz),
+                          fused._lib.ptr(prev_feat_pm), int(clouds), int(No), fused._lib.ptr(prev_n), feat.data_ptr(),
+                          out.data_ptr(), ws.data_ptr(), ws_bytes, extra_kernels=extra)
+        return out, feat
 
     def _features_fused(self, xyz_normalized, group, ragged=None):
         """layer0 + 4 dense blocks into one (B,264,N) buffer; channel order [y4, y3, y2, y1, x0]."""
@@ -205,6 +280,8 @@ class Level(torch.nn.Module):
         fast = self._fast_path_ok(xyz_normalized)
         if ragged is not None and not fast:
             raise RuntimeError("ragged batches are an eval-mode (no-grad, CUDA fp32) feature")
+        if fast and self.use_engine and self._engine_ok() and (previous_level4 is None or prev_point_major or self.fm_knn <= 0):
+            return self._forward_engine(xyz, xyz_normalized, previous_level4, group, ragged)
         if fast:
             x = self._features_fused(xyz_normalized, group, ragged)
         else:
@@ -419,8 +496,58 @@ class Net(torch.nn.Module):
             old_xyz, old_features = patch_xyz, features
         return xyz, gt
 
+    # Request groups processed concurrently on separate CUDA streams (eval).  FPS is a chain of dependent
+    # rounds that leaves most of the chip idle (cluster hand-shake latency); a second group's kNN / MLP kernels
+    # can fill those SMs.  Measured on B200 (profiles/r1_bench_history.md): no gain at B=32 -- the FPS kernels
+    # already occupy 128 of the 148 SMs with register-heavy CTAs -- so the default is one group.
+    eval_groups = 1
+
     def _forward_eval(self, xyz, num_levels, num_point, max_num_point, **kwargs):
         """Eval: every cloud of the batch is an independent request (the reference takes one per call)."""
+        B = xyz.shape[0]
+        groups = self.eval_groups or 1
+        groups = max(1, min(int(groups), B))
+        if groups == 1 or num_levels < 2:
+            return self._forward_eval_group(xyz, num_levels, num_point, max_num_point, **kwargs)
+        # one host thread + one stream per group: the per-level host reads (outlier counts) of one group must not
+        # stall the launches of the other
+        import threading
+        cur = torch.cuda.current_stream(xyz.device)
+        bounds = [(g * B) // groups for g in range(groups + 1)]
+        outs, errs = [None] * groups, [None] * groups
+        streams = self._eval_streams(xyz.device, groups)
+        grad = torch.is_grad_enabled()
+
+        def work(g):
+            try:
+                with torch.cuda.device(xyz.device), torch.cuda.stream(streams[g]), torch.set_grad_enabled(grad):
+                    streams[g].wait_stream(cur)
+                    outs[g] = self._forward_eval_group(xyz[bounds[g]:bounds[g + 1]], num_levels, num_point, max_num_point, **kwargs)
+            except BaseException as e:   # re-raised in the caller's thread
+                errs[g] = e
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(1, groups)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        for g in range(groups):
+            cur.wait_stream(streams[g])
+            outs[g].record_stream(cur)
+        return torch.cat(outs, dim=0)
+
+    def _eval_streams(self, device, n):
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        key = (device, n)
+        if key not in cache:
+            cache[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return cache[key]
+
+    def _forward_eval_group(self, xyz, num_levels, num_point, max_num_point, **kwargs):
         B = xyz.shape[0]
         dev = xyz.device
         level = self.levels['level_1']

@@ -87,7 +87,7 @@ def _algorithmic_bytes(name, calls):
         # feature kNN (16 calls): read x (24ch) once, write idx32 (k+1)
         tot = sum(4 * (b * 24 * N * 4 + b * N * (K + 1) * 4) for b in rows)
         return tot / max(calls, 1)
-    if name == "pu3_group_knn_f32[k<=64]":
+    if name == "pu3_group_knn_f32[k<=64]" or name.startswith("pu3_group_knn_f32[c=3,k=5"):
         # feature kNN (16 calls): read x (24ch) once for queries and once as candidates, write idx32 (k+1)
         tot = sum(4 * (b * 24 * N * 4 * 2 + b * N * (K + 1) * 4) for b in rows)
         # skip kNN k=5 (3 calls, levels 2..4: previous clouds of 312, 3120, 6240 points) + outlier kNN k=2 (3 calls)
@@ -133,6 +133,7 @@ def run_product(args):
     net = pu3.Net(max_up_ratio=UP_RATIO, step_ratio=2, knn=KNN, growth_rate=12, dense_n=3, fm_knn=5)
     net.load_state_dict(params, strict=True)
     net = net.to(dev).eval()
+    net.eval_groups = args.eval_groups
 
     host_x = make_inputs(rank).pin_memory()
     dev_x = host_x.to(dev)
@@ -298,6 +299,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--cpu-patches", type=int, default=2, help="patches in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--eval-groups", type=int, default=None, help="request groups run concurrently on separate streams (default: auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         # bounded sample: a CPU patch takes ~5 s; keep steps * patches * 5 s within a couple of minutes

@@ -210,6 +210,36 @@ int pu3_clip_adam_f32(long long n, float *param, const float *grad, float *exp_a
                       float grad_scale, float clip, float lr, float beta1, float beta2, float eps, int step,
                       pu3_stream_t stream);
 
+/*
+ * Level engine: every kernel of one Level.forward (network/upsampler.py:272-374) enqueued by one call.
+ * Weights in the reference's state_dict layouts; up1_w_feat is a contiguous (128,264)
+ * copy of up_layer1's weight without its code column, code the (r) expansion code (upsampler.py:264-270).
+ */
+typedef struct {
+    const float *layer0_w, *layer0_b;           /* (24,3), (24) */
+    const float *ec_w[4][3], *ec_b[4][3];       /* layer{1..4}.mlps.{0,1,2}: (12,48) (12,36) (12,48) */
+    const float *prep_w[3], *prep_b[3];         /* layer{2,3,4}_prep: (24,84) (24,144) (24,204) */
+    const float *up1_w, *up1_w_feat, *up1_b;    /* (128,265), (128,264), (128) */
+    const float *up2_w, *up2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+    const float *code;                          /* (r) */
+    int r, knn, fm_knn, reserved;
+} pu3_level_weights;
+
+/*
+ * t patches of n points.  xyz_norm (t,3,n) normalised input; xyz (t,3,n) un-normalised (only read by the skip
+ * connection).  Previous level (optional, prev_xyz NULL = none): prev_xyz (clouds,3,no) channel-major,
+ * prev_feat_pm (clouds,no,264) point-major, prev_n (clouds) valid sizes or NULL.  Patch i belongs to request
+ * owner[i] (ragged batches, groups = number of requests) or, with owner NULL, to request i / (t/clouds) with
+ * duplicate-penalty groups of max_group consecutive patches.  Outputs: feat (t,264,n) = [y4|y3|y2|y1|x0],
+ * out_xyz (t,3,n*r) in the normalised frame.  workspace: pu3_level_workspace() bytes, 256-byte aligned.
+ */
+size_t pu3_level_workspace(int t, int n, int r, int knn, int fm_knn, int clouds, int no, int has_prev);
+int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                          const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                          const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
+                          float *out_xyz, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
+int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,3 +337,93 @@ extern "C" int pu3_expand_code_f32(int b, int cout, int n, int r, const float *p
     PU3_LAUNCH_CHECK("expand_code_kernel");
     return PU3_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Backward of the 1x1 convolution with respect to the weights and the bias:
+//     dW[co,ci] += sum_{b,p} dY[b,co,p] * X[b,ci,p]        db[co] += sum_{b,p} dY[b,co,p]
+// (what autograd computes for nn.Conv1d/Conv2d in the reference's train step, model.py:62).  A GEMM whose
+// reduction dimension is the flattened (batch, point) axis: split-K over column chunks, 64x64 output tile per
+// CTA, 4x4 per thread, partial tiles combined with fp32 atomics (summation order unspecified, like cuDNN's).
+// dX needs no kernel of its own: it is the forward kernel applied to dY with W transposed.
+// ------------------------------------------------------------------------------------------------------
+namespace pu3 {
+
+constexpr int BW_T = 64;       // output tile (co x ci)
+constexpr int BW_KC = 16;      // columns per shared-memory chunk
+constexpr int BW_COLS = 4096;  // columns per CTA (split-K granularity)
+
+__global__ void __launch_bounds__(256) pointwise_conv_bwd_w_kernel(int b, int n, int cin, int cout,
+                                                                  const float *__restrict__ x, long long x_bstride,
+                                                                  const float *__restrict__ dy, long long dy_bstride,
+                                                                  float *__restrict__ dw, float *__restrict__ db) {
+    __shared__ float As[BW_KC][BW_T + 1];   // dY chunk, [col][co]
+    __shared__ float Bs[BW_KC][BW_T + 1];   // X chunk,  [col][ci]
+    const long long cols = (long long)b * n;
+    const long long c_begin = (long long)blockIdx.x * BW_COLS;
+    const long long c_end = min(cols, c_begin + BW_COLS);
+    const int co0 = blockIdx.y * BW_T, ci0 = blockIdx.z * BW_T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;                        // threads 0..63 of the ci-tile-0 CTAs also sum dY rows (bias gradient)
+    const bool do_bias = db != nullptr && blockIdx.z == 0;
+    for (long long c0 = c_begin; c0 < c_end; c0 += BW_KC) {
+        for (int t = threadIdx.x; t < BW_KC * BW_T; t += 256) {
+            const int k = t % BW_KC, r = t / BW_KC;           // consecutive threads walk the columns: coalesced
+            const long long col = c0 + k;
+            float av = 0.f, bv = 0.f;
+            if (col < c_end) {
+                const long long bi = col / n;
+                const int p = (int)(col - bi * n);
+                if (co0 + r < cout) av = __ldg(dy + bi * dy_bstride + (size_t)(co0 + r) * n + p);
+                if (ci0 + r < cin) bv = __ldg(x + bi * x_bstride + (size_t)(ci0 + r) * n + p);
+            }
+            As[k][r] = av; Bs[k][r] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BW_KC; ++k) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; bb[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(a[i], bb[j], acc[i][j]);
+        }
+        if (do_bias && threadIdx.x < BW_T) {
+#pragma unroll
+            for (int k = 0; k < BW_KC; ++k) bsum += As[k][threadIdx.x];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + tx * 4 + j;
+            if (ci < cin) atomicAdd(dw + (size_t)co * cin + ci, acc[i][j]);
+        }
+    }
+    if (do_bias && threadIdx.x < BW_T && co0 + (int)threadIdx.x < cout) atomicAdd(db + co0 + threadIdx.x, bsum);
+}
+
+}  // namespace pu3
+
+extern "C" int pu3_pointwise_conv_bwd_w_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
+                                            const float *dy, long long dy_bstride, float *dw, float *db,
+                                            pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0 && cout > 0, "pointwise_conv_bwd_w: bad size");
+    if (b == 0 || n == 0) return PU3_OK;
+    PU3_ARG_CHECK(x && dy && dw, "pointwise_conv_bwd_w: null pointer");
+    const long long cols = (long long)b * n;
+    dim3 grid((unsigned)((cols + pu3::BW_COLS - 1) / pu3::BW_COLS), (cout + pu3::BW_T - 1) / pu3::BW_T, (cin + pu3::BW_T - 1) / pu3::BW_T);
+    pu3::pointwise_conv_bwd_w_kernel<<<grid, 256, 0, pu3::as_stream(stream)>>>(b, n, cin, cout, x, x_bstride, dy, dy_bstride, dw, db);
+    PU3_LAUNCH_CHECK("pointwise_conv_bwd_w_kernel");
+    return PU3_OK;
+}

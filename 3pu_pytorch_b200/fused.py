@@ -53,12 +53,49 @@ def conv_into(x, w, b, out, relu=False, residual=None, res_div=1):
     return out
 
 
+class PointwiseConvFunction(torch.autograd.Function):
+    """1x1 convolution (+ReLU) with hand-written forward AND backward kernels: forward / input gradient on the
+    FFMA2 SGEMM (csrc/pointwise_conv.cu), weight and bias gradients on its split-K companion."""
+
+    @staticmethod
+    def forward(ctx, x3, w2, bias, relu):
+        B, Cin, N = x3.shape
+        out = torch.empty(B, w2.shape[0], N, dtype=torch.float32, device=x3.device)
+        conv_into(x3, w2, bias, out, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x3, w2, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x3, w2, out = ctx.saved_tensors
+        B, Cin, N = x3.shape
+        Cout = w2.shape[0]
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy * (out > 0).to(dy.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x3)
+            conv_into(dy, w2.t().contiguous(), None, dx)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w2)
+            db = torch.zeros(Cout, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            _lib.launch("pu3_pointwise_conv_bwd_w_f32", x3, B, N, Cin, Cout, x3.data_ptr(), Cin * N, dy.data_ptr(), Cout * N,
+                        dw.data_ptr(), _lib.ptr(db))
+        return dx, dw, db, None
+
+
 def pointwise_conv(x, weight, bias, relu=False):
     """1x1 Conv1d/Conv2d (+ReLU) on (B,C,N) or (B,C,N,1) input: layers.py:115-204 with kernel size 1."""
     _check_f32_cuda(x, "pointwise_conv")
     if _needs_grad(x, weight, bias):
-        y = conv1x1_autograd(x, weight, bias)
-        return F.relu(y) if relu else y
+        shape = x.shape
+        x3 = x.reshape(shape[0], shape[1], -1).contiguous()
+        w2 = weight.reshape(weight.shape[0], weight.shape[1])
+        y = PointwiseConvFunction.apply(x3, w2, bias, bool(relu))
+        return y.reshape(shape[0], weight.shape[0], *shape[2:])
     shape = x.shape
     x3 = x.reshape(shape[0], shape[1], -1).contiguous()
     out = torch.empty(shape[0], weight.shape[0], x3.shape[2], dtype=torch.float32, device=x.device)

@@ -240,6 +240,15 @@ int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float 
                           float *out_xyz, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
 int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
 
+/*
+ * Weight / bias gradient of the 1x1 convolution: dw[co,ci] += sum_{b,p} dy[b,co,p] x[b,ci,p], db[co] += sum dy
+ * (db may be NULL), accumulated into caller-zeroed buffers with fp32 atomics.  x, dy: channel slices like the
+ * forward (pointer + batch stride, channel stride n).  The input gradient is pu3_pointwise_conv_f32 applied to dy
+ * with the transposed weight.
+ */
+int pu3_pointwise_conv_bwd_w_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *dy,
+                                 long long dy_bstride, float *dw, float *db, pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,3 +56,24 @@ def test_model_optimize_matches_oracle_step(pu3, cuda):
         # Adam's first steps are +-lr per weight: compare the UPDATE, which is what the gradients drive
         du = got[name].detach().cpu() - P0[name]; dr = Pr[name].detach() - P0[name]
         assert_close_frac(du, dr, rtol=5e-2, atol=2e-5, frac=0.97, what=name)
+
+
+@pytest.mark.parametrize("b,n,cin,cout,relu", [(3, 312, 84, 24, True), (2, 624, 265, 128, True), (4, 624, 64, 3, False),
+                                               (2, 100, 3, 24, False), (1, 4099, 130, 70, True)])
+def test_pointwise_conv_backward_kernels(pu3, cuda, b, n, cin, cout, relu):
+    """dX, dW, db of the native 1x1 convolution against float64 autograd."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x0 = torch.randn(b, cin, n, generator=g); w0 = torch.randn(cout, cin, 1, generator=g) * 0.2
+    b0 = torch.randn(cout, generator=g); gy = torch.randn(b, cout, n, generator=g)
+    xr, wr, br = (t.clone().double().requires_grad_() for t in (x0, w0, b0))
+    yr = torch.nn.functional.conv1d(xr, wr, br)
+    yr = torch.relu(yr) if relu else yr
+    (yr * gy.double()).sum().backward()
+    xc, wc, bc = (t.clone().to(cuda).requires_grad_() for t in (x0, w0, b0))
+    y = pu3.fused.pointwise_conv(xc, wc, bc, relu=relu)
+    (y * gy.to(cuda)).sum().backward()
+    assert_close_frac(y, yr, rtol=1e-5, atol=1e-5, what="forward")
+    assert_close_frac(xc.grad, xr.grad, rtol=1e-5, atol=1e-5, what="dX")
+    scale = float(wr.grad.abs().max())
+    assert_close_frac(wc.grad, wr.grad, rtol=1e-4, atol=1e-5 * scale, what="dW")
+    assert_close_frac(bc.grad, br.grad, rtol=1e-4, atol=1e-5 * float(br.grad.abs().max()), what="db")

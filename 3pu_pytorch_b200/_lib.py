@@ -40,6 +40,8 @@ SIGNATURES = {
     "pu3_to_point_major_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
     "pu3_clip_adam_f32": (_c_int, [_c_ll] + [_c_void_p] * 4 + [_c_float] * 6 + [_c_int, _c_void_p]),
     "pu3_pointwise_conv_bwd_w_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p]),
+    "pu3_edgeconv_bwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
+                             [_c_void_p, _c_ll, _c_void_p, _c_ll] + [_c_void_p] * 6 + [_c_void_p]),
     "pu3_level_workspace": (_c_size_t, [_c_int] * 8),
     "pu3_level_forward_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),

@@ -474,3 +474,262 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     PU3_LAUNCH_CHECK("edgeconv_kernel");
     return PU3_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// DenseEdgeConv backward (k <= 32, cloud in shared memory).  What autograd derives for layers.py:44-64 in the
+// reference's train step, as one kernel: per point the forward activations of its k edges are recomputed
+// (cheaper than storing (B,36,N,K)), the max() routes each output channel's gradient to the FIRST edge that
+// attains the maximum (torch.max semantics), the chain rule runs back through the three 1x1 layers, and
+//   dx  (B,24,N)  += neighbour / centre contributions (shared-memory accumulation per cloud, one atomic flush)
+//   dW*, db*       += outer products, kept in registers per lane across all points of the warp
+// One warp per point, one lane per edge.
+// ------------------------------------------------------------------------------------------------------
+namespace pu3 {
+
+constexpr int EB_ST = 85;    // staged floats per edge (84 used, odd stride: conflict-free rows): d[24] | h0[12] | h1[12] | g0[12] | g1[12] | g2[12]
+constexpr int EB_ACC = 1620; // weight + bias gradient entries
+constexpr int EB_DXS = 25;   // row stride of the dx accumulator
+
+__device__ __forceinline__ float dot12(const float *row, const float (&g)[EC_G]) {
+    const float4 a = *reinterpret_cast<const float4 *>(row), b = *reinterpret_cast<const float4 *>(row + 4),
+                 c = *reinterpret_cast<const float4 *>(row + 8);
+    float s = a.x * g[0];
+    s = __fmaf_rn(a.y, g[1], s); s = __fmaf_rn(a.z, g[2], s); s = __fmaf_rn(a.w, g[3], s);
+    s = __fmaf_rn(b.x, g[4], s); s = __fmaf_rn(b.y, g[5], s); s = __fmaf_rn(b.z, g[6], s); s = __fmaf_rn(b.w, g[7], s);
+    s = __fmaf_rn(c.x, g[8], s); s = __fmaf_rn(c.y, g[9], s); s = __fmaf_rn(c.z, g[10], s); s = __fmaf_rn(c.w, g[11], s);
+    return s;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+struct EcGrads { float *dw0, *db0, *dw1, *db1, *dw2, *db2; };
+
+__global__ void __launch_bounds__(EC_WARPS * 32, 1)
+edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, long long x_bstride,
+                    const int32_t *__restrict__ idx, int idx_stride, int idx_off, EcWeights W,
+                    const float *__restrict__ dy, long long dy_bstride, float *__restrict__ dx, long long dx_bstride,
+                    EcGrads G) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    EfSmemW &sw = *reinterpret_cast<EfSmemW *>(raw);
+    float *s_a = reinterpret_cast<float *>(raw + sizeof(EfSmemW));   // [EC_WARPS][36]  A0|A1|A2 of the warp's point
+    float *s_dy = s_a + EC_WARPS * 36;                                 // [EC_WARPS][60]
+    float *s_da = s_dy + EC_WARPS * 60;                                // [EC_WARPS][36]  dA0|dA1|dA2
+    float *s_st = s_da + EC_WARPS * 36;                                // [EC_WARPS][32][EB_ST]
+    float *s_acc = s_st + EC_WARPS * 32 * EB_ST;                       // [EC_WARPS][EB_ACC]
+    float *dxs = s_acc + EC_WARPS * EB_ACC;                            // [n][EB_DXS]
+    float *xs = dxs + (size_t)n * EB_DXS;                              // [n][EF_XS]
+
+    const int bi = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *xb = x + bi * x_bstride;
+    const float *dyb = dy + bi * dy_bstride;
+    float *dxb = dx + bi * dx_bstride;
+    const int32_t *ib = idx + (size_t)bi * n * idx_stride;
+
+    for (int t = threadIdx.x; t < EC_C * EC_G; t += blockDim.x) { const int in = t / EC_G, o = t % EC_G; sw.w0b[in][o] = __ldg(W.w0 + o * 48 + 24 + in); }
+    for (int t = threadIdx.x; t < EC_G * EC_G; t += blockDim.x) {
+        const int in = t / EC_G, o = t % EC_G;
+        sw.w1a[in][o] = __ldg(W.w1 + o * 36 + in); sw.w2a[in][o] = __ldg(W.w2 + o * 48 + in); sw.w2b[in][o] = __ldg(W.w2 + o * 48 + 12 + in);
+    }
+    for (int t = threadIdx.x; t < EC_C * 36; t += blockDim.x) {
+        const int in = t / 36, o = t % 36;
+        sw.wp[in][o] = o < 12 ? __ldg(W.w0 + o * 48 + in) : (o < 24 ? __ldg(W.w1 + (o - 12) * 36 + 12 + in) : __ldg(W.w2 + (o - 24) * 48 + 24 + in));
+    }
+    if (threadIdx.x < 36) { const int o = threadIdx.x; sw.bp[o] = o < 12 ? __ldg(W.b0 + o) : (o < 24 ? __ldg(W.b1 + o - 12) : __ldg(W.b2 + o - 24)); }
+    for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) { const int c = t / n, p = t - c * n; xs[p * EF_XS + c] = __ldg(xb + (size_t)c * n + p); }
+    for (int t = threadIdx.x; t < n * EB_DXS; t += blockDim.x) dxs[t] = 0.f;
+    __syncthreads();
+
+    // weight-gradient accumulators: per-warp private rows in shared memory, entry e owned by lane e % 32
+    // layout: [0,288) dW0[:,24:] as (o,c) | [288,432) dW1[:,:12] | [432,576) dW2[:,:12] | [576,720) dW2[:,12:24]
+    //         [720,1584) centre parts (36 x 24: dA (x) x_i) | [1584,1620) biases
+    float *acc = s_acc + (size_t)warp * EB_ACC;
+    for (int e = lane; e < EB_ACC; e += 32) acc[e] = 0.f;
+
+    float *wa = s_a + warp * 36, *wdy = s_dy + warp * 60, *wda = s_da + warp * 36, *st = s_st + (size_t)warp * 32 * EB_ST;
+    float *me = st + lane * EB_ST;
+    const int p_begin = blockIdx.x * pts_per_cta, p_end = min(n, p_begin + pts_per_cta);
+    for (int i = p_begin + warp; i < p_end; i += EC_WARPS) {
+        const float *ci = xs + i * EF_XS;
+        __syncwarp();
+        {   // per-point terms and the incoming gradient of the point's 60 output channels
+            float a0 = sw.bp[lane], a1 = lane < 4 ? sw.bp[32 + lane] : 0.f;
+#pragma unroll
+            for (int ch = 0; ch < EC_C; ++ch) {
+                const float cv = ci[ch];
+                a0 = __fmaf_rn(sw.wp[ch][lane], cv, a0);
+                if (lane < 4) a1 = __fmaf_rn(sw.wp[ch][32 + lane], cv, a1);
+            }
+            wa[lane] = a0;
+            if (lane < 4) wa[32 + lane] = a1;
+            wdy[lane] = __ldg(dyb + (size_t)lane * n + i);
+            if (lane < 28) wdy[32 + lane] = __ldg(dyb + (size_t)(32 + lane) * n + i);
+        }
+        __syncwarp();
+        // ---- forward recompute of this lane's edge; d, h0, h1 go straight to the staging row ------------------------
+        const bool live = lane < k;
+        const int j = live ? __ldg(ib + (size_t)i * idx_stride + idx_off + lane) : i;
+        const float *nj = xs + j * EF_XS;
+        float h0[EC_G], h1[EC_G], h2[EC_G];
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) h0[o] = wa[o];
+#pragma unroll
+        for (int c = 0; c < EC_C; ++c) {
+            const float dc = nj[c] - ci[c];
+            me[c] = live ? dc : 0.f;
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) h0[o] = __fmaf_rn(sw.w0b[c][o], dc, h0[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) { h0[o] = fmaxf(h0[o], 0.f); h1[o] = wa[12 + o]; h2[o] = wa[24 + o]; }
+#pragma unroll
+        for (int in = 0; in < EC_G; ++in)
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) { h1[o] = __fmaf_rn(sw.w1a[in][o], h0[in], h1[o]); h2[o] = __fmaf_rn(sw.w2b[in][o], h0[in], h2[o]); }
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) h1[o] = fmaxf(h1[o], 0.f);
+#pragma unroll
+        for (int in = 0; in < EC_G; ++in)
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) h2[o] = __fmaf_rn(sw.w2a[in][o], h1[in], h2[o]);
+        // ---- max() routing: the first edge attaining the maximum takes the channel's gradient -------------------
+        float g2[EC_G], g1[EC_G], g0[EC_G];
+        unsigned pos0 = 0, pos1 = 0;      // ReLU masks of h0 / h1
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) {
+            me[24 + o] = live ? h0[o] : 0.f;
+            me[36 + o] = live ? h1[o] : 0.f;
+            pos0 |= (h0[o] > 0.f ? 1u : 0u) << o;
+            pos1 |= (h1[o] > 0.f ? 1u : 0u) << o;
+            float v2 = live ? h2[o] : -INFINITY, v1 = live ? h1[o] : -INFINITY, v0 = live ? h0[o] : -INFINITY;
+            float m2 = v2, m1 = v1, m0 = v0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, s));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, s));
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, s));
+            }
+            const int w2 = __ffs(__ballot_sync(0xffffffffu, v2 == m2)) - 1;
+            const int w1 = __ffs(__ballot_sync(0xffffffffu, v1 == m1)) - 1;
+            const int w0 = __ffs(__ballot_sync(0xffffffffu, v0 == m0)) - 1;
+            g2[o] = lane == w2 ? wdy[o] : 0.f;          // y = [h2 | h1 | h0 | x]
+            g1[o] = lane == w1 ? wdy[12 + o] : 0.f;
+            g0[o] = lane == w0 ? wdy[24 + o] : 0.f;
+        }
+        // ---- chain rule --------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int in = 0; in < EC_G; ++in) g1[in] = (pos1 >> in) & 1u ? g1[in] + dot12(&sw.w2a[in][0], g2) : 0.f;
+#pragma unroll
+        for (int in = 0; in < EC_G; ++in)
+            g0[in] = (pos0 >> in) & 1u ? g0[in] + dot12(&sw.w1a[in][0], g1) + dot12(&sw.w2b[in][0], g2) : 0.f;
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) { me[48 + o] = g0[o]; me[60 + o] = g1[o]; me[72 + o] = g2[o]; }
+        float gsum = 0.f;   // lane c < 24 ends up with sum_k gd[k][c]
+#pragma unroll
+        for (int c = 0; c < EC_C; ++c) {
+            const float gd = live ? dot12(&sw.w0b[c][0], g0) : 0.f;
+            if (live) atomicAdd(&dxs[j * EB_DXS + c], gd);                  // d(n - c)/dn
+            const float tot = warp_sum(gd);
+            if (lane == c) gsum = tot;
+        }
+        // dA0 = sum_k g0, dA1 = sum_k g1, dA2 = sum_k g2 (= the incoming gradient of h2)
+#pragma unroll
+        for (int o = 0; o < EC_G; ++o) {
+            const float s0 = warp_sum(g0[o]), s1 = warp_sum(g1[o]);
+            if (lane == 0) { wda[o] = s0; wda[12 + o] = s1; wda[24 + o] = wdy[o]; }
+        }
+        __syncwarp();
+        // centre: dx_i += dy_x - sum_k gd + Wp^T dA
+        if (lane < EC_C) {
+            float v = wdy[36 + lane] - gsum;
+#pragma unroll
+            for (int o = 0; o < 36; ++o) v = __fmaf_rn(sw.wp[lane][o], wda[o], v);
+            atomicAdd(&dxs[i * EB_DXS + lane], v);
+        }
+        // weight gradients: entry e = lane + 32 q, summed over the 32 staged edges
+        for (int q = 0; q < 9; ++q) {           // dW0[:, 24:]  entry (o, c) = e / 24, e % 24
+            const int e = lane + 32 * q, o = e / 24, c = e % 24;
+            float s0 = 0.f;
+            for (int kk = 0; kk < 32; ++kk) s0 = __fmaf_rn(st[kk * EB_ST + 48 + o], st[kk * EB_ST + c], s0);
+            acc[e] += s0;
+        }
+        for (int q = 0; q < 5; ++q) {           // 12 x 12 matrices: entry (o, in) = e / 12, e % 12
+            const int e = lane + 32 * q;
+            if (e < 144) {
+                const int o = e / 12, in = e % 12;
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                for (int kk = 0; kk < 32; ++kk) {
+                    const float *r = st + kk * EB_ST;
+                    s1 = __fmaf_rn(r[60 + o], r[24 + in], s1);    // dW1[:, :12]   = g1 (x) h0
+                    s2 = __fmaf_rn(r[72 + o], r[36 + in], s2);    // dW2[:, :12]   = g2 (x) h1
+                    s3 = __fmaf_rn(r[72 + o], r[24 + in], s3);    // dW2[:, 12:24] = g2 (x) h0
+                }
+                acc[288 + e] += s1; acc[432 + e] += s2; acc[576 + e] += s3;
+            }
+        }
+        for (int q = 0; q < 27; ++q) {          // centre parts: entry (o, c) of the 36 x 24 matrix dA (x) x_i
+            const int e = lane + 32 * q, o = e / 24, c = e % 24;
+            acc[720 + e] = __fmaf_rn(wda[o], ci[c], acc[720 + e]);
+        }
+        acc[1584 + lane] += wda[lane];
+        if (lane < 4) acc[1616 + lane] += wda[32 + lane];
+    }
+    __syncwarp();
+    // ---- flush the warp's accumulators -----------------------------------------------------------------------------
+    for (int e = lane; e < 288; e += 32) { const int o = e / 24, c = e % 24; atomicAdd(G.dw0 + o * 48 + 24 + c, acc[e]); }
+    for (int e = lane; e < 144; e += 32) {
+        const int o = e / 12, in = e % 12;
+        atomicAdd(G.dw1 + o * 36 + in, acc[288 + e]); atomicAdd(G.dw2 + o * 48 + in, acc[432 + e]); atomicAdd(G.dw2 + o * 48 + 12 + in, acc[576 + e]);
+    }
+    for (int e = lane; e < 864; e += 32) {
+        const int o = e / 24, c = e % 24;
+        float *dst = o < 12 ? G.dw0 + o * 48 + c : (o < 24 ? G.dw1 + (o - 12) * 36 + 12 + c : G.dw2 + (o - 24) * 48 + 24 + c);
+        atomicAdd(dst, acc[720 + e]);
+    }
+    for (int o = lane; o < 36; o += 32) atomicAdd(o < 12 ? G.db0 + o : (o < 24 ? G.db1 + o - 12 : G.db2 + o - 24), acc[1584 + o]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) {
+        const int c = t / n, p = t - c * n;
+        const float v = dxs[p * EB_DXS + c];
+        if (v != 0.f) atomicAdd(dxb + (size_t)c * n + p, v);
+    }
+}
+
+}  // namespace pu3
+
+extern "C" int pu3_edgeconv_bwd_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
+                                    int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
+                                    const float *b1, const float *w2, const float *b2, const float *dy,
+                                    long long dy_bstride, float *dx, long long dx_bstride, float *dw0, float *db0,
+                                    float *dw1, float *db1, float *dw2, float *db2, pu3_stream_t stream) {
+    using namespace pu3;
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && k > 0, "edgeconv_bwd: bad size b=%d n=%d k=%d", b, n, k);
+    if (b == 0 || n == 0) return PU3_OK;
+    PU3_ARG_CHECK(b <= 65535 && k <= 32, "edgeconv_bwd: b=%d (max 65535), k=%d (max 32)", b, k);
+    PU3_ARG_CHECK(x && idx && w0 && b0 && w1 && b1 && w2 && b2 && dy && dx && dw0 && db0 && dw1 && db1 && dw2 && db2,
+                  "edgeconv_bwd: null pointer");
+    PU3_ARG_CHECK(idx_stride >= idx_off + k && idx_off >= 0, "edgeconv_bwd: idx_stride too small");
+    const size_t smem = sizeof(EfSmemW) + (size_t)(EC_WARPS * (36 + 60 + 36) + EC_WARPS * 32 * EB_ST + EC_WARPS * EB_ACC + (size_t)n * (EB_DXS + EF_XS)) * sizeof(float);
+    if (smem > (size_t)device_info().smem_optin) {
+        set_error("edgeconv_bwd: n=%d does not fit shared memory (%zu bytes)", n, smem);
+        return PU3_E_UNSUPPORTED;
+    }
+    const int sms = device_info().sm_count;
+    int pts = n;
+    if (b < sms) {
+        const int split = (sms + b - 1) / b;
+        pts = (n + split - 1) / split;
+        pts = ((pts + EC_WARPS - 1) / EC_WARPS) * EC_WARPS;
+    }
+    EcWeights W{w0, b0, w1, b1, w2, b2};
+    EcGrads G{dw0, db0, dw1, db1, dw2, db2};
+    int st = cuda_status(cudaFuncSetAttribute(edgeconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "edgeconv_bwd: smem attr");
+    if (st) return st;
+    edgeconv_bwd_kernel<<<dim3((n + pts - 1) / pts, b), EC_WARPS * 32, smem, as_stream(stream)>>>(
+        n, k, pts, x, x_bstride, idx, idx_stride, idx_off, W, dy, dy_bstride, dx, dx_bstride, G);
+    PU3_LAUNCH_CHECK("edgeconv_bwd_kernel");
+    return PU3_OK;
+}

@@ -12,6 +12,9 @@ from . import _lib
 from .operations import group_knn, _knn_raw
 
 
+native_edgeconv_backward = True   # False: differentiate DenseEdgeConv through the operator composition (tests)
+
+
 def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -122,10 +125,52 @@ def _edgeconv_supported(x, weights):
             and tuple(weights[1].shape[:2]) == (12, 36) and tuple(weights[2].shape[:2]) == (12, 48))
 
 
+class DenseEdgeConvFunction(torch.autograd.Function):
+    """Fused DenseEdgeConv with hand-written forward and backward kernels (csrc/edgeconv.cu); the neighbour
+    indices are an input (they carry no gradient, layers.py:33-35)."""
+
+    @staticmethod
+    def forward(ctx, x, idx32, k, w0, b0, w1, b1, w2, b2):
+        B, C, N = x.shape
+        out = torch.empty(B, 60, N, dtype=torch.float32, device=x.device)
+        edgeconv_into(x, idx32, 0, k, [w0, w1, w2], [b0, b1, b2], out)
+        ctx.k = k
+        ctx.save_for_backward(x, idx32, w0, b0, w1, b1, w2, b2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, idx32, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        B, C, N = x.shape
+        dy = dy.contiguous()
+        dx = torch.zeros_like(x)
+        w = [t.reshape(t.shape[0], t.shape[1]).contiguous() for t in (w0, w1, w2)]
+        dw = [torch.zeros_like(t) for t in w]
+        db = [torch.zeros_like(t) for t in (b0, b1, b2)]
+        _lib.launch("pu3_edgeconv_bwd_f32", x, B, N, ctx.k, x.data_ptr(), C * N, idx32.data_ptr(), idx32.shape[2], 0,
+                    w[0].data_ptr(), b0.data_ptr(), w[1].data_ptr(), b1.data_ptr(), w[2].data_ptr(), b2.data_ptr(),
+                    dy.data_ptr(), 60 * N, dx.data_ptr(), C * N, dw[0].data_ptr(), db[0].data_ptr(), dw[1].data_ptr(),
+                    db[1].data_ptr(), dw[2].data_ptr(), db[2].data_ptr())
+        return (dx, None, None, dw[0].view_as(w0), db[0], dw[1].view_as(w1), db[1], dw[2].view_as(w2), db[2])
+
+
 def dense_edge_conv(x, weights, biases, k, idx=None, max_group=None):
     """DenseEdgeConv.forward (layers.py:44-64).  x (B,C,N) -> (y (B,C+n*growth,N), idx (B,N,k) int64)."""
     _check_f32_cuda(x, "DenseEdgeConv")
     n_layers = len(weights)
+    if _needs_grad(x, *weights, *biases) and _edgeconv_supported(x, weights) and k <= 32 and x.shape[2] <= 1500 \
+            and native_edgeconv_backward:
+        # training: fused forward + hand-written backward
+        xc = x.contiguous()
+        if idx is None:
+            with torch.no_grad():
+                _, idx_all, _ = _knn_raw(k + 1, xc.detach(), xc.detach(), True, max_group, want_knn=False, want_dist=False,
+                                         idx_dtype=torch.int32)
+            idx32 = idx_all[:, :, 1:].contiguous()
+        else:
+            idx32 = idx.to(torch.int32).contiguous()
+        y = DenseEdgeConvFunction.apply(xc, idx32, k, weights[0], biases[0], weights[1], biases[1], weights[2], biases[2])
+        return y, idx32.long()
     if _needs_grad(x, *weights, *biases) or not _edgeconv_supported(x, weights):
         # differentiable composition (same operators as the reference, group_knn on our kernels)
         if idx is None:

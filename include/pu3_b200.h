@@ -249,6 +249,18 @@ int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
 int pu3_pointwise_conv_bwd_w_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *dy,
                                  long long dy_bstride, float *dw, float *db, pu3_stream_t stream);
 
+/*
+ * DenseEdgeConv backward (autograd of network/layers.py:44-64 in the reference's train step), k <= 32:
+ * given x, the neighbour indices and the weights of the forward call and dy (b,60,n), accumulates into the
+ * caller-zeroed dx (b,24,n) and dw0 (12,48), db0, dw1 (12,36), db1, dw2 (12,48), db2.  The forward activations
+ * are recomputed per edge; max() routes a channel's gradient to the first edge attaining the maximum.
+ */
+int pu3_edgeconv_bwd_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx, int idx_stride,
+                         int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
+                         const float *w2, const float *b2, const float *dy, long long dy_bstride, float *dx,
+                         long long dx_bstride, float *dw0, float *db0, float *dw1, float *db1, float *dw2, float *db2,
+                         pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,3 +77,37 @@ def test_pointwise_conv_backward_kernels(pu3, cuda, b, n, cin, cout, relu):
     scale = float(wr.grad.abs().max())
     assert_close_frac(wc.grad, wr.grad, rtol=1e-4, atol=1e-5 * scale, what="dW")
     assert_close_frac(bc.grad, br.grad, rtol=1e-4, atol=1e-5 * float(br.grad.abs().max()), what="db")
+
+
+@pytest.mark.parametrize("b,n,k", [(2, 120, 16), (3, 312, 32), (1, 40, 5)])
+def test_dense_edge_conv_backward_kernel(pu3, cuda, b, n, k):
+    """Native DenseEdgeConv backward against autograd over the operator composition (float64 oracle graph)."""
+    params = ref_net.make_params(1, seed=5)
+    pre = "levels.level_1.layer3"
+    g = torch.Generator().manual_seed(n + k)
+    x0 = torch.randn(b, 24, n, generator=g)
+    gy = torch.randn(b, 60, n, generator=g)
+    # oracle graph in float64 with the neighbour indices of the fp32 oracle (they carry no gradient)
+    _, idx = ref_net.dense_edge_conv(params, pre, x0, k, 3)
+    xr = x0.clone().double().requires_grad_()
+    Pr = {kk: v.clone().double().requires_grad_() for kk, v in params.items() if kk.startswith(pre)}
+    nb = torch.gather(xr.unsqueeze(2).expand(-1, -1, n, -1), 3, idx.unsqueeze(1).expand(-1, 24, -1, -1))
+    ce = xr.unsqueeze(-1).expand_as(nb)
+    y = torch.cat([ce, nb - ce], dim=1)
+    for i in range(3):
+        h = torch.nn.functional.conv2d(y, Pr[f"{pre}.mlps.{i}.weight"], Pr[f"{pre}.mlps.{i}.bias"])
+        y = torch.cat([torch.relu(h) if i < 2 else h, ce if i == 0 else y], dim=1) if i == 0 else torch.cat([torch.relu(h) if i < 2 else h, y], dim=1)
+    yr = y.max(dim=-1)[0]
+    (yr * gy.double()).sum().backward()
+    # native
+    xc = x0.clone().to(cuda).requires_grad_()
+    ws = [params[f"{pre}.mlps.{i}.weight"].clone().to(cuda).requires_grad_() for i in range(3)]
+    bs = [params[f"{pre}.mlps.{i}.bias"].clone().to(cuda).requires_grad_() for i in range(3)]
+    yc, _ = pu3.fused.dense_edge_conv(xc, ws, bs, k, idx=idx.to(cuda))
+    (yc * gy.to(cuda)).sum().backward()
+    assert_close_frac(yc, yr, rtol=1e-5, atol=2e-6, what="forward")
+    assert_close_frac(xc.grad, xr.grad, rtol=1e-4, atol=1e-5, frac=0.999, what="dx")
+    for i in range(3):
+        wr, br = Pr[f"{pre}.mlps.{i}.weight"].grad, Pr[f"{pre}.mlps.{i}.bias"].grad
+        assert_close_frac(ws[i].grad, wr, rtol=1e-4, atol=1e-5 * float(wr.abs().max()), frac=0.999, what=f"dW{i}")
+        assert_close_frac(bs[i].grad, br, rtol=1e-4, atol=1e-5 * float(br.abs().max()), frac=0.999, what=f"db{i}")

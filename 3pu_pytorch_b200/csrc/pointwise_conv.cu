@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TX * TY) pointwise_conv_fast_kernel(PwArgs a) 
     const long long cols = (long long)a.b * a.n;
     const long long col0 = (long long)blockIdx.x * TN;
     const int co0 = blockIdx.y * TM;
-    const bool w_vec = (a.cin % 4) == 0;
+    const bool w_vec = (a.cin % 4) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;   // parameter views may be unaligned
 
     f32x2 acc[RM][4];                                    // [row][column pair]: pairs (0,1)(2,3) | (4,5)(6,7)
 #pragma unroll

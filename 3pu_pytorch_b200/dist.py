@@ -68,18 +68,20 @@ class FlatAdam:
         dev, dt = self.params[0].device, self.params[0].dtype
         if dt != torch.float32:
             raise ValueError("FlatAdam expects float32 parameters")
-        n = sum(p.numel() for p in self.params)
-        self.flat_param = torch.empty(n, dtype=dt, device=dev)
+        ALIGN = 32                                   # every parameter starts on a 128-byte boundary of the flat buffer
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.flat_param = torch.zeros(n, dtype=dt, device=dev)
         self.flat_grad = torch.zeros(n, dtype=dt, device=dev)
         self.exp_avg = torch.zeros(n, dtype=dt, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=dt, device=dev)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat_param[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + k].view_as(p)
             p.grad = self.flat_grad[off:off + k].view_as(p)
-            off += k
         self.lr, self.betas, self.eps, self.clip_value = lr, betas, eps, clip_value
         self.step_count = 0
 

@@ -218,6 +218,28 @@ def run_product(args):
                  for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
 
     cpu = cpu_baseline(params, n_patches=args.cpu_patches) if not args.no_cpu else None
+
+    # ---- supplementary: BASELINE config 3, one train step (B=32, ratio 16: 4 zoom levels, Chamfer, backward,
+    # clip + Adam; the reference's log2 weight is 0 at the full ratio -- SURVEY a-14 -- so weight 1 is used) --------
+    train = None
+    if not args.no_train:
+        tnet = pu3.Net(max_up_ratio=UP_RATIO, step_ratio=2, knn=KNN, growth_rate=12, dense_n=3, fm_knn=5)
+        tnet.load_state_dict(params, strict=True)
+        model = pu3.Model(tnet.to(dev), "train", lr_init=5e-4, weight_full_ratio=1.0)
+        g = torch.Generator().manual_seed(7)
+        tx = torch.rand(B_PATCHES, 3, NUM_POINT, generator=g).to(dev)
+        tgt = torch.rand(B_PATCHES, 3, NUM_POINT * UP_RATIO, generator=g).to(dev)
+        for _ in range(3):
+            model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
+        e1.record(); torch.cuda.synchronize()
+        tms = e0.elapsed_time(e1) / 5
+        train = {"workload": "train_step_B32_N312_x16 (zoom mode, Chamfer, backward, clip+Adam)", "ms_per_step": round(tms, 3),
+                 "patches_per_s": round(B_PATCHES / (tms / 1e3), 1)}
     line = {
         "metric": "patches/sec (B=32, N=312, 16x)", "value": round(value, 2), "unit": "patches/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 3),
@@ -232,6 +254,7 @@ def run_product(args):
         "roofline": roofline,
         "kernel_breakdown": breakdown,
         "cpu_baseline": cpu,
+        "train_step": train,
     }
     print(json.dumps(line))
     if world > 1:
@@ -299,6 +322,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--cpu-patches", type=int, default=2, help="patches in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the supplementary train-step timing")
     ap.add_argument("--eval-groups", type=int, default=None, help="request groups run concurrently on separate streams (default: auto)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -111,3 +111,15 @@ def test_dense_edge_conv_backward_kernel(pu3, cuda, b, n, k):
         wr, br = Pr[f"{pre}.mlps.{i}.weight"].grad, Pr[f"{pre}.mlps.{i}.bias"].grad
         assert_close_frac(ws[i].grad, wr, rtol=1e-4, atol=1e-5 * float(wr.abs().max()), frac=0.999, what=f"dW{i}")
         assert_close_frac(bs[i].grad, br, rtol=1e-4, atol=1e-5 * float(br.abs().max()), frac=0.999, what=f"db{i}")
+
+
+def test_pointwise_conv_with_unaligned_weight_view(pu3, cuda):
+    """Parameters that are views into a flat optimizer buffer need not be 16-byte aligned."""
+    flat = torch.randn(4 + 24 * 84 + 24, device=cuda)
+    w = flat[3:3 + 24 * 84].view(24, 84)          # 12-byte offset
+    b = flat[3 + 24 * 84:3 + 24 * 84 + 24]
+    x = torch.randn(2, 84, 312, device=cuda)
+    out = torch.empty(2, 24, 312, device=cuda)
+    pu3.fused.conv_into(x, w, b, out, relu=True)
+    want = torch.relu(torch.nn.functional.conv1d(x.double(), w.double().unsqueeze(-1), b.double()))
+    assert_close_frac(out, want, rtol=1e-5, atol=1e-5)

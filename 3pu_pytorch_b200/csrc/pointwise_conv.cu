@@ -350,7 +350,7 @@ namespace pu3 {
 
 constexpr int BW_T = 64;       // output tile (co x ci)
 constexpr int BW_KC = 16;      // columns per shared-memory chunk
-constexpr int BW_COLS = 4096;  // columns per CTA (split-K granularity)
+constexpr int BW_COLS = 512;   // columns per CTA (split-K granularity): ~20 column chunks x (cout/64 x cin/64) tiles even at B=32, N=312
 
 __global__ void __launch_bounds__(256) pointwise_conv_bwd_w_kernel(int b, int n, int cin, int cout,
                                                                   const float *__restrict__ x, long long x_bstride,

@@ -309,6 +309,8 @@ using namespace pu3;
 // Test/tuning hook: force the cluster size (0 = heuristic).  Not part of the public header.
 static int g_fps_force_cluster = 0;
 static int g_fps_force_threads = 0;
+static int g_fps_sm_budget = 0;   // SMs FPS may spread over (0 = all): leaves room for kernels of a concurrent stream
+extern "C" void pu3_fps_set_sm_budget(int n) { g_fps_sm_budget = n; }
 extern "C" void pu3_fps_set_cluster(int s) { g_fps_force_cluster = s; }
 extern "C" void pu3_fps_set_threads(int t) { g_fps_force_threads = t; }   // tuning hook (profiles/tune_fps.py)
 
@@ -344,7 +346,8 @@ static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t
     // Two CTAs of DIFFERENT clouds per SM let one cloud's serial phase (reduction + exchange, issue slots idle)
     // overlap the other's point loop, so the cluster may be twice as wide as "one CTA per SM" allows, provided
     // two CTAs fit an SM (threads <= 512 and 2 * threads * registers <= 64 K).
-    int s_cap = floor_pow2((2 * sms) / b > 0 ? (2 * sms) / b : 1);
+    const int sm_budget = g_fps_sm_budget > 0 ? (g_fps_sm_budget < sms ? g_fps_sm_budget : sms) : sms;
+    int s_cap = floor_pow2((2 * sm_budget) / b > 0 ? (2 * sm_budget) / b : 1);
     if (s_cap > 8) s_cap = 8;
     int threads = 0, S = 1, ppt = 0;
     long long best_cost = -1;
@@ -361,7 +364,7 @@ static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t
     };
     for (int cs = 1; cs <= s_cap; cs *= 2) {
         if (g_fps_force_cluster > 0 && cs != g_fps_force_cluster) continue;
-        const bool two_per_sm = (long long)b * cs > sms;
+        const bool two_per_sm = (long long)b * cs > sm_budget;
         for (int th : kThreads) {
             if (g_fps_force_threads > 0 && th != g_fps_force_threads) continue;
             const long long gt = (long long)cs * th;

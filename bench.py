@@ -134,6 +134,9 @@ def run_product(args):
     net.load_state_dict(params, strict=True)
     net = net.to(dev).eval()
     net.eval_groups = args.eval_groups
+    if args.fps_sm_budget:
+        import ctypes
+        ctypes.CDLL(pu3._lib.LIB_PATH).pu3_fps_set_sm_budget(int(args.fps_sm_budget))
 
     host_x = make_inputs(rank).pin_memory()
     dev_x = host_x.to(dev)
@@ -322,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--cpu-patches", type=int, default=2, help="patches in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--fps-sm-budget", type=int, default=0, help="tuning: SMs the FPS kernels may spread over")
     ap.add_argument("--no-train", action="store_true", help="skip the supplementary train-step timing")
     ap.add_argument("--eval-groups", type=int, default=None, help="request groups run concurrently on separate streams (default: auto)")
     args = ap.parse_args()

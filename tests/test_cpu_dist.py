@@ -39,8 +39,9 @@ def _worker(rank, world, port, q):
         model(x[l:h]).square().mean().backward()
         scale = opt.reduce_gradients()
         ref(x).square().mean().backward()
-        want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
-        out["grad_err"] = float((opt.flat_grad * scale - want).abs().max())
+        # segments of the flat buffer are padded to 128 bytes: compare through the per-parameter views
+        out["grad_err"] = max(float((p.grad * scale - r.grad).abs().max())
+                              for p, r in zip(model.parameters(), ref.parameters()))
         out["views"] = bool(all(p.grad.data_ptr() >= opt.flat_grad.data_ptr() for p in model.parameters()))
         try:
             opt.step()
@@ -59,7 +60,7 @@ def test_world_size_2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=180) for _ in range(world))
+    results = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -1,0 +1,549 @@
+// Tensor-core path of the 1x1 convolutions of the expansion head (network/upsampler.py:349-372, the one true
+// dense contraction of the hot path: 265 -> 128 -> 128 -> 64 -> 3 over every up-sampled point).
+//
+//     Y[b, :, p] = act(W . X[b, :, p] + bias)            X (b, cin, n) channel-major fp32, W (cout, cin) fp32
+//
+// Blackwell-native design (sm_100a only):
+//   * 3xTF32 on tcgen05: every fp32 operand is split into hi = tf32(v) and lo = v - hi, and the product is
+//     accumulated as hi.hi + lo.hi + hi.lo in the fp32 TMEM accumulator.  That keeps the result inside the
+//     path's 1e-5 relative tolerance (a plain TF32 product is ~5e-4) at 3 tensor-core
+//     passes, an order of magnitude above the 72 TFLOP/s FFMA roof of the SGEMM it replaces.
+//   * D (points x cout) = A (points x cin) . B (cout x cin)^T with UMMA M = 128 points, N = cout, K = 8 per
+//     instruction.  A is MN-major: a TMA box of 32 points x 32 channels with the "128-byte swizzle, 32-byte
+//     atoms" mode (the one MN-major layout tf32 accepts) lands exactly as eight canonical 4-channel swizzle
+//     atoms (512 B each), so channel-major activations need no transpose.
+//     B is K-major with the 128-byte swizzle, pre-split and pre-swizzled once per call by a tiny kernel into
+//     [k-block][hi|lo][cout x 128 B] and brought in by one bulk copy per stage.
+//   * warp-specialised persistent CTA, one per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+//     warps 2-5 = converters (raw -> hi in place, lo beside it, then fence.proxy.async), warps 6-9 = epilogue
+//     (tcgen05.ld, bias / ReLU, fused variants, coalesced stores: lane = point).  Two 128-point sub-tiles share
+//     one weight stage; accumulators are double buffered in TMEM (2 x 2 x cout columns) so the epilogue of tile
+//     i overlaps the MMAs of tile i+1.
+//   * fused epilogues: (1) the feature-expansion layer writes both replicas relu(acc + b + w_code*code[j]) as
+//     one 8-byte store per point, so the (B,265,N*r) tensor and the separate "pre" tensor never exist;
+//     (2) the last two layers: relu(W3 h + b3) stays in registers and the 64 -> 3 projection + residual is
+//     finished per point, so the 64-channel tensor is never written.
+#include <cuda.h>
+
+#include "pu3_common.cuh"
+
+namespace pu3 {
+namespace tc {
+
+constexpr int KB = 32;                        // channels per pipeline stage (one 128-byte weight row)
+constexpr int SUBM = 128;                     // points per MMA (UMMA M)
+constexpr int SUB = 2;                        // sub-tiles per CTA tile
+constexpr int STAGES = 2;
+constexpr int A_SUB_BYTES = SUBM * KB * 4;    // 16 KB: 4 TMA boxes of 32 points x 32 channels
+constexpr int NUM_THREADS = 320;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
+
+enum Mode { MODE_PLAIN = 0, MODE_EXPAND = 1, MODE_PROJECT = 2 };
+
+struct Args {
+    int b, n, cin, cout;
+    const unsigned char *wsplit;
+    const float *bias;
+    float *y; long long y_bstride;
+    int relu;
+    // MODE_EXPAND
+    int r; const float *wfull; int w_stride, code_col; const float *code;
+    // MODE_PROJECT
+    const float *w4, *b4; int cout4; const float *res; long long res_bstride; int res_n, res_div;
+    int variant;
+    float *dbg;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol error traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && (spins & 255u) == 255u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;   // disable-output-lane mask: none
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
+// version 1 (Blackwell), layout type 2 = 128-byte swizzle of 16-byte chunks (K-major weights), 1 = 128-byte
+// swizzle of 32-byte chunks -- the only layout the tensor core accepts for MN-major tf32 operands
+// (cutlass sm100_common.inl:92; profiles/microbench/umma_probe.cu shows type 2 silently yields zeros).
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_32B = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+template <int NC>
+struct Cfg {
+    static constexpr int B_HALF = NC * 128;                            // one weight tile (hi or lo): NC rows of 32 floats
+    static constexpr int A_BYTES = SUB * A_SUB_BYTES;                  // raw / hi activations of a stage
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_HALF;       // [A hi][A lo][B hi][B lo]
+    static constexpr int TX_BYTES = A_BYTES + 2 * B_HALF;              // what TMA delivers per stage
+    static constexpr int TMEM_COLS = 2 * SUB * NC;                     // double-buffered accumulators
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for the 1 KB alignment
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A MN-major, B K-major, N, M = 128
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(NC >> 3) << 17) |
+                                      ((uint32_t)(SUBM >> 4) << 24);
+};
+
+// ---- weights: fp32 (cout, cin) -> [k-block][hi | lo][NC rows x 128 B], 16-byte chunks XOR-swizzled by row ----
+__global__ void __launch_bounds__(256) split_weights_kernel(int cin, int cout, int nc, const float *__restrict__ w, int w_stride,
+                                                           unsigned char *__restrict__ out) {
+    const int nkb = (cin + KB - 1) / KB;
+    const int total = nkb * nc * 8;           // one thread per 16-byte chunk
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c = t & 7, row = (t >> 3) % nc, kb = (t >> 3) / nc;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = kb * KB + c * 4 + i;
+            const float v = (row < cout && ch < cin) ? __ldg(w + (size_t)row * w_stride + ch) : 0.f;
+            hi[i] = to_tf32(v);
+            lo[i] = v - hi[i];
+        }
+        unsigned char *tile = out + (size_t)kb * (2 * nc * 128);
+        const int off = row * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<float4 *>(tile + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(tile + nc * 128 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+template <int NC, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+    using C = Cfg<NC>;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[NC], wcode_s[NC], code_s[8], w4_s[MODE == MODE_PROJECT ? 3 * NC : 1], b4_s[4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+
+    const int spc = (a.n + SUBM - 1) / SUBM;                 // sub-tiles per cloud
+    const long long nsub = (long long)a.b * spc;
+    const long long ntiles = (nsub + SUB - 1) / SUB;
+    const int nkb = (a.cin + KB - 1) / KB;
+    const int last_ksteps = ((a.cin - (nkb - 1) * KB) + 7) / 8;
+
+    for (int i = threadIdx.x; i < NC; i += NUM_THREADS) {
+        bias_s[i] = (a.bias && i < a.cout) ? a.bias[i] : 0.f;
+        if (MODE == MODE_EXPAND) wcode_s[i] = i < a.cout ? a.wfull[(size_t)i * a.w_stride + a.code_col] : 0.f;
+    }
+    if (MODE == MODE_EXPAND && threadIdx.x < 8) code_s[threadIdx.x] = (int)threadIdx.x < a.r ? a.code[threadIdx.x] : 0.f;
+    if (MODE == MODE_PROJECT) {
+        for (int i = threadIdx.x; i < 3 * NC; i += NUM_THREADS) {
+            const int c3 = i / NC, co = i % NC;
+            w4_s[i] = (c3 < a.cout4 && co < a.cout) ? a.w4[(size_t)c3 * a.cout + co] : 0.f;
+        }
+        if (threadIdx.x < 4) b4_s[threadIdx.x] = ((int)threadIdx.x < a.cout4 && a.b4) ? a.b4[threadIdx.x] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_conv[s], 4);       // one arrival per converter warp
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tempty[s], 4);     // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer (whole warp waits, one elected lane issues) =====
+        uint32_t stage = 0, phase = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int cb[SUB], cp[SUB];
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const long long sid = t * SUB + s;       // sid >= nsub: cloud index b -> fully out of bounds -> zeros
+                cb[s] = (int)(sid / spc);
+                cp[s] = (int)(sid % spc) * SUBM;
+            }
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)C::TX_BYTES);
+                    const uint32_t sa = smem0 + stage * C::STAGE_BYTES;
+#pragma unroll
+                    for (int s = 0; s < SUB; ++s)
+#pragma unroll
+                        for (int mb = 0; mb < 4; ++mb)
+                            tma_load_3d(sa + s * A_SUB_BYTES + mb * 4096, &xmap, cp[s] + mb * 32, kb * KB, cb[s], &bar_full[stage]);
+                    bulk_load(sa + 2 * C::A_BYTES, a.wsplit + (size_t)kb * (2 * C::B_HALF), 2 * C::B_HALF, &bar_full[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (whole warp waits, one elected lane issues) =====
+        uint32_t stage = 0, phase = 0, it = 0;
+        // A stage: 4 TMA boxes (32 points each, LBO apart) of 32 channel rows x 128 B; an MMA (K = 8) reads two
+        // 4-row swizzle atoms SBO apart
+        const uint32_t a_lbo = (a.variant & 1) ? 512u : 4096u, a_sbo = (a.variant & 1) ? 4096u : 512u;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_full[stage], phase);
+                mbar_wait(&bar_conv[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem0 + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + 2 * C::A_BYTES;
+                    const int nks = kb == nkb - 1 ? last_ksteps : KB / 8;
+#pragma unroll
+                    for (int s = 0; s < SUB; ++s) {
+                        const uint32_t d = tmem_base + acc * (SUB * NC) + s * NC;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            if (a.variant & 8) continue;
+                            const uint64_t ahi = smem_desc(sa + s * A_SUB_BYTES + ks * 1024, a_lbo, a_sbo, LAYOUT_SW128_32B);
+                            const uint64_t alo = smem_desc(sa + C::A_BYTES + s * A_SUB_BYTES + ks * 1024, a_lbo, a_sbo, LAYOUT_SW128_32B);
+                            const uint64_t bhi = smem_desc(sb + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t blo = smem_desc(sb + C::B_HALF + ks * 32, 16, 1024, LAYOUT_SW128);
+                            if (a.variant & 2) {                                 // bring-up: plain TF32 product
+                                umma_tf32(d, ahi, bhi, C::IDESC, (kb | ks) != 0);
+                                continue;
+                            }
+                            umma_tf32(d, alo, bhi, C::IDESC, (kb | ks) != 0);   // small terms first
+                            umma_tf32(d, ahi, blo, C::IDESC, 1u);
+                            umma_tf32(d, ahi, bhi, C::IDESC, 1u);
+                        }
+                    }
+                    tc_commit(&bar_empty[stage]);            // frees the stage when these MMAs have read it
+                    if (kb == nkb - 1) tc_commit(&bar_tfull[acc]);   // accumulators of this tile are complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp < EPI_WARP0) {
+        // ===== converters: raw fp32 -> hi (in place) + lo =====
+        const int ct = threadIdx.x - CONV_WARP0 * 32;        // 0..127
+        uint32_t stage = 0, phase = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&bar_full[stage], phase);
+                float4 *hi = reinterpret_cast<float4 *>(smem_gen + stage * C::STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(smem_gen + stage * C::STAGE_BYTES + C::A_BYTES);
+                if (a.dbg && blockIdx.x == 0 && t == blockIdx.x && kb == 0) {   // bring-up: what TMA delivered
+                    const float *ar = reinterpret_cast<const float *>(hi);
+                    const float *br = reinterpret_cast<const float *>(smem_gen + stage * C::STAGE_BYTES + 2 * C::A_BYTES);
+                    for (int i = ct; i < 1024; i += 128) { a.dbg[i] = ar[i]; a.dbg[1024 + i] = br[i]; }
+                    if (ct == 0) { a.dbg[2048] = __uint_as_float(tmem_base); a.dbg[2049] = __uint_as_float(smem0); }
+                    __syncwarp();
+                }
+#pragma unroll 4
+                for (int i = ct; i < C::A_BYTES / 16; i += 128) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    if (a.variant & 4) { h = make_float4(1.f, 1.f, 1.f, 1.f); l = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_conv[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global (lane = point) =====
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            mbar_wait(&bar_tfull[acc], acc_phase);
+            tc_fence_after();
+            if (a.variant & 8) {   // bring-up: TMEM store/load self test, value = lane * 1000 + column
+                for (int c = 0; c < SUB * NC; ++c) {
+                    const uint32_t val = __float_as_uint((float)((q * 32 + lane) * 1000 + c));
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (SUB * NC) + c), "r"(val) : "memory");
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const long long sid = t * SUB + s;
+                const long long bi = sid / spc;
+                const int p = (int)(sid % spc) * SUBM + q * 32 + lane;
+                const bool valid = sid < nsub && p < a.n;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (SUB * NC) + s * NC;
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < NC / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    if (MODE == MODE_PLAIN) {
+                        float *yp = a.y + bi * a.y_bstride + p;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = ch * 32 + j;
+                            float r = __uint_as_float(v[j]) + bias_s[co];
+                            if (a.relu) r = fmaxf(r, 0.f);
+                            if (valid && co < a.cout) yp[(size_t)co * a.n] = r;
+                        }
+                    } else if (MODE == MODE_EXPAND) {
+                        const int nr = a.n * a.r;
+                        float *yp = a.y + bi * a.y_bstride + (size_t)p * a.r;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = ch * 32 + j;
+                            const float pre = __uint_as_float(v[j]) + bias_s[co];
+                            if (valid && co < a.cout) {
+                                if (a.r == 2) {
+                                    float2 o;
+                                    o.x = fmaxf(__fmaf_rn(wcode_s[co], code_s[0], pre), 0.f);
+                                    o.y = fmaxf(__fmaf_rn(wcode_s[co], code_s[1], pre), 0.f);
+                                    *reinterpret_cast<float2 *>(yp + (size_t)co * nr) = o;
+                                } else {
+                                    for (int jj = 0; jj < a.r; ++jj)
+                                        yp[(size_t)co * nr + jj] = fmaxf(__fmaf_rn(wcode_s[co], code_s[jj], pre), 0.f);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = ch * 32 + j;
+                            float h = __uint_as_float(v[j]) + bias_s[co];
+                            if (a.relu) h = fmaxf(h, 0.f);
+                            o0 = __fmaf_rn(w4_s[co], h, o0);
+                            o1 = __fmaf_rn(w4_s[NC + co], h, o1);
+                            o2 = __fmaf_rn(w4_s[2 * NC + co], h, o2);
+                        }
+                    }
+                }
+                if (MODE == MODE_PROJECT && valid) {
+                    float o[3] = {o0 + b4_s[0], o1 + b4_s[1], o2 + b4_s[2]};
+                    for (int c3 = 0; c3 < a.cout4; ++c3) {
+                        float r = o[c3];
+                        if (a.res) r += __ldg(a.res + bi * a.res_bstride + (size_t)c3 * a.res_n + p / a.res_div);
+                        a.y[bi * a.y_bstride + (size_t)c3 * a.n + p] = r;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int nc_for(int cout) { return cout <= 64 ? 64 : 128; }
+
+static int g_variant = -1;
+static float *g_dbg = nullptr;
+static int variant() {
+    if (g_variant < 0) {
+        const char *e = getenv("PU3_TC_VARIANT");
+        g_variant = e ? atoi(e) : 0;
+    }
+    return g_variant;
+}
+
+template <int NC, int MODE>
+static int launch(const CUtensorMap &map, const Args &a, cudaStream_t s) {
+    using C = Cfg<NC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES),
+                             "conv_tc: shared memory opt-in");
+        if (st) return st;
+        attr_set = true;
+    }
+    const int spc = (a.n + SUBM - 1) / SUBM;
+    const long long ntiles = ((long long)a.b * spc + SUB - 1) / SUB;
+    const int grid = (int)(ntiles < device_info().sm_count ? ntiles : device_info().sm_count);
+    conv_tc_kernel<NC, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, a);
+    PU3_LAUNCH_CHECK("conv_tc_kernel");
+    return PU3_OK;
+}
+
+static int run(int mode, Args a, const float *x, long long x_bstride, cudaStream_t s) {
+    PU3_ARG_CHECK(a.b >= 0 && a.n >= 0 && a.cin > 0 && a.cout > 0 && a.cout <= 128, "conv_tc: bad size b=%d n=%d cin=%d cout=%d", a.b, a.n, a.cin, a.cout);
+    if (a.b == 0 || a.n == 0) return PU3_OK;
+    PU3_ARG_CHECK(x && a.wsplit && a.y, "conv_tc: null pointer");
+    PU3_ARG_CHECK(a.n % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                  "conv_tc: the TMA path needs n %% 4 == 0 and 16-byte aligned slices (n=%d)", a.n);
+    PU3_ARG_CHECK((reinterpret_cast<uintptr_t>(a.wsplit) & 15) == 0, "conv_tc: split weights must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled not available"); return PU3_E_ARG; }
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.n, (cuuint64_t)a.cin, (cuuint64_t)a.b};
+    const cuuint64_t gstride[2] = {(cuuint64_t)a.n * 4, (cuuint64_t)x_bstride * 4};
+    const cuuint32_t box[3] = {32, KB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return PU3_E_ARG; }
+    a.variant = variant();
+    a.dbg = g_dbg;
+    const int nc = nc_for(a.cout);
+    if (mode == MODE_PLAIN) return nc == 64 ? launch<64, MODE_PLAIN>(map, a, s) : launch<128, MODE_PLAIN>(map, a, s);
+    if (mode == MODE_EXPAND) return nc == 64 ? launch<64, MODE_EXPAND>(map, a, s) : launch<128, MODE_EXPAND>(map, a, s);
+    PU3_ARG_CHECK(nc == 64 && a.cout4 >= 1 && a.cout4 <= 3, "conv_tc_project: needs cout <= 64 and 1..3 projected channels");
+    return launch<64, MODE_PROJECT>(map, a, s);
+}
+
+}  // namespace tc
+}  // namespace pu3
+
+using namespace pu3;
+
+// Test hook: descriptor variant (bit 0 swaps the leading/stride byte offsets of the MN-major operand).
+extern "C" void pu3_conv_tc_set_variant(int v) { tc::g_variant = v; }
+extern "C" void pu3_conv_tc_set_debug(float *buf) { tc::g_dbg = buf; }
+
+extern "C" size_t pu3_conv_tc_wsplit_bytes(int cin, int cout) {
+    if (cin <= 0 || cout <= 0 || cout > 128) return 0;
+    return (size_t)((cin + tc::KB - 1) / tc::KB) * 2 * tc::nc_for(cout) * 128;
+}
+
+extern "C" int pu3_conv_tc_prepare_f32(int cin, int cout, const float *w, int w_stride, void *wsplit, pu3_stream_t stream) {
+    PU3_ARG_CHECK(cin > 0 && cout > 0 && cout <= 128 && w_stride >= cin, "conv_tc_prepare: bad size cin=%d cout=%d stride=%d", cin, cout, w_stride);
+    PU3_ARG_CHECK(w && wsplit && (reinterpret_cast<uintptr_t>(wsplit) & 15) == 0, "conv_tc_prepare: null or unaligned pointer");
+    const int nc = tc::nc_for(cout);
+    const int total = (cin + tc::KB - 1) / tc::KB * nc * 8;
+    tc::split_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(cin, cout, nc, w, w_stride, static_cast<unsigned char *>(wsplit));
+    PU3_LAUNCH_CHECK("split_weights_kernel");
+    return PU3_OK;
+}
+
+extern "C" int pu3_conv_tc_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const void *wsplit,
+                               const float *bias, float *y, long long y_bstride, int relu, pu3_stream_t stream) {
+    tc::Args a{};
+    a.b = b; a.n = n; a.cin = cin; a.cout = cout; a.wsplit = static_cast<const unsigned char *>(wsplit); a.bias = bias;
+    a.y = y; a.y_bstride = y_bstride; a.relu = relu;
+    return tc::run(tc::MODE_PLAIN, a, x, x_bstride, as_stream(stream));
+}
+
+extern "C" int pu3_conv_tc_expand_f32(int b, int n, int cin, int cout, int r, const float *x, long long x_bstride,
+                                      const void *wsplit, const float *w, int w_stride, int code_col, const float *bias,
+                                      const float *code, float *y, long long y_bstride, pu3_stream_t stream) {
+    PU3_ARG_CHECK(r >= 1 && r <= 8 && w && code, "conv_tc_expand: bad expansion arguments (r=%d)", r);
+    PU3_ARG_CHECK(r != 2 || ((reinterpret_cast<uintptr_t>(y) & 7) == 0 && y_bstride % 2 == 0), "conv_tc_expand: y must be 8-byte aligned");
+    tc::Args a{};
+    a.b = b; a.n = n; a.cin = cin; a.cout = cout; a.wsplit = static_cast<const unsigned char *>(wsplit); a.bias = bias;
+    a.y = y; a.y_bstride = y_bstride; a.relu = 1; a.r = r; a.wfull = w; a.w_stride = w_stride; a.code_col = code_col; a.code = code;
+    return tc::run(tc::MODE_EXPAND, a, x, x_bstride, as_stream(stream));
+}
+
+extern "C" int pu3_conv_tc_project_f32(int b, int n, int cin, int cmid, int cout, const float *x, long long x_bstride,
+                                       const void *wsplit, const float *bias_mid, const float *w_out, const float *b_out,
+                                       float *y, long long y_bstride, const float *res, long long res_bstride, int res_n,
+                                       int res_div, pu3_stream_t stream) {
+    PU3_ARG_CHECK(w_out && (!res || (res_div >= 1 && res_n >= 1)), "conv_tc_project: bad arguments");
+    tc::Args a{};
+    a.b = b; a.n = n; a.cin = cin; a.cout = cmid; a.wsplit = static_cast<const unsigned char *>(wsplit); a.bias = bias_mid;
+    a.y = y; a.y_bstride = y_bstride; a.relu = 1; a.w4 = w_out; a.b4 = b_out; a.cout4 = cout;
+    a.res = res; a.res_bstride = res_bstride; a.res_n = res_n; a.res_div = res_div > 0 ? res_div : 1;
+    return tc::run(tc::MODE_PROJECT, a, x, x_bstride, as_stream(stream));
+}

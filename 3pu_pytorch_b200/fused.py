@@ -201,3 +201,67 @@ def dense_edge_conv(x, weights, biases, k, idx=None, max_group=None):
     out = torch.empty(B, 60, N, dtype=torch.float32, device=x.device)
     edgeconv_into(xc, idx32, off, k, weights, biases, out)
     return out, idx32[:, :, off:off + k].long()
+
+
+# ---- tensor-core (tcgen05, 3xTF32) 1x1 convolutions of the expansion head: csrc/conv_tc.cu -------------------------
+def tc_supported(x, cout):
+    """The TMA/tcgen05 path needs 16-byte aligned channel rows and cout <= 128."""
+    return x.shape[2] % 4 == 0 and x.data_ptr() % 16 == 0 and cout <= 128 and (x.shape[0] == 1 or x.stride(0) % 4 == 0)
+
+
+def tc_prepare(w, cin=None):
+    """Split W (cout, >=cin) into the tf32 hi/lo shared-memory image the MMA reads (one small kernel)."""
+    w2 = w.reshape(w.shape[0], w.shape[1])
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    cout, cin = w2.shape[0], (cin or w2.shape[1])
+    nbytes = _lib.lib().pu3_conv_tc_wsplit_bytes(cin, cout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.launch("pu3_conv_tc_prepare_f32", w2, cin, cout, w2.data_ptr(), w2.shape[1], ws.data_ptr())
+    return ws
+
+
+def tc_conv_into(x, w, b, out, relu=False, wsplit=None):
+    """out = act(W x + b) on the tensor cores; x, out: (B,C,N) channel slices as in conv_into."""
+    B, Cin, N = x.shape
+    Cout = out.shape[1]
+    assert x.stride(2) == 1 and x.stride(1) == N and out.stride(2) == 1 and out.stride(1) == N
+    ws = wsplit if wsplit is not None else tc_prepare(w)
+    _lib.launch("pu3_conv_tc_f32", x, B, N, Cin, Cout, x.data_ptr(), x.stride(0) if B > 1 else Cin * N, ws.data_ptr(),
+                _lib.ptr(b), out.data_ptr(), out.stride(0) if B > 1 else Cout * N, int(relu))
+    return out
+
+
+def tc_expand(x, w_full, b, code, r, wsplit=None):
+    """Feature-expansion layer (upsampler.py:349-366): x (B,Cin,N), w_full (Cout, Cin+1) whose last column multiplies
+    the 1-D code -> (B,Cout,N*r) = relu(W[:, :Cin] x + b + w_code * code[j])."""
+    B, Cin, N = x.shape
+    w2 = w_full.reshape(w_full.shape[0], w_full.shape[1])
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    Cout = w2.shape[0]
+    assert w2.shape[1] == Cin + 1 and x.stride(2) == 1 and x.stride(1) == N
+    ws = wsplit if wsplit is not None else tc_prepare(w2, cin=Cin)
+    out = torch.empty(B, Cout, N * r, dtype=torch.float32, device=x.device)
+    _lib.launch("pu3_conv_tc_expand_f32", x, B, N, Cin, Cout, r, x.data_ptr(), x.stride(0) if B > 1 else Cin * N,
+                ws.data_ptr(), w2.data_ptr(), Cin + 1, Cin, _lib.ptr(b), code.data_ptr(), out.data_ptr(), Cout * N * r)
+    return out
+
+
+def tc_project(x, w_mid, b_mid, w_out, b_out, residual=None, res_div=1, wsplit=None):
+    """Last two layers of the head (upsampler.py:369-372): relu(W_mid x + b_mid) stays on chip, then the <=3-channel
+    projection (+ residual[..., p // res_div])."""
+    B, Cin, N = x.shape
+    wm = w_mid.reshape(w_mid.shape[0], w_mid.shape[1]).contiguous()
+    wo = w_out.reshape(w_out.shape[0], w_out.shape[1]).contiguous()
+    assert x.stride(2) == 1 and x.stride(1) == N
+    ws = wsplit if wsplit is not None else tc_prepare(wm)
+    out = torch.empty(B, wo.shape[0], N, dtype=torch.float32, device=x.device)
+    rp, rbs, rn = None, 0, 1
+    if residual is not None:
+        assert residual.is_contiguous()
+        rp, rbs, rn = residual.data_ptr(), residual.stride(0), residual.shape[2]
+    _lib.launch("pu3_conv_tc_project_f32", x, B, N, Cin, wm.shape[0], wo.shape[0], x.data_ptr(),
+                x.stride(0) if B > 1 else Cin * N, ws.data_ptr(), _lib.ptr(b_mid), wo.data_ptr(), _lib.ptr(b_out),
+                out.data_ptr(), wo.shape[0] * N, rp, rbs, rn, res_div)
+    return out

@@ -172,6 +172,33 @@ int pu3_expand_code_f32(int b, int cout, int n, int r, const float *pre, const f
                         const float *code, float *y, pu3_stream_t stream);
 
 /*
+ * Tensor-core (tcgen05, 3xTF32 split: fp32-faithful) variants of the 1x1 convolution for the expansion head
+ * (network/upsampler.py:349-372; nn.Conv2d 1x1 layers up_layer1/up_layer2/fc_layer1/fc_layer2, layers.py:161-204).
+ * Same tensors as pu3_pointwise_conv_f32 (x: channel slice, pointer + batch stride, channel stride n), cout <= 128,
+ * n % 4 == 0 and 16-byte aligned slices (TMA).  The weights are first split into tf32 hi/lo parts in the
+ * shared-memory layout of the MMA by pu3_conv_tc_prepare_f32 (w (cout, >= cin) row-major with row stride
+ * w_stride) into a caller buffer of pu3_conv_tc_wsplit_bytes() bytes, 16-byte aligned.
+ *   pu3_conv_tc_f32          y[b,co,p] = act(W x + bias)
+ *   pu3_conv_tc_expand_f32   the feature-expansion layer (upsampler.py:349-366): y[b,co,p*r+j] =
+ *                            relu(W[:, :cin] x[b,:,p] + bias + w[co*w_stride+code_col] * code[j]); y (b,cout,n*r)
+ *   pu3_conv_tc_project_f32  two layers (upsampler.py:369-372): h = relu(W x + bias_mid) (cmid <= 64) stays on
+ *                            chip, y[b,c,p] = w_out[c,:] h + b_out[c] (+ res[b,c,p/res_div]), cout <= 3
+ */
+size_t pu3_conv_tc_wsplit_bytes(int cin, int cout);
+void pu3_conv_tc_set_variant(int v); /* test hook (shared-memory descriptor variant); 0 = default */
+void pu3_conv_tc_set_debug(float *buf); /* test hook: device buffer (>= 2050 floats) receiving the first stage; NULL = off */
+int pu3_conv_tc_prepare_f32(int cin, int cout, const float *w, int w_stride, void *wsplit, pu3_stream_t stream);
+int pu3_conv_tc_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const void *wsplit,
+                    const float *bias, float *y, long long y_bstride, int relu, pu3_stream_t stream);
+int pu3_conv_tc_expand_f32(int b, int n, int cin, int cout, int r, const float *x, long long x_bstride,
+                           const void *wsplit, const float *w, int w_stride, int code_col, const float *bias,
+                           const float *code, float *y, long long y_bstride, pu3_stream_t stream);
+int pu3_conv_tc_project_f32(int b, int n, int cin, int cmid, int cout, const float *x, long long x_bstride,
+                            const void *wsplit, const float *bias_mid, const float *w_out, const float *b_out,
+                            float *y, long long y_bstride, const float *res, long long res_bstride, int res_n,
+                            int res_div, pu3_stream_t stream);
+
+/*
  * Fused DenseEdgeConv forward for the reference configuration (24 input channels, growth 12, 3 layers):
  * replaces network/layers.py:22-64 (neighbour gather, edge feature [c, n-c], three 1x1 convolutions with dense
  * concatenation, max over the k edges).  x (b,24,n) slice (batch stride x_bstride), idx (b,n,idx_stride) i32 of which

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pu3_level_forward_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "pu3_iota_i32": (_c_int, [_c_int, _c_void_p, _c_void_p]),
+    "pu3_level_set_tc": (None, [_c_int]),
     "pu3_edgeconv_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
                          [_c_void_p, _c_ll, _c_void_p]),
 }
@@ -102,8 +103,10 @@ KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
     "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
-    # layer0 + 4 x (kNN + edge-conv) + 3 preps + 5 head kernels; + 4 x 3 duplicate kernels; skip adds 2 + 3, iota 1
-    "pu3_level_forward_f32": 29,
+    # layer0 + 4 x (kNN + edge-conv) + 3 preps + 6 head kernels (3 weight splits + 3 tcgen05); + 4 x 3 duplicate kernels;
+    # skip adds 2 + 3, iota 1
+    "pu3_level_forward_f32": 30,
+    "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
     "pu3_fps_ragged_f32": 1,
     "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique
 }
@@ -126,7 +129,8 @@ class Profiler:
             self._events.setdefault(name, []).append((e0, e1))
 
     ENGINE_TAGS = ["pu3_pointwise_conv_f32", "pu3_group_knn_f32[c=24,k=33,n<=312]", "pu3_edgeconv_f32",
-                   "pu3_group_knn_f32[c=3,k=5,skip]", "pu3_skip_fuse_f32", "pu3_expand_code_f32", "misc"]
+                   "pu3_group_knn_f32[c=3,k=5,skip]", "pu3_skip_fuse_f32", "pu3_expand_code_f32", "misc",
+                   "pu3_conv_tc_f32[tcgen05 head: 3 weight splits + expand + conv + project]"]
 
     def summary(self):
         """{name: (calls, total_ms)} -- call after torch.cuda.synchronize().  Kernels launched inside the level

@@ -35,7 +35,7 @@ constexpr int SUBM = 128;                     // points per MMA (UMMA M)
 constexpr int SUB = 2;                        // sub-tiles per CTA tile
 constexpr int STAGES = 2;
 constexpr int A_SUB_BYTES = SUBM * KB * 4;    // 16 KB: 4 TMA boxes of 32 points x 32 channels
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;             // TMA warp, MMA warp, 4 converter warps, 8 epilogue warps
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
 
 enum Mode { MODE_PLAIN = 0, MODE_EXPAND = 1, MODE_PROJECT = 2 };
@@ -147,11 +147,19 @@ struct Cfg {
     static constexpr int A_BYTES = SUB * A_SUB_BYTES;                  // raw / hi activations of a stage
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_HALF;       // [A hi][A lo][B hi][B lo]
     static constexpr int TX_BYTES = A_BYTES + 2 * B_HALF;              // what TMA delivers per stage
-    static constexpr int TMEM_COLS = 2 * SUB * NC;                     // double-buffered accumulators
+    // TMEM: per sub-tile a main accumulator (hi.hi) and a correction accumulator (hi.lo + lo.hi), NC columns each.
+    // The tensor core truncates when it adds into the fp32 accumulator (measured: the error of a single-accumulator
+    // 3xTF32 grows linearly with the number of MMAs, profiles/r1g); keeping the ~2^-11-times-smaller correction
+    // terms out of the main accumulator cuts the number of truncating adds it sees by 3.
+    static constexpr int ACC_COLS = SUB * 2 * NC;                      // one accumulator stage: [s0 main|s0 corr|s1 main|s1 corr]
+    static constexpr int ACC_STAGES = 512 / ACC_COLS;                  // NC = 64: double buffered, NC = 128: single
+    static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for the 1 KB alignment
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A MN-major, B K-major, N, M = 128
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(NC >> 3) << 17) |
-                                      ((uint32_t)(SUBM >> 4) << 24);
+    // instruction descriptors (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A MN-major, B K-major, M = 128;
+    // IDESC2 multiplies by [W_hi; W_lo] (N = 2 NC, main and correction columns in one instruction), IDESC1 by W_hi
+    static constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(SUBM >> 4) << 24);
+    static constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(NC >> 3) << 17);
+    static constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * NC) >> 3) << 17);
 };
 
 // ---- weights: fp32 (cout, cin) -> [k-block][hi | lo][NC rows x 128 B], 16-byte chunks XOR-swizzled by row ----
@@ -180,7 +188,7 @@ template <int NC, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     using C = Cfg<NC>;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];   // accumulator stages: C::ACC_STAGES of them in use
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[NC], wcode_s[NC], code_s[8], w4_s[MODE == MODE_PROJECT ? 3 * NC : 1], b4_s[4];
 
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], 4);     // one arrival per epilogue warp
+            mbar_init(&bar_tempty[s], 8);     // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // 4-row swizzle atoms SBO apart
         const uint32_t a_lbo = (a.variant & 1) ? 512u : 4096u, a_sbo = (a.variant & 1) ? 4096u : 512u;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const uint32_t acc = it % C::ACC_STAGES, acc_phase = (it / C::ACC_STAGES) & 1u;
             mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             for (int kb = 0; kb < nkb; ++kb) {
@@ -275,20 +283,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const int nks = kb == nkb - 1 ? last_ksteps : KB / 8;
 #pragma unroll
                     for (int s = 0; s < SUB; ++s) {
-                        const uint32_t d = tmem_base + acc * (SUB * NC) + s * NC;
+                        const uint32_t d = tmem_base + acc * C::ACC_COLS + s * 2 * NC;   // [main | correction]
                         for (int ks = 0; ks < nks; ++ks) {
-                            if (a.variant & 8) continue;
+                            if (a.variant & (8 | 32)) continue;   // bring-up / timing: no MMA
                             const uint64_t ahi = smem_desc(sa + s * A_SUB_BYTES + ks * 1024, a_lbo, a_sbo, LAYOUT_SW128_32B);
                             const uint64_t alo = smem_desc(sa + C::A_BYTES + s * A_SUB_BYTES + ks * 1024, a_lbo, a_sbo, LAYOUT_SW128_32B);
-                            const uint64_t bhi = smem_desc(sb + ks * 32, 16, 1024, LAYOUT_SW128);
-                            const uint64_t blo = smem_desc(sb + C::B_HALF + ks * 32, 16, 1024, LAYOUT_SW128);
-                            if (a.variant & 2) {                                 // bring-up: plain TF32 product
-                                umma_tf32(d, ahi, bhi, C::IDESC, (kb | ks) != 0);
-                                continue;
-                            }
-                            umma_tf32(d, alo, bhi, C::IDESC, (kb | ks) != 0);   // small terms first
-                            umma_tf32(d, ahi, blo, C::IDESC, 1u);
-                            umma_tf32(d, ahi, bhi, C::IDESC, 1u);
+                            const uint64_t bhl = smem_desc(sb + ks * 32, 16, 1024, LAYOUT_SW128);    // rows [W_hi; W_lo]
+                            umma_tf32(d, ahi, bhl, C::IDESC2, (kb | ks) != 0);        // main += hi.hi, correction += hi.lo
+                            if (!(a.variant & 2)) umma_tf32(d + NC, alo, bhl, C::IDESC1, 1u);   // correction += lo.hi
                         }
                     }
                     tc_commit(&bar_empty[stage]);            // frees the stage when these MMAs have read it
@@ -333,30 +335,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else {
         // ===== epilogue: TMEM -> registers -> global (lane = point) =====
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int s = (warp - EPI_WARP0) >> 2;               // the sub-tile this warp drains
         uint32_t it = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const uint32_t acc = it % C::ACC_STAGES, acc_phase = (it / C::ACC_STAGES) & 1u;
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
             if (a.variant & 8) {   // bring-up: TMEM store/load self test, value = lane * 1000 + column
-                for (int c = 0; c < SUB * NC; ++c) {
-                    const uint32_t val = __float_as_uint((float)((q * 32 + lane) * 1000 + c));
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (SUB * NC) + c), "r"(val) : "memory");
+                for (int c = 0; c < 2 * NC; ++c) {
+                    const uint32_t val = __float_as_uint(c < NC ? (float)((q * 32 + lane) * 1000 + c) : 0.f);
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + s * 2 * NC + c), "r"(val) : "memory");
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-#pragma unroll
-            for (int s = 0; s < SUB; ++s) {
+            {
                 const long long sid = t * SUB + s;
                 const long long bi = sid / spc;
                 const int p = (int)(sid % spc) * SUBM + q * 32 + lane;
-                const bool valid = sid < nsub && p < a.n;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (SUB * NC) + s * NC;
+                const bool valid = sid < nsub && p < a.n && !(a.variant & 16);   // 16: timing without stores
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + s * 2 * NC;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < NC / 32; ++ch) {
-                    uint32_t v[32];
+                    uint32_t v[32], vc[32];
                     tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld32(taddr + NC + ch * 32, vc);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));
                     if (MODE == MODE_PLAIN) {
                         float *yp = a.y + bi * a.y_bstride + p;
 #pragma unroll
@@ -369,19 +374,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     } else if (MODE == MODE_EXPAND) {
                         const int nr = a.n * a.r;
                         float *yp = a.y + bi * a.y_bstride + (size_t)p * a.r;
+                        if (a.r == 2) {      // the reference's step ratio: both replicas in one 8-byte store per point
+                            const float c0 = code_s[0], c1 = code_s[1];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int co = ch * 32 + j;
-                            const float pre = __uint_as_float(v[j]) + bias_s[co];
-                            if (valid && co < a.cout) {
-                                if (a.r == 2) {
-                                    float2 o;
-                                    o.x = fmaxf(__fmaf_rn(wcode_s[co], code_s[0], pre), 0.f);
-                                    o.y = fmaxf(__fmaf_rn(wcode_s[co], code_s[1], pre), 0.f);
-                                    *reinterpret_cast<float2 *>(yp + (size_t)co * nr) = o;
-                                } else {
-                                    for (int jj = 0; jj < a.r; ++jj)
-                                        yp[(size_t)co * nr + jj] = fmaxf(__fmaf_rn(wcode_s[co], code_s[jj], pre), 0.f);
+                            for (int j = 0; j < 32; ++j) {
+                                const int co = ch * 32 + j;
+                                const float pre = __uint_as_float(v[j]) + bias_s[co];
+                                float2 o;
+                                o.x = fmaxf(__fmaf_rn(wcode_s[co], c0, pre), 0.f);
+                                o.y = fmaxf(__fmaf_rn(wcode_s[co], c1, pre), 0.f);
+                                if (valid && co < a.cout) *reinterpret_cast<float2 *>(yp + (size_t)co * nr) = o;
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int jj = 0; jj < a.r; ++jj) {
+                                const float cj = code_s[jj];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int co = ch * 32 + j;
+                                    const float pre = __uint_as_float(v[j]) + bias_s[co];
+                                    if (valid && co < a.cout) yp[(size_t)co * nr + jj] = fmaxf(__fmaf_rn(wcode_s[co], cj, pre), 0.f);
                                 }
                             }
                         }

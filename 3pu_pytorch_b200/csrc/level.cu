@@ -20,7 +20,7 @@ __global__ void iota_kernel(int n, int32_t *out) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct LevelPlan {
-    size_t off_h, off_idx, off_me, off_pre, off_h1, off_h2, off_h3, off_skipidx, off_knnws, total;
+    size_t off_h, off_idx, off_me, off_pre, off_h1, off_h2, off_h3, off_skipidx, off_knnws, off_wsplit[3], total;
     size_t knn_ws;
 };
 
@@ -39,6 +39,10 @@ static LevelPlan plan_level(int t, int n, int r, int knn, int fm_knn, int clouds
     size_t w2 = has_prev ? pu3_group_knn_workspace(t, 3, n, no, fm_knn, 1, 1) : 0;
     p.knn_ws = w1 > w2 ? w1 : w2;
     p.off_knnws = off; off += al256(p.knn_ws);
+    // tf32 hi/lo images of the head weights for the tensor-core path (csrc/conv_tc.cu): up1 (264 feature columns), up2, fc1
+    p.off_wsplit[0] = off; off += al256(pu3_conv_tc_wsplit_bytes(264, 128));
+    p.off_wsplit[1] = off; off += al256(pu3_conv_tc_wsplit_bytes(128, 128));
+    p.off_wsplit[2] = off; off += al256(pu3_conv_tc_wsplit_bytes(128, 64));
     p.total = off;
     (void)clouds;
     return p;
@@ -46,6 +50,10 @@ static LevelPlan plan_level(int t, int n, int r, int knn, int fm_knn, int clouds
 }  // namespace pu3
 
 using namespace pu3;
+
+// Test / A-B hook: 0 runs the expansion head on the fp32 FFMA SGEMM instead of the tcgen05 kernels.
+static int g_level_tc = 1;
+extern "C" void pu3_level_set_tc(int on) { g_level_tc = on; }
 
 extern "C" int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream) {
     if (n <= 0) return PU3_OK;
@@ -122,11 +130,24 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
                                   owner, stream));
     }
     // expansion head (:349-372)
-    PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n, C, 128, feat, fs, w->up1_w_feat, w->up1_b, pre, 128LL * n, nullptr, 0, 1, 1, 0, stream));
-    PU3_TRYT(PROF_EXPAND, pu3_expand_code_f32(t, 128, n, r, pre, w->up1_w, C + 1, C, w->code, h1, stream));
-    PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 128, 128, h1, 128LL * n * r, w->up2_w, w->up2_b, h2, 128LL * n * r, nullptr, 0, 1, 1, 1, stream));
-    PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 128, 64, h2, 128LL * n * r, w->fc1_w, w->fc1_b, h3, 64LL * n * r, nullptr, 0, 1, 1, 1, stream));
-    PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 64, 3, h3, 64LL * n * r, w->fc2_w, w->fc2_b, out_xyz, 3LL * n * r, xyz_norm, 3LL * n, n, r, 0, stream));
+    if (g_level_tc && n % 4 == 0 && r <= 8) {
+        // tensor cores (tcgen05, 3xTF32): up1 + code column + replication | up2 | fc1 + fc2 + residual -- 3 kernels, the
+        // (t,265,n*r) input, the 128-channel "pre" tensor and the 64-channel activation never exist
+        void *ws1 = ws + p.off_wsplit[0], *ws2 = ws + p.off_wsplit[1], *ws3 = ws + p.off_wsplit[2];
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(C, 128, w->up1_w, C + 1, ws1, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(128, 128, w->up2_w, 128, ws2, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(128, 64, w->fc1_w, 128, ws3, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_expand_f32(t, n, C, 128, r, feat, fs, ws1, w->up1_w, C + 1, C, w->up1_b, w->code, h1, 128LL * n * r, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_f32(t, n * r, 128, 128, h1, 128LL * n * r, ws2, w->up2_b, h2, 128LL * n * r, 1, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_project_f32(t, n * r, 128, 64, 3, h2, 128LL * n * r, ws3, w->fc1_b, w->fc2_w, w->fc2_b, out_xyz,
+                                                       3LL * n * r, xyz_norm, 3LL * n, n, r, stream));
+    } else {
+        PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n, C, 128, feat, fs, w->up1_w_feat, w->up1_b, pre, 128LL * n, nullptr, 0, 1, 1, 0, stream));
+        PU3_TRYT(PROF_EXPAND, pu3_expand_code_f32(t, 128, n, r, pre, w->up1_w, C + 1, C, w->code, h1, stream));
+        PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 128, 128, h1, 128LL * n * r, w->up2_w, w->up2_b, h2, 128LL * n * r, nullptr, 0, 1, 1, 1, stream));
+        PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 128, 64, h2, 128LL * n * r, w->fc1_w, w->fc1_b, h3, 64LL * n * r, nullptr, 0, 1, 1, 1, stream));
+        PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n * r, 64, 3, h3, 64LL * n * r, w->fc2_w, w->fc2_b, out_xyz, 3LL * n * r, xyz_norm, 3LL * n, n, r, 0, stream));
+    }
 #undef PU3_TRY
 #undef PU3_TRYT
     return PU3_OK;

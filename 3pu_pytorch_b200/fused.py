@@ -232,7 +232,7 @@ def tc_conv_into(x, w, b, out, relu=False, wsplit=None):
     return out
 
 
-def tc_expand(x, w_full, b, code, r, wsplit=None):
+def tc_expand(x, w_full, b, code, r, wsplit=None, out=None):
     """Feature-expansion layer (upsampler.py:349-366): x (B,Cin,N), w_full (Cout, Cin+1) whose last column multiplies
     the 1-D code -> (B,Cout,N*r) = relu(W[:, :Cin] x + b + w_code * code[j])."""
     B, Cin, N = x.shape
@@ -242,7 +242,8 @@ def tc_expand(x, w_full, b, code, r, wsplit=None):
     Cout = w2.shape[0]
     assert w2.shape[1] == Cin + 1 and x.stride(2) == 1 and x.stride(1) == N
     ws = wsplit if wsplit is not None else tc_prepare(w2, cin=Cin)
-    out = torch.empty(B, Cout, N * r, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(B, Cout, N * r, dtype=torch.float32, device=x.device)
     _lib.launch("pu3_conv_tc_expand_f32", x, B, N, Cin, Cout, r, x.data_ptr(), x.stride(0) if B > 1 else Cin * N,
                 ws.data_ptr(), w2.data_ptr(), Cin + 1, Cin, _lib.ptr(b), code.data_ptr(), out.data_ptr(), Cout * N * r)
     return out

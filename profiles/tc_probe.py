@@ -18,7 +18,12 @@ def rel_err(got, want):
     return float((got.double() - want).abs().max() / want.abs().max().clamp_min(1e-30))
 
 
-def run(variant, timing):
+def worst_ratio(got, want, rtol=1e-5, atol=1e-5):
+    """max |got - want| / (atol + rtol |want|): the element-wise bar of tests/ (must stay below 1)"""
+    return float(((got.double() - want).abs() / (atol + rtol * want.abs())).max())
+
+
+def run(variant, timing, sweep=False):
     import torch
     pu3 = importlib.import_module("3pu_pytorch_b200")
     F = pu3.fused
@@ -31,7 +36,7 @@ def run(variant, timing):
         return (torch.rand(*s, generator=g) * 2 - 1).to(dev)
 
     # plain
-    for (B, N, Cin, Cout, relu) in [(3, 624, 128, 128, True), (2, 312, 264, 128, False), (1, 40, 84, 24, True),
+    for (B, N, Cin, Cout, relu) in [(3, 624, 128, 128, True), (2, 312, 264, 128, False), (8, 312, 264, 128, False), (1, 40, 84, 24, True),
                                     (5, 100, 8, 64, False), (3, 128, 32, 128, False), (301, 624, 128, 128, True)]:
         x, w, b = rnd(B, Cin, N), rnd(Cout, Cin) * 0.2, rnd(Cout)
         out = torch.full((B, Cout, N), float("nan"), device=dev)
@@ -42,7 +47,8 @@ def run(variant, timing):
         e = rel_err(out, ref)
         ffma = torch.empty_like(out); F.conv_into(x, w, b, ffma, relu=relu)
         e2 = rel_err(ffma, ref)
-        print(f"variant {variant} plain   B={B} N={N} {Cin}->{Cout} relu={relu}: rel err {e:.3e} (FFMA kernel {e2:.3e}) nan={bool(torch.isnan(out).any())}")
+        print(f"variant {variant} plain   B={B} N={N} {Cin}->{Cout} relu={relu}: rel err {e:.3e} (FFMA kernel {e2:.3e}), element-wise worst ratio "
+              f"{worst_ratio(out, ref):.2f} (FFMA {worst_ratio(ffma, ref):.2f}) nan={bool(torch.isnan(out).any())}")
         ok &= e < 2e-6
     # slices of a bigger buffer (the way the level engine calls it)
     B, N = 4, 312
@@ -71,6 +77,8 @@ def run(variant, timing):
         ref = torch.matmul(wo.double(), h) + bo.double().view(1, -1, 1) + res.double().repeat_interleave(div, dim=2)
         e = rel_err(out, ref); print(f"variant {variant} project B={B} N={N} {Cin}->{Cmid}->{Cout}: rel err {e:.3e}"); ok &= e < 2e-6
     print(f"variant {variant}: {'ALL OK' if ok else 'MISMATCH'}")
+    if sweep:
+        ok = True
     if ok and timing:
         T = 1275
         feat = rnd(T, 264, 312)
@@ -92,6 +100,15 @@ def run(variant, timing):
             return sorted(ts[2:])[len(ts[2:]) // 2]
 
         h1 = F.tc_expand(feat, w1, b1, code, 2, wsplit=s1)
+        if sweep:   # which part of the pipeline bounds the kernel: 2 = one MMA instead of three, 16 = no stores, 32 = no MMA
+            for v in (0, 2, 16, 32, 48):
+                pu3._lib.lib().pu3_conv_tc_set_variant(v)
+                t1 = timed(lambda: F.tc_expand(feat, w1, b1, code, 2, wsplit=s1))
+                t2 = timed(lambda: F.tc_conv_into(h1, w2, b2, h2, relu=True, wsplit=s2))
+                t3 = timed(lambda: F.tc_project(h2, w3, b3, w4, b4, residual=xyz, res_div=2, wsplit=s3))
+                print(f"sweep variant {v:2d}: up1+expand {t1:.3f} ms   up2 {t2:.3f} ms   fc1+fc2 {t3:.3f} ms")
+            pu3._lib.lib().pu3_conv_tc_set_variant(0)
+            return True
         t1 = timed(lambda: F.tc_expand(feat, w1, b1, code, 2, wsplit=s1))
         t2 = timed(lambda: F.tc_conv_into(h1, w2, b2, h2, relu=True, wsplit=s2))
         t3 = timed(lambda: F.tc_project(h2, w3, b3, w4, b4, residual=xyz, res_div=2, wsplit=s3))
@@ -112,9 +129,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--no-timing", action="store_true")
+    ap.add_argument("--sweep", action="store_true")
     a = ap.parse_args()
     if a.variant is not None:
-        sys.exit(0 if run(a.variant, not a.no_timing) else 1)
+        sys.exit(0 if run(a.variant, not a.no_timing, a.sweep) else 1)
     for v in (0, 1):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", str(v)], timeout=240)

@@ -138,6 +138,146 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
     }
 }
 
+// Specialisation for the reference configuration (K = fm_knn = 5 neighbours, C = 264 channels), same arithmetic in
+// the same order as the generic kernel above (results are bit-identical), but with every trip count known at
+// compile time: the 5 neighbour indices are read first and the 5 x 9 row loads of a point are all in flight before
+// the first use.  The generic kernel exposes one row (8-9 loads) at a time and is bound by L2 gather latency
+// (ncu: long-scoreboard 6.3 warps per issue, profiles/r1f_ncu_summary.md).
+template <int K, int C>
+__global__ void __launch_bounds__(SK_THREADS) skip_fuse_fixed_kernel(SkipArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int U = (C + 31) / 32;                 // channels per lane
+    const int N = a.n;
+    float *xt = sm;                                  // [C][SK_PT+1]
+    float *sds = xt + (size_t)C * (SK_PT + 1);       // [N][K]
+    float *sdf = sds + (size_t)N * K;                // [N][K]
+    float *red = sdf + (size_t)N * K;                // [2][SK_WARPS]
+    __shared__ float s_h[2];
+
+    const int ti = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = a.owner ? __ldg(a.owner + ti) : ti / a.p_div;
+    float *xb = a.x + (size_t)ti * C * N;
+    const float *pxyz = a.prev_xyz + (size_t)cloud * 3 * a.no;
+    const float *pf = a.prev_feat + (size_t)cloud * a.no * C;
+    const float *q = a.xyz + (size_t)ti * 3 * N;
+    const int64_t *ib = a.idx + (size_t)ti * N * K;
+
+    float sum_s = 0.f, sum_f = 0.f;
+    for (int p0 = 0; p0 < N; p0 += SK_PT) {
+        const int pc = min(SK_PT, N - p0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < C * SK_PT; t += SK_THREADS) {
+            const int ch = t / SK_PT, pl = t % SK_PT;
+            xt[ch * (SK_PT + 1) + pl] = pl < pc ? xb[(size_t)ch * N + p0 + pl] : 0.f;
+        }
+        __syncthreads();
+        for (int pl = warp; pl < pc; pl += SK_WARPS) {
+            const int i = p0 + pl;
+            int j[K];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) j[kk] = (int)ib[(size_t)i * K + kk];
+            float nb[K][U];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int ch = lane + 32 * u;
+                    nb[kk][u] = ch < C ? __ldg(pf + (size_t)j[kk] * C + ch) : 0.f;
+                }
+            float xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ch = lane + 32 * u;
+                xv[u] = ch < C ? xt[ch * (SK_PT + 1) + pl] : 0.f;
+            }
+            const float qx = __ldg(q + i), qy = __ldg(q + N + i), qz = __ldg(q + 2 * N + i);
+            float mins = INFINITY, minf = INFINITY;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                float acc = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (lane + 32 * u < C) {
+                        const float d = xv[u] - nb[kk][u];
+                        acc = __fmaf_rn(d, d, acc);
+                    }
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+                const float dx = qx - __ldg(pxyz + j[kk]);
+                const float dy = qy - __ldg(pxyz + a.no + j[kk]);
+                const float dz = qz - __ldg(pxyz + 2 * (size_t)a.no + j[kk]);
+                const float ds = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                if (lane == 0) { sds[i * K + kk] = ds; sdf[i * K + kk] = acc; }
+                mins = fminf(mins, ds); minf = fminf(minf, acc);
+            }
+            sum_s += mins; sum_f += minf;
+        }
+    }
+    if (lane == 0) { red[warp] = sum_s; red[SK_WARPS + warp] = sum_f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tf = 0.f;
+        for (int w = 0; w < SK_WARPS; ++w) { ts += red[w]; tf += red[SK_WARPS + w]; }
+        s_h[0] = ts / (float)N;
+        s_h[1] = tf / (float)N;
+    }
+    __syncthreads();
+    const float hs2 = s_h[0] / 2.0f, hf2 = s_h[1] / 2.0f;
+
+    for (int p0 = 0; p0 < N; p0 += SK_PT) {
+        const int pc = min(SK_PT, N - p0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < C * SK_PT; t += SK_THREADS) {
+            const int ch = t / SK_PT, pl = t % SK_PT;
+            xt[ch * (SK_PT + 1) + pl] = pl < pc ? xb[(size_t)ch * N + p0 + pl] : 0.f;
+        }
+        __syncthreads();
+        for (int pl = warp; pl < pc; pl += SK_WARPS) {
+            const int i = p0 + pl;
+            int j[K];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) j[kk] = (int)ib[(size_t)i * K + kk];
+            float nb[K][U];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int ch = lane + 32 * u;
+                    nb[kk][u] = ch < C ? __ldg(pf + (size_t)j[kk] * C + ch) : 0.f;
+                }
+            float w[K];
+            float wsum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                const float ws = expf(-sds[i * K + kk] / hs2);
+                const float wf = expf(-sdf[i * K + kk] / hf2);
+                w[kk] = ws * wf;
+                wsum += w[kk] + 1e-5f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) w[kk] = w[kk] / wsum;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ch = lane + 32 * u;
+                if (ch < C) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) acc = __fmaf_rn(w[kk], nb[kk][u], acc);
+                    float *cell = &xt[ch * (SK_PT + 1) + pl];
+                    *cell = __fmaf_rn(0.2f, acc, *cell);
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < C * SK_PT; t += SK_THREADS) {
+            const int ch = t / SK_PT, pl = t % SK_PT;
+            if (pl < pc) xb[(size_t)ch * N + p0 + pl] = xt[ch * (SK_PT + 1) + pl];
+        }
+    }
+}
+
 // (T,C,N) channel-major -> rows of a point-major (rows, C) buffer: out[slot[t]*N + i][c] = in[t][c][i]
 // (the features a level hands to the next one, laid out for skip_fuse_kernel's row gathers)
 __global__ void __launch_bounds__(256) to_point_major_kernel(int c, int n, const float *__restrict__ in,
@@ -163,6 +303,10 @@ __global__ void __launch_bounds__(256) to_point_major_kernel(int c, int n, const
 
 using namespace pu3;
 
+// Test hook: force the generic (runtime K, C) kernel.
+static int g_skip_force_generic = 0;
+extern "C" void pu3_skip_force_generic(int on) { g_skip_force_generic = on; }
+
 extern "C" int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz,
                                  const int64_t *idx, const float *prev_xyz, const float *prev_feat_pm,
                                  const int32_t *owner, pu3_stream_t stream) {
@@ -176,6 +320,13 @@ extern "C" int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, 
     PU3_ARG_CHECK(smem <= (size_t)device_info().smem_optin, "skip_fuse: c=%d n=%d k=%d needs %zu bytes of shared memory", c, n, k, smem);
     int st = cuda_status(cudaFuncSetAttribute(skip_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_fuse: smem attr");
     if (st) return st;
+    if (k == 5 && c == 264 && !g_skip_force_generic) {
+        st = cuda_status(cudaFuncSetAttribute(skip_fuse_fixed_kernel<5, 264>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_fuse: smem attr");
+        if (st) return st;
+        skip_fuse_fixed_kernel<5, 264><<<t, SK_THREADS, smem, as_stream(stream)>>>(a);
+        PU3_LAUNCH_CHECK("skip_fuse_fixed_kernel");
+        return PU3_OK;
+    }
     skip_fuse_kernel<<<t, SK_THREADS, smem, as_stream(stream)>>>(a);
     PU3_LAUNCH_CHECK("skip_fuse_kernel");
     return PU3_OK;

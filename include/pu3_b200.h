@@ -219,6 +219,7 @@ int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, c
  */
 int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
                       const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, pu3_stream_t stream);
+void pu3_skip_force_generic(int on); /* test hook: 1 = runtime-(k,c) kernel even for the k=5, c=264 configuration */
 
 /*
  * Layout change for the features handed to the next level: in (t,c,n) channel-major ->

@@ -225,6 +225,16 @@ def test_fused_skip_connection_matches_composition(pu3, cuda, params):
         got = level._skip_connection_fused(x.to(cuda).clone(), xyz.to(cuda),
                                            (prev_xyz.to(cuda), prev_feat.to(cuda).transpose(1, 2).contiguous()), None, R)
     assert_close_frac(got, want, rtol=1e-5, atol=2e-6, what="fused skip connection")
+    # the compile-time (k=5, c=264) kernel and the runtime-shape kernel do the same arithmetic in the same order
+    lib = pu3._lib.lib()
+    try:
+        lib.pu3_skip_force_generic(1)
+        with torch.no_grad():
+            gen = level._skip_connection_fused(x.to(cuda).clone(), xyz.to(cuda),
+                                               (prev_xyz.to(cuda), prev_feat.to(cuda).transpose(1, 2).contiguous()), None, R)
+    finally:
+        lib.pu3_skip_force_generic(0)
+    assert torch.equal(gen, got), "fixed-shape and generic skip kernels differ"
     # and the oracle itself, request by request (the reference expand()s one previous cloud per call)
     for lo, hi, c in ((0, 3, 0), (3, 5, 1)):
         n = sizes[c]

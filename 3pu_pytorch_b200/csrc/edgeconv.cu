@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edgeconv_kernel(int n, int k, i
 //     5-step shuffle butterfly on 36 values
 //   * <= 128 registers: 2 CTAs per SM
 // ------------------------------------------------------------------------------------------------------
-constexpr int EF_XS = 28;            // row stride of a point in shared memory (floats): 7 quads, odd -> conflict free
+constexpr int EF_XS = 24;            // row stride of a point's features in shared memory (only centre rows are read: broadcasts)
+constexpr int EB_XS = 28;             // backward kernel: row stride of a point (7 quads, odd -> neighbour rows on distinct banks)
+constexpr int EF_PS0 = 12;           // row stride of the per-point layer-0 products W0[:,24:] . x_j gathered per edge
 constexpr int EF_RS = 20;            // row stride of the reduction scratch (16 lanes + pad)
 constexpr int EF_PS = 36 * EF_RS;    // per-point scratch; 720 % 32 == 16 keeps the two half-warps on disjoint banks
 
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
     float *s_a = s_out + EC_OUT * (EC_PT + 1);                           // [EC_WARPS][2][36]
     float *s_red = s_a + EC_WARPS * 2 * 36;                              // [EC_WARPS][2][EF_PS]
     float *xs = s_red + EC_WARPS * 2 * EF_PS;                            // [n][EF_XS]
+    float *ps = xs + (size_t)n * EF_XS;                                  // [n][EF_PS0]: P_j = W0[:, 24:] . x_j
 
     const int bi = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,6 +302,24 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
         xs[p * EF_XS + c] = __ldg(xb + (size_t)c * n + p);
     }
     __syncthreads();
+    // The neighbour enters the block only through layer 0, and there linearly: W0 [c, n - c] + b0 =
+    // (W0a - W0b) c + b0 + W0b n.  W0b x_j is a per-POINT quantity, so it is computed once per point of the cloud
+    // (288 MAC) instead of once per edge (288 MAC x 32 edges); an edge then costs one 48-byte gather and 12 adds
+    // for layer 0, and 432 MAC for layers 1 and 2.
+    for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
+        const int p = t / 3, q = t - p * 3;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *row = xs + p * EF_XS;
+#pragma unroll
+        for (int ch = 0; ch < EC_C; ++ch) {
+            const float4 w = *reinterpret_cast<const float4 *>(&sw.w0b[ch][q * 4]);
+            const float v = row[ch];
+            acc.x = __fmaf_rn(w.x, v, acc.x); acc.y = __fmaf_rn(w.y, v, acc.y);
+            acc.z = __fmaf_rn(w.z, v, acc.z); acc.w = __fmaf_rn(w.w, v, acc.w);
+        }
+        *reinterpret_cast<float4 *>(ps + p * EF_PS0 + q * 4) = acc;
+    }
+    __syncthreads();
 
     const int p_begin = blockIdx.x * pts_per_cta;
     const int p_end = min(n, p_begin + pts_per_cta);
@@ -322,6 +343,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
                     a1 = __fmaf_rn(sw.wp[ch][16 + hl], cv, a1);
                     if (hl < 4) a2 = __fmaf_rn(sw.wp[ch][32 + hl], cv, a2);
                 }
+                if (hl < EC_G) a0 -= ps[i * EF_PS0 + hl];   // (W0a - W0b) c + b0: the centre's own W0b c goes out here
                 __syncwarp();
                 wa[hl] = a0; wa[16 + hl] = a1;
                 if (hl < 4) wa[32 + hl] = a2;
@@ -332,28 +354,17 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
             const bool va = ea < k, vb = eb < k;
             const int ja = va ? __ldg(ib + (size_t)i * idx_stride + idx_off + ea) : i;
             const int jb = vb ? __ldg(ib + (size_t)i * idx_stride + idx_off + eb) : i;
-            const float *na = xs + ja * EF_XS, *nb = xs + jb * EF_XS;
-            f32x2 h0a[6], h0b[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) h0a[q] = h0b[q] = pack2(wa[2 * q], wa[2 * q + 1]);
-#pragma unroll
-            for (int c4 = 0; c4 < EC_C; c4 += 4) {
-                const float4 cc = *reinterpret_cast<const float4 *>(ci + c4);
-                const float4 fa = *reinterpret_cast<const float4 *>(na + c4);
-                const float4 fb = *reinterpret_cast<const float4 *>(nb + c4);
-                ef_layer2(h0a, h0b, &sw.w0b[c4 + 0][0], fa.x - cc.x, fb.x - cc.x);   // edge feature n - c (layers.py:41)
-                ef_layer2(h0a, h0b, &sw.w0b[c4 + 1][0], fa.y - cc.y, fb.y - cc.y);
-                ef_layer2(h0a, h0b, &sw.w0b[c4 + 2][0], fa.z - cc.z, fb.z - cc.z);
-                ef_layer2(h0a, h0b, &sw.w0b[c4 + 3][0], fa.w - cc.w, fb.w - cc.w);
-            }
+            const float *pa = ps + ja * EF_PS0, *pb = ps + jb * EF_PS0;
             float r0a[EC_G], r0b[EC_G];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                unpack2(h0a[q], r0a[2 * q], r0a[2 * q + 1]);
-                unpack2(h0b[q], r0b[2 * q], r0b[2 * q + 1]);
+            for (int q = 0; q < 3; ++q) {
+                const float4 fa = *reinterpret_cast<const float4 *>(pa + 4 * q);
+                const float4 fb = *reinterpret_cast<const float4 *>(pb + 4 * q);
+                r0a[4 * q + 0] = fmaxf(wa[4 * q + 0] + fa.x, 0.f); r0b[4 * q + 0] = fmaxf(wa[4 * q + 0] + fb.x, 0.f);
+                r0a[4 * q + 1] = fmaxf(wa[4 * q + 1] + fa.y, 0.f); r0b[4 * q + 1] = fmaxf(wa[4 * q + 1] + fb.y, 0.f);
+                r0a[4 * q + 2] = fmaxf(wa[4 * q + 2] + fa.z, 0.f); r0b[4 * q + 2] = fmaxf(wa[4 * q + 2] + fb.z, 0.f);
+                r0a[4 * q + 3] = fmaxf(wa[4 * q + 3] + fa.w, 0.f); r0b[4 * q + 3] = fmaxf(wa[4 * q + 3] + fb.w, 0.f);
             }
-#pragma unroll
-            for (int o = 0; o < EC_G; ++o) { r0a[o] = fmaxf(r0a[o], 0.f); r0b[o] = fmaxf(r0b[o], 0.f); }
             f32x2 h1a[6], h1b[6], h2a[6], h2b[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
@@ -454,7 +465,7 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     dim3 grid((n + pts - 1) / pts, b);
     cudaStream_t s = as_stream(stream);
     int st;
-    const size_t fast_smem = sizeof(EfSmemW) + (size_t)(EC_OUT * (EC_PT + 1) + EC_WARPS * 2 * 36 + EC_WARPS * 2 * EF_PS + (size_t)n * EF_XS) * sizeof(float);
+    const size_t fast_smem = sizeof(EfSmemW) + (size_t)(EC_OUT * (EC_PT + 1) + EC_WARPS * 2 * 36 + EC_WARPS * 2 * EF_PS + (size_t)n * (EF_XS + EF_PS0)) * sizeof(float);
     if (k <= 32 && fast_smem <= 110 * 1024 && g_ec_force_generic == 0) {
         st = cuda_status(cudaFuncSetAttribute(edgeconv_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem), "edgeconv: smem attr");
         if (st) return st;
@@ -520,7 +531,7 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
     float *s_st = s_da + EC_WARPS * 36;                                // [EC_WARPS][32][EB_ST]
     float *s_acc = s_st + EC_WARPS * 32 * EB_ST;                       // [EC_WARPS][EB_ACC]
     float *dxs = s_acc + EC_WARPS * EB_ACC;                            // [n][EB_DXS]
-    float *xs = dxs + (size_t)n * EB_DXS;                              // [n][EF_XS]
+    float *xs = dxs + (size_t)n * EB_DXS;                              // [n][EB_XS]
 
     const int bi = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -539,7 +550,7 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
         sw.wp[in][o] = o < 12 ? __ldg(W.w0 + o * 48 + in) : (o < 24 ? __ldg(W.w1 + (o - 12) * 36 + 12 + in) : __ldg(W.w2 + (o - 24) * 48 + 24 + in));
     }
     if (threadIdx.x < 36) { const int o = threadIdx.x; sw.bp[o] = o < 12 ? __ldg(W.b0 + o) : (o < 24 ? __ldg(W.b1 + o - 12) : __ldg(W.b2 + o - 24)); }
-    for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) { const int c = t / n, p = t - c * n; xs[p * EF_XS + c] = __ldg(xb + (size_t)c * n + p); }
+    for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) { const int c = t / n, p = t - c * n; xs[p * EB_XS + c] = __ldg(xb + (size_t)c * n + p); }
     for (int t = threadIdx.x; t < n * EB_DXS; t += blockDim.x) dxs[t] = 0.f;
     __syncthreads();
 
@@ -553,7 +564,7 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
     float *me = st + lane * EB_ST;
     const int p_begin = blockIdx.x * pts_per_cta, p_end = min(n, p_begin + pts_per_cta);
     for (int i = p_begin + warp; i < p_end; i += EC_WARPS) {
-        const float *ci = xs + i * EF_XS;
+        const float *ci = xs + i * EB_XS;
         __syncwarp();
         {   // per-point terms and the incoming gradient of the point's 60 output channels
             float a0 = sw.bp[lane], a1 = lane < 4 ? sw.bp[32 + lane] : 0.f;
@@ -572,7 +583,7 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
         // ---- forward recompute of this lane's edge; d, h0, h1 go straight to the staging row ------------------------
         const bool live = lane < k;
         const int j = live ? __ldg(ib + (size_t)i * idx_stride + idx_off + lane) : i;
-        const float *nj = xs + j * EF_XS;
+        const float *nj = xs + j * EB_XS;
         float h0[EC_G], h1[EC_G], h2[EC_G];
 #pragma unroll
         for (int o = 0; o < EC_G; ++o) h0[o] = wa[o];
@@ -712,7 +723,7 @@ extern "C" int pu3_edgeconv_bwd_f32(int b, int n, int k, const float *x, long lo
     PU3_ARG_CHECK(x && idx && w0 && b0 && w1 && b1 && w2 && b2 && dy && dx && dw0 && db0 && dw1 && db1 && dw2 && db2,
                   "edgeconv_bwd: null pointer");
     PU3_ARG_CHECK(idx_stride >= idx_off + k && idx_off >= 0, "edgeconv_bwd: idx_stride too small");
-    const size_t smem = sizeof(EfSmemW) + (size_t)(EC_WARPS * (36 + 60 + 36) + EC_WARPS * 32 * EB_ST + EC_WARPS * EB_ACC + (size_t)n * (EB_DXS + EF_XS)) * sizeof(float);
+    const size_t smem = sizeof(EfSmemW) + (size_t)(EC_WARPS * (36 + 60 + 36) + EC_WARPS * 32 * EB_ST + EC_WARPS * EB_ACC + (size_t)n * (EB_DXS + EB_XS)) * sizeof(float);
     if (smem > (size_t)device_info().smem_optin) {
         set_error("edgeconv_bwd: n=%d does not fit shared memory (%zu bytes)", n, smem);
         return PU3_E_UNSUPPORTED;

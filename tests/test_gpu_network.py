@@ -163,17 +163,25 @@ def test_net_eval_batched_equals_per_patch_calls(pu3, cuda, params):
 def test_net_eval_against_oracle(pu3, cuda, params, ratio):
     levels = {4: 2, 16: 4}[ratio]
     net = _net(pu3, params, cuda, levels=levels).eval()
-    g = torch.Generator().manual_seed(13)
-    x = ref_net.normalize_point_batch(torch.rand(1, 3, 312, generator=g))[0]
     P = {k: v for k, v in params.items() if int(k.split(".")[1].split("_")[1]) <= levels}
-    with torch.no_grad():
-        want = ref_net.net_forward(P, x, ratio=ratio, max_up_ratio=ratio)
-        got = net(x.to(cuda), ratio=ratio).cpu()
-    assert got.shape == want.shape == (1, 3, 312 * ratio)
     # End to end the result passes through FPS arg-max rounds and kNN selections whose near-ties may break
-    # differently (1e-7 coordinate noise); the clouds must still coincide: almost every point has a twin.
-    share = cloud_match_fraction(got[0], want[0], tol=1e-4)
-    assert share > 0.97, share
+    # differently (1e-7 coordinate noise): one flipped seed moves a whole tile, so the share of points with an exact
+    # twin is chaotic in the last few percent (profiles/e2e_share.py: 0.967 .. 1.000 over inputs and over
+    # rounding-equivalent kernel variants).  Three inputs: the clouds must coincide almost everywhere on each, essentially
+    # everywhere on most, and lie on the same surface sampling (Chamfer distance far below the point spacing) on all.
+    shares = []
+    for seed in (13, 14, 15):
+        g = torch.Generator().manual_seed(seed)
+        x = ref_net.normalize_point_batch(torch.rand(1, 3, 312, generator=g))[0]
+        with torch.no_grad():
+            want = ref_net.net_forward(P, x, ratio=ratio, max_up_ratio=ratio)
+            got = net(x.to(cuda), ratio=ratio).cpu()
+        assert got.shape == want.shape == (1, 3, 312 * ratio)
+        shares.append(cloud_match_fraction(got[0], want[0], tol=1e-4))
+        d = torch.cdist(got[0].t().double(), want[0].t().double())
+        spacing = torch.cdist(want[0].t().double(), want[0].t().double()).topk(2, largest=False)[0][:, 1].mean()
+        assert float(d.min(1)[0].mean()) < 0.02 * float(spacing) and float(d.min(0)[0].mean()) < 0.02 * float(spacing)
+    assert min(shares) > 0.95 and sorted(shares)[1] > 0.99, shares
 
 
 def test_net_train_forward_backward_against_oracle(pu3, cuda, params):
@@ -281,7 +289,9 @@ def test_pointwise_conv_fast_and_generic_kernels_agree(pu3, cuda):
 
 
 def test_edgeconv_fast_and_generic_kernels_agree(pu3, cuda, params):
-    """k <= 32 takes the FFMA2 two-edges-per-lane kernel; it accumulates in the same order as the generic one."""
+    """k <= 32 takes the FFMA2 two-edges-per-lane kernel.  Layers 1 and 2 accumulate in the generic kernel's order; layer 0
+    is re-associated further (W0b n_j is computed once per point and gathered per edge instead of W0b (n_j - c) per edge),
+    which changes its rounding by a few ulp of |W0b| |x| -- far inside the path's 1e-5 tolerance."""
     import ctypes
     lib = ctypes.CDLL(pu3._lib.LIB_PATH)
     g = torch.Generator().manual_seed(5)
@@ -299,7 +309,8 @@ def test_edgeconv_fast_and_generic_kernels_agree(pu3, cuda, params):
                     outs.append(pu3.fused.dense_edge_conv(x, ws, bs, k, idx=idx)[0])
             finally:
                 lib.pu3_edgeconv_force_generic(0)
-        assert torch.equal(outs[0], outs[1]), (b, n, k)
+        assert_close_frac(outs[0], outs[1], rtol=1e-5, atol=2e-6, what=f"fast vs generic edge-conv {(b, n, k)}")
+        assert torch.equal(outs[0][:, 36:], outs[1][:, 36:])             # the pass-through channels are copies
 
 
 def test_reference_import_names_resolve_through_the_shim(pu3, cuda):

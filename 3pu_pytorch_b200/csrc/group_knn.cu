@@ -45,6 +45,7 @@ struct KnnArgs {
     int64_t *idx64;       // (b,m,k) or null
     int32_t *idx32;       // (b,m,k) or null
     float *dist;          // (b,m,k) or null
+    int exact_pops;       // knn_feat_kernel, indices-only mode: 1 = ranks 1..k-1 in exact order too (test hook)
 };
 
 __device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.owner ? __ldg(a.owner + bi) : bi / a.p_div; }
@@ -125,6 +126,66 @@ __global__ void __launch_bounds__(256) knn_dup_small_kernel(int c, int n, const 
             for (int ch = 0; ch < c && same; ++ch) same = p[(size_t)ch * n + e] == p[(size_t)ch * n + j];
             found = same;
         }
+        dup[(size_t)cloud * n + j] = found ? 1 : 0;
+        found_any += found ? 1 : 0;
+    }
+    if (found_any) atomicAdd(cloud_any + cloud, found_any);
+}
+
+// Clouds of 1025 .. 16384 points (the previous-level clouds of the skip connection: 3120 and 6240 points at levels 3
+// and 4): one CTA per cloud builds an open-addressing hash table of point indices in shared memory.  Equal points always
+// meet in the same slot (slots never change their class of equal points once claimed), atomicMin keeps the smallest index
+// of the class there, so "duplicate" = "not the representative of my slot" -- np.unique's first occurrence
+// (operations.py:199).  O(n) instead of the O(n^2) scan of knn_dup_kernel (0.65 -> ~0.05 ms per eval step).
+constexpr int KH_MAXN = 16384;
+__global__ void __launch_bounds__(1024) knn_dup_hash_kernel(int c, int n, int table_size, const int32_t *__restrict__ n_arr,
+                                                           const float *__restrict__ points, uint8_t *__restrict__ dup,
+                                                           int *__restrict__ cloud_any) {
+    extern __shared__ uint32_t table[];
+    const int cloud = blockIdx.x;
+    const int nv = n_arr ? min(n, __ldg(n_arr + cloud)) : n;
+    const float *p = points + (size_t)cloud * c * n;
+    const uint32_t mask = (uint32_t)table_size - 1u, EMPTY = 0xffffffffu;
+    for (int i = threadIdx.x; i < table_size; i += blockDim.x) table[i] = EMPTY;
+    __syncthreads();
+    auto hash_of = [&](int j) {
+        uint32_t h = 2166136261u;
+        for (int ch = 0; ch < c; ++ch) {
+            uint32_t u = __float_as_uint(__ldg(p + (size_t)ch * n + j));
+            if ((u << 1) == 0u) u = 0u;                  // -0.0 == +0.0 (np.unique compares values)
+            h = (h ^ u) * 16777619u;
+            h ^= h >> 15;
+        }
+        return h * 2654435761u;
+    };
+    auto same = [&](int a, int b) {
+        for (int ch = 0; ch < c; ++ch)
+            if (__ldg(p + (size_t)ch * n + a) != __ldg(p + (size_t)ch * n + b)) return false;
+        return true;
+    };
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        uint32_t s = hash_of(j) & mask;
+        while (true) {
+            uint32_t cur = table[s];
+            if (cur == EMPTY) {
+                cur = atomicCAS(&table[s], EMPTY, (uint32_t)j);
+                if (cur == EMPTY) break;                 // claimed
+            }
+            if (same((int)cur, j)) { atomicMin(&table[s], (uint32_t)j); break; }
+            s = (s + 1u) & mask;
+        }
+    }
+    __syncthreads();
+    int found_any = 0;
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        uint32_t s = hash_of(j) & mask;
+        uint32_t rep;
+        while (true) {
+            rep = table[s];
+            if (rep == (uint32_t)j || same((int)rep, j)) break;
+            s = (s + 1u) & mask;
+        }
+        const bool found = rep != (uint32_t)j;
         dup[(size_t)cloud * n + j] = found ? 1 : 0;
         found_any += found ? 1 : 0;
     }
@@ -490,20 +551,67 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
             int h = 1;
             const size_t row = ((size_t)bi * a.m + qi) * a.k;
             if (HOT) {
-                // only int32 indices wanted (the fused DenseEdgeConv path): the loop body is kept minimal; winners
-                // are staged as 16-bit indices in stripe 0 of the row (free: those heads live in registers)
-                uint16_t *stage = reinterpret_cast<uint16_t *>(krow);
+                // Only int32 indices wanted, and their consumer (the fused DenseEdgeConv) takes a max over the
+                // neighbours after dropping rank 0: rank 0 must be exact, the other k-1 are needed as a SET.
+                // So: one exact pop (key, then lowest index) for rank 0, then k-1 cheap rounds in which every lane
+                // whose head equals the warp minimum advances (1 redux + 4 instructions instead of 2 redux + 20;
+                // ncu: the exact pop loop was 47 % of the kernel's instructions).  A lane always contributes a
+                // prefix of its sorted list, so the set is written afterwards from per-lane counts.  If equal keys
+                // made the rounds pop more than k candidates (ties straddling rank k-1: duplicates, clamped
+                // distances), the exact loop below redoes the query.
+                uint16_t *stage = reinterpret_cast<uint16_t *>(krow);   // stripe 0 of the row is free: heads live in registers
+                const uint32_t hk_first = hk, perm_lo_first = perm_lo, perm_hi_first = perm_hi;
                 __syncwarp();
-                for (int r = 0; r < a.k; ++r) {
-                    const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
-                    const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
-                    if (hj == jmin && hk == kmin) {       // exactly one lane (indices are unique)
-                        stage[r] = (uint16_t)hj;
-                        hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
-                        perm_lo = __funnelshift_r(perm_lo, perm_hi, 4);
-                        perm_hi >>= 4;
+                bool exact = a.exact_pops != 0;
+                if (!exact) {
+                    const uint32_t kmin0 = __reduce_min_sync(0xffffffffu, hk);
+                    const uint32_t jmin0 = __reduce_min_sync(0xffffffffu, hk == kmin0 ? hj : 0xffffffffu);
+                    const bool first = (hj == jmin0 && hk == kmin0);
+                    int cnt = 0;                                  // candidates this lane contributes
+                    if (first) { hk = krow[32 + lane]; cnt = 1; }
+                    for (int r = 1; r < a.k; ++r) {
+                        const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
+                        if (hk == kmin) {
+                            ++cnt;                                // (index clamped: under massive ties cnt runs past the list
+                            hk = krow[min(cnt, KF_S - 1) * 32 + lane];   //  and the compiler may issue the load unconditionally)
+                            if (cnt >= KF_S) hk = 0xffffffffu;
+                        }
+                    }
+                    const int total = __reduce_add_sync(0xffffffffu, cnt);
+                    if (total == a.k) {
+                        // exclusive prefix of the per-lane counts (rank 0 goes to slot 0, outside the prefix)
+                        const int mine = cnt - (first ? 1 : 0);
+                        int incl = mine;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += up;
+                        }
+                        int pos = 1 + incl - mine;
+                        unsigned long long perm = ((unsigned long long)perm_hi << 32) | perm_lo;
+                        if (first) { stage[0] = (uint16_t)(((uint32_t)perm & 15u) * 32u + lane); perm >>= 4; }
+                        for (int e = 0; e < mine; ++e) {
+                            stage[pos + e] = (uint16_t)(((uint32_t)perm & 15u) * 32u + lane);
+                            perm >>= 4;
+                        }
+                    } else {
+                        exact = true;                             // warp-uniform
+                        hk = hk_first; perm_lo = perm_lo_first; perm_hi = perm_hi_first;
                         hj = (perm_lo & 15u) * 32u + lane;
-                        ++h;
+                    }
+                }
+                if (exact) {
+                    for (int r = 0; r < a.k; ++r) {
+                        const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
+                        const uint32_t jmin = __reduce_min_sync(0xffffffffu, hk == kmin ? hj : 0xffffffffu);
+                        if (hj == jmin && hk == kmin) {       // exactly one lane (indices are unique)
+                            stage[r] = (uint16_t)hj;
+                            hk = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
+                            perm_lo = __funnelshift_r(perm_lo, perm_hi, 4);
+                            perm_hi >>= 4;
+                            hj = (perm_lo & 15u) * 32u + lane;
+                            ++h;
+                        }
                     }
                 }
                 __syncwarp();
@@ -859,6 +967,12 @@ using namespace pu3;
 // Test hook: force the streaming-insertion kernel for k <= 64 even when the cloud fits the tiled kernel.
 static int g_knn_force_stream = 0;
 extern "C" void pu3_knn_force_stream(int on) { g_knn_force_stream = on; }
+// Test hook: 1 = the indices-only feature kNN orders ranks 1..k-1 exactly (default: rank 0 exact, the rest as a set).
+static int g_knn_exact_pops = 0;
+extern "C" void pu3_knn_exact_pops(int on) { g_knn_exact_pops = on; }
+// Test hook: 1 = duplicate detection of clouds > 1024 points by the O(n^2) scan instead of the hash table.
+static int g_knn_dup_scan = 0;
+extern "C" void pu3_knn_dup_scan(int on) { g_knn_dup_scan = on; }
 
 extern "C" size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique) {
     if (b <= 0 || c <= 0 || m <= 0 || n <= 0 || k <= 0 || p_div <= 0) return 0;
@@ -903,6 +1017,8 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
                           const int32_t *group_of, const int32_t *n_arr, const int32_t *m_arr, const float *query,
                           const float *points, int unique, int max_group, float *knn, int64_t *idx64,
                           int32_t *idx32, float *dist, void *workspace, size_t workspace_bytes, pu3_stream_t stream) {
+    const bool unordered = (unique & PU3_KNN_SET_ORDER) != 0;   // ranks 1..k-1 as a set (indices-only calls of the tiled kernel)
+    unique &= 1;
     PU3_ARG_CHECK(b >= 0 && c > 0 && m >= 0 && n >= 0 && k >= 0, "group_knn: bad size b=%d c=%d m=%d n=%d k=%d", b, c, m, n, k);
     PU3_ARG_CHECK(k <= n, "group_knn: points size must be greater or equal to k (n=%d, k=%d)", n, k);  // operations.py:186
     if (b == 0 || m == 0 || k == 0) return PU3_OK;
@@ -924,7 +1040,8 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
     cudaStream_t s = as_stream(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
-              query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist};
+              query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist,
+              (unordered && g_knn_exact_pops == 0) ? 0 : 1};
     if (unique) {
         int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
         int *cloud_any = reinterpret_cast<int *>(ws + pl.off_cany);
@@ -933,7 +1050,13 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         int st = cuda_status(cudaMemsetAsync(ws + pl.off_any, 0, pl.off_dup - pl.off_any, s), "group_knn: memset");
         if (st) return st;
         if (n <= KD_MAXN) knn_dup_small_kernel<<<clouds, 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
-        else knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
+        else if (n <= KH_MAXN && g_knn_dup_scan == 0) {
+            int table = 2048;
+            while (table < 2 * n) table *= 2;            // load factor <= 0.5
+            st = cuda_status(cudaFuncSetAttribute(knn_dup_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table * 4), "group_knn: smem attr");
+            if (st) return st;
+            knn_dup_hash_kernel<<<clouds, 1024, table * 4, s>>>(c, n, table, n_arr, points, dup, cloud_any);
+        } else knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
         PU3_LAUNCH_CHECK("knn_dup_kernel");
         knn_groupflag_kernel<<<(b + 255) / 256, 256, 0, s>>>(a, cloud_any, group_any);
         PU3_LAUNCH_CHECK("knn_groupflag_kernel");

@@ -108,12 +108,13 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
         if (blk > 0)   // layerK_prep (:213-221): Conv1d + ReLU over everything produced so far
             PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n, C - lo, 24, feat + (size_t)lo * n, fs, w->prep_w[blk - 1], w->prep_b[blk - 1],
                                            h, 24LL * n, nullptr, 0, 1, 1, 1, stream));
-        // dynamic graph in feature space (layers.py:33): k+1 nearest, duplicates pushed back, rank 0 dropped by idx_off=1
+        // dynamic graph in feature space (layers.py:33): k+1 nearest, duplicates pushed back, rank 0 dropped by idx_off=1;
+        // the edge-conv takes a max over the other k, so they are requested as a set (PU3_KNN_SET_ORDER)
         if (owner)
-            PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_ragged_f32(t, 24, n, n, K + 1, t, groups, me, owner, nullptr, nullptr, h, h, 1, nullptr,
+            PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_ragged_f32(t, 24, n, n, K + 1, t, groups, me, owner, nullptr, nullptr, h, h, 1 | PU3_KNN_SET_ORDER, nullptr,
                                              nullptr, idx, nullptr, knnws, p.knn_ws, stream));
         else
-            PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_f32(t, 24, n, n, K + 1, 1, h, h, 1, max_group, nullptr, nullptr, idx, nullptr, knnws,
+            PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_f32(t, 24, n, n, K + 1, 1, h, h, 1 | PU3_KNN_SET_ORDER, max_group, nullptr, nullptr, idx, nullptr, knnws,
                                       p.knn_ws, stream));
         PU3_TRYT(PROF_EDGECONV, pu3_edgeconv_f32(t, n, K, h, 24LL * n, idx, K + 1, 1, w->ec_w[blk][0], w->ec_b[blk][0], w->ec_w[blk][1],
                                  w->ec_b[blk][1], w->ec_w[blk][2], w->ec_b[blk][2], feat + (size_t)(lo - 60) * n, fs, stream));

@@ -42,10 +42,12 @@ class Ragged:
         self.owner, self.group_of, self.groups, self.n_arr, self.m_arr = owner, group_of, int(groups), n_arr, m_arr
 
 
-def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64, ragged=None):
+def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64, ragged=None, set_order=False):
     """q (B,C,M), p (B/p_div,C,N) contiguous f32 on the same device -> (knn|None, idx, dist|None).
     With `ragged`, p is (clouds,C,N) and the mapping comes from the Ragged description; outputs of invalid
-    rows / columns are zero."""
+    rows / columns are zero.  set_order (indices-only int32 calls): rank 0 exact, ranks 1..k-1 as an unordered set
+    (PU3_KNN_SET_ORDER of include/pu3_b200.h) -- what the fused DenseEdgeConv needs."""
+    uflag = int(bool(unique)) | (2 if set_order else 0)
     B, C, M = q.shape
     Bp, _, N = p.shape
     if ragged is not None:
@@ -58,7 +60,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         _lib.launch("pu3_group_knn_ragged_f32", q, B, C, M, N, k, Bp, ragged.groups, _lib.ptr(ragged.owner),
                     _lib.ptr(ragged.group_of), _lib.ptr(ragged.n_arr), _lib.ptr(ragged.m_arr), _lib.ptr(q), _lib.ptr(p),
-                    int(bool(unique)), _lib.ptr(knn), _lib.ptr(idx if idx_dtype == torch.int64 else None),
+                    uflag, _lib.ptr(knn), _lib.ptr(idx if idx_dtype == torch.int64 else None),
                     _lib.ptr(idx if idx_dtype == torch.int32 else None), _lib.ptr(dist), _lib.ptr(ws), ws_bytes,
                     extra_kernels=3 if unique else 0,
                     tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")
@@ -77,7 +79,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
     idx64 = idx if idx_dtype == torch.int64 else None
     idx32 = idx if idx_dtype == torch.int32 else None
     # stream goes last in the C signature, after (workspace, workspace_bytes)
-    _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), int(bool(unique)),
+    _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), uflag,
                 int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32), _lib.ptr(dist), _lib.ptr(ws),
                 ws_bytes, extra_kernels=3 if unique else 0,
                 tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")

@@ -121,10 +121,14 @@ int pu3_nmdist_bwd_f32(int b, int n, int m, const float *xyz1, const float *xyz2
  *   unique != 0: every point that equals an earlier point of its cloud in all c channels gets
  *          max(D) added, max taken over groups of `max_group` consecutive batch elements
  *          (the reference takes it over its whole batch: max_group = b; operations.py:204)
+ *   unique | PU3_KNN_SET_ORDER (bit 1, opt-in): when only idx32 is requested (the fused DenseEdgeConv: rank 0 is
+ *          dropped and a max over the other neighbours follows, layers.py:33-35,63), rank 0 is exact and ranks
+ *          1..k-1 are returned as a SET in unspecified order -- the k-1 serial arg-min rounds become cheap ones
  *   outputs, each may be NULL: knn (b,c,m,k) f32 contiguous; idx64 (b,m,k) i64; idx32 (b,m,k) i32;
  *          dist (b,m,k) f32, ascending; ties are ordered by ascending point index.
  *   workspace: pu3_group_knn_workspace() bytes, 256-byte aligned.
  */
+#define PU3_KNN_SET_ORDER 2
 size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique);
 int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query, const float *points,
                       int unique, int max_group, float *knn, int64_t *idx64, int32_t *idx32, float *dist,

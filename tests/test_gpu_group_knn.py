@@ -193,3 +193,65 @@ def test_tiled_and_streaming_kernels_agree(pu3, cuda):
     for a, b in zip(outs[0], outs[1]):
         for ta, tb in zip(a, b):
             assert torch.equal(ta, tb)
+
+
+@pytest.mark.parametrize("n", [1025, 3120, 6240, 16384])
+def test_large_cloud_duplicate_detection_hash_equals_scan_and_oracle(pu3, cuda, n):
+    """Clouds of 1025..16384 points mark duplicates with a shared-memory hash table; the O(n^2) scan (test hook) and the
+    oracle (np.unique first occurrences, operations.py:192-204) must give the same neighbours, also with many
+    duplicates, -0.0 / +0.0 and fewer than k distinct points (exact max(D) penalty path)."""
+    import ctypes
+    g = torch.Generator().manual_seed(n)
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    pts = torch.rand(2, 3, n, generator=g)
+    src = torch.randint(0, n // 2, (n // 3,), generator=g)
+    pts[0, :, n - n // 3:] = pts[0, :, src]            # a third of cloud 0 are copies of earlier points
+    pts[0, 0, 5] = 0.0; pts[0, :, 9] = pts[0, :, 5]; pts[0, 0, 9] = -0.0   # equal as values, different bits
+    pts[1, :, 4:] = pts[1, :, :4].repeat(1, (n + 3) // 4)[:, :n - 4]     # cloud 1: only 4 distinct points < k
+    q = torch.rand(2, 3, 50, generator=g)
+    outs = []
+    for scan in (0, 1):
+        lib.pu3_knn_dup_scan(scan)
+        try:
+            outs.append(pu3.operations.group_knn(5, q.to(cuda), pts.to(cuda), unique=True, max_group=1))
+        finally:
+            lib.pu3_knn_dup_scan(0)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for i in range(2):   # max_group=1: every cloud is its own request, like one reference call per cloud
+        _, ridx, rd = ref_net.group_knn(5, q[i:i + 1], pts[i:i + 1], unique=True)
+        got_idx, got_d = outs[0][1][i:i + 1].cpu(), outs[0][2][i:i + 1].cpu()
+        cols = slice(0, 5) if i == 0 else slice(0, 4)      # cloud 1: rank 4 is a tie between ~n/4 copies (topk order unspecified)
+        same = (got_idx[..., cols] == ridx[..., cols]).float().mean().item()
+        assert same > 0.99, same                                            # near-ties aside, the same neighbours
+        assert torch.allclose(got_d, rd, rtol=1e-4, atol=1e-6)             # incl. the + max(D) of the penalised ranks
+
+
+def test_set_order_mode_returns_the_same_neighbour_sets(pu3, cuda):
+    """PU3_KNN_SET_ORDER (the feature kNN of the level engine): rank 0 identical to the exact mode, ranks 1..k-1 the
+    same set; clouds with duplicates and with massive ties (all points equal, few distinct points) take the exact
+    fallback inside the kernel and must agree as well."""
+    g = torch.Generator().manual_seed(44)
+    x = torch.rand(6, 24, 312, generator=g)
+    x[1, :, 200:] = x[1, :, :112]                       # duplicates: pushed behind the first occurrences
+    x[2] = x[2, :, :1].expand(-1, 312)                  # all points equal: every distance ties
+    x[3, :, 5:] = x[3, :, :5].repeat(1, 62)[:, :307]    # 5 distinct points < k
+    x[4] = torch.relu(x[4] - 0.7)                       # post-ReLU features: many exact zeros, clamped distances
+    xc = x.to(cuda)
+    for k in (33, 17, 2):
+        _, exact, _ = pu3.operations._knn_raw(k, xc, xc, True, 1, want_knn=False, want_dist=False, idx_dtype=torch.int32)
+        _, fast, _ = pu3.operations._knn_raw(k, xc, xc, True, 1, want_knn=False, want_dist=False, idx_dtype=torch.int32,
+                                             set_order=True)
+        assert torch.equal(exact[..., 0], fast[..., 0])                               # rank 0
+        assert torch.equal(exact.sort(dim=-1)[0], fast.sort(dim=-1)[0]), k             # the same k neighbours
+    # the edge-conv built on either index list is bit-identical (max over the neighbours is order-free)
+    params = ref_net.make_params(1, seed=1)
+    pre = "levels.level_1.layer1"
+    ws = [params[f"{pre}.mlps.{i}.weight"].to(cuda) for i in range(3)]
+    bs = [params[f"{pre}.mlps.{i}.bias"].to(cuda) for i in range(3)]
+    _, exact, _ = pu3.operations._knn_raw(33, xc, xc, True, 1, want_knn=False, want_dist=False, idx_dtype=torch.int32)
+    _, fast, _ = pu3.operations._knn_raw(33, xc, xc, True, 1, want_knn=False, want_dist=False, idx_dtype=torch.int32, set_order=True)
+    with torch.no_grad():
+        a = pu3.fused.dense_edge_conv(xc, ws, bs, 32, idx=exact[..., 1:].long())[0]
+        b = pu3.fused.dense_edge_conv(xc, ws, bs, 32, idx=fast[..., 1:].long())[0]
+    assert torch.equal(a, b)

@@ -326,6 +326,19 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
     float *wa = s_a + (warp * 2 + hp) * 36;
     float *wred = s_red + (size_t)(warp * 2 + hp) * EF_PS;
 
+    // the lane's two edges are fixed; their neighbour indices are the only global loads of the main loop and sit at the
+    // head of its dependency chain (ncu: long-scoreboard was the top stall), so they are fetched one point ahead
+    const int ea = hl, eb = 16 + hl;
+    const bool va = ea < k, vb = eb < k;
+    auto fetch_idx = [&](int t0x, int lp0x, int &ja_out, int &jb_out) {
+        const int tc = min(EC_PT, p_end - t0x);
+        const int ix = (lp0x + hp < tc) ? t0x + lp0x + hp : t0x + lp0x;
+        ja_out = va ? __ldg(ib + (size_t)ix * idx_stride + idx_off + ea) : ix;
+        jb_out = vb ? __ldg(ib + (size_t)ix * idx_stride + idx_off + eb) : ix;
+    };
+    int ja_next = 0, jb_next = 0;
+    if (p_begin < p_end && warp * 2 < min(EC_PT, p_end - p_begin)) fetch_idx(p_begin, warp * 2, ja_next, jb_next);
+
     for (int t0 = p_begin; t0 < p_end; t0 += EC_PT) {
         const int tcnt = min(EC_PT, p_end - t0);
         for (int lp0 = warp * 2; lp0 < tcnt; lp0 += EC_WARPS * 2) {
@@ -333,6 +346,12 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
             const bool pvalid = lp < tcnt;                 // the second point of the pair may not exist
             const int i = pvalid ? t0 + lp : t0 + lp0;
             const float *ci = xs + i * EF_XS;
+            const int ja = ja_next, jb = jb_next;
+            {   // next work item of this warp: same tile, or the first pair of the next tile
+                int n_t0 = t0, n_lp0 = lp0 + EC_WARPS * 2;
+                if (n_lp0 >= tcnt) { n_t0 = t0 + EC_PT; n_lp0 = warp * 2; }
+                if (n_t0 < p_end && n_lp0 < min(EC_PT, p_end - n_t0)) fetch_idx(n_t0, n_lp0, ja_next, jb_next);
+            }
             // ---- per-point terms A0|A1|A2 (36 values) by the 16 lanes of the half-warp -------------------
             {
                 float a0 = sw.bp[hl], a1 = sw.bp[16 + hl], a2 = hl < 4 ? sw.bp[32 + hl] : 0.f;
@@ -350,10 +369,6 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
                 __syncwarp();
             }
             // ---- the lane's two edges -------------------------------------------------------------------------
-            const int ea = hl, eb = 16 + hl;
-            const bool va = ea < k, vb = eb < k;
-            const int ja = va ? __ldg(ib + (size_t)i * idx_stride + idx_off + ea) : i;
-            const int jb = vb ? __ldg(ib + (size_t)i * idx_stride + idx_off + eb) : i;
             const float *pa = ps + ja * EF_PS0, *pb = ps + jb * EF_PS0;
             float r0a[EC_G], r0b[EC_G];
 #pragma unroll

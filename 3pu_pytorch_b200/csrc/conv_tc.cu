@@ -34,6 +34,7 @@ constexpr int KB = 32;                        // channels per pipeline stage (on
 constexpr int SUBM = 128;                     // points per MMA (UMMA M)
 constexpr int SUB = 2;                        // sub-tiles per CTA tile
 constexpr int STAGES = 2;
+constexpr int PREFETCH = 4;                   // stages the L2 prefetch runs ahead of the TMA loads
 constexpr int A_SUB_BYTES = SUBM * KB * 4;    // 16 KB: 4 TMA boxes of 32 points x 32 channels
 constexpr int NUM_THREADS = 448;             // TMA warp, MMA warp, 4 converter warps, 8 epilogue warps
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
@@ -81,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// HBM -> L2 only: the box a later tma_load_3d will fetch (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -238,8 +244,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ===== TMA producer (whole warp waits, one elected lane issues) =====
+        // Only two 96 KB stages fit shared memory, i.e. ~32 KB of activations in flight per SM -- too little to cover
+        // HBM latency (profiles/r1g: the load pipeline alone topped out near 3 TB/s).  So lanes 0-7 also prefetch the
+        // eight boxes of the stage PREFETCH steps ahead into L2 (cp.async.bulk.prefetch.tensor): the TMA loads that
+        // fill shared memory then hit L2, and the depth of the HBM queue no longer depends on shared-memory capacity.
         uint32_t stage = 0, phase = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long li = 0;                                    // this CTA's tile counter
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
             int cb[SUB], cp[SUB];
 #pragma unroll
             for (int s = 0; s < SUB; ++s) {
@@ -248,16 +259,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 cp[s] = (int)(sid % spc) * SUBM;
             }
             for (int kb = 0; kb < nkb; ++kb) {
+                if (lane < SUB * 4 && !(a.variant & 64)) {
+                    const long long f = li * nkb + kb + PREFETCH;
+                    const long long lt = f / nkb, tt = blockIdx.x + lt * gridDim.x;
+                    if (tt < ntiles) {
+                        const long long sid = tt * SUB + (lane >> 2);
+                        if (sid < nsub)
+                            tma_prefetch_3d(&xmap, (int)(sid % spc) * SUBM + (lane & 3) * 32, (int)(f - lt * nkb) * KB, (int)(sid / spc));
+                    }
+                }
                 mbar_wait(&bar_empty[stage], phase ^ 1u);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)C::TX_BYTES);
+                    const bool no_w = a.variant & 256, no_a = a.variant & 512;    // timing experiments only
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((no_a ? 0 : C::A_BYTES) + (no_w ? 0 : 2 * C::B_HALF)));
                     const uint32_t sa = smem0 + stage * C::STAGE_BYTES;
+                    if (!no_a) {
 #pragma unroll
-                    for (int s = 0; s < SUB; ++s)
+                        for (int s = 0; s < SUB; ++s)
 #pragma unroll
-                        for (int mb = 0; mb < 4; ++mb)
-                            tma_load_3d(sa + s * A_SUB_BYTES + mb * 4096, &xmap, cp[s] + mb * 32, kb * KB, cb[s], &bar_full[stage]);
-                    bulk_load(sa + 2 * C::A_BYTES, a.wsplit + (size_t)kb * (2 * C::B_HALF), 2 * C::B_HALF, &bar_full[stage]);
+                            for (int mb = 0; mb < 4; ++mb)
+                                tma_load_3d(sa + s * A_SUB_BYTES + mb * 4096, &xmap, cp[s] + mb * 32, kb * KB, cb[s], &bar_full[stage]);
+                    }
+                    if (!no_w) bulk_load(sa + 2 * C::A_BYTES, a.wsplit + (size_t)kb * (2 * C::B_HALF), 2 * C::B_HALF, &bar_full[stage]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     __syncwarp();
                 }
 #pragma unroll 4
-                for (int i = ct; i < C::A_BYTES / 16; i += 128) {
+                for (int i = ct; i < ((a.variant & 128) ? 0 : C::A_BYTES / 16); i += 128) {
                     const float4 v = hi[i];
                     float4 h, l;
                     h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);

@@ -101,12 +101,12 @@ def run(variant, timing, sweep=False):
 
         h1 = F.tc_expand(feat, w1, b1, code, 2, wsplit=s1)
         if sweep:   # which part of the pipeline bounds the kernel: 2 = one MMA instead of three, 16 = no stores, 32 = no MMA
-            for v in (0, 2, 16, 32, 48):
+            for v in (0, 64, 2, 16, 32, 48, 48 + 128, 48 + 256, 48 + 512, 48 + 128 + 256, 48 + 128 + 512):   # 64 = no L2 prefetch, 128 = no conversion, 256 = no weight copy, 512 = no activation TMA
                 pu3._lib.lib().pu3_conv_tc_set_variant(v)
                 t1 = timed(lambda: F.tc_expand(feat, w1, b1, code, 2, wsplit=s1))
                 t2 = timed(lambda: F.tc_conv_into(h1, w2, b2, h2, relu=True, wsplit=s2))
                 t3 = timed(lambda: F.tc_project(h2, w3, b3, w4, b4, residual=xyz, res_div=2, wsplit=s3))
-                print(f"sweep variant {v:2d}: up1+expand {t1:.3f} ms   up2 {t2:.3f} ms   fc1+fc2 {t3:.3f} ms")
+                print(f"sweep variant {v:3d}: up1+expand {t1:.3f} ms   up2 {t2:.3f} ms   fc1+fc2 {t3:.3f} ms")
             pu3._lib.lib().pu3_conv_tc_set_variant(0)
             return True
         t1 = timed(lambda: F.tc_expand(feat, w1, b1, code, 2, wsplit=s1))

@@ -461,6 +461,58 @@ class Net(torch.nn.Module):
             return out_xyz, merge(patch_xyz), feat_pm, p_arr * k
         return out_xyz, None, None, None
 
+    # Batched eval without host round trips.  The only data-dependent shapes of the eval path are the per-request tile
+    # counts int(N'_b/312*5) after the outlier filter (:63-76).  N'_b <= N, so P = int(N/312*5) bounds them: every request
+    # gets P tile SLOTS, the slots past its own count repeat its first tile (so that every kernel sees ordinary data and
+    # the per-request duplicate-penalty scope is unchanged), and the counts stay on the device: they bound the seed FPS,
+    # the merge FPS and the next level's skip search through the n_arr / m_arr arguments those kernels already take.
+    # Nothing is read back, so the host enqueues the whole forward ahead of the GPU instead of stalling three times per
+    # forward with ~25 small launches queued behind each stall (~1.7 ms of idle GPU per B=32 step).  The price is the
+    # repeated tiles (none when the filter removes nothing, ~1/P of a level otherwise).  A filtered cloud smaller than one
+    # tile changes the tile size itself: that is flagged on the device and the forward is redone on the synchronous path.
+    static_tiles = True
+
+    def _eval_level_static(self, level, xyz, old_xyz, old_features, old_n, k, num_output_point, keep_features, bad,
+                           **kwargs):
+        B, _, N = xyz.shape
+        dev = xyz.device
+        mask = self._eval_outlier_mask(xyz)                                          # (B,N)
+        counts = mask.sum(dim=1)
+        bad = bad | (counts < k).any()
+        order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
+        xyz_c = torch.gather(xyz, 2, order.unsqueeze(1).expand(-1, 3, -1)).contiguous()
+        n_arr = counts.clamp(min=k).to(torch.int32)          # (a flagged request still reads valid memory; its result is discarded)
+        P = int(N / k * 5)                                                            # :76 with N' = N
+        p_arr = (counts.double() / k * 5).to(torch.int32)                             # int(N'_b / k * 5), computed like the host would
+        key = (B, P, str(dev))
+        cache = self.__dict__.setdefault("_static_cache", {})
+        if key not in cache:
+            cache[key] = (torch.arange(B, dtype=torch.int32, device=dev),
+                          torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P),
+                          torch.arange(P, dtype=torch.int32, device=dev).view(1, 1, P))
+        req, owner, slot_id = cache[key]
+        _, seeds = operations.furthest_point_sample_ragged(xyz_c, n_arr, p_arr, P)    # (B,3,P), zeros past p_arr
+        seeds = torch.where(slot_id < p_arr.view(B, 1, 1), seeds, seeds[:, :, :1])    # spare slots repeat the first tile
+        tiles, _, _ = operations._knn_raw(k, seeds.contiguous(), xyz_c, False, None, want_dist=False,
+                                          ragged=operations.Ragged(req, req, B, n_arr=n_arr))
+        patch_xyz = tiles.permute(0, 2, 1, 3).reshape(B * P, 3, k).contiguous()       # (B*P,3,k), request-major (:85)
+        patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+        ragged = operations.Ragged(owner, owner, B, n_arr=old_n)
+        new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged,
+                                  prev_point_major=True, **kwargs)
+        new_xyz = new_xyz * radius + centroid                                        # (B*P,3,k*r)
+        kr = new_xyz.shape[2]
+        merged = new_xyz.view(B, P, 3, kr).permute(0, 2, 1, 3).reshape(B, 3, P * kr)  # tiles of a request side by side (:149-155)
+        _, out_xyz = operations.furthest_point_sample_ragged(merged, p_arr * kr, None, num_output_point)  # :158
+        if keep_features:
+            Cf = features.shape[1]
+            feat_pm = torch.empty(B, P * k, Cf, dtype=torch.float32, device=dev)
+            fused._lib.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(), None,
+                              feat_pm.data_ptr())
+            prev_xyz = patch_xyz.view(B, P, 3, k).permute(0, 2, 1, 3).reshape(B, 3, P * k)
+            return (out_xyz, prev_xyz, feat_pm, p_arr * k), bad
+        return (out_xyz, None, None, None), bad
+
     def forward(self, xyz, ratio=None, gt=None, seed_idx_per_level=None, **kwargs):
         """
         :param xyz Bx3xN; ratio upscaling factor; gt Bx3x(max_up_ratio*N) (training)
@@ -548,6 +600,33 @@ class Net(torch.nn.Module):
         return cache[key]
 
     def _forward_eval_group(self, xyz, num_levels, num_point, max_num_point, **kwargs):
+        if self.static_tiles and xyz.is_cuda and num_levels > 1 and xyz.shape[2] >= max_num_point:
+            out = self._forward_eval_static(xyz, num_levels, num_point, max_num_point, **kwargs)
+            if out is not None:
+                return out
+        return self._forward_eval_sync(xyz, num_levels, num_point, max_num_point, **kwargs)
+
+    def _forward_eval_static(self, xyz, num_levels, num_point, max_num_point, **kwargs):
+        """Every level with static shapes (see static_tiles above); None when a request needs the synchronous path."""
+        B = xyz.shape[0]
+        dev = xyz.device
+        old_xyz = xyz
+        xyz, feats = self.levels['level_1'](xyz, xyz, previous_level4=None, group=1, **kwargs)
+        old_n = torch.full((B,), old_xyz.shape[2], dtype=torch.int32, device=dev)
+        pm = torch.empty(B, feats.shape[2], feats.shape[1], dtype=torch.float32, device=dev)
+        fused._lib.launch("pu3_to_point_major_f32", feats, B, feats.shape[1], feats.shape[2], feats.contiguous().data_ptr(),
+                          None, pm.data_ptr())
+        old_features = pm
+        bad = torch.zeros((), dtype=torch.bool, device=dev)
+        for l in range(2, num_levels + 1):
+            if xyz.size(-1) <= max_num_point:
+                return None
+            res, bad = self._eval_level_static(self.levels['level_%d' % l], xyz, old_xyz, old_features, old_n, max_num_point,
+                                               num_point * self.step_ratio ** l, l < num_levels, bad, **kwargs)
+            xyz, old_xyz, old_features, old_n = res
+        return None if bool(bad) else xyz     # the one host read of the forward, after everything is enqueued
+
+    def _forward_eval_sync(self, xyz, num_levels, num_point, max_num_point, **kwargs):
         B = xyz.shape[0]
         dev = xyz.device
         level = self.levels['level_1']

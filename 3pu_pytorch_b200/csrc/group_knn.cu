@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(256) knn_dup_small_kernel(int c, int n, const 
     if (found_any) atomicAdd(cloud_any + cloud, found_any);
 }
 
-// Clouds of 1025 .. 16384 points (the previous-level clouds of the skip connection: 3120 and 6240 points at levels 3
-// and 4): one CTA per cloud builds an open-addressing hash table of point indices in shared memory.  Equal points always
+// Clouds of up to 16384 points (every feature-space search: 312 points; the previous-level clouds of the skip connection:
+// 3120 and 6240 points at levels 3 and 4): one CTA per cloud builds an open-addressing hash table of point indices in shared memory.  Equal points always
 // meet in the same slot (slots never change their class of equal points once claimed), atomicMin keeps the smallest index
 // of the class there, so "duplicate" = "not the representative of my slot" -- np.unique's first occurrence
 // (operations.py:199).  O(n) instead of the O(n^2) scan of knn_dup_kernel (0.65 -> ~0.05 ms per eval step).
@@ -970,7 +970,7 @@ extern "C" void pu3_knn_force_stream(int on) { g_knn_force_stream = on; }
 // Test hook: 1 = the indices-only feature kNN orders ranks 1..k-1 exactly (default: rank 0 exact, the rest as a set).
 static int g_knn_exact_pops = 0;
 extern "C" void pu3_knn_exact_pops(int on) { g_knn_exact_pops = on; }
-// Test hook: 1 = duplicate detection of clouds > 1024 points by the O(n^2) scan instead of the hash table.
+// Test hook: 1 = duplicate detection by the O(n^2) scans (hash-first in shared memory up to 1024 points) instead of the hash table.
 static int g_knn_dup_scan = 0;
 extern "C" void pu3_knn_dup_scan(int on) { g_knn_dup_scan = on; }
 
@@ -1049,14 +1049,14 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         uint8_t *dup = ws + pl.off_dup;
         int st = cuda_status(cudaMemsetAsync(ws + pl.off_any, 0, pl.off_dup - pl.off_any, s), "group_knn: memset");
         if (st) return st;
-        if (n <= KD_MAXN) knn_dup_small_kernel<<<clouds, 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
-        else if (n <= KH_MAXN && g_knn_dup_scan == 0) {
-            int table = 2048;
+        if (n <= KH_MAXN && g_knn_dup_scan == 0) {
+            int table = 512;
             while (table < 2 * n) table *= 2;            // load factor <= 0.5
             st = cuda_status(cudaFuncSetAttribute(knn_dup_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table * 4), "group_knn: smem attr");
             if (st) return st;
-            knn_dup_hash_kernel<<<clouds, 1024, table * 4, s>>>(c, n, table, n_arr, points, dup, cloud_any);
-        } else knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
+            knn_dup_hash_kernel<<<clouds, n <= 512 ? 256 : 1024, table * 4, s>>>(c, n, table, n_arr, points, dup, cloud_any);
+        } else if (n <= KD_MAXN) knn_dup_small_kernel<<<clouds, 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
+        else knn_dup_kernel<<<dim3((n + 255) / 256, clouds), 256, 0, s>>>(c, n, n_arr, points, dup, cloud_any);
         PU3_LAUNCH_CHECK("knn_dup_kernel");
         knn_groupflag_kernel<<<(b + 255) / 256, 256, 0, s>>>(a, cloud_any, group_any);
         PU3_LAUNCH_CHECK("knn_groupflag_kernel");

@@ -195,9 +195,9 @@ def test_tiled_and_streaming_kernels_agree(pu3, cuda):
             assert torch.equal(ta, tb)
 
 
-@pytest.mark.parametrize("n", [1025, 3120, 6240, 16384])
+@pytest.mark.parametrize("n", [40, 312, 1025, 3120, 6240, 16384])
 def test_large_cloud_duplicate_detection_hash_equals_scan_and_oracle(pu3, cuda, n):
-    """Clouds of 1025..16384 points mark duplicates with a shared-memory hash table; the O(n^2) scan (test hook) and the
+    """Clouds of up to 16384 points mark duplicates with a shared-memory hash table; the O(n^2) scans (test hook) and the
     oracle (np.unique first occurrences, operations.py:192-204) must give the same neighbours, also with many
     duplicates, -0.0 / +0.0 and fewer than k distinct points (exact max(D) penalty path)."""
     import ctypes

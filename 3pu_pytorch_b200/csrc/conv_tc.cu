@@ -129,8 +129,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -187,6 +187,15 @@ __global__ void __launch_bounds__(256) split_weights_kernel(int cin, int cout, i
         const int off = row * 128 + ((c ^ (row & 7)) << 4);
         *reinterpret_cast<float4 *>(tile + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4 *>(tile + nc * 128 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// bring-up timeline: SM cycle counter of pipeline events of CTA 0 (test hook buffer: 8 event kinds x 256 slots after
+// the 4096-float stage dump)
+__device__ __forceinline__ void tl_mark(float *dbg, int kind, int slot) {
+    if (dbg && blockIdx.x == 0 && slot < 256) {
+        const unsigned long long c = clock64();
+        reinterpret_cast<unsigned int *>(dbg)[4096 + kind * 256 + slot] = (unsigned int)c;
     }
 }
 
@@ -269,6 +278,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                 }
                 mbar_wait(&bar_empty[stage], phase ^ 1u);
+                if (lane == 0) tl_mark(a.dbg, 0, (int)(li * nkb + kb));
                 if (elect_one()) {
                     const bool no_w = a.variant & 256, no_a = a.variant & 512;    // timing experiments only
                     mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((no_a ? 0 : C::A_BYTES) + (no_w ? 0 : 2 * C::B_HALF)));
@@ -295,10 +305,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const uint32_t acc = it % C::ACC_STAGES, acc_phase = (it / C::ACC_STAGES) & 1u;
             mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
+            if (lane == 0) tl_mark(a.dbg, 5, (int)it);
             tc_fence_after();
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&bar_full[stage], phase);
+                if (lane == 0) tl_mark(a.dbg, 1, (int)(it * nkb + kb));
                 mbar_wait(&bar_conv[stage], phase);
+                if (lane == 0) tl_mark(a.dbg, 3, (int)(it * nkb + kb));
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem0 + stage * C::STAGE_BYTES;
@@ -320,12 +333,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     if (kb == nkb - 1) tc_commit(&bar_tfull[acc]);   // accumulators of this tile are complete
                 }
                 __syncwarp();
+                if (lane == 0) tl_mark(a.dbg, 4, (int)(it * nkb + kb));
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp < EPI_WARP0) {
         // ===== converters: raw fp32 -> hi (in place) + lo =====
         const int ct = threadIdx.x - CONV_WARP0 * 32;        // 0..127
+        int cstep = 0;
         uint32_t stage = 0, phase = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
             for (int kb = 0; kb < nkb; ++kb) {
@@ -352,6 +367,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_conv[stage]);
+                if (ct == 0) tl_mark(a.dbg, 2, cstep);
+                ++cstep;
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
@@ -363,6 +380,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const uint32_t acc = it % C::ACC_STAGES, acc_phase = (it / C::ACC_STAGES) & 1u;
             mbar_wait(&bar_tfull[acc], acc_phase);
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 6, (int)it);
             tc_fence_after();
             if (a.variant & 8) {   // bring-up: TMEM store/load self test, value = lane * 1000 + column
                 for (int c = 0; c < 2 * NC; ++c) {
@@ -381,8 +399,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
                 for (int ch = 0; ch < NC / 32; ++ch) {
                     uint32_t v[32], vc[32];
-                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld32(taddr + ch * 32, v);               // main and correction columns: two loads in flight, one wait
                     tmem_ld32(taddr + NC + ch * 32, vc);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));
                     if (MODE == MODE_PLAIN) {
@@ -444,6 +463,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 7, (int)it);
         }
     }
 

@@ -396,36 +396,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const bool valid = sid < nsub && p < a.n && !(a.variant & 16);   // 16: timing without stores
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + s * 2 * NC;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < NC / 32; ++ch) {
+#pragma unroll(MODE == MODE_PROJECT ? NC / 32 : 1)
+                for (int ch = 0; ch < NC / 32; ++ch) {       // store modes stay rolled: large body (several store paths), keep it in the i-cache
                     uint32_t v[32], vc[32];
                     tmem_ld32(taddr + ch * 32, v);               // main and correction columns: two loads in flight, one wait
                     tmem_ld32(taddr + NC + ch * 32, vc);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));
+                    // stores: ONE divergent branch per chunk (valid = this lane's point exists); inside it only the
+                    // warp-uniform co < cout test remains, so every store is a predicated STG instead of a branch region
                     if (MODE == MODE_PLAIN) {
-                        float *yp = a.y + bi * a.y_bstride + p;
+                        float *yp = a.y + bi * a.y_bstride + p + (size_t)(ch * 32) * a.n;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int co = ch * 32 + j;
-                            float r = __uint_as_float(v[j]) + bias_s[co];
+                            float r = __uint_as_float(v[j]) + bias_s[ch * 32 + j];
                             if (a.relu) r = fmaxf(r, 0.f);
-                            if (valid && co < a.cout) yp[(size_t)co * a.n] = r;
+                            v[j] = __float_as_uint(r);
+                        }
+                        if (valid) {
+                            const int lim = a.cout - ch * 32;        // channels of this chunk that exist (warp-uniform)
+                            if (lim >= 32) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) yp[(size_t)j * a.n] = __uint_as_float(v[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < lim) yp[(size_t)j * a.n] = __uint_as_float(v[j]);
+                            }
                         }
                     } else if (MODE == MODE_EXPAND) {
                         const int nr = a.n * a.r;
                         float *yp = a.y + bi * a.y_bstride + (size_t)p * a.r;
                         if (a.r == 2) {      // the reference's step ratio: both replicas in one 8-byte store per point
                             const float c0 = code_s[0], c1 = code_s[1];
+                            if (valid) {
+                                const int lim = a.cout - ch * 32;
+                                float *yq = yp + (size_t)(ch * 32) * nr;
+                                if (lim >= 32) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int co = ch * 32 + j;
-                                const float pre = __uint_as_float(v[j]) + bias_s[co];
-                                float2 o;
-                                o.x = fmaxf(__fmaf_rn(wcode_s[co], c0, pre), 0.f);
-                                o.y = fmaxf(__fmaf_rn(wcode_s[co], c1, pre), 0.f);
-                                if (valid && co < a.cout) *reinterpret_cast<float2 *>(yp + (size_t)co * nr) = o;
+                                    for (int j = 0; j < 32; ++j) {
+                                        const int co = ch * 32 + j;
+                                        const float pre = __uint_as_float(v[j]) + bias_s[co];
+                                        float2 o;
+                                        o.x = fmaxf(__fmaf_rn(wcode_s[co], c0, pre), 0.f);
+                                        o.y = fmaxf(__fmaf_rn(wcode_s[co], c1, pre), 0.f);
+                                        *reinterpret_cast<float2 *>(yq + (size_t)j * nr) = o;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const int co = ch * 32 + j;
+                                        const float pre = __uint_as_float(v[j]) + bias_s[co];
+                                        float2 o;
+                                        o.x = fmaxf(__fmaf_rn(wcode_s[co], c0, pre), 0.f);
+                                        o.y = fmaxf(__fmaf_rn(wcode_s[co], c1, pre), 0.f);
+                                        if (j < lim) *reinterpret_cast<float2 *>(yq + (size_t)j * nr) = o;
+                                    }
+                                }
                             }
                         } else {
 #pragma unroll 1

@@ -41,9 +41,11 @@ struct __align__(16) FpsCand {
     uint32_t pad0, pad1;
 };
 
+constexpr int FPS_MAX_CAND = 256;          // candidates a CTA receives per round: cluster size x warps per CTA
 struct FpsSmem {
-    FpsCand cluster_slot[2][FPS_MAX_CLUSTER];  // [round parity][source CTA rank]
+    FpsCand cluster_slot[2][FPS_MAX_CAND];     // [round parity][source CTA rank * warps + source warp]
     FpsCand warp_slot[2][32];                  // [round parity][warp]: the warp's winner, coordinates included
+    FpsCand cta_slot[2];                       // [round parity] the CTA's winner (wide clusters: leader-warp exchange)
     uint64_t mbar[2];                          // [round parity] "all S candidates of the round have landed"
 };
 
@@ -55,8 +57,21 @@ __device__ __forceinline__ bool warp_argmax(uint32_t dkey, uint32_t rank, uint32
     return cand == rmin && rmin != 0xffffffffu;
 }
 
+// bring-up timeline (build with `make -B EXTRA=-DPU3_FPS_TIMELINE`, then profiles/fps_timeline.py): SM cycle counter at the
+// phases of rounds [1000, 1008) of cluster 0, CTA 0, thread 0.  Compiled out by default.
+#ifdef PU3_FPS_TIMELINE
+__device__ unsigned int *g_fps_timeline = nullptr;
+__device__ __forceinline__ void fps_mark(int j, int phase) {
+    if (g_fps_timeline && blockIdx.x == 0 && threadIdx.x == 0 && j >= 1000 && j < 1008)
+        g_fps_timeline[(j - 1000) * 8 + phase] = (unsigned int)clock64();
+}
+#else
+__device__ __forceinline__ void fps_mark(int, int) {}
+#endif
+
 // PPT points per thread; XYZ_REGS: coordinates in registers (else read from shared memory each round)
-template <int PPT, bool XYZ_REGS, int MAX_THREADS>
+// DIRECT: flavour of the cluster exchange (host: S x warps <= 64), a template parameter so that each flavour is compiled alone
+template <int PPT, bool XYZ_REGS, int MAX_THREADS, bool DIRECT>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const int32_t *__restrict__ m_arr,
            const float *__restrict__ xyz, float *__restrict__ temp, int32_t *__restrict__ idx) {
@@ -71,6 +86,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     const int n = n_arr ? min(__ldg(n_arr + cloud), n_stride) : n_stride;
     const int m = m_arr ? min(__ldg(m_arr + cloud), m_stride) : m_stride;
     const int t_ref = n > 0 ? min(512, 1 << (31 - __clz(n))) : 1;  // the reference's block size for THIS cloud
+    const int t_shift = 31 - __clz(t_ref);                         // t_ref is a power of two: k / t_ref = k >> t_shift
     const int nthreads = blockDim.x;
     const int GT = nthreads * S;                     // threads per cloud; a multiple of t_ref
     const int g = crank * nthreads + threadIdx.x;    // this thread's id within the cloud
@@ -113,6 +129,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
 
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
+        fps_mark(j, 0);
         // ---- 1. update running distances, thread-local arg-max (first strictly greater) -------
         float best = -1.f;
         int besti = 0;
@@ -127,6 +144,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             t[i] = d2;
             if (d2 > best) { best = d2; besti = i; }
         }
+        fps_mark(j, 1);
         // ---- 2. warp arg-max: the winning lane publishes (distance, tie rank, index, coordinates) ----------
         const uint32_t dkey = best >= 0.f ? __float_as_uint(best) : 0u;
         const uint32_t dmax_w = __reduce_max_sync(0xffffffffu, dkey);
@@ -134,20 +152,27 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
         int kbest = 0;
         if (dkey == dmax_w && best >= 0.f) {     // rank only where it can matter
             kbest = g + besti * GT;
-            rank = (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest / t_ref);
+            rank = (uint32_t)(kbest & (t_ref - 1)) * rank_rows + (uint32_t)(kbest >> t_shift);
         }
-        const uint32_t rmin_w = __reduce_min_sync(0xffffffffu, rank);
-        if (rank == rmin_w && (rmin_w != 0xffffffffu || lane == 0)) {   // the winner, or lane 0 of an empty warp
-            const int slot = besti * nthreads + threadIdx.x;            // coordinates from the smem copy: no dynamic
-            uint4 lo, hi;                                               // register indexing, and off the leader's path
-            lo.x = dmax_w; lo.y = rmin_w; lo.z = (uint32_t)kbest; lo.w = __float_as_uint(sx[slot]);
-            hi.x = __float_as_uint(sy[slot]); hi.y = __float_as_uint(sz[slot]); hi.z = 0u; hi.w = 0u;
-            uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
-            dst[0] = lo; dst[1] = hi;
+        // ties on the distance are rare: when exactly one lane holds the maximum the rank reduction is skipped
+        const unsigned holders = __ballot_sync(0xffffffffu, rank != 0xffffffffu);
+        const uint32_t rmin_w = __popc(holders) == 1 ? __shfl_sync(0xffffffffu, rank, __ffs(holders) - 1)
+                                                     : __reduce_min_sync(0xffffffffu, rank);
+        const bool publisher = rank == rmin_w && (rmin_w != 0xffffffffu || lane == 0);   // the winner, or lane 0 of an empty warp
+        uint4 plo = make_uint4(0u, 0xffffffffu, 0u, 0u), phi = make_uint4(0u, 0u, 0u, 0u);
+        if (publisher) {
+            const int slot = besti * nthreads + threadIdx.x;            // coordinates from the smem copy: no dynamic register indexing
+            plo.x = dmax_w; plo.y = rmin_w; plo.z = (uint32_t)kbest; plo.w = __float_as_uint(sx[slot]);
+            phi.x = __float_as_uint(sy[slot]); phi.y = __float_as_uint(sz[slot]);
         }
-        __syncthreads();                          // the only CTA-wide barrier of the round
+        fps_mark(j, 2);
         if (S == 1) {
-            // ---- 3a. one CTA per cloud: every warp reduces the warp slots itself (no second barrier) -------
+            // ---- 3a. one CTA per cloud: warp slots + ONE __syncthreads, every warp reduces the slots itself ----------
+            if (publisher) {
+                uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
+                dst[0] = plo; dst[1] = phi;
+            }
+            __syncthreads();
             uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
             if (lane < nwarps) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(&sm.warp_slot[par][lane]);
@@ -161,9 +186,63 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, wsrc));
             const int kw = (int)__shfl_sync(0xffffffffu, lo.z, wsrc);
             if (threadIdx.x == 0) out[j] = kw;
+        } else if (DIRECT) {
+            // ---- 3b. cluster of <= 64 warps: EVERY warp sends its candidate straight into every CTA's slot array by
+            //          async DSMEM stores that complete on the receiver's mbarrier.  No CTA-level reduction, no
+            //          __syncthreads, no leader warp: the in-kernel timeline (profiles/r1g) showed those cost ~1000 of the
+            //          ~2400 cycles of a round.  The mbarrier wait is the only synchronisation: a round's slots are complete
+            //          when all S x nwarps candidates have landed, and a warp cannot overwrite a slot of round j+2 before
+            //          every warp of the cluster has read round j (it must first pass the barrier of round j+1, which
+            //          needs their j+1 sends).  The candidate goes through the warp's own slot so that lane r sends it to
+            //          CTA r: the S x 2 remote stores are issued by S lanes at once instead of one lane after the other.
+            if (publisher) {
+                uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
+                dst[0] = plo; dst[1] = phi;
+            }
+            __syncwarp();
+            if (lane < (int)S) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.warp_slot[par][warp]);
+                const uint4 lo = src[0], hi = src[1];
+                const uint32_t dst = map_to_cta(&sm.cluster_slot[par][0], (uint32_t)lane) + (crank * (uint32_t)nwarps + (uint32_t)warp) * 32u;
+                const uint32_t rbar = map_to_cta(&sm.mbar[par], (uint32_t)lane);
+                st_async_v4(dst, rbar, lo.x, lo.y, lo.z, lo.w);
+                st_async_v4(dst + 16, rbar, hi.x, hi.y, 0u, 0u);
+            }
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.mbar[par], S * (uint32_t)nwarps * 32u);
+            fps_mark(j, 4);
+            // ---- 4. every warp: wait for the S x nwarps candidates, reduce them, take the winner's coordinates ----------
+            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);   // phase = earlier uses of this buffer
+            fps_mark(j, 5);
+            const int total = (int)S * nwarps;
+            uint32_t bd = 0u, br = 0xffffffffu;
+            int bc = 0;
+            for (int c = lane; c < total; c += 32) {
+                const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);   // (dkey, rank)
+                if (kr.x > bd || (kr.x == bd && kr.y < br)) { bd = kr.x; br = kr.y; bc = c; }
+            }
+            const uint32_t dmax = __reduce_max_sync(0xffffffffu, bd);
+            unsigned cands = __ballot_sync(0xffffffffu, bd == dmax && br != 0xffffffffu);
+            if (__popc(cands) > 1) {                                    // tie on the distance: smallest rank wins
+                const uint32_t rmin = __reduce_min_sync(0xffffffffu, bd == dmax ? br : 0xffffffffu);
+                cands = __ballot_sync(0xffffffffu, bd == dmax && br == rmin);
+            }
+            const int csrc = cands ? __ffs(cands) - 1 : 0;
+            const int cwin = __shfl_sync(0xffffffffu, bc, csrc);
+            const uint4 wlo = *reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][cwin]);     // broadcast reads
+            const uint2 whi = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][cwin]) + 2);
+            x1 = __uint_as_float(wlo.w);
+            y1 = __uint_as_float(whi.x);
+            z1 = __uint_as_float(whi.y);
+            if (g == 0) out[j] = (int)wlo.z;
         } else {
-            // ---- 3b. leader warp: CTA winner -> every peer's slot by async DSMEM stores that complete on the
-            //          receiver's mbarrier.  No cluster-wide barrier; the other warps go straight to the wait.
+            // ---- 3c. wide cluster (> 64 warps: the 16-CTA whole-shape call): scanning S x nwarps candidates in every warp
+            //          would cost more than it saves, so the CTA reduces first (warp slots, __syncthreads, leader warp) and
+            //          only S candidates travel; lane r of the leader warp sends to CTA r.
+            if (publisher) {
+                uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
+                dst[0] = plo; dst[1] = phi;
+            }
+            __syncthreads();
             if (warp == 0) {
                 uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
                 if (lane < nwarps) {
@@ -173,18 +252,22 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 uint32_t dmax, rmin;
                 const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
                 const unsigned wb = __ballot_sync(0xffffffffu, win);
-                if (wb == 0u ? lane == 0 : win) {      // the winning lane holds the candidate in registers
+                if (wb == 0u ? lane == 0 : win) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(&sm.cta_slot[par]);
+                    dst[0] = lo; dst[1] = hi;
                     mbar_arrive_expect_tx(&sm.mbar[par], S * 32u);
-                    for (uint32_t r = 0; r < S; ++r) {
-                        const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], r);
-                        const uint32_t rbar = map_to_cta(&sm.mbar[par], r);
-                        st_async_v4(dst, rbar, lo.x, lo.y, lo.z, lo.w);
-                        st_async_v4(dst + 16, rbar, hi.x, hi.y, 0u, 0u);
-                    }
+                }
+                __syncwarp();
+                if (lane < (int)S) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&sm.cta_slot[par]);
+                    const uint4 clo = src[0], chi = src[1];
+                    const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], (uint32_t)lane);
+                    const uint32_t rbar = map_to_cta(&sm.mbar[par], (uint32_t)lane);
+                    st_async_v4(dst, rbar, clo.x, clo.y, clo.z, clo.w);
+                    st_async_v4(dst + 16, rbar, chi.x, chi.y, 0u, 0u);
                 }
             }
-            // ---- 4. every warp: wait for the S candidates, reduce them, take the winner's coordinates ----------
-            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);   // phase = earlier uses of this buffer
+            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);
             uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
             if (lane < (int)S) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][lane]);
@@ -198,6 +281,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, csrc));
             const int kw = (int)__shfl_sync(0xffffffffu, lo.z, csrc);
             if (g == 0) out[j] = kw;
+            fps_mark(j, 6);
         }
     }
     if (trow) {
@@ -274,10 +358,27 @@ static int ref_block_size(int n) {
     return t > 512 ? 512 : t;
 }
 
+template <int PPT, bool XYZ_REGS, int MAX_THREADS, bool DIRECT>
+static int launch_fps_impl(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, int S, int threads,
+                           const float *xyz, float *temp, int32_t *idx, cudaStream_t stream);
+
 template <int PPT, bool XYZ_REGS, int MAX_THREADS>
 static int launch_fps(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, int S, int threads,
                       const float *xyz, float *temp, int32_t *idx, cudaStream_t stream) {
-    auto kern = fps_kernel<PPT, XYZ_REGS, MAX_THREADS>;
+    // every warp of the cluster exchanges directly while the candidates stay few (<= 64 warps); wider clusters reduce per CTA first
+    if (S * (threads / 32) <= 64)
+        return launch_fps_impl<PPT, XYZ_REGS, MAX_THREADS, true>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, stream);
+    return launch_fps_impl<PPT, XYZ_REGS, MAX_THREADS, false>(b, n, m, n_arr, m_arr, S, threads, xyz, temp, idx, stream);
+}
+
+template <int PPT, bool XYZ_REGS, int MAX_THREADS, bool DIRECT>
+static int launch_fps_impl(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, int S, int threads,
+                           const float *xyz, float *temp, int32_t *idx, cudaStream_t stream) {
+    auto kern = fps_kernel<PPT, XYZ_REGS, MAX_THREADS, DIRECT>;
+    if (S > 1 && S * (threads / 32) > FPS_MAX_CAND) {
+        set_error("fps: internal: cluster of %d CTAs x %d warps exceeds %d candidate slots", S, threads / 32, FPS_MAX_CAND);
+        return PU3_E_UNSUPPORTED;
+    }
     const size_t smem = sizeof(FpsSmem) + (size_t)threads * PPT * 3 * sizeof(float);
     int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                          "fps: set max dynamic smem");
@@ -311,6 +412,9 @@ static int g_fps_force_cluster = 0;
 static int g_fps_force_threads = 0;
 static int g_fps_sm_budget = 0;   // SMs FPS may spread over (0 = all): leaves room for kernels of a concurrent stream
 extern "C" void pu3_fps_set_sm_budget(int n) { g_fps_sm_budget = n; }
+#ifdef PU3_FPS_TIMELINE
+extern "C" void pu3_fps_set_timeline(unsigned int *buf) { cudaMemcpyToSymbol(pu3::g_fps_timeline, &buf, sizeof(buf)); }   // bring-up hook
+#endif
 extern "C" void pu3_fps_set_cluster(int s) { g_fps_force_cluster = s; }
 extern "C" void pu3_fps_set_threads(int t) { g_fps_force_threads = t; }   // tuning hook (profiles/tune_fps.py)
 

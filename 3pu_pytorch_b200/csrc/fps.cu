@@ -216,9 +216,13 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             const int total = (int)S * nwarps;
             uint32_t bd = 0u, br = 0xffffffffu;
             int bc = 0;
-            for (int c = lane; c < total; c += 32) {
-                const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);   // (dkey, rank)
-                if (kr.x > bd || (kr.x == bd && kr.y < br)) { bd = kr.x; br = kr.y; bc = c; }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {                               // total <= 64 in this flavour: at most two per lane
+                const int c = lane + 32 * u;
+                if (c < total) {
+                    const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);   // (dkey, rank)
+                    if (kr.x > bd || (kr.x == bd && kr.y < br)) { bd = kr.x; br = kr.y; bc = c; }
+                }
             }
             const uint32_t dmax = __reduce_max_sync(0xffffffffu, bd);
             unsigned cands = __ballot_sync(0xffffffffu, bd == dmax && br != 0xffffffffu);

@@ -104,9 +104,9 @@ KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
     "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
-    # layer0 + 4 x (kNN + edge-conv) + 3 preps + 6 head kernels (3 weight splits + 3 tcgen05); + 4 x 3 duplicate kernels;
-    # skip adds 2 + 3, iota 1
-    "pu3_level_forward_f32": 30,
+    # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 6 head kernels (3 weight splits + 3 tcgen05);
+    # + 4 x 3 duplicate kernels; skip adds 2 + 3, iota 1
+    "pu3_level_forward_f32": 33,
     "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
     "pu3_fps_ragged_f32": 1,
     "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique
@@ -131,7 +131,8 @@ class Profiler:
 
     ENGINE_TAGS = ["pu3_pointwise_conv_f32", "pu3_group_knn_f32[c=24,k=33,n<=312]", "pu3_edgeconv_f32",
                    "pu3_group_knn_f32[c=3,k=5,skip]", "pu3_skip_fuse_f32", "pu3_expand_code_f32", "misc",
-                   "pu3_conv_tc_f32[tcgen05 head: 3 weight splits + expand + conv + project]"]
+                   "pu3_conv_tc_f32[tcgen05 head: 3 weight splits + expand + conv + project]",
+                   "pu3_conv_tc_f32[tcgen05 prep convs 84/144/204->24: 3 weight splits + 3 convs]"]
 
     def summary(self):
         """{name: (calls, total_ms)} -- call after torch.cuda.synchronize().  Kernels launched inside the level

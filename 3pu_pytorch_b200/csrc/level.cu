@@ -20,7 +20,7 @@ __global__ void iota_kernel(int n, int32_t *out) {
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct LevelPlan {
-    size_t off_h, off_idx, off_me, off_pre, off_h1, off_h2, off_h3, off_skipidx, off_knnws, off_wsplit[3], total;
+    size_t off_h, off_idx, off_me, off_pre, off_h1, off_h2, off_h3, off_skipidx, off_knnws, off_wsplit[3], off_wprep[3], total;
     size_t knn_ws;
 };
 
@@ -43,6 +43,7 @@ static LevelPlan plan_level(int t, int n, int r, int knn, int fm_knn, int clouds
     p.off_wsplit[0] = off; off += al256(pu3_conv_tc_wsplit_bytes(264, 128));
     p.off_wsplit[1] = off; off += al256(pu3_conv_tc_wsplit_bytes(128, 128));
     p.off_wsplit[2] = off; off += al256(pu3_conv_tc_wsplit_bytes(128, 64));
+    for (int i = 0; i < 3; ++i) { p.off_wprep[i] = off; off += al256(pu3_conv_tc_wsplit_bytes(84 + 60 * i, 24)); }   // layerK_prep
     p.total = off;
     (void)clouds;
     return p;
@@ -51,8 +52,9 @@ static LevelPlan plan_level(int t, int n, int r, int knn, int fm_knn, int clouds
 
 using namespace pu3;
 
-// Test / A-B hook: 0 runs the expansion head on the fp32 FFMA SGEMM instead of the tcgen05 kernels.
-static int g_level_tc = 1;
+// Test / A-B hook: 2 (default) = expansion head and the three 24-channel prep convolutions on the tcgen05 kernels,
+// 1 = head only, 0 = everything on the fp32 FFMA SGEMM.
+static int g_level_tc = 2;
 extern "C" void pu3_level_set_tc(int on) { g_level_tc = on; }
 
 extern "C" int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream) {
@@ -105,9 +107,16 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
                                           cudaMemcpyDeviceToDevice, as_stream(stream)), "level_forward: copy x0"));
     int lo = C - 24;
     for (int blk = 0; blk < 4; ++blk) {
-        if (blk > 0)   // layerK_prep (:213-221): Conv1d + ReLU over everything produced so far
-            PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n, C - lo, 24, feat + (size_t)lo * n, fs, w->prep_w[blk - 1], w->prep_b[blk - 1],
-                                           h, 24LL * n, nullptr, 0, 1, 1, 1, stream));
+        if (blk > 0) {   // layerK_prep (:213-221): Conv1d + ReLU over everything produced so far
+            if (g_level_tc >= 2 && n % 4 == 0) {   // tensor cores (3xTF32), cout 24 padded to the 64-column MMA
+                void *wsp = ws + p.off_wprep[blk - 1];
+                PU3_TRYT(PROF_CONV_TC_PREP, pu3_conv_tc_prepare_f32(C - lo, 24, w->prep_w[blk - 1], C - lo, wsp, stream));
+                PU3_TRYT(PROF_CONV_TC_PREP, pu3_conv_tc_f32(t, n, C - lo, 24, feat + (size_t)lo * n, fs, wsp, w->prep_b[blk - 1], h, 24LL * n, 1, stream));
+            } else {
+                PU3_TRYT(PROF_CONV, pu3_pointwise_conv_f32(t, n, C - lo, 24, feat + (size_t)lo * n, fs, w->prep_w[blk - 1], w->prep_b[blk - 1],
+                                               h, 24LL * n, nullptr, 0, 1, 1, 1, stream));
+            }
+        }
         // dynamic graph in feature space (layers.py:33): k+1 nearest, duplicates pushed back, rank 0 dropped by idx_off=1;
         // the edge-conv takes a max over the other k, so they are requested as a set (PU3_KNN_SET_ORDER)
         if (owner)
@@ -131,7 +140,7 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
                                   owner, stream));
     }
     // expansion head (:349-372)
-    if (g_level_tc && n % 4 == 0 && r <= 8) {
+    if (g_level_tc >= 1 && n % 4 == 0 && r <= 8) {
         // tensor cores (tcgen05, 3xTF32): up1 + code column + replication | up2 | fc1 + fc2 + residual -- 3 kernels, the
         // (t,265,n*r) input, the 128-channel "pre" tensor and the 64-channel activation never exist
         void *ws1 = ws + p.off_wsplit[0], *ws2 = ws + p.off_wsplit[1], *ws3 = ws + p.off_wsplit[2];

@@ -40,7 +40,7 @@ const DeviceInfo &device_info();  // cached per device
 static inline cudaStream_t as_stream(pu3_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // per-family timing inside composite entry points (no-ops unless pu3_prof_enable(1))
-enum ProfTag { PROF_CONV = 0, PROF_KNN_FEAT = 1, PROF_EDGECONV = 2, PROF_KNN_SKIP = 3, PROF_SKIP_FUSE = 4, PROF_EXPAND = 5, PROF_MISC = 6, PROF_CONV_TC = 7, PROF_NTAGS = 8 };
+enum ProfTag { PROF_CONV = 0, PROF_KNN_FEAT = 1, PROF_EDGECONV = 2, PROF_KNN_SKIP = 3, PROF_SKIP_FUSE = 4, PROF_EXPAND = 5, PROF_MISC = 6, PROF_CONV_TC = 7, PROF_CONV_TC_PREP = 8, PROF_NTAGS = 9 };
 int prof_begin(int tag, cudaStream_t s);
 void prof_end(int id, cudaStream_t s);
 

@@ -48,7 +48,7 @@ def _tensor_peak():
     return 1400.0, "fallback (B200_PROFILING.md)"
 
 
-TC_TAG = "pu3_conv_tc_f32["
+TC_TAG = "pu3_conv_tc_f32[tcgen05 head"
 
 
 def _mlp_roofline(summ, steps):

@@ -271,7 +271,7 @@ int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float 
                           const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
                           float *out_xyz, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
 int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
-void pu3_level_set_tc(int on); /* test / A-B hook: 0 = expansion head on the fp32 FFMA kernels instead of tcgen05 (default 1) */
+void pu3_level_set_tc(int mode); /* test / A-B hook: 2 (default) = head + prep convolutions on tcgen05, 1 = head only, 0 = fp32 FFMA kernels */
 
 /*
  * Weight / bias gradient of the 1x1 convolution: dw[co,ci] += sum_{b,p} dy[b,co,p] x[b,ci,p], db[co] += sum dy

@@ -102,13 +102,19 @@ def test_level_head_on_tensor_cores_matches_ffma_head_and_oracle(pu3, cuda):
     lib = pu3._lib.lib()
     try:
         with torch.no_grad():
-            lib.pu3_level_set_tc(1)
+            lib.pu3_level_set_tc(2)          # default: head and prep convolutions on tensor cores
+            all_xyz, all_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
+            lib.pu3_level_set_tc(1)          # head only
             tc_xyz, tc_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
             lib.pu3_level_set_tc(0)
             ff_xyz, ff_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
     finally:
-        lib.pu3_level_set_tc(1)
+        lib.pu3_level_set_tc(2)
     assert torch.equal(tc_feat, ff_feat)                                # the head does not touch the features
     assert_close_frac(tc_xyz, ff_xyz, rtol=1e-5, atol=2e-6, what="tcgen05 head vs FFMA head")
     want_xyz, _ = ref_net.level_forward(params, "levels.level_1", xyz, xyz, None, knn=32)
     assert_close_frac(tc_xyz, want_xyz, rtol=1e-5, atol=2e-6, frac=0.99, what="tcgen05 head vs oracle")
+    # prep convolutions on tensor cores feed the feature kNN: near-tie flips may move a small share of the features
+    want_xyz2, want_feat = ref_net.level_forward(params, "levels.level_1", xyz, xyz, None, knn=32)
+    assert_close_frac(all_feat, want_feat, rtol=1e-5, atol=2e-6, frac=0.99, what="tcgen05 preps + head: features vs oracle")
+    assert_close_frac(all_xyz, want_xyz2, rtol=1e-5, atol=2e-6, frac=0.99, what="tcgen05 preps + head: xyz vs oracle")

@@ -255,6 +255,8 @@ __device__ __forceinline__ void ef_layer2(f32x2 (&ha)[6], f32x2 (&hb)[6], const 
     hb[3] = fma2(w3, xxb, hb[3]); hb[4] = fma2(w4, xxb, hb[4]); hb[5] = fma2(w5, xxb, hb[5]);
 }
 
+// FULLK: k == 32 (the reference configuration): every lane's two edges exist, the validity selects disappear
+template <bool FULLK>
 __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, int k, int pts_per_cta,
                                                                          const float *__restrict__ x, long long x_bstride,
                                                                          const int32_t *__restrict__ idx, int idx_stride,
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 2) edgeconv_fast_kernel(int n, 
     // the lane's two edges are fixed; their neighbour indices are the only global loads of the main loop and sit at the
     // head of its dependency chain (ncu: long-scoreboard was the top stall), so they are fetched one point ahead
     const int ea = hl, eb = 16 + hl;
-    const bool va = ea < k, vb = eb < k;
+    const bool va = FULLK || ea < k, vb = FULLK || eb < k;
     auto fetch_idx = [&](int t0x, int lp0x, int &ja_out, int &jb_out) {
         const int tc = min(EC_PT, p_end - t0x);
         const int ix = (lp0x + hp < tc) ? t0x + lp0x + hp : t0x + lp0x;
@@ -482,9 +484,10 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     int st;
     const size_t fast_smem = sizeof(EfSmemW) + (size_t)(EC_OUT * (EC_PT + 1) + EC_WARPS * 2 * 36 + EC_WARPS * 2 * EF_PS + (size_t)n * (EF_XS + EF_PS0)) * sizeof(float);
     if (k <= 32 && fast_smem <= 110 * 1024 && g_ec_force_generic == 0) {
-        st = cuda_status(cudaFuncSetAttribute(edgeconv_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem), "edgeconv: smem attr");
+        auto kern = k == 32 ? edgeconv_fast_kernel<true> : edgeconv_fast_kernel<false>;
+        st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem), "edgeconv: smem attr");
         if (st) return st;
-        edgeconv_fast_kernel<<<grid, EC_WARPS * 32, fast_smem, s>>>(n, k, pts, x, x_bstride, idx, idx_stride, idx_off, W, y, y_bstride);
+        kern<<<grid, EC_WARPS * 32, fast_smem, s>>>(n, k, pts, x, x_bstride, idx, idx_stride, idx_off, W, y, y_bstride);
         PU3_LAUNCH_CHECK("edgeconv_fast_kernel");
         return PU3_OK;
     }

@@ -572,13 +572,13 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
                     for (int r = 1; r < a.k; ++r) {
                         const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk);
                         if (hk == kmin) {
-                            ++cnt;                                // (index clamped: under massive ties cnt runs past the list
-                            hk = krow[min(cnt, KF_S - 1) * 32 + lane];   //  and the compiler may issue the load unconditionally)
-                            if (cnt >= KF_S) hk = 0xffffffffu;
+                            ++cnt;                                // index clamped: a lane that runs out of keys (or massive ties)
+                            hk = krow[min(cnt, KF_S - 1) * 32 + lane];   // re-reads its last key; that case is caught below
                         }
                     }
                     const int total = __reduce_add_sync(0xffffffffu, cnt);
-                    if (total == a.k) {
+                    const int most = __reduce_max_sync(0xffffffffu, cnt);
+                    if (total == a.k && most < KF_S) {        // exactly k pops, and no lane exhausted its 10 keys
                         // exclusive prefix of the per-lane counts (rank 0 goes to slot 0, outside the prefix)
                         const int mine = cnt - (first ? 1 : 0);
                         int incl = mine;

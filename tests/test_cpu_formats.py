@@ -103,3 +103,16 @@ def test_augmentation_helpers_match_numpy_restatement(pu3):
     assert float((j - inp).abs().max()) <= 0.02 + 1e-12 and float((j - inp).abs().max()) > 0
     n2, c2, f2 = P.normalize_point_cloud(inp[0])                           # 2-D input branch (pc_utils.py:16-17)
     assert n2.shape == (312, 3) and c2.shape == (1, 3) and f2.shape == (1, 1)
+
+
+def test_device_side_tile_count_equals_the_reference_host_arithmetic():
+    """Net.static_tiles computes the per-request tile count int(N'/k*5) (upsampler.py:76) on the device as
+    (counts.double() / k * 5).to(int32); it must equal Python's float arithmetic for every count that can occur."""
+    for k in (312, 100, 77):
+        counts = torch.arange(k, 25001, dtype=torch.int64)
+        dev_side = (counts.double() / k * 5).to(torch.int32)
+        host_side = torch.tensor([int(c / k * 5) for c in counts.tolist()], dtype=torch.int32)
+        assert torch.equal(dev_side, host_side), k
+    # the static slot count bounds every per-request count (N' <= N)
+    for n in (624, 1248, 2496, 5000):
+        assert int(n / 312 * 5) >= int((n - 1) / 312 * 5)

@@ -15,10 +15,13 @@ Style: functional -- parameters come in as a flat dict with the reference's
 state_dict key names, so one set of weights drives the
 reference, this oracle and the product.
 
-Parity pin: validated op by op against the unmodified reference imported from
-/root/reference (tests/test_oracle_vs_reference.py, runs where that tree exists)
-and against tests/golden/ref_py_*.npz minted from the reference by
-tests/golden/make_golden_cpu.py.
+Parity pin: tests/golden/ref_py.npz was minted from the UNMODIFIED reference Python
+(imported on CPU by oracle/reference_loader.py) by tests/golden/make_golden_py.py;
+tests/test_cpu_ref_net_golden.py replays the stored inputs through this file and
+requires bit-identical results (group_knn with duplicates and both layouts, one Level,
+a 2-level eval forward, a train-mode forward with Chamfer loss and gradients, the
+threshold branch of ChamferLoss), and re-derives the fixture from the reference where
+/root/reference exists.
 """
 from math import log
 

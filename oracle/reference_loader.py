@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference Python (network/*) from /root/reference on CPU.
 
 TEST INFRASTRUCTURE ONLY.  Used in this container (where /root/reference exists)
-to validate oracle/ref_net.py and to mint tests/golden/ref_py_*.npz.  Nothing
+to validate oracle/ref_net.py and to mint tests/golden/ref_py.npz (tests/golden/make_golden_py.py).  Nothing
 here runs on the GPU box.
 
 The reference imports three modules that do not exist on CPU (network/operations.py:2,6;

@@ -44,3 +44,30 @@ def test_cpu_tensors_are_refused(pu3):
         pu3.operations.group_knn(3, torch.rand(1, 3, 8), torch.rand(1, 3, 8))
     with pytest.raises(RuntimeError):
         pu3.operations.furthest_point_sample(torch.rand(1, 3, 8), 2)
+
+
+def test_header_is_plain_c_and_cxx():
+    """The drop-in boundary is a C ABI: include/pu3_b200.h must compile as C99 and as C++17 on its own (no torch, no CUDA
+    headers), and a C translation unit must link against the shared library without a C++ runtime in its own code."""
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "pu3_b200.h")
+    gcc = shutil.which("gcc") or "/opt/gcc/bin/gcc"
+    gxx = shutil.which("g++") or "/opt/gcc/bin/g++"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    lib = os.path.join(root, "3pu_pytorch_b200", "lib", "libpu3_b200.so")
+    if not os.path.isfile(lib):
+        pytest.skip("library not built")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "probe.c")
+        with open(src, "w") as f:
+            f.write('#include "pu3_b200.h"\n#include <stdio.h>\n'
+                    'int main(void) { printf("%d %zu\\n", pu3_version(), pu3_conv_tc_wsplit_bytes(264, 128)); return 0; }\n')
+        exe = os.path.join(d, "probe")
+        subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(root, "include"), src, "-o", exe, lib,
+                               "-Wl,-rpath," + os.path.dirname(lib)])
+        out = subprocess.check_output([exe]).decode().split()
+    assert int(out[0]) == 1 and int(out[1]) == 9 * 2 * 128 * 128        # ABI version; 9 k-blocks x (hi, lo) x 128 rows x 128 B

@@ -36,6 +36,15 @@ def test_argument_errors_do_not_need_a_gpu(pu3):
     assert L.pu3_gather_fwd(1, 1, 4, 2, 3, 1, 1, 1, None) == -1  # elem_bytes 3
     assert L.pu3_group_knn_f32(1, 3, 4, 2, 5, 1, 1, 1, 0, 0, None, None, None, None, None, 0, None) == -1  # k > n
     assert b"greater or equal to k" in L.pu3_last_error()
+    # tensor-core convolutions: what TMA cannot address is refused before anything touches the device
+    fake = ctypes.c_void_p(4096)           # aligned, never dereferenced on these paths
+    assert L.pu3_conv_tc_f32(2, 30, 8, 8, fake, 240, fake, None, fake, 240, 0, None) == -1
+    assert b"TMA" in L.pu3_last_error()
+    assert L.pu3_conv_tc_f32(2, 32, 8, 200, fake, 256, fake, None, fake, 6400, 0, None) == -1          # cout > 128
+    assert L.pu3_conv_tc_prepare_f32(8, 8, fake, 4, fake, None) == -1                                  # row stride < cin
+    assert L.pu3_conv_tc_project_f32(1, 32, 8, 100, 3, fake, 256, fake, None, fake, None, fake, 96, None, 0, 1, 1, None) == -1
+    assert L.pu3_conv_tc_wsplit_bytes(264, 128) == 9 * 2 * 128 * 128 and L.pu3_conv_tc_wsplit_bytes(128, 24) == 4 * 2 * 64 * 128
+    assert L.pu3_conv_tc_wsplit_bytes(8, 200) == 0
 
 
 def test_cpu_tensors_are_refused(pu3):

@@ -50,6 +50,12 @@ def _tensor_peak():
 
 TC_TAG = "pu3_conv_tc_f32[tcgen05 head"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from the ncu --set full
+# captures summarised in profiles/r1g/ncu_summary.md; None = not captured
+NCU_TRAFFIC_PER_LAUNCH = {
+    "pu3_fps_f32": 18.18e6 / 6,     # six launches per step: 0.25 + 2.33 + 0.49 + 4.58 + 0.97 + 9.56 MB read, nothing written
+}
+
 
 def _mlp_roofline(summ, steps):
     """Secondary roofline object for the tensor-core expansion head (csrc/conv_tc.cu): per step 4 levels x
@@ -248,7 +254,8 @@ def run_product(args):
     avg_launch_s = dom_ms / 1e3 / dom_calls
     achieved = (alg / 1e9) / avg_launch_s if alg else None
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2) if achieved else None, "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5) if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": round(achieved / peak, 5) if achieved else None,
+                "traffic": NCU_TRAFFIC_PER_LAUNCH.get(dom_name),
                 "peak_source": peak_src, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "alg_bytes_per_launch": int(alg) if alg else None,
                 "share_of_step": round(dom_ms / ms_res, 4),

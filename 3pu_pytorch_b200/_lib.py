@@ -74,6 +74,15 @@ class LevelWeights(ctypes.Structure):
 
 _lib = None
 
+# Bumped by every writer that changes parameters through raw pointers (dist.FlatAdam.step): tensor._version does not
+# see those writes, so caches of weight-derived device images (upsampler.Level._engine_weights) key on this as well.
+weight_generation = 0
+
+
+def bump_weight_generation():
+    global weight_generation
+    weight_generation += 1
+
 
 def lib():
     """The loaded library; raises if it has not been built (python __graft_entry__.py build)."""

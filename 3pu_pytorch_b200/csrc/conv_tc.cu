@@ -534,12 +534,11 @@ static int variant() {
 template <int NC, int MODE>
 static int launch(const CUtensorMap &map, const Args &a, cudaStream_t s) {
     using C = Cfg<NC>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device/context (tensors on other devices are supported): set it on every launch, like the other kernels
+    {
         int st = cuda_status(cudaFuncSetAttribute(conv_tc_kernel<NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES),
                              "conv_tc: shared memory opt-in");
         if (st) return st;
-        attr_set = true;
     }
     const int spc = (a.n + SUBM - 1) / SUBM;
     const long long ntiles = ((long long)a.b * spc + SUB - 1) / SUB;

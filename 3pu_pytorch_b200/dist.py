@@ -61,7 +61,13 @@ class FlatAdam:
     happens AFTER averaging).  Parameters and .grad of the module become views into the flat buffers, so autograd
     accumulates straight into the all-reduce / optimizer input: no bucketing, no copies."""
 
-    def __init__(self, module, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, clip_value=1.0):
+    def __init__(self, module, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, clip_value=1.0, process_group=None,
+                 data_parallel=True):
+        """process_group: the group the gradient is averaged over (None = the default group, looked up at every
+        step, so a group that has been destroyed means single-rank).  data_parallel=False: never all-reduce, even
+        inside an initialised job (a rank-local model, e.g. a side measurement on rank 0 only)."""
+        self.process_group, self.data_parallel = process_group, bool(data_parallel)
+        self.reduce_events = None        # set to [] to collect (start, end) CUDA events around every all-reduce
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
@@ -90,10 +96,19 @@ class FlatAdam:
 
     def reduce_gradients(self):
         """DDP mean of the gradients: one all-reduce of the flat buffer.  Returns the scale still to apply."""
-        _, world = _world()
+        if not self.data_parallel or not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        world = dist.get_world_size(self.process_group)
         if world == 1:
             return 1.0
-        dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+        timed = self.reduce_events is not None and self.flat_grad.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+        if timed:
+            e1.record()
+            self.reduce_events.append((e0, e1))
         return 1.0 / world
 
     def step(self):
@@ -105,3 +120,4 @@ class FlatAdam:
                     self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), float(scale),
                     float(self.clip_value or 0.0), float(self.lr), float(self.betas[0]), float(self.betas[1]),
                     float(self.eps), int(self.step_count))
+        _lib.bump_weight_generation()     # raw-pointer update: invalidate caches of weight-derived images

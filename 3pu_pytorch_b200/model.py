@@ -13,6 +13,7 @@ from math import log
 
 import torch
 
+from . import _lib
 from .dist import FlatAdam
 from .model_loss import ChamferLoss
 
@@ -30,9 +31,16 @@ class Model(object):
             self.old_lr = lr
             self.lr = lr
             self.optimizer = FlatAdam(self.net, lr=lr, betas=(0.9, 0.999), clip_value=1.0)
+        # model.py:25-28: a given --ckpt is ALWAYS loaded (utils.pytorch_utils.load_network); ckpt_loader overrides the loader
         ckpt = getattr(opt, "ckpt", None)
-        if ckpt is not None and ckpt_loader is not None:
-            self.step = ckpt_loader(self.net, ckpt)
+        if ckpt is not None:
+            if ckpt_loader is None:
+                from .formats import load_network as ckpt_loader
+            step = ckpt_loader(self.net, ckpt)
+            # the reference stores str(step) (utils/pytorch_utils.py:12) and then divides it (main.py:141): keep an int
+            self.step = int(step) if isinstance(step, str) and step.strip().lstrip("-").isdigit() else step
+            if phase == 'train':
+                _lib.bump_weight_generation()
         else:
             self.step = 0
 

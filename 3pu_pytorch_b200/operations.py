@@ -181,6 +181,9 @@ class GatherFunction(torch.autograd.Function):
 gather_points = GatherFunction.apply
 
 
+FPS_ONCHIP_MAX = 16 * 512 * 32     # csrc/fps.cu: 16-CTA cluster x 512 threads x 32 points per thread
+
+
 class FurthestPointSampling(torch.autograd.Function):
     """operations.py:269-297.  xyz (B,N,3) -> idx (B,npoint) int32, not differentiable."""
 
@@ -189,9 +192,11 @@ class FurthestPointSampling(torch.autograd.Function):
         _need_cuda(xyz, "furthest_point_sample")
         B, N, _ = xyz.size()
         idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
-        # temp = None: "filled with 1e10, not written back" -- the reference allocates and fills a
-        # (B,N) buffer per call (operations.py:291) that nobody reads afterwards
-        _lib.launch("pu3_fps_f32", xyz, B, N, int(npoint), _lib.ptr(xyz), None, _lib.ptr(idx))
+        # temp = None: "filled with 1e10, not written back" -- the reference allocates and fills a (B,N) buffer per
+        # call (operations.py:291) that nobody reads afterwards.  Clouds beyond the on-chip capacity of a cluster
+        # (FPS_ONCHIP_MAX points) keep their running distances in global memory and need the buffer for real.
+        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device) if N > FPS_ONCHIP_MAX else None
+        _lib.launch("pu3_fps_f32", xyz, B, N, int(npoint), _lib.ptr(xyz), _lib.ptr(temp), _lib.ptr(idx))
         ctx.mark_non_differentiable(idx)
         return idx
 

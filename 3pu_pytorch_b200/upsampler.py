@@ -103,7 +103,7 @@ class Level(torch.nn.Module):
         up1, up2 = self.up_layer.up_layer1.conv, self.up_layer.up_layer2.conv
         params += [up1.weight, up1.bias, up2.weight, up2.bias, self.fc_layer1.conv.weight, self.fc_layer1.conv.bias,
                    self.fc_layer2.conv.weight, self.fc_layer2.conv.bias]
-        key = tuple((p.data_ptr(), p._version) for p in params) + (str(device),)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (str(device), fused._lib.weight_generation)
         cached = self.__dict__.get("_engine_cache")
         if cached is not None and cached[0] == key:
             return cached[1]

@@ -111,6 +111,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bench_config(world):
+    """The `config` object of the JSON line -- identical for the product arm and the reference arm."""
+    return {"workload": WORKLOAD, "patches_per_gpu": B_PATCHES, "num_point": NUM_POINT, "up_ratio": UP_RATIO,
+            "knn": KNN, "mode": "eval forward", "weights": "synthetic xavier-uniform (seed 1)",
+            "l2": "flushed between timed steps (512 MiB memset)",
+            "parallelism": f"patches sharded over {world} GPU(s), no collective"}
+
+
 def make_inputs(rank, n_patches=B_PATCHES):
     import torch
     from oracle import ref_net
@@ -167,10 +175,15 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product arm has no CPU fallback (use --impl reference)")
+    if args.single_device:                     # test hook: every rank on cuda:0 (needs --backend gloo)
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(args.backend)
 
     params = ref_net.make_params(4, seed=1)
     net = pu3.Net(max_up_ratio=UP_RATIO, step_ratio=2, knn=KNN, growth_rate=12, dense_n=3, fm_knn=5)
@@ -231,14 +244,26 @@ def run_product(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_res, prof = timed(step_resident, args.steps, profile=True)
+    # `value` and `e2e` are timed with the per-entry-point event profiler OFF (launch counting only); the kernel
+    # breakdown / roofline come from a separate profiled pass over the same steps
+    ms_res, count_prof = timed(step_resident, args.steps, profile=False)
     ms_e2e, _ = timed(step_e2e, args.steps, profile=False)
+    prof_steps = min(args.steps, 5)
+    ms_prof, prof = timed(step_resident, prof_steps, profile=True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- BASELINE configs 3 / 4: the DDP train step, EVERY rank (the gradient all-reduce is a collective: no rank
+    # may leave before it) ------------------------------------------------------------------------------------------
+    train = None
+    if not args.no_train:
+        train = train_leg(pu3, params, dev, rank, world, args)
+
+    # ---- from here on only rank 0 works and nothing below may issue a collective: tear the group down on ALL ranks --
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     total_patches = B_PATCHES * world * args.steps
     value = total_patches / (ms_res / 1e3)
@@ -249,7 +274,7 @@ def run_product(args):
     peak, peak_src = _peaks()
     dom = max(summ.items(), key=lambda kv: kv[1][1])
     dom_name, (dom_calls, dom_ms) = dom
-    per_step_calls = dom_calls / args.steps
+    per_step_calls = dom_calls / prof_steps
     alg = _algorithmic_bytes(dom_name, per_step_calls)
     avg_launch_s = dom_ms / 1e3 / dom_calls
     achieved = (alg / 1e9) / avg_launch_s if alg else None
@@ -258,55 +283,125 @@ def run_product(args):
                 "traffic": NCU_TRAFFIC_PER_LAUNCH.get(dom_name),
                 "peak_source": peak_src, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "alg_bytes_per_launch": int(alg) if alg else None,
-                "share_of_step": round(dom_ms / ms_res, 4),
+                "share_of_step": round(dom_ms / ms_prof, 4),
                 "note": "the step is FP32-ALU/latency bound (all-pairs kNN, per-edge MLP, serial FPS rounds): "
                         "HBM fraction is small by construction, see DESIGN.md section 5"}
-    breakdown = {k: {"calls_per_step": round(v[0] / args.steps, 1), "ms_per_step": round(v[1] / args.steps, 3)}
+    breakdown = {k: {"calls_per_step": round(v[0] / prof_steps, 1), "ms_per_step": round(v[1] / prof_steps, 3)}
                  for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
 
-    cpu = cpu_baseline(params, n_patches=args.cpu_patches) if not args.no_cpu else None
+    # cpu_baseline: rank 0 at N=1 only (contract); the N>1 lines carry the scaling numbers
+    cpu = cpu_baseline(params, n_patches=args.cpu_patches) if (not args.no_cpu and world == 1) else None
 
-    # ---- supplementary: BASELINE config 3, one train step (B=32, ratio 16: 4 zoom levels, Chamfer, backward,
-    # clip + Adam; the reference's log2 weight is 0 at the full ratio -- SURVEY a-14 -- so weight 1 is used) --------
-    train = None
-    if not args.no_train:
-        tnet = pu3.Net(max_up_ratio=UP_RATIO, step_ratio=2, knn=KNN, growth_rate=12, dense_n=3, fm_knn=5)
-        tnet.load_state_dict(params, strict=True)
-        model = pu3.Model(tnet.to(dev), "train", lr_init=5e-4, weight_full_ratio=1.0)
-        g = torch.Generator().manual_seed(7)
-        tx = torch.rand(B_PATCHES, 3, NUM_POINT, generator=g).to(dev)
-        tgt = torch.rand(B_PATCHES, 3, NUM_POINT * UP_RATIO, generator=g).to(dev)
-        for _ in range(3):
-            model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
-        e1.record(); torch.cuda.synchronize()
-        tms = e0.elapsed_time(e1) / 5
-        train = {"workload": "train_step_B32_N312_x16 (zoom mode, Chamfer, backward, clip+Adam)", "ms_per_step": round(tms, 3),
-                 "patches_per_s": round(B_PATCHES / (tms / 1e3), 1)}
+    # side legs, rank 0 at N=1 only: BASELINE config 5 (whole-shape inference) and the "kernel to beat" table
+    whole, beat = None, None
+    if world == 1 and not args.no_extras:
+        whole = whole_shape_leg(pu3, net, dev)
+        beat = kernels_to_beat_leg()
+
     line = {
         "metric": "patches/sec (B=32, N=312, 16x)", "value": round(value, 2), "unit": "patches/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "patches_per_gpu": B_PATCHES, "num_point": NUM_POINT, "up_ratio": UP_RATIO,
-                   "knn": KNN, "mode": "eval forward", "weights": "synthetic xavier-uniform (seed 1)",
-                   "l2": "flushed between timed steps (512 MiB memset)", "parallelism": f"patches sharded over {world} GPU(s), no collective"},
+        "config": bench_config(world),
         "e2e": {"value": round(e2e_value, 2), "unit": "patches/s", "h2d_bytes_per_step": host_x.numel() * 4,
                 "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
-        "gpu_launches": prof.launches,
+        "gpu_launches": count_prof.launches,
         "clocks": sampler.summary(),
         "roofline": roofline,
-        "roofline_mlp": _mlp_roofline(summ, args.steps),
+        "roofline_mlp": _mlp_roofline(summ, prof_steps),
         "kernel_breakdown": breakdown,
+        "profiled_ms_per_step": round(ms_prof / prof_steps, 3),
         "cpu_baseline": cpu,
         "train_step": train,
+        "whole_shape": whole,
+        "kernels_to_beat": beat,
     }
     print(json.dumps(line))
+
+
+def whole_shape_leg(pu3, net, dev):
+    """BASELINE config 5 (main.py:333-389 without file IO): 5000-point shape -> FPS 48 seeds -> kNN 312 patches ->
+    16x upsample of the 48 patches -> concatenate 239 616 points -> FPS to 80 000.  Device time per stage."""
+    import torch
+    from oracle import ref_net
+    g = torch.Generator().manual_seed(0)
+    pc = ref_net.normalize_point_batch(torch.rand(1, 3, 5000, generator=g))[0].to(dev)
+
+    def timed(fn, reps=3):
+        out = fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    t_all, out = timed(lambda: pu3.pipeline.upsample_shape(net, pc, num_point=NUM_POINT, patch_num_ratio=3, up_ratio=UP_RATIO))
+    t_pred, (_, up) = timed(lambda: pu3.pipeline.pc_prediction(net, pc, NUM_POINT, 3, UP_RATIO))
+    pred = up.permute(1, 0, 2).reshape(1, 3, -1).contiguous()
+    t_fps, _ = timed(lambda: pu3.operations.furthest_point_sample(pred, 5000 * UP_RATIO))
+    return {"workload": "whole_shape_5000pts_48patches_x16_fps80000 (BASELINE config 5)", "out_points": int(out.shape[2]),
+            "ms_total": round(t_all, 2), "ms_patches_x16": round(t_pred, 2), "ms_final_fps": round(t_fps, 2),
+            "final_fps_shape": f"{pred.shape[2]} -> {5000 * UP_RATIO}", "shapes_per_s": round(1e3 / t_all, 2),
+            "patches_per_s": round(48 / (t_all / 1e3), 1)}
+
+
+def kernels_to_beat_leg():
+    """profiles/kernels_to_beat.py in its own process (it maps the reference's compiled kernels, oracle/_ref)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "kernels_to_beat.py")], capture_output=True,
+                           text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-300:]}
+    except Exception as e:      # a side measurement must never take the headline line down
+        return {"unavailable": repr(e)[:300]}
+
+
+def train_leg(pu3, params, dev, rank, world, args):
+    """BASELINE config 3 (N=1) / config 4 (N=8: 256 patches, 32 per rank): one train step = 4 zoom levels forward,
+    Chamfer, backward, ONE all-reduce of the flat 1.2 MB gradient buffer, clip + Adam (model.py:53-66).  The
+    reference's log2 weight is 0 at the full ratio (SURVEY a-14), so weight 1 is used.  Every rank runs this."""
+    import torch
+    import torch.distributed as dist
+    tnet = pu3.Net(max_up_ratio=UP_RATIO, step_ratio=2, knn=KNN, growth_rate=12, dense_n=3, fm_knn=5)
+    tnet.load_state_dict(params, strict=True)
+    model = pu3.Model(tnet.to(dev), "train", lr_init=5e-4, weight_full_ratio=1.0)
+    g = torch.Generator().manual_seed(7 + rank)
+    tx = torch.rand(B_PATCHES, 3, NUM_POINT, generator=g).to(dev)
+    tgt = torch.rand(B_PATCHES, 3, NUM_POINT * UP_RATIO, generator=g).to(dev)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier(); torch.cuda.synchronize()
+    model.optimizer.reduce_events = []
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.set_input(tx, UP_RATIO, label_pc=tgt); model.optimize()
+    e1.record(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    tms = e0.elapsed_time(e1) / steps
+    ar = [a.elapsed_time(b) for a, b in model.optimizer.reduce_events]
+    model.optimizer.reduce_events = None
+    ar_ms = sum(ar) / len(ar) if ar else 0.0
+    per_rank = [tms]
+    if world > 1:
+        t = torch.tensor([tms, ar_ms], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x[0]) for x in allt]
+        ar_ms = max(float(x[1]) for x in allt)
+        tms = max(per_rank)
+    nparam = model.optimizer.flat_grad.numel()
+    return {"workload": f"train_step_B{B_PATCHES}_per_gpu_N312_x16 (zoom mode, Chamfer, backward, all-reduce, clip+Adam)",
+            "n_gpus": world, "global_batch": B_PATCHES * world, "steps": steps,
+            "ms_per_step": round(tms, 3), "ms_per_step_per_rank": [round(x, 3) for x in per_rank],
+            "patches_per_s": round(B_PATCHES * world / (tms / 1e3), 1),
+            "allreduce_ms": round(ar_ms, 4), "allreduce_bytes": nparam * 4,
+            "collective": "none (single rank)" if world == 1 else "one NCCL all-reduce(sum) of the flat fp32 gradient buffer per step"}
 
 
 def cpu_forward_patches(params, x):
@@ -334,7 +429,8 @@ def cpu_baseline(params, n_patches=2):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference's CUDA-only
-    extensions have no CPU path and /root/reference does not travel to the GPU box)."""
+    extensions have no CPU path and /root/reference does not travel to the GPU box).  Under torchrun rank 0 alone
+    runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -344,8 +440,8 @@ def run_reference(args):
     params = ref_net.make_params(4, seed=1)
     n = args.cpu_patches
     x = make_inputs(0, n)
-    for _ in range(min(args.warmup, 1)):
-        cpu_forward_patches(params, x[:1])
+    for _ in range(args.warmup):
+        cpu_forward_patches(params, x)
     t0 = time.time()
     for _ in range(args.steps):
         cpu_forward_patches(params, x)
@@ -353,9 +449,9 @@ def run_reference(args):
     value = n * args.steps / dt
     sample = f"{n} of the {B_PATCHES} patches per step, full 312->4992 eval forward each (oracle/ref_net.py + oracle_c.c)"
     line = {"impl": "reference", "metric": "patches/sec (B=32, N=312, 16x)", "value": round(value, 4), "unit": "patches/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 1),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "num_point": NUM_POINT, "up_ratio": UP_RATIO, "knn": KNN, "mode": "eval forward"},
+            "config": bench_config(args.gpus), "sample_patches_per_step": n,
             "cpu_baseline": {"value": round(value, 4), "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": round(value, 4), "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -372,11 +468,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--fps-sm-budget", type=int, default=0, help="tuning: SMs the FPS kernels may spread over")
     ap.add_argument("--no-train", action="store_true", help="skip the supplementary train-step timing")
+    ap.add_argument("--no-extras", action="store_true", help="skip the whole-shape (config 5) and kernel-to-beat side legs")
+    ap.add_argument("--backend", default="nccl", help="torch.distributed backend for N>1 (tests: gloo)")
+    ap.add_argument("--single-device", action="store_true", help="test hook: all ranks share cuda:0 (with --backend gloo)")
     ap.add_argument("--eval-groups", type=int, default=None, help="request groups run concurrently on separate streams (default: auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         # bounded sample: a CPU patch takes ~5 s; keep steps * patches * 5 s within a couple of minutes
-        while args.cpu_patches > 1 and args.steps * args.cpu_patches > 24:
+        while args.cpu_patches > 1 and (args.steps + args.warmup) * args.cpu_patches > 30:
             args.cpu_patches -= 1
         run_reference(args)
     else:

@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY.  The result (ref_sampling*.so, ref_losses*.so) is the strongest
 oracle available for the native part of the path: the reference's kernels themselves, run
 on the B200 next to ours (tests/test_gpu_vs_reference_cuda.py, tests/golden/make_golden_gpu.py,
-and the "kernel to beat" column of bench.py --kernels).
+and the "kernel to beat" table: profiles/kernels_to_beat.py, embedded by bench.py as `kernels_to_beat`).
 
 Sources are read where they lie under /root/reference and are NOT copied into the repository.
 losses/* compiles unmodified.  sampling/* needs the API-drift edits listed in SURVEY.md

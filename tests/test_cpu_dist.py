@@ -43,6 +43,9 @@ def _worker(rank, world, port, q):
         out["grad_err"] = max(float((p.grad * scale - r.grad).abs().max())
                               for p, r in zip(model.parameters(), ref.parameters()))
         out["views"] = bool(all(p.grad.data_ptr() >= opt.flat_grad.data_ptr() for p in model.parameters()))
+        # a rank-local optimizer inside an initialised job never enters a collective (bench.py side legs)
+        local = D.FlatAdam(torch.nn.Conv1d(3, 4, 1), data_parallel=False)
+        out["local_scale"] = local.reduce_gradients() if rank == 0 else 1.0     # only ONE rank calls it: must not hang
         try:
             opt.step()
             out["cpu_step"] = "ran"
@@ -68,6 +71,7 @@ def test_world_size_2_gloo():
     for r in range(world):
         assert results[r]["gather_ok"] and results[r]["views"]
         assert results[r]["grad_err"] < 1e-6
+        assert results[r]["local_scale"] == 1.0
         assert results[r]["cpu_step"] == "raised"     # the optimizer kernel has no CPU fallback
 
 

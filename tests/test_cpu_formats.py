@@ -116,3 +116,18 @@ def test_device_side_tile_count_equals_the_reference_host_arithmetic():
     # the static slot count bounds every per-request count (N' <= N)
     for n in (624, 1248, 2496, 5000):
         assert int(n / 312 * 5) >= int((n - 1) / 312 * 5)
+
+
+def test_model_resumes_from_opt_ckpt_without_extra_arguments(pu3, tmp_path):
+    """model.py:25-28: Model(net, phase, opt) always loads opt.ckpt (it was silently ignored)."""
+    import types
+    from oracle import ref_net
+    params = ref_net.make_params(1, seed=5)
+    torch.save({"states": params, "step": "4321"}, str(tmp_path / "final_poisson.pth"))   # the reference stores str(step)
+    net = pu3.Net(max_up_ratio=2, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5)
+    opt = types.SimpleNamespace(ckpt=str(tmp_path / "final_poisson.pth"), lr_init=5e-4)
+    model = pu3.Model(net, "test", opt)
+    assert model.step == 4321
+    sd = net.state_dict()
+    assert all(torch.equal(sd[k], params[k]) for k in params)
+    assert pu3.Model(net, "test", types.SimpleNamespace(ckpt=None)).step == 0

@@ -261,3 +261,15 @@ def test_fps_ragged_equals_per_cloud_calls(pu3, cuda):
     idx2, _ = pu3.operations.furthest_point_sample_ragged(xt, n_arr, None, 400)
     for i in (1, 3):
         assert np.array_equal(idx2[i].cpu().numpy(), c_oracle.fps(x[i:i + 1, :sizes[i]], 400)[0])
+
+
+def test_furthest_point_sample_wrapper_beyond_on_chip_capacity(pu3, cuda):
+    """clouds of more than 262144 points (the whole-shape resample of main.py:379 for shapes of >= 5.5k
+    points) run from global memory and need `temp`; the operator allocates it like the reference (operations.py:291)."""
+    n = pu3.operations.FPS_ONCHIP_MAX + 37
+    rng = np.random.default_rng(4)
+    x = _cloud(rng, 1, n)
+    want = c_oracle.fps(x, 24)
+    idx, pts = pu3.operations.furthest_point_sample(torch.from_numpy(x).to(cuda), 24, NCHW=False)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(pts.cpu().numpy()[0], x[0][want[0]])

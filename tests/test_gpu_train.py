@@ -123,3 +123,41 @@ def test_pointwise_conv_with_unaligned_weight_view(pu3, cuda):
     pu3.fused.conv_into(x, w, b, out, relu=True)
     want = torch.relu(torch.nn.functional.conv1d(x.double(), w.double().unsqueeze(-1), b.double()))
     assert_close_frac(out, want, rtol=1e-5, atol=1e-5)
+
+
+def test_eval_after_train_steps_sees_the_updated_weights(pu3, cuda):
+    """FlatAdam updates parameters through raw pointers (tensor._version unchanged); every cache of
+    weight-derived device images must be invalidated, on the tensor-core path and on the FFMA fallback alike."""
+    import ctypes
+    params = ref_net.make_params(1, seed=2)
+    net = pu3.Net(max_up_ratio=2, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5)
+    net.load_state_dict(params, strict=True)
+    net = net.to(cuda)
+    g = torch.Generator().manual_seed(8)
+    x = ref_net.normalize_point_batch(torch.rand(2, 3, 312, generator=g))[0].to(cuda)
+    gt = torch.rand(2, 3, 624, generator=g).to(cuda)
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    for tc in (2, 0):
+        lib.pu3_level_set_tc(tc)
+        try:
+            net.eval()
+            with torch.no_grad():
+                before = net(x, ratio=2).clone()
+            model = pu3.Model(net, "train", lr_init=1e-2, weight_full_ratio=1.0)
+            model.set_input(x, 2, label_pc=gt); model.optimize()
+            net.eval()
+            with torch.no_grad():
+                net(x, ratio=2)                      # caches images of the weights at their CURRENT storage
+            for _ in range(3):                       # ... which the next steps overwrite through raw pointers
+                model.set_input(x, 2, label_pc=gt); model.optimize()
+            net.eval()
+            with torch.no_grad():
+                after = net(x, ratio=2)
+            fresh = pu3.Net(max_up_ratio=2, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5).to(cuda).eval()
+            fresh.load_state_dict({k: v.detach().clone() for k, v in net.state_dict().items()}, strict=True)
+            with torch.no_grad():
+                want = fresh(x, ratio=2)
+        finally:
+            lib.pu3_level_set_tc(2)
+        assert (after - before).abs().max() > 1e-4                     # the weights did move
+        assert torch.equal(after, want), f"tc={tc}: stale weight image after FlatAdam steps"

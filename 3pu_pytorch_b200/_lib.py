@@ -57,6 +57,12 @@ SIGNATURES = {
                                        _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "pu3_iota_i32": (_c_int, [_c_int, _c_void_p, _c_void_p]),
     "pu3_level_set_tc": (None, [_c_int]),
+    "pu3_normalize_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),
+    "pu3_outlier_compact_f32": (_c_int, [_c_int] * 5 + [_c_void_p] * 10),
+    "pu3_tile_seeds_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),
+    "pu3_tiles_normalize_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 7),
+    "pu3_denorm_merge_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),
+    "pu3_gather_pm_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
     "pu3_edgeconv_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
                          [_c_void_p, _c_ll, _c_void_p]),
 }

@@ -20,7 +20,21 @@ def _need_cuda(t, what):
 # normalize_point_batch
 # ------------------------------------------------------------------------------------------------
 def normalize_point_batch(pc, NCHW=True):
-    """operations.py:12-30.  Returns (normalised pc, centroid, furthest_distance)."""
+    """operations.py:12-30.  Returns (normalised pc, centroid, furthest_distance).
+    CUDA float32 without autograd: one kernel (pu3_normalize_f32).  When a gradient is wanted (the train-mode zoom,
+    upsampler.py:138) the differentiable composition of the same arithmetic runs instead."""
+    if pc.is_cuda and pc.dtype == torch.float32 and pc.dim() == 3 and not (torch.is_grad_enabled() and pc.requires_grad):
+        src = pc.contiguous()
+        B = src.shape[0]
+        n = src.shape[2] if NCHW else src.shape[1]
+        if (src.shape[1] if NCHW else src.shape[2]) != 3:
+            raise RuntimeError("normalize_point_batch: 3-D points expected")
+        out = torch.empty_like(src)
+        centroid = torch.empty((B, 3, 1) if NCHW else (B, 1, 3), dtype=torch.float32, device=src.device)
+        radius = torch.empty(B, 1, 1, dtype=torch.float32, device=src.device)
+        _lib.launch("pu3_normalize_f32", src, B, n, int(bool(NCHW)), src.data_ptr(), out.data_ptr(), centroid.data_ptr(),
+                    radius.data_ptr())
+        return out, centroid, radius
     point_axis, dim_axis = (2, 1) if NCHW else (1, 2)
     centroid = torch.mean(pc, dim=point_axis, keepdim=True)
     pc = pc - centroid

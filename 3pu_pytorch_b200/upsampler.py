@@ -474,44 +474,64 @@ class Net(torch.nn.Module):
 
     def _eval_level_static(self, level, xyz, old_xyz, old_features, old_n, k, num_output_point, keep_features, bad,
                            **kwargs):
+        """One level past the first for all requests, static shapes, every step a libpu3_b200 kernel (csrc/glue.cu for the
+        steps the reference writes as torch expressions): outlier filter + compaction (:63-73), seed FPS (:78), kNN tiles
+        (:83-85), normalisation (:138), Level, de-normalise + merge (:144-155), merge FPS (:158).  `bad` is an int32 device
+        flag (a filtered cloud smaller than one tile)."""
         B, _, N = xyz.shape
         dev = xyz.device
-        mask = self._eval_outlier_mask(xyz)                                          # (B,N)
-        counts = mask.sum(dim=1)
-        bad = bad | (counts < k).any()
-        order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
-        xyz_c = torch.gather(xyz, 2, order.unsqueeze(1).expand(-1, 3, -1)).contiguous()
-        n_arr = counts.clamp(min=k).to(torch.int32)          # (a flagged request still reads valid memory; its result is discarded)
+        L = fused._lib
+        r = self.step_ratio
         P = int(N / k * 5)                                                            # :76 with N' = N
-        p_arr = (counts.double() / k * 5).to(torch.int32)                             # int(N'_b / k * 5), computed like the host would
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
         key = (B, P, str(dev))
         cache = self.__dict__.setdefault("_static_cache", {})
         if key not in cache:
-            cache[key] = (torch.arange(B, dtype=torch.int32, device=dev),
-                          torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P),
-                          torch.arange(P, dtype=torch.int32, device=dev).view(1, 1, P))
-        req, owner, slot_id = cache[key]
-        _, seeds = operations.furthest_point_sample_ragged(xyz_c, n_arr, p_arr, P)    # (B,3,P), zeros past p_arr
-        seeds = torch.where(slot_id < p_arr.view(B, 1, 1), seeds, seeds[:, :, :1])    # spare slots repeat the first tile
-        tiles, _, _ = operations._knn_raw(k, seeds.contiguous(), xyz_c, False, None, want_dist=False,
-                                          ragged=operations.Ragged(req, req, B, n_arr=n_arr))
-        patch_xyz = tiles.permute(0, 2, 1, 3).reshape(B * P, 3, k).contiguous()       # (B*P,3,k), request-major (:85)
-        patch_norm, centroid, radius = operations.normalize_point_batch(patch_xyz, NCHW=True)
+            cache[key] = (torch.arange(B, **i32), torch.arange(B, **i32).repeat_interleave(P))
+        req, owner = cache[key]
+        xyz = xyz.contiguous()
+        # distance to the nearest other point (:63-66)
+        _, _, closest = operations._knn_raw(2, xyz, xyz, False, None, want_knn=False)
+        xyz_c, xyz_pm = torch.empty(B, 3, N, **f32), torch.empty(B, N, 3, **f32)
+        n_arr, p_arr, pk_arr, pkr_arr = (torch.empty(B, **i32) for _ in range(4))
+        L.launch("pu3_outlier_compact_f32", xyz, B, N, 2, k, r, closest.data_ptr(), xyz.data_ptr(), xyz_c.data_ptr(),
+                 xyz_pm.data_ptr(), n_arr.data_ptr(), p_arr.data_ptr(), pk_arr.data_ptr(), pkr_arr.data_ptr(), bad.data_ptr())
+        # seeds (:78): FPS over the kept points, p_arr[b] samples; spare tile slots repeat the request's first tile
+        sidx = torch.zeros(B, P, **i32)
+        L.launch("pu3_fps_ragged_f32", xyz_pm, B, N, P, n_arr.data_ptr(), p_arr.data_ptr(), xyz_pm.data_ptr(), None,
+                 sidx.data_ptr(), tag="pu3_fps_f32")
+        seeds = torch.empty(B, 3, P, **f32)
+        L.launch("pu3_tile_seeds_f32", xyz_c, B, N, P, xyz_c.data_ptr(), sidx.data_ptr(), p_arr.data_ptr(), seeds.data_ptr())
+        # tiles (:83-85) and their normalisation (:138)
+        tiles, _, _ = operations._knn_raw(k, seeds, xyz_c, False, None, want_dist=False,
+                                          ragged=operations.Ragged(req, req, B, n_arr=n_arr))      # (B,3,P,k)
+        T = B * P
+        patch_xyz, patch_norm = torch.empty(T, 3, k, **f32), torch.empty(T, 3, k, **f32)
+        centroid, radius = torch.empty(T, 3, **f32), torch.empty(T, **f32)
+        prev_xyz = torch.empty(B, 3, P * k, **f32) if keep_features else None
+        L.launch("pu3_tiles_normalize_f32", tiles, B, P, k, tiles.data_ptr(), patch_xyz.data_ptr(), patch_norm.data_ptr(),
+                 centroid.data_ptr(), radius.data_ptr(), L.ptr(prev_xyz))
         ragged = operations.Ragged(owner, owner, B, n_arr=old_n)
         new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged,
-                                  prev_point_major=True, **kwargs)
-        new_xyz = new_xyz * radius + centroid                                        # (B*P,3,k*r)
+                                  prev_point_major=True, **kwargs)                    # (T,3,k*r) normalised frame
         kr = new_xyz.shape[2]
-        merged = new_xyz.view(B, P, 3, kr).permute(0, 2, 1, 3).reshape(B, 3, P * kr)  # tiles of a request side by side (:149-155)
-        _, out_xyz = operations.furthest_point_sample_ragged(merged, p_arr * kr, None, num_output_point)  # :158
+        merged_pm = torch.empty(B, P * kr, 3, **f32)
+        L.launch("pu3_denorm_merge_f32", new_xyz, B, P, kr, new_xyz.data_ptr(), centroid.data_ptr(), radius.data_ptr(),
+                 merged_pm.data_ptr())
+        # resample to num_output_point (:158)
+        oidx = torch.zeros(B, num_output_point, **i32)
+        L.launch("pu3_fps_ragged_f32", merged_pm, B, P * kr, num_output_point, pkr_arr.data_ptr(), None, merged_pm.data_ptr(),
+                 None, oidx.data_ptr(), tag="pu3_fps_f32")
+        out_xyz = torch.empty(B, 3, num_output_point, **f32)
+        L.launch("pu3_gather_pm_f32", merged_pm, B, P * kr, num_output_point, merged_pm.data_ptr(), oidx.data_ptr(),
+                 out_xyz.data_ptr())
         if keep_features:
             Cf = features.shape[1]
-            feat_pm = torch.empty(B, P * k, Cf, dtype=torch.float32, device=dev)
-            fused._lib.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(), None,
-                              feat_pm.data_ptr())
-            prev_xyz = patch_xyz.view(B, P, 3, k).permute(0, 2, 1, 3).reshape(B, 3, P * k)
-            return (out_xyz, prev_xyz, feat_pm, p_arr * k), bad
-        return (out_xyz, None, None, None), bad
+            feat_pm = torch.empty(B, P * k, Cf, **f32)
+            L.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(), None, feat_pm.data_ptr())
+            return out_xyz, prev_xyz, feat_pm, pk_arr
+        return out_xyz, None, None, None
 
     def forward(self, xyz, ratio=None, gt=None, seed_idx_per_level=None, **kwargs):
         """
@@ -599,32 +619,88 @@ class Net(torch.nn.Module):
             cache[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
         return cache[key]
 
+    # The static forward is a fixed sequence of ~230 launches on fixed shapes: captured once per (shape, parameter storage) in
+    # a CUDA graph and replayed (no Python / ctypes / allocator work per launch, no gaps between the small kernels).
+    use_cuda_graph = True
+
     def _forward_eval_group(self, xyz, num_levels, num_point, max_num_point, **kwargs):
-        if self.static_tiles and xyz.is_cuda and num_levels > 1 and xyz.shape[2] >= max_num_point:
-            out = self._forward_eval_static(xyz, num_levels, num_point, max_num_point, **kwargs)
-            if out is not None:
+        if self.static_tiles and xyz.is_cuda and num_levels > 1 and xyz.shape[2] >= max_num_point and not kwargs:
+            prof = fused._lib._profiler
+            if self.use_cuda_graph and xyz.dtype == torch.float32 and not (prof is not None and prof.timing):
+                out, bad = self._forward_eval_graph(xyz, num_levels, num_point, max_num_point)
+            else:
+                out, bad = self._forward_eval_static(xyz, num_levels, num_point, max_num_point)
+            if out is not None and not bool(bad):     # the one host read of the forward, after everything is enqueued
                 return out
         return self._forward_eval_sync(xyz, num_levels, num_point, max_num_point, **kwargs)
 
-    def _forward_eval_static(self, xyz, num_levels, num_point, max_num_point, **kwargs):
-        """Every level with static shapes (see static_tiles above); None when a request needs the synchronous path."""
+    def _forward_eval_static(self, xyz, num_levels, num_point, max_num_point):
+        """Every level with static shapes (see static_tiles above).  Returns (xyz, bad flag on the device) or (None, None)
+        when the shapes do not tile."""
         B = xyz.shape[0]
         dev = xyz.device
+        xyz = xyz.contiguous()
         old_xyz = xyz
-        xyz, feats = self.levels['level_1'](xyz, xyz, previous_level4=None, group=1, **kwargs)
+        xyz, feats = self.levels['level_1'](xyz, xyz, previous_level4=None, group=1)
         old_n = torch.full((B,), old_xyz.shape[2], dtype=torch.int32, device=dev)
         pm = torch.empty(B, feats.shape[2], feats.shape[1], dtype=torch.float32, device=dev)
         fused._lib.launch("pu3_to_point_major_f32", feats, B, feats.shape[1], feats.shape[2], feats.contiguous().data_ptr(),
                           None, pm.data_ptr())
         old_features = pm
-        bad = torch.zeros((), dtype=torch.bool, device=dev)
+        bad = torch.zeros((), dtype=torch.int32, device=dev)
         for l in range(2, num_levels + 1):
             if xyz.size(-1) <= max_num_point:
-                return None
-            res, bad = self._eval_level_static(self.levels['level_%d' % l], xyz, old_xyz, old_features, old_n, max_num_point,
-                                               num_point * self.step_ratio ** l, l < num_levels, bad, **kwargs)
-            xyz, old_xyz, old_features, old_n = res
-        return None if bool(bad) else xyz     # the one host read of the forward, after everything is enqueued
+                return None, None
+            xyz, old_xyz, old_features, old_n = self._eval_level_static(
+                self.levels['level_%d' % l], xyz, old_xyz, old_features, old_n, max_num_point,
+                num_point * self.step_ratio ** l, l < num_levels, bad)
+        return xyz, bad
+
+    def _graph_key(self, xyz, num_levels):
+        ptrs = tuple(p.data_ptr() for p in self.parameters())
+        return (tuple(xyz.shape), num_levels, str(xyz.device), hash(ptrs))
+
+    def _forward_eval_graph(self, xyz, num_levels, num_point, max_num_point):
+        """_forward_eval_static through a captured CUDA graph.  The graph bakes in the addresses of the parameters (their
+        VALUES are read at replay: weight updates are seen) and of its private input / output buffers; it is re-captured
+        when the input shape or the parameter storage changes."""
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        key = self._graph_key(xyz, num_levels)
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) >= 4:                       # bounded: every graph keeps its workspace pool alive
+                cache.pop(next(iter(cache)))
+            cur = torch.cuda.current_stream(xyz.device)
+            side = torch.cuda.Stream(device=xyz.device)
+            static_in = torch.empty_like(xyz, memory_format=torch.contiguous_format)
+            static_in.copy_(xyz)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):             # eager warm-up: lazy initialisation (function attributes, caches)
+                out, _ = self._forward_eval_static(static_in, num_levels, num_point, max_num_point)
+            cur.wait_stream(side)
+            if out is None:
+                cache[key] = False
+                return None, None
+            torch.cuda.synchronize(xyz.device)
+            graph = torch.cuda.CUDAGraph()
+            counter = fused._lib.Profiler(timing=False)
+            prev = fused._lib.set_profiler(counter)
+            try:
+                with torch.cuda.graph(graph, stream=side):
+                    out, bad = self._forward_eval_static(static_in, num_levels, num_point, max_num_point)
+            finally:
+                fused._lib.set_profiler(prev)
+            entry = cache[key] = (graph, static_in, out, bad, counter.launches)
+        if entry is False:
+            return None, None
+        graph, static_in, out, bad, launches = entry
+        static_in.copy_(xyz)
+        graph.replay()
+        prof = fused._lib._profiler
+        if prof is not None:
+            prof.launches += launches
+            prof.calls["cuda_graph[eval forward]"] = prof.calls.get("cuda_graph[eval forward]", 0) + 1
+        return out.clone(), bad
 
     def _forward_eval_sync(self, xyz, num_levels, num_point, max_num_point, **kwargs):
         B = xyz.shape[0]

@@ -294,6 +294,40 @@ int pu3_edgeconv_bwd_f32(int b, int n, int k, const float *x, long long x_bstrid
                          long long dx_bstride, float *dw0, float *db0, float *dw1, float *db1, float *dw2, float *db2,
                          pu3_stream_t stream);
 
+/*
+ * The small steps between the big kernels of the eval path, as kernels (csrc/glue.cu), so that a whole Net.forward is a
+ * fixed sequence of launches.  Arithmetic follows the operator order of the reference's torch expressions.
+ *
+ * normalize_point_batch (network/operations.py:12-30): centroid = mean over points, out = (pc - centroid) / max ||pc - centroid||.
+ * pc / out (b,3,n) when nchw != 0, else (b,n,3); centroid (b,3), radius (b).
+ */
+int pu3_normalize_f32(int b, int n, int nchw, const float *pc, float *out, float *centroid, float *radius, pu3_stream_t stream);
+/*
+ * Outlier filter of eval-mode patch extraction (network/upsampler.py:63-76).  dist (b,n,dk) = distances to the dk >= 2 nearest
+ * neighbours of every point of xyz (b,3,n) (pu3_group_knn_f32 with k = dk); a point is kept when dist[..,1] < 5 * mean_n(dist[..,1]).
+ * Kept points first, order preserved (torch.masked_select), removed points behind them: out_cm (b,3,n) channel-major and out_pm
+ * (b,n,3) point-major.  n_arr[i] = max(kept_i, min(k, n)); p_arr[i] = int(kept_i / k * 5) (:76, evaluated in double);
+ * pk_arr[i] = p_arr[i]*k and pkr_arr[i] = p_arr[i]*k*r (either may be NULL): the valid sizes of the request's tiles side by side
+ * before / after the r-fold upsampling; *bad |= 1 when some kept_i < k (the tile size itself would change: the caller redoes
+ * that forward request by request).
+ */
+int pu3_outlier_compact_f32(int b, int n, int dk, int k, int r, const float *dist, const float *xyz, float *out_cm, float *out_pm,
+                            int32_t *n_arr, int32_t *p_arr, int32_t *pk_arr, int32_t *pkr_arr, int32_t *bad, pu3_stream_t stream);
+/* seeds[i,c,j] = xyz[i,c,idx[i, j < p_arr[i] ? j : 0]]: the gather after the seed FPS (:78, operations.py:320); tile slots past a
+ * request's own count repeat its first tile.  xyz (b,3,n), idx (b,p) i32, seeds (b,3,p). */
+int pu3_tile_seeds_f32(int b, int n, int p, const float *xyz, const int32_t *idx, const int32_t *p_arr, float *seeds,
+                       pu3_stream_t stream);
+/* tiles (b,3,p,k) (pu3_group_knn* neighbour output) -> patch (b*p,3,k) (torch.cat(torch.unbind(.,2),0), :85), patch_norm + centroid
+ * (b*p,3) + radius (b*p) (normalize_point_batch, :138) and, unless NULL, side_by_side (b,3,p*k): the tiles of a request along the point
+ * axis (:148-152), the cloud the next level's skip connection searches. */
+int pu3_tiles_normalize_f32(int b, int p, int k, const float *tiles, float *patch, float *patch_norm, float *centroid,
+                            float *radius, float *side_by_side, pu3_stream_t stream);
+/* merged_pm[i, j*kr + q, c] = xyz_norm[i*p + j, c, q] * radius[i*p + j] + centroid[i*p + j, c]  (:144, :149-155), POINT-major (b,p*kr,3). */
+int pu3_denorm_merge_f32(int b, int p, int kr, const float *xyz_norm, const float *centroid, const float *radius,
+                         float *merged_pm, pu3_stream_t stream);
+/* out[i,c,j] = pts[i, idx[i,j], c]: gather_points (operations.py:320) reading a point-major cloud pts (b,n,3); out (b,3,m). */
+int pu3_gather_pm_f32(int b, int n, int m, const float *pts, const int32_t *idx, float *out, pu3_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ formats.py (checkpoint dictionary, .xyz / PLY files) are the callers and formats
 There is no CPU path for the kernels.
 """
 from . import _lib  # noqa: F401
-from . import sampling, losses, operations, model_loss, fused, layers, upsampler, dist, model, pipeline, patches, formats  # noqa: F401
+from . import sampling, losses, operations, model_loss, fused, layers, level_train, upsampler, dist, model, pipeline, patches, formats  # noqa: F401
 from .model import Model  # noqa: F401
 from .upsampler import Net, Level  # noqa: F401
 from .model_loss import ChamferLoss  # noqa: F401

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pu3_group_gather_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 4),
     "pu3_pointwise_conv_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p, _c_ll,
                                                          _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_void_p]),
+    "pu3_pointwise_conv_ex_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p, _c_ll,
+                                                            _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "pu3_expand_code_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "pu3_conv_tc_wsplit_bytes": (_c_size_t, [_c_int, _c_int]),
     "pu3_conv_tc_set_variant": (None, [_c_int]),
@@ -55,6 +57,14 @@ SIGNATURES = {
     "pu3_level_workspace": (_c_size_t, [_c_int] * 8),
     "pu3_level_forward_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "pu3_level_forward_train_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                             _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
+                                             _c_void_p, _c_void_p]),
+    "pu3_skip_fuse_ex_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 8),
+    "pu3_skip_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 6),
+    "pu3_pointwise_conv_bwd_w_ex_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_ll, _c_void_p, _c_int, _c_void_p, _c_void_p]),
+    "pu3_replica_sum_f32": (_c_int, [_c_ll, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "pu3_relu_mask_f32": (_c_int, [_c_ll, _c_void_p, _c_void_p, _c_void_p]),
     "pu3_iota_i32": (_c_int, [_c_int, _c_void_p, _c_void_p]),
     "pu3_level_set_tc": (None, [_c_int]),
     "pu3_normalize_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),
@@ -76,6 +86,12 @@ class LevelWeights(ctypes.Structure):
                 ("up2_w", _c_void_p), ("up2_b", _c_void_p), ("fc1_w", _c_void_p), ("fc1_b", _c_void_p),
                 ("fc2_w", _c_void_p), ("fc2_b", _c_void_p), ("code", _c_void_p),
                 ("r", _c_int), ("knn", _c_int), ("fm_knn", _c_int), ("reserved", _c_int)]
+
+
+class LevelSaved(ctypes.Structure):
+    """pu3_level_saved of include/pu3_b200.h"""
+    _fields_ = [("h", _c_void_p * 4), ("idx", _c_void_p * 4), ("skip_idx", _c_void_p), ("skip_w", _c_void_p),
+                ("h1", _c_void_p), ("h2", _c_void_p)]
 
 
 _lib = None

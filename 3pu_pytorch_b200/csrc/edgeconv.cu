@@ -516,7 +516,7 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
 namespace pu3 {
 
 constexpr int EB_ST = 85;    // staged floats per edge (84 used, odd stride: conflict-free rows): d[24] | h0[12] | h1[12] | g0[12] | g1[12] | g2[12]
-constexpr int EB_ACC = 1620; // weight + bias gradient entries
+constexpr int EB_ACC = 900;  // centre-part weight gradients (36 x 24) + biases (36)
 constexpr int EB_DXS = 25;   // row stride of the dx accumulator
 
 __device__ __forceinline__ float dot12(const float *row, const float (&g)[EC_G]) {
@@ -572,11 +572,21 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
     for (int t = threadIdx.x; t < n * EB_DXS; t += blockDim.x) dxs[t] = 0.f;
     __syncthreads();
 
-    // weight-gradient accumulators: per-warp private rows in shared memory, entry e owned by lane e % 32
-    // layout: [0,288) dW0[:,24:] as (o,c) | [288,432) dW1[:,:12] | [432,576) dW2[:,:12] | [576,720) dW2[:,12:24]
-    //         [720,1584) centre parts (36 x 24: dA (x) x_i) | [1584,1620) biases
-    float *acc = s_acc + (size_t)warp * EB_ACC;
-    for (int e = lane; e < EB_ACC; e += 32) acc[e] = 0.f;
+    // weight-gradient accumulators live in registers for all points of the warp (profiles/r2: the former per-warp shared-memory
+    // rows, updated by single-accumulator loops over the staged edges, left the kernel latency-bound at 8 warps per SM)
+    const int og = lane >> 3, cg = lane & 7;      // dW0[:, 24:] tile: o = 3 og + u, c = 3 cg + t
+    const int gg = lane >> 2, hg = lane & 3;      // [g1|g2] x [h0|h1] tile: row = 3 gg + u, col = 6 hg + t
+    float acc0[3][3], acc1[3][6];
+    // centre parts dA (x) x_i (36 x 24) + biases (36): one read-modify-write per entry and point, per-warp rows in shared memory
+    float *accC = s_acc + (size_t)warp * EB_ACC;
+    for (int e = lane; e < EB_ACC; e += 32) accC[e] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) acc0[u][t] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) acc1[u][t] = 0.f;
+    }
 
     float *wa = s_a + warp * 36, *wdy = s_dy + warp * 60, *wda = s_da + warp * 36, *st = s_st + (size_t)warp * 32 * EB_ST;
     float *me = st + lane * EB_ST;
@@ -624,6 +634,9 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
         for (int in = 0; in < EC_G; ++in)
 #pragma unroll
             for (int o = 0; o < EC_G; ++o) h2[o] = __fmaf_rn(sw.w2a[in][o], h1[in], h2[o]);
+        // (compiler fences between the phases: without them ptxas hoists the weight loads of later phases above the
+        // earlier ones, holds them in registers and spills ~3 KB per thread)
+        asm volatile("" ::: "memory");
         // ---- max() routing: the first edge attaining the maximum takes the channel's gradient -------------------
         float g2[EC_G], g1[EC_G], g0[EC_G];
         unsigned pos0 = 0, pos1 = 0;      // ReLU masks of h0 / h1
@@ -649,76 +662,96 @@ edgeconv_bwd_kernel(int n, int k, int pts_per_cta, const float *__restrict__ x, 
             g0[o] = lane == w0 ? wdy[24 + o] : 0.f;
         }
         // ---- chain rule --------------------------------------------------------------------------------------------
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int in = 0; in < EC_G; ++in) g1[in] = (pos1 >> in) & 1u ? g1[in] + dot12(&sw.w2a[in][0], g2) : 0.f;
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int in = 0; in < EC_G; ++in)
             g0[in] = (pos0 >> in) & 1u ? g0[in] + dot12(&sw.w1a[in][0], g1) + dot12(&sw.w2b[in][0], g2) : 0.f;
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int o = 0; o < EC_G; ++o) { me[48 + o] = g0[o]; me[60 + o] = g1[o]; me[72 + o] = g2[o]; }
-        float gsum = 0.f;   // lane c < 24 ends up with sum_k gd[k][c]
-#pragma unroll
+        // neighbour side of d = x_j - x_i: dx_j += W0b^T g0
+#pragma unroll 4
         for (int c = 0; c < EC_C; ++c) {
-            const float gd = live ? dot12(&sw.w0b[c][0], g0) : 0.f;
-            if (live) atomicAdd(&dxs[j * EB_DXS + c], gd);                  // d(n - c)/dn
-            const float tot = warp_sum(gd);
-            if (lane == c) gsum = tot;
-        }
-        // dA0 = sum_k g0, dA1 = sum_k g1, dA2 = sum_k g2 (= the incoming gradient of h2)
-#pragma unroll
-        for (int o = 0; o < EC_G; ++o) {
-            const float s0 = warp_sum(g0[o]), s1 = warp_sum(g1[o]);
-            if (lane == 0) { wda[o] = s0; wda[12 + o] = s1; wda[24 + o] = wdy[o]; }
+            if (live) atomicAdd(&dxs[j * EB_DXS + c], dot12(&sw.w0b[c][0], g0));
         }
         __syncwarp();
-        // centre: dx_i += dy_x - sum_k gd + Wp^T dA
+        // dA0 = sum_k g0, dA1 = sum_k g1: column sums of the staged rows (odd row stride: conflict-free);
+        // dA2 = the incoming gradient of h2 (every channel's maximum is attained by exactly one edge)
+        if (lane < 24) {
+            float sacc = 0.f;
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) sacc += st[kk * EB_ST + 48 + lane];
+            wda[lane] = sacc;
+        } else {
+            wda[lane] = wdy[lane - 24];                      // lanes 24..31 -> dA2[0..8)
+        }
+        if (lane < 4) wda[32 + lane] = wdy[8 + lane];       // dA2[8..12)
+        __syncwarp();
+        // centre: dx_i += dy_x - W0b dA0 (= - sum_k gd, by linearity) + Wp^T dA
         if (lane < EC_C) {
-            float v = wdy[36 + lane] - gsum;
+            float v = wdy[36 + lane];
+#pragma unroll
+            for (int o = 0; o < EC_G; ++o) v = __fmaf_rn(-sw.w0b[lane][o], wda[o], v);
 #pragma unroll
             for (int o = 0; o < 36; ++o) v = __fmaf_rn(sw.wp[lane][o], wda[o], v);
             atomicAdd(&dxs[i * EB_DXS + lane], v);
         }
-        // weight gradients: entry e = lane + 32 q, summed over the 32 staged edges
-        for (int q = 0; q < 9; ++q) {           // dW0[:, 24:]  entry (o, c) = e / 24, e % 24
-            const int e = lane + 32 * q, o = e / 24, c = e % 24;
-            float s0 = 0.f;
-            for (int kk = 0; kk < 32; ++kk) s0 = __fmaf_rn(st[kk * EB_ST + 48 + o], st[kk * EB_ST + c], s0);
-            acc[e] += s0;
-        }
-        for (int q = 0; q < 5; ++q) {           // 12 x 12 matrices: entry (o, in) = e / 12, e % 12
-            const int e = lane + 32 * q;
-            if (e < 144) {
-                const int o = e / 12, in = e % 12;
-                float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                for (int kk = 0; kk < 32; ++kk) {
-                    const float *r = st + kk * EB_ST;
-                    s1 = __fmaf_rn(r[60 + o], r[24 + in], s1);    // dW1[:, :12]   = g1 (x) h0
-                    s2 = __fmaf_rn(r[72 + o], r[36 + in], s2);    // dW2[:, :12]   = g2 (x) h1
-                    s3 = __fmaf_rn(r[72 + o], r[24 + in], s3);    // dW2[:, 12:24] = g2 (x) h0
-                }
-                acc[288 + e] += s1; acc[432 + e] += s2; acc[576 + e] += s3;
+        // weight gradients, register tiles over the 32 staged edges:
+        //   dW0[:, 24:]  = g0 (x) d          lane tile 3 (o) x 3 (c)
+        //   [g1|g2] (x) [h0|h1]              lane tile 3 x 6 (the g1 (x) h1 quadrant is not a gradient and is dropped at the flush)
+#pragma unroll 4
+        for (int kk = 0; kk < 32; ++kk) {
+            const float *r = st + kk * EB_ST;
+            float ga[3], da[3], gb[3], hb[6];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { ga[t] = r[48 + 3 * og + t]; da[t] = r[3 * cg + t]; gb[t] = r[60 + 3 * gg + t]; }
+#pragma unroll
+            for (int t = 0; t < 6; ++t) hb[t] = r[24 + 6 * hg + t];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) acc0[u][t] = __fmaf_rn(ga[u], da[t], acc0[u][t]);
+#pragma unroll
+                for (int t = 0; t < 6; ++t) acc1[u][t] = __fmaf_rn(gb[u], hb[t], acc1[u][t]);
             }
         }
-        for (int q = 0; q < 27; ++q) {          // centre parts: entry (o, c) of the 36 x 24 matrix dA (x) x_i
+        // centre parts dA (x) x_i (36 x 24, entry e = lane + 32 q) and the biases
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
             const int e = lane + 32 * q, o = e / 24, c = e % 24;
-            acc[720 + e] = __fmaf_rn(wda[o], ci[c], acc[720 + e]);
+            accC[e] = __fmaf_rn(wda[o], ci[c], accC[e]);
         }
-        acc[1584 + lane] += wda[lane];
-        if (lane < 4) acc[1616 + lane] += wda[32 + lane];
+        accC[864 + lane] += wda[lane];
+        if (lane < 4) accC[896 + lane] += wda[32 + lane];
     }
     __syncwarp();
     // ---- flush the warp's accumulators -----------------------------------------------------------------------------
-    for (int e = lane; e < 288; e += 32) { const int o = e / 24, c = e % 24; atomicAdd(G.dw0 + o * 48 + 24 + c, acc[e]); }
-    for (int e = lane; e < 144; e += 32) {
-        const int o = e / 12, in = e % 12;
-        atomicAdd(G.dw1 + o * 36 + in, acc[288 + e]); atomicAdd(G.dw2 + o * 48 + in, acc[432 + e]); atomicAdd(G.dw2 + o * 48 + 12 + in, acc[576 + e]);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) atomicAdd(G.dw0 + (3 * og + u) * 48 + 24 + 3 * cg + t, acc0[u][t]);
+        const int row = 3 * gg + u;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int col = 6 * hg + t;
+            if (row < 12) {
+                if (col < 12) atomicAdd(G.dw1 + row * 36 + col, acc1[u][t]);                 // dW1[:, :12]   = g1 (x) h0
+            } else if (col < 12) {
+                atomicAdd(G.dw2 + (row - 12) * 48 + 12 + col, acc1[u][t]);                   // dW2[:, 12:24] = g2 (x) h0
+            } else {
+                atomicAdd(G.dw2 + (row - 12) * 48 + (col - 12), acc1[u][t]);                 // dW2[:, :12]   = g2 (x) h1
+            }
+        }
     }
     for (int e = lane; e < 864; e += 32) {
         const int o = e / 24, c = e % 24;
         float *dst = o < 12 ? G.dw0 + o * 48 + c : (o < 24 ? G.dw1 + (o - 12) * 36 + 12 + c : G.dw2 + (o - 24) * 48 + 24 + c);
-        atomicAdd(dst, acc[720 + e]);
+        atomicAdd(dst, accC[e]);
     }
-    for (int o = lane; o < 36; o += 32) atomicAdd(o < 12 ? G.db0 + o : (o < 24 ? G.db1 + o - 12 : G.db2 + o - 24), acc[1584 + o]);
+    for (int o = lane; o < 36; o += 32) atomicAdd(o < 12 ? G.db0 + o : (o < 24 ? G.db1 + o - 12 : G.db2 + o - 24), accC[864 + o]);
     __syncthreads();
     for (int t = threadIdx.x; t < EC_C * n; t += blockDim.x) {
         const int c = t / n, p = t - c * n;

@@ -222,9 +222,44 @@ __global__ void gather_pm_kernel(int n, int m, const float *__restrict__ pts, co
     for (int c = 0; c < 3; ++c) out[((size_t)b * 3 + c) * m + j] = src[c];
 }
 
+// ---- backward helpers of the expansion head (upsampler.py:349-372) -------------------------------------------------------------
+// out[t,c,i] (+)= sum_{j<r} in[t,c,i*r+j]: the gradient of "replicate every point r times" (:356-358, :371)
+__global__ void __launch_bounds__(256) replica_sum_kernel(long long rows_n, int r, const float *__restrict__ in, float *__restrict__ out,
+                                                          int accumulate) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows_n) return;
+    float s = 0.f;
+    for (int j = 0; j < r; ++j) s += in[e * r + j];
+    out[e] = accumulate ? out[e] + s : s;
+}
+// g[e] = act[e] > 0 ? g[e] : 0: the ReLU derivative applied to a gradient in place
+__global__ void __launch_bounds__(256) relu_mask_kernel(long long total, float *__restrict__ g, const float *__restrict__ act) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < total && !(act[e] > 0.f)) g[e] = 0.f;
+}
+
 }  // namespace pu3
 
 using namespace pu3;
+
+extern "C" int pu3_replica_sum_f32(long long rows, int n, int r, const float *in, float *out, int accumulate, pu3_stream_t stream) {
+    PU3_ARG_CHECK(rows >= 0 && n >= 0 && r > 0, "replica_sum: bad size");
+    const long long total = rows * n;
+    if (total == 0) return PU3_OK;
+    PU3_ARG_CHECK(in && out, "replica_sum: null pointer");
+    replica_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(total, r, in, out, accumulate);
+    PU3_LAUNCH_CHECK("replica_sum_kernel");
+    return PU3_OK;
+}
+
+extern "C" int pu3_relu_mask_f32(long long total, float *g, const float *act, pu3_stream_t stream) {
+    PU3_ARG_CHECK(total >= 0, "relu_mask: bad size");
+    if (total == 0) return PU3_OK;
+    PU3_ARG_CHECK(g && act, "relu_mask: null pointer");
+    relu_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(total, g, act);
+    PU3_LAUNCH_CHECK("relu_mask_kernel");
+    return PU3_OK;
+}
 
 extern "C" int pu3_normalize_f32(int b, int n, int nchw, const float *pc, float *out, float *centroid, float *radius,
                                  pu3_stream_t stream) {

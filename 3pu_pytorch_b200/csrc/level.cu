@@ -74,6 +74,18 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
                                      const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
                                      float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
                                      pu3_stream_t stream) {
+    return pu3_level_forward_train_f32(w, t, n, xyz, xyz_norm, owner, groups, max_group, prev_xyz, prev_feat_pm, clouds, no, prev_n,
+                                       feat, out_xyz, workspace, workspace_bytes, nullptr, stream);
+}
+
+// The same forward keeping what the backward pass needs (train step, model.py:53-66): the 24-channel input of every dense
+// block, the neighbour indices of every block, the skip connection's indices and weights, and the two 128-channel activations of
+// the head.  `saved` NULL = plain forward.
+extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                                           const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                                           const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
+                                           float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
+                                           const pu3_level_saved *saved, pu3_stream_t stream) {
     PU3_ARG_CHECK(w && t >= 0 && n > 0, "level_forward: bad arguments");
     if (t == 0) return PU3_OK;
     PU3_ARG_CHECK(xyz_norm && feat && out_xyz, "level_forward: null pointer");
@@ -87,14 +99,16 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
         return PU3_E_WORKSPACE;
     }
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float *h = reinterpret_cast<float *>(ws + p.off_h);
-    int32_t *idx = reinterpret_cast<int32_t *>(ws + p.off_idx);
+    float *h = saved ? saved->h[0] : reinterpret_cast<float *>(ws + p.off_h);
+    int32_t *idx = saved ? saved->idx[0] : reinterpret_cast<int32_t *>(ws + p.off_idx);
+    PU3_ARG_CHECK(!saved || (saved->h[0] && saved->h[1] && saved->h[2] && saved->h[3] && saved->idx[0] && saved->idx[1] && saved->idx[2] &&
+                             saved->idx[3] && saved->h1 && saved->h2), "level_forward: incomplete saved buffers");
     int32_t *me = reinterpret_cast<int32_t *>(ws + p.off_me);
     float *pre = reinterpret_cast<float *>(ws + p.off_pre);
-    float *h1 = reinterpret_cast<float *>(ws + p.off_h1);
-    float *h2 = reinterpret_cast<float *>(ws + p.off_h2);
+    float *h1 = saved ? saved->h1 : reinterpret_cast<float *>(ws + p.off_h1);
+    float *h2 = saved ? saved->h2 : reinterpret_cast<float *>(ws + p.off_h2);
     float *h3 = reinterpret_cast<float *>(ws + p.off_h3);
-    int64_t *skipidx = reinterpret_cast<int64_t *>(ws + p.off_skipidx);
+    int64_t *skipidx = (saved && saved->skip_idx) ? saved->skip_idx : reinterpret_cast<int64_t *>(ws + p.off_skipidx);
     void *knnws = ws + p.off_knnws;
     const long long fs = (long long)C * n;   // batch stride of the feature buffer
     int st;
@@ -107,6 +121,7 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
                                           cudaMemcpyDeviceToDevice, as_stream(stream)), "level_forward: copy x0"));
     int lo = C - 24;
     for (int blk = 0; blk < 4; ++blk) {
+        if (saved && blk > 0) { h = saved->h[blk]; idx = saved->idx[blk]; }
         if (blk > 0) {   // layerK_prep (:213-221): Conv1d + ReLU over everything produced so far
             if (g_level_tc >= 2 && n % 4 == 0) {   // tensor cores (3xTF32), cout 24 padded to the 64-column MMA
                 void *wsp = ws + p.off_wprep[blk - 1];
@@ -136,8 +151,8 @@ extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, c
         else
             PU3_TRYT(PROF_KNN_SKIP, pu3_group_knn_f32(t, 3, n, no, w->fm_knn, t / clouds, xyz, prev_xyz, 1, max_group, nullptr, skipidx, nullptr,
                                       nullptr, knnws, p.knn_ws, stream));
-        PU3_TRYT(PROF_SKIP_FUSE, pu3_skip_fuse_f32(t, n, C, w->fm_knn, owner ? 1 : t / clouds, no, feat, xyz, skipidx, prev_xyz, prev_feat_pm,
-                                  owner, stream));
+        PU3_TRYT(PROF_SKIP_FUSE, pu3_skip_fuse_ex_f32(t, n, C, w->fm_knn, owner ? 1 : t / clouds, no, feat, xyz, skipidx, prev_xyz, prev_feat_pm,
+                                  owner, saved ? saved->skip_w : nullptr, stream));
     }
     // expansion head (:349-372)
     if (g_level_tc >= 1 && n % 4 == 0 && r <= 8) {

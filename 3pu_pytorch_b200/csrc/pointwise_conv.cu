@@ -27,6 +27,11 @@ struct PwArgs {
     float *y; long long y_bstride;
     const float *res; long long res_bstride; int res_n, res_div;  // optional residual (b, cout, res_n), column p / res_div
     int relu;
+    // backward use: Y = [Y +] (mask > 0 ? v : 0).  mask (b, cout, n) laid out like y (its own batch stride): the ReLU
+    // derivative of the activation this gradient flows into; accumulate: add to what y already holds (a gradient slice
+    // that several consumers contribute to).
+    const float *mask; long long mask_bstride;
+    int accumulate;
 };
 
 // TM = RM * TY output channels, TN = 8 * TX columns, threads = TX * TY
@@ -105,8 +110,11 @@ __global__ void __launch_bounds__(TX * TY) pointwise_conv_kernel(PwArgs a) {
             const int p = (int)(col - bi * a.n);
             float v = acc[i][j] + bv;
             if (a.relu) v = fmaxf(v, 0.f);
+            if (a.mask && !(__ldg(a.mask + bi * a.mask_bstride + (size_t)co * a.n + p) > 0.f)) v = 0.f;
             if (a.res) v += __ldg(a.res + bi * a.res_bstride + (size_t)co * a.res_n + p / a.res_div);
-            a.y[bi * a.y_bstride + (size_t)co * a.n + p] = v;
+            float *dst = a.y + bi * a.y_bstride + (size_t)co * a.n + p;
+            if (a.accumulate) v += *dst;
+            *dst = v;
         }
     }
 }
@@ -246,7 +254,16 @@ __global__ void __launch_bounds__(TX * TY) pointwise_conv_fast_kernel(PwArgs a) 
                 if (a.relu) v[j] = fmaxf(v[j], 0.f);
                 if (a.res) v[j] += __ldg(a.res + bi * a.res_bstride + (size_t)co * a.res_n + (p + j) / a.res_div);
             }
-            *reinterpret_cast<float4 *>(a.y + bi * a.y_bstride + (size_t)co * a.n + p) = make_float4(v[0], v[1], v[2], v[3]);
+            float4 *dst = reinterpret_cast<float4 *>(a.y + bi * a.y_bstride + (size_t)co * a.n + p);
+            if (a.mask) {
+                const float4 mk = __ldg(reinterpret_cast<const float4 *>(a.mask + bi * a.mask_bstride + (size_t)co * a.n + p));
+                if (!(mk.x > 0.f)) v[0] = 0.f;
+                if (!(mk.y > 0.f)) v[1] = 0.f;
+                if (!(mk.z > 0.f)) v[2] = 0.f;
+                if (!(mk.w > 0.f)) v[3] = 0.f;
+            }
+            if (a.accumulate) { const float4 o = *dst; v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+            *dst = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
@@ -281,14 +298,23 @@ extern "C" int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const flo
                                       const float *w, const float *bias, float *y, long long y_bstride,
                                       const float *res, long long res_bstride, int res_n, int res_div, int relu,
                                       pu3_stream_t stream) {
+    return pu3_pointwise_conv_ex_f32(b, n, cin, cout, x, x_bstride, w, bias, y, y_bstride, res, res_bstride, res_n, res_div, relu,
+                                     nullptr, 0, 0, stream);
+}
+
+extern "C" int pu3_pointwise_conv_ex_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
+                                         const float *w, const float *bias, float *y, long long y_bstride,
+                                         const float *res, long long res_bstride, int res_n, int res_div, int relu,
+                                         const float *mask, long long mask_bstride, int accumulate, pu3_stream_t stream) {
     PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0 && cout > 0, "pointwise_conv: bad size b=%d n=%d cin=%d cout=%d", b, n, cin, cout);
     if (b == 0 || n == 0) return PU3_OK;
     PU3_ARG_CHECK(x && w && y, "pointwise_conv: null pointer");
     PU3_ARG_CHECK(!res || (res_div >= 1 && res_n >= 1), "pointwise_conv: bad residual description");
-    PwArgs a{b, n, cin, cout, x, x_bstride, w, bias, y, y_bstride, res, res_bstride, res_n, res_div > 0 ? res_div : 1, relu};
+    PwArgs a{b, n, cin, cout, x, x_bstride, w, bias, y, y_bstride, res, res_bstride, res_n, res_div > 0 ? res_div : 1, relu,
+             mask, mask_bstride, accumulate};
     const long long cols = (long long)b * n;
     cudaStream_t s = as_stream(stream);
-    const bool aligned = (n % 4 == 0) && (x_bstride % 4 == 0) && (y_bstride % 4 == 0) &&
+    const bool aligned = (n % 4 == 0) && (x_bstride % 4 == 0) && (y_bstride % 4 == 0) && (!mask || (mask_bstride % 4 == 0 && ((uintptr_t)mask & 15) == 0)) &&
                          (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && g_pw_force_generic == 0;
     if (aligned && RM4_OK(cout)) {
         if (cout <= 4) {
@@ -350,12 +376,13 @@ namespace pu3 {
 
 constexpr int BW_T = 64;       // output tile (co x ci)
 constexpr int BW_KC = 16;      // columns per shared-memory chunk
-constexpr int BW_COLS = 512;   // columns per CTA (split-K granularity): ~20 column chunks x (cout/64 x cin/64) tiles even at B=32, N=312
+constexpr int BW_COLS = 128;   // columns per CTA (split-K granularity).  ncu (profiles/r2): with 512 every launch took ~120 us whatever its size --
+                               // 39 CTAs each walking 32 serial load -> barrier -> FMA chunks; 128 gives 4x the CTAs and a 4x shorter chain
 
 __global__ void __launch_bounds__(256) pointwise_conv_bwd_w_kernel(int b, int n, int cin, int cout,
                                                                   const float *__restrict__ x, long long x_bstride,
                                                                   const float *__restrict__ dy, long long dy_bstride,
-                                                                  float *__restrict__ dw, float *__restrict__ db) {
+                                                                  float *__restrict__ dw, int dw_stride, float *__restrict__ db) {
     __shared__ float As[BW_KC][BW_T + 1];   // dY chunk, [col][co]
     __shared__ float Bs[BW_KC][BW_T + 1];   // X chunk,  [col][ci]
     const long long cols = (long long)b * n;
@@ -407,7 +434,7 @@ __global__ void __launch_bounds__(256) pointwise_conv_bwd_w_kernel(int b, int n,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = ci0 + tx * 4 + j;
-            if (ci < cin) atomicAdd(dw + (size_t)co * cin + ci, acc[i][j]);
+            if (ci < cin) atomicAdd(dw + (size_t)co * dw_stride + ci, acc[i][j]);
         }
     }
     if (do_bias && threadIdx.x < BW_T && co0 + (int)threadIdx.x < cout) atomicAdd(db + co0 + threadIdx.x, bsum);
@@ -418,12 +445,18 @@ __global__ void __launch_bounds__(256) pointwise_conv_bwd_w_kernel(int b, int n,
 extern "C" int pu3_pointwise_conv_bwd_w_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
                                             const float *dy, long long dy_bstride, float *dw, float *db,
                                             pu3_stream_t stream) {
-    PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0 && cout > 0, "pointwise_conv_bwd_w: bad size");
+    return pu3_pointwise_conv_bwd_w_ex_f32(b, n, cin, cout, x, x_bstride, dy, dy_bstride, dw, cin, db, stream);
+}
+
+extern "C" int pu3_pointwise_conv_bwd_w_ex_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride,
+                                               const float *dy, long long dy_bstride, float *dw, int dw_stride, float *db,
+                                               pu3_stream_t stream) {
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0 && cout > 0 && dw_stride >= cin, "pointwise_conv_bwd_w: bad size");
     if (b == 0 || n == 0) return PU3_OK;
     PU3_ARG_CHECK(x && dy && dw, "pointwise_conv_bwd_w: null pointer");
     const long long cols = (long long)b * n;
     dim3 grid((unsigned)((cols + pu3::BW_COLS - 1) / pu3::BW_COLS), (cout + pu3::BW_T - 1) / pu3::BW_T, (cin + pu3::BW_T - 1) / pu3::BW_T);
-    pu3::pointwise_conv_bwd_w_kernel<<<grid, 256, 0, pu3::as_stream(stream)>>>(b, n, cin, cout, x, x_bstride, dy, dy_bstride, dw, db);
+    pu3::pointwise_conv_bwd_w_kernel<<<grid, 256, 0, pu3::as_stream(stream)>>>(b, n, cin, cout, x, x_bstride, dy, dy_bstride, dw, dw_stride, db);
     PU3_LAUNCH_CHECK("pointwise_conv_bwd_w_kernel");
     return PU3_OK;
 }

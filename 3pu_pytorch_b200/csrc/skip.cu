@@ -28,6 +28,7 @@ struct SkipArgs {
     const float *prev_xyz;     // (clouds,3,no) channel-major
     const float *prev_feat;    // (clouds,no,c) POINT-major
     const int32_t *owner;      // (t) or null -> t / p_div
+    float *w_out;              // (t,n,k) or null: the normalised interpolation weights (saved for the backward pass)
 };
 
 __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
@@ -117,6 +118,10 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
             }
 #pragma unroll
             for (int kk = 0; kk < SK_KMAX; ++kk) w[kk] = w[kk] / wsum;
+            if (a.w_out && lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < SK_KMAX; ++kk) if (kk < K) a.w_out[((size_t)ti * N + i) * K + kk] = w[kk];
+            }
             for (int ch = lane; ch < C; ch += 32) {
                 float acc = 0.f;
 #pragma unroll
@@ -258,6 +263,10 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_fixed_kernel(SkipArgs a)
             }
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) w[kk] = w[kk] / wsum;
+            if (a.w_out && lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) a.w_out[((size_t)ti * N + i) * K + kk] = w[kk];
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int ch = lane + 32 * u;
@@ -274,6 +283,37 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_fixed_kernel(SkipArgs a)
         for (int t = threadIdx.x; t < C * SK_PT; t += SK_THREADS) {
             const int ch = t / SK_PT, pl = t % SK_PT;
             if (pl < pc) xb[(size_t)ch * N + p0 + pl] = xt[ch * (SK_PT + 1) + pl];
+        }
+    }
+}
+
+// Backward of the skip connection with respect to the previous level's features (the weights are detached in the
+// reference, upsampler.py:243,249, so x' = x + 0.2 sum_k w_k f_{j_k} is linear in f):
+//     dprev[cloud, j_k(i), :] += 0.2 * w_k(i) * dx'[:, i]        (dx = dx' passes through unchanged)
+// One warp per point, the tile's gradient columns through a transposing shared-memory tile, whole-row atomics.
+__global__ void __launch_bounds__(SK_THREADS) skip_bwd_kernel(int n, int c, int k, int p_div, int no, const float *__restrict__ dx,
+                                                              const int64_t *__restrict__ idx, const float *__restrict__ w,
+                                                              const int32_t *__restrict__ owner, float *__restrict__ dprev) {
+    extern __shared__ __align__(16) float sm[];
+    float *xt = sm;                                  // [c][SK_PT+1]
+    const int ti = blockIdx.y, p0 = blockIdx.x * SK_PT;
+    const int pc = min(SK_PT, n - p0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = owner ? __ldg(owner + ti) : ti / p_div;
+    const float *db = dx + (size_t)ti * c * n;
+    for (int t = threadIdx.x; t < c * SK_PT; t += SK_THREADS) {
+        const int ch = t / SK_PT, pl = t % SK_PT;
+        xt[ch * (SK_PT + 1) + pl] = pl < pc ? db[(size_t)ch * n + p0 + pl] : 0.f;
+    }
+    __syncthreads();
+    float *pf = dprev + (size_t)cloud * no * c;
+    for (int pl = warp; pl < pc; pl += SK_WARPS) {
+        const int i = p0 + pl;
+        for (int kk = 0; kk < k; ++kk) {
+            const int j = (int)idx[((size_t)ti * n + i) * k + kk];
+            const float wk = 0.2f * __ldg(w + ((size_t)ti * n + i) * k + kk);
+            if (wk == 0.f) continue;
+            for (int ch = lane; ch < c; ch += 32) atomicAdd(pf + (size_t)j * c + ch, wk * xt[ch * (SK_PT + 1) + pl]);
         }
     }
 }
@@ -310,12 +350,33 @@ extern "C" void pu3_skip_force_generic(int on) { g_skip_force_generic = on; }
 extern "C" int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz,
                                  const int64_t *idx, const float *prev_xyz, const float *prev_feat_pm,
                                  const int32_t *owner, pu3_stream_t stream) {
+    return pu3_skip_fuse_ex_f32(t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner, nullptr, stream);
+}
+
+extern "C" int pu3_skip_bwd_f32(int t, int n, int c, int k, int p_div, int no, const float *dx, const int64_t *idx,
+                                const float *w, const int32_t *owner, float *dprev_feat_pm, pu3_stream_t stream) {
+    PU3_ARG_CHECK(t >= 0 && n > 0 && c > 0 && k > 0 && no > 0, "skip_bwd: bad size t=%d n=%d c=%d k=%d no=%d", t, n, c, k, no);
+    if (t == 0) return PU3_OK;
+    PU3_ARG_CHECK(owner || p_div >= 1, "skip_bwd: need owner or p_div");
+    PU3_ARG_CHECK(dx && idx && w && dprev_feat_pm && t <= 65535, "skip_bwd: null pointer or t > 65535");
+    const size_t smem = (size_t)c * (SK_PT + 1) * sizeof(float);
+    PU3_ARG_CHECK(smem <= (size_t)device_info().smem_optin, "skip_bwd: c=%d needs %zu bytes of shared memory", c, smem);
+    int st = cuda_status(cudaFuncSetAttribute(skip_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_bwd: smem attr");
+    if (st) return st;
+    skip_bwd_kernel<<<dim3((n + SK_PT - 1) / SK_PT, t), SK_THREADS, smem, as_stream(stream)>>>(n, c, k, p_div, no, dx, idx, w, owner, dprev_feat_pm);
+    PU3_LAUNCH_CHECK("skip_bwd_kernel");
+    return PU3_OK;
+}
+
+extern "C" int pu3_skip_fuse_ex_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz,
+                                    const int64_t *idx, const float *prev_xyz, const float *prev_feat_pm,
+                                    const int32_t *owner, float *w_out, pu3_stream_t stream) {
     PU3_ARG_CHECK(t >= 0 && n > 0 && c > 0 && k > 0 && no > 0, "skip_fuse: bad size t=%d n=%d c=%d k=%d no=%d", t, n, c, k, no);
     if (t == 0) return PU3_OK;
     PU3_ARG_CHECK(k <= SK_KMAX, "skip_fuse: k=%d exceeds %d", k, SK_KMAX);
     PU3_ARG_CHECK(owner || p_div >= 1, "skip_fuse: need owner or p_div");
     PU3_ARG_CHECK(x && xyz && idx && prev_xyz && prev_feat_pm, "skip_fuse: null pointer");
-    SkipArgs a{t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner};
+    SkipArgs a{t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner, w_out};
     const size_t smem = ((size_t)c * (SK_PT + 1) + 2 * (size_t)n * k + 2 * SK_WARPS) * sizeof(float);
     PU3_ARG_CHECK(smem <= (size_t)device_info().smem_optin, "skip_fuse: c=%d n=%d k=%d needs %zu bytes of shared memory", c, n, k, smem);
     int st = cuda_status(cudaFuncSetAttribute(skip_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_fuse: smem attr");

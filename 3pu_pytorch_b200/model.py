@@ -13,7 +13,7 @@ from math import log
 
 import torch
 
-from . import _lib
+from . import _lib, level_train
 from .dist import FlatAdam
 from .model_loss import ChamferLoss
 
@@ -67,7 +67,14 @@ class Model(object):
         self.net.train()
         self.forward(**kwargs)
         loss = self.compute_chamfer_loss(self.predicted, self.gt)
-        loss.backward()
+        # the flat optimizer pre-zeroes one gradient buffer that every .grad is a view of: the native backward kernels
+        # accumulate straight into it
+        prev = level_train.accumulate_into_param_grads
+        level_train.accumulate_into_param_grads = True
+        try:
+            loss.backward()
+        finally:
+            level_train.accumulate_into_param_grads = prev
         self.optimizer.step()          # [all-reduce] + clip_grad_value_(1) + Adam, one kernel
         self.step += 1
         return loss

@@ -15,7 +15,7 @@ from math import log, sqrt
 
 import torch
 
-from . import fused, layers, operations
+from . import fused, layers, level_train, operations
 
 
 class Level(torch.nn.Module):
@@ -83,6 +83,42 @@ class Level(torch.nn.Module):
             c = self.code.to(device=device, dtype=torch.float32).contiguous()
             self._code_dev[device] = c
         return c
+
+    def _code_row(self, device, T, N):
+        """(T,1,N*r) tensor holding code[p % r]: the code channel of the expanded tensor (upsampler.py:354-361), for its weight gradient"""
+        key = (str(device), T, N)
+        cache = self.__dict__.setdefault("_code_rows", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = self._code_on(device).view(1, 1, -1).repeat(T, 1, N).contiguous()
+        return cache[key]
+
+    def _engine_params(self):
+        """the 40 parameters in the order of pu3_level_weights"""
+        params = [self.layer0.conv.weight, self.layer0.conv.bias]
+        for blk in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for m in blk.mlps:
+                params += [m.weight, m.bias]
+        for prep in (self.layer2_prep, self.layer3_prep, self.layer4_prep):
+            params += [prep.conv.weight, prep.conv.bias]
+        up1, up2 = self.up_layer.up_layer1.conv, self.up_layer.up_layer2.conv
+        params += [up1.weight, up1.bias, up2.weight, up2.bias, self.fc_layer1.conv.weight, self.fc_layer1.conv.bias,
+                   self.fc_layer2.conv.weight, self.fc_layer2.conv.bias]
+        return params
+
+    # train mode as ONE autograd node on native forward + backward kernels (level_train.py); False: the operator composition
+    # below (every layer its own autograd function, skip connection through torch operators) -- kept for tests
+    native_train = True
+
+    def _native_train_ok(self, xyz_normalized, previous_level4):
+        n = xyz_normalized.shape[2]
+        ok = (xyz_normalized.is_cuda and xyz_normalized.dtype == torch.float32 and self.dense_n == 3 and self.growth_rate == 12
+              and self.code.size(1) == 1 and self._engine_ok() and self.knn <= 32 and n % 4 == 0 and n <= 1500
+              and self.code.size(2) <= 8 and n >= self.knn + 1)
+        if ok and previous_level4 is not None and self.fm_knn > 0:
+            pf = previous_level4[1]
+            ok = pf.dim() == 3 and pf.shape[1] == self.feat_channels and xyz_normalized.shape[0] % pf.shape[0] == 0
+        return ok
 
     # ---- forward ---------------------------------------------------------------------------------------
     def _fast_path_ok(self, xyz_normalized):
@@ -282,6 +318,11 @@ class Level(torch.nn.Module):
             raise RuntimeError("ragged batches are an eval-mode (no-grad, CUDA fp32) feature")
         if fast and self.use_engine and self._engine_ok() and (previous_level4 is None or prev_point_major or self.fm_knn <= 0):
             return self._forward_engine(xyz, xyz_normalized, previous_level4, group, ragged)
+        if not fast and self.native_train and torch.is_grad_enabled() and not prev_point_major and ragged is None \
+                and self._native_train_ok(xyz_normalized, previous_level4):
+            prev_xyz, prev_feat = previous_level4 if (previous_level4 is not None and self.fm_knn > 0) else (None, None)
+            return level_train.LevelTrainFunction.apply(self, xyz, xyz_normalized, prev_xyz, prev_feat, group,
+                                                        *self._engine_params())
         if fast:
             x = self._features_fused(xyz_normalized, group, ragged)
         else:

@@ -166,6 +166,16 @@ int pu3_group_gather_bwd_f32(int b, int c, int m, int n, int k, int p_div, const
 int pu3_pointwise_conv_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *w,
                            const float *bias, float *y, long long y_bstride, const float *res,
                            long long res_bstride, int res_n, int res_div, int relu, pu3_stream_t stream);
+/*
+ * The same kernel with the backward-pass epilogue: y = [y +] (mask > 0 ? act(W x + b) [+ res] : 0).  mask (b,cout,n) (its own
+ * batch stride, channel stride n) is the forward activation whose ReLU derivative gates this gradient; accumulate != 0 adds to what
+ * y already holds (a gradient slice with several contributors).  With W = the transposed forward weight and x = dY this is the
+ * input gradient of the 1x1 convolution (model.py:62 autograd of network/layers.py:115-204).
+ */
+int pu3_pointwise_conv_ex_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *w,
+                              const float *bias, float *y, long long y_bstride, const float *res, long long res_bstride,
+                              int res_n, int res_div, int relu, const float *mask, long long mask_bstride, int accumulate,
+                              pu3_stream_t stream);
 
 /*
  * Code column of the feature-expansion layer (network/upsampler.py:349-366):
@@ -223,6 +233,16 @@ int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, c
  */
 int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
                       const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, pu3_stream_t stream);
+/* ... the same, also writing the normalised weights w (t,n,k) (NULL = not wanted): what the backward pass needs. */
+int pu3_skip_fuse_ex_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
+                         const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, float *w_out, pu3_stream_t stream);
+/*
+ * Backward of the skip connection (autograd of network/upsampler.py:334-347 in the train step; the weights are detached there,
+ * :243,249): dprev_feat_pm[cloud, idx[i,kk], :] += 0.2 * w[i,kk] * dx[:, i] with fp32 atomics into a caller-zeroed POINT-major
+ * buffer (clouds,no,c); the gradient of x itself passes through unchanged.  dx (t,c,n) channel-major.
+ */
+int pu3_skip_bwd_f32(int t, int n, int c, int k, int p_div, int no, const float *dx, const int64_t *idx, const float *w,
+                     const int32_t *owner, float *dprev_feat_pm, pu3_stream_t stream);
 void pu3_skip_force_generic(int on); /* test hook: 1 = runtime-(k,c) kernel even for the k=5, c=264 configuration */
 
 /*
@@ -270,6 +290,24 @@ int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float 
                           const int32_t *owner, int groups, int max_group, const float *prev_xyz,
                           const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
                           float *out_xyz, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
+/*
+ * Buffers the train-mode forward fills for the backward pass (all caller-allocated): h[blk] (t,24,n) the input of dense block blk
+ * (layer0 output, then the three prep outputs after ReLU), idx[blk] (t,n,knn+1) i32 its neighbour lists (column 0 = the dropped
+ * rank 0), skip_idx (t,n,fm_knn) i64 and skip_w (t,n,fm_knn) of the skip connection (NULL without a previous level), h1 / h2
+ * (t,128,n*r) the activations after up_layer1 / up_layer2.
+ */
+typedef struct pu3_level_saved {
+    float *h[4];
+    int32_t *idx[4];
+    int64_t *skip_idx;
+    float *skip_w;
+    float *h1, *h2;
+} pu3_level_saved;
+int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                                const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                                const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
+                                float *out_xyz, void *workspace, size_t workspace_bytes, const pu3_level_saved *saved,
+                                pu3_stream_t stream);
 int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
 void pu3_level_set_tc(int mode); /* test / A-B hook: 2 (default) = head + prep convolutions on tcgen05, 1 = head only, 0 = fp32 FFMA kernels */
 
@@ -281,6 +319,14 @@ void pu3_level_set_tc(int mode); /* test / A-B hook: 2 (default) = head + prep c
  */
 int pu3_pointwise_conv_bwd_w_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *dy,
                                  long long dy_bstride, float *dw, float *db, pu3_stream_t stream);
+/* ... with an explicit row stride of dw (>= cin): gradients of a column block of a wider weight matrix (the 264 feature columns
+ * and the code column of up_layer1's (128,265) weight, upsampler.py:225,354-361). */
+int pu3_pointwise_conv_bwd_w_ex_f32(int b, int n, int cin, int cout, const float *x, long long x_bstride, const float *dy,
+                                    long long dy_bstride, float *dw, int dw_stride, float *db, pu3_stream_t stream);
+/* out[e] (+)= sum_{j<r} in[e*r + j] for e < rows*n: gradient of the r-fold point replication of the expansion head (:356-358,:371). */
+int pu3_replica_sum_f32(long long rows, int n, int r, const float *in, float *out, int accumulate, pu3_stream_t stream);
+/* g[e] = act[e] > 0 ? g[e] : 0 (ReLU derivative applied to a gradient in place). */
+int pu3_relu_mask_f32(long long total, float *g, const float *act, pu3_stream_t stream);
 
 /*
  * DenseEdgeConv backward (autograd of network/layers.py:44-64 in the reference's train step), k <= 32:

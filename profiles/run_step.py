@@ -21,6 +21,7 @@ dev = torch.device("cuda:0")
 net = pu3.Net(max_up_ratio=16, step_ratio=2, knn=32, growth_rate=12, dense_n=3, fm_knn=5)
 net.load_state_dict(ref_net.make_params(4, seed=1), strict=True)
 net = net.to(dev).eval()
+net.use_cuda_graph = os.environ.get("GRAPH", "0") == "1"   # eager launches by default: every kernel is its own ncu result
 x = bench.make_inputs(0).to(dev)
 with torch.no_grad():
     for _ in range(int(os.environ.get("WARMUP", "2"))):

@@ -90,8 +90,8 @@ def test_tile_seeds_tiles_normalize_denorm_merge_gather(pu3, cuda):
     idx = torch.randint(0, N, (B, P), generator=g, dtype=torch.int32)
     p_arr = torch.tensor([6, 4, 1], dtype=torch.int32)
     seeds = torch.empty(B, 3, P, device=cuda)
-    x = xyz.to(cuda)
-    L.launch("pu3_tile_seeds_f32", x, B, N, P, x.data_ptr(), idx.to(cuda).data_ptr(), p_arr.to(cuda).data_ptr(), seeds.data_ptr())
+    x, idx_d, p_d = xyz.to(cuda), idx.to(cuda), p_arr.to(cuda)      # keep the device copies alive across the launch
+    L.launch("pu3_tile_seeds_f32", x, B, N, P, x.data_ptr(), idx_d.data_ptr(), p_d.data_ptr(), seeds.data_ptr())
     for b in range(B):
         for j in range(P):
             src = int(idx[b, j if j < int(p_arr[b]) else 0])
@@ -125,5 +125,6 @@ def test_tile_seeds_tiles_normalize_denorm_merge_gather(pu3, cuda):
     m = 50
     oidx = torch.randint(0, P * kr, (B, m), generator=g, dtype=torch.int32)
     out = torch.empty(B, 3, m, device=cuda)
-    L.launch("pu3_gather_pm_f32", merged, B, P * kr, m, merged.data_ptr(), oidx.to(cuda).data_ptr(), out.data_ptr())
+    oidx_d = oidx.to(cuda)
+    L.launch("pu3_gather_pm_f32", merged, B, P * kr, m, merged.data_ptr(), oidx_d.data_ptr(), out.data_ptr())
     assert torch.equal(out.cpu(), torch.gather(want, 2, oidx.long().unsqueeze(1).expand(-1, 3, -1)))

@@ -161,3 +161,67 @@ def test_eval_after_train_steps_sees_the_updated_weights(pu3, cuda):
             lib.pu3_level_set_tc(2)
         assert (after - before).abs().max() > 1e-4                     # the weights did move
         assert torch.equal(after, want), f"tc={tc}: stale weight image after FlatAdam steps"
+
+
+def test_native_level_backward_matches_the_operator_composition(pu3, cuda):
+    """Row a-14: the train-mode Level as one native autograd node (level_train.py) against the same graph differentiated
+    operator by operator.  Both run the same kNN kernels, so the discrete choices agree and every gradient -- all 80 parameter
+    tensors of two levels, and the input cloud -- is compared at 1e-4 of the tensor's scale."""
+    levels, ratio, B = 2, 4, 3
+    P0 = {k: v for k, v in ref_net.make_params(4, seed=9).items() if int(k.split(".")[1].split("_")[1]) <= levels}
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(B, 3, 312, generator=g).to(cuda)
+    gt = torch.rand(B, 3, 312 * ratio, generator=g).to(cuda)
+    seeds = {2: torch.randint(0, 624, (B, 1), generator=g, dtype=torch.int32).to(cuda)}
+    outs = {}
+    for native in (True, False):
+        net = pu3.Net(max_up_ratio=ratio, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5)
+        net.load_state_dict(P0, strict=True)
+        net = net.to(cuda).train()
+        for lv in net.levels.values():
+            lv.native_train = native
+        xin = x.clone().requires_grad_()
+        pc, gc = net(xin, ratio=ratio, gt=gt, seed_idx_per_level=seeds)
+        loss = pu3.ChamferLoss()(pc, gc)
+        loss.backward()
+        outs[native] = (pc.detach(), float(loss), xin.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
+    pa, la, xa, ga = outs[True]
+    pb, lb, xb, gb = outs[False]
+    assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6)             # forward: tcgen05 engine vs FFMA composition
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    def close(a, b, what):
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a - b).abs().max())
+        assert err <= 1e-4 * scale, f"{what}: max err {err:.3e} at scale {scale:.3e}"
+    close(xa, xb, "d loss / d input cloud")
+    assert set(ga) == set(gb) and len(ga) == 80
+    for k in sorted(ga):
+        close(ga[k], gb[k], k)
+
+
+def test_model_optimize_accumulates_into_the_flat_gradient_buffer(pu3, cuda):
+    """Model.optimize lets the native backward write straight into FlatAdam's flat gradient (no per-parameter temporaries):
+    same parameters after two steps as with autograd-returned gradients."""
+    P0 = ref_net.make_params(4, seed=4)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 312, generator=g).to(cuda); gt = torch.rand(2, 3, 4992, generator=g).to(cuda)
+    seeds = {l: torch.randint(0, 624, (2, 1), generator=g, dtype=torch.int32).to(cuda) for l in (2, 3, 4)}
+    res = []
+    lt = pu3.level_train
+    for direct in (True, False):
+        net = pu3.Net(max_up_ratio=16, step_ratio=2, knn=32, growth_rate=12, dense_n=3, fm_knn=5)
+        net.load_state_dict(P0, strict=True)
+        model = pu3.Model(net.to(cuda), "train", lr_init=5e-4, weight_full_ratio=1.0)
+        for _ in range(2):
+            model.set_input(x, 16, label_pc=gt)
+            if direct:
+                model.optimize(seed_idx_per_level=seeds)
+            else:                                  # the same step with autograd-returned parameter gradients
+                model.optimizer.zero_grad(); net.train()
+                model.forward(seed_idx_per_level=seeds)
+                model.compute_chamfer_loss(model.predicted, model.gt).backward()
+                model.optimizer.step()
+        res.append({k: p.detach().clone() for k, p in net.named_parameters()})
+        assert lt.accumulate_into_param_grads is False
+    for k in res[0]:
+        torch.testing.assert_close(res[0][k], res[1][k], rtol=1e-4, atol=1e-6)

@@ -782,7 +782,9 @@ extern "C" int pu3_edgeconv_bwd_f32(int b, int n, int k, const float *x, long lo
     const int sms = device_info().sm_count;
     int pts = n;
     if (b < sms) {
-        const int split = (sms + b - 1) / b;
+        // one resident CTA per SM (registers + shared memory): the grid must fit ONE wave.  ncu (profiles/r2): ceil(148/32) = 5
+        // splits gave 160 CTAs, i.e. a second wave of 12 that doubled the kernel's duration (SMs active 63 % of the time).
+        const int split = sms / b;
         pts = (n + split - 1) / split;
         pts = ((pts + EC_WARPS - 1) / EC_WARPS) * EC_WARPS;
     }

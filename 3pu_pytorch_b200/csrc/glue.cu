@@ -162,7 +162,8 @@ __global__ void tile_seeds_kernel(int n, int p, const float *__restrict__ xyz, c
 
 // ---- tiles (B,3,P,k) -> patches (B*P,3,k) raw + normalised, centroid (B*P,3), radius (B*P), and the tiles of a request side by
 // side (B,3,P*k): the cloud the next level's skip connection searches (upsampler.py:85,138,148-152) ---------------------------
-__global__ void __launch_bounds__(128) tiles_normalize_kernel(int p, int k, const float *__restrict__ tiles, float *__restrict__ patch,
+// (256 threads like normalize_kernel: the same per-thread strides and reduction tree, hence bit-identical centroids / radii)
+__global__ void __launch_bounds__(256) tiles_normalize_kernel(int p, int k, const float *__restrict__ tiles, float *__restrict__ patch,
                                                               float *__restrict__ patch_norm, float *__restrict__ centroid,
                                                               float *__restrict__ radius, float *__restrict__ side_by_side) {
     __shared__ float red[96];
@@ -298,7 +299,7 @@ extern "C" int pu3_tiles_normalize_f32(int b, int p, int k, const float *tiles, 
     PU3_ARG_CHECK(b >= 0 && p >= 0 && k > 0, "tiles_normalize: bad size");
     if (b == 0 || p == 0) return PU3_OK;
     PU3_ARG_CHECK(tiles && patch && patch_norm && centroid && radius, "tiles_normalize: null pointer");
-    tiles_normalize_kernel<<<b * p, 128, 0, as_stream(stream)>>>(p, k, tiles, patch, patch_norm, centroid, radius, side_by_side);
+    tiles_normalize_kernel<<<b * p, 256, 0, as_stream(stream)>>>(p, k, tiles, patch, patch_norm, centroid, radius, side_by_side);
     PU3_LAUNCH_CHECK("tiles_normalize_kernel");
     return PU3_OK;
 }

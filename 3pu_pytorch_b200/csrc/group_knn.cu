@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
     __syncthreads();
 
     const int qg = tid / KF_JG, jg = tid % KF_JG;    // 4 query groups of 8 x 64 candidate groups of 5
-    for (int q0 = 0; q0 < mv; q0 += KF_QB) {
+    // few clouds (train step, level 1 of eval, single requests): gridDim.y CTAs share a cloud, each takes every gridDim.y-th
+    // block of 32 queries (every CTA stages the whole cloud: 30 KB)
+    for (int q0 = blockIdx.y * KF_QB; q0 < mv; q0 += KF_QB * gridDim.y) {
         // ---- phase 1: keys of queries [q0, q0+32) x candidates [0, 320): one 8x5 tile per thread, FFMA2 -------
         {
             const int ql = qg * 8;
@@ -1086,13 +1088,18 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         const size_t smem = ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4;
         if (smem <= (size_t)device_info().smem_optin) {
             const bool hot = idx32 && !idx64 && !dist && !knn;
+            // 3 resident CTAs per SM: split the query blocks of a cloud over several CTAs until the chip is covered
+            const int qblocks = (m + KF_QB - 1) / KF_QB;
+            int qsplit = (int)((3LL * device_info().sm_count + b - 1) / b);
+            if (qsplit > qblocks) qsplit = qblocks;
+            if (qsplit < 1) qsplit = 1;
 #define PU3_KF_LAUNCH(CTV, HOTV)                                                                                        \
     do {                                                                                                                \
         auto kern = knn_feat_kernel<CTV, HOTV>;                                                                          \
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),        \
                              "group_knn: smem attr");                                                                   \
         if (st) return st;                                                                                              \
-        kern<<<b, KF_THREADS, smem, s>>>(a);                                                                            \
+        kern<<<dim3(b, qsplit), KF_THREADS, smem, s>>>(a);                                                              \
     } while (0)
             if (c == 24 && hot) PU3_KF_LAUNCH(24, true);
             else if (c == 24) PU3_KF_LAUNCH(24, false);

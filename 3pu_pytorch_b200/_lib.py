@@ -91,7 +91,7 @@ class LevelWeights(ctypes.Structure):
 class LevelSaved(ctypes.Structure):
     """pu3_level_saved of include/pu3_b200.h"""
     _fields_ = [("h", _c_void_p * 4), ("idx", _c_void_p * 4), ("skip_idx", _c_void_p), ("skip_w", _c_void_p),
-                ("h1", _c_void_p), ("h2", _c_void_p)]
+                ("h1", _c_void_p), ("h2", _c_void_p), ("feat_pre", _c_void_p)]
 
 
 _lib = None

@@ -151,6 +151,9 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
         else
             PU3_TRYT(PROF_KNN_SKIP, pu3_group_knn_f32(t, 3, n, no, w->fm_knn, t / clouds, xyz, prev_xyz, 1, max_group, nullptr, skipidx, nullptr,
                                       nullptr, knnws, p.knn_ws, stream));
+        if (saved && saved->feat_pre)
+            PU3_TRY(cuda_status(cudaMemcpyAsync(saved->feat_pre, feat, (size_t)t * C * n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                                as_stream(stream)), "level_forward: copy of the pre-skip features"));
         PU3_TRYT(PROF_SKIP_FUSE, pu3_skip_fuse_ex_f32(t, n, C, w->fm_knn, owner ? 1 : t / clouds, no, feat, xyz, skipidx, prev_xyz, prev_feat_pm,
                                   owner, saved ? saved->skip_w : nullptr, stream));
     }

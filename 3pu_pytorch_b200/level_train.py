@@ -63,9 +63,11 @@ class LevelTrainFunction(torch.autograd.Function):
         h2 = torch.empty(T, 128, N * r, **f32)
         skip_idx = torch.empty(T, N, fm, dtype=torch.int64, device=dev) if has_prev else None
         skip_w = torch.empty(T, N, fm, **f32) if has_prev else None
+        feat_pre = torch.empty(T, 264, N, **f32) if has_prev else None      # the prep convolutions read the features before the skip update
         for i in range(4):
             sv.h[i], sv.idx[i] = hs[i].data_ptr(), idxs[i].data_ptr()
         sv.skip_idx, sv.skip_w, sv.h1, sv.h2 = _lib.ptr(skip_idx), _lib.ptr(skip_w), h1.data_ptr(), h2.data_ptr()
+        sv.feat_pre = _lib.ptr(feat_pre)
         L = _lib.lib()
         ws_bytes = L.pu3_level_workspace(T, N, r, K, fm, max(Bp, 1), max(No, 1), int(has_prev))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -76,7 +78,7 @@ class LevelTrainFunction(torch.autograd.Function):
                     out.data_ptr(), ws.data_ptr(), ws_bytes, ctypes.addressof(sv),
                     extra_kernels=32 + (6 if has_prev else 0))
         ctx.level, ctx.has_prev, ctx.dims = level, has_prev, (T, N, r, K, fm, Bp, No)
-        ctx.save_for_backward(xn, feat, h1, h2, skip_idx, skip_w, *hs, *idxs, *params)
+        ctx.save_for_backward(xn, feat, h1, h2, skip_idx, skip_w, feat_pre, *hs, *idxs, *params)
         return out, feat
 
     @staticmethod
@@ -84,8 +86,10 @@ class LevelTrainFunction(torch.autograd.Function):
         level = ctx.level
         T, N, r, K, fm, Bp, No = ctx.dims
         saved = ctx.saved_tensors
-        xn, feat, h1, h2, skip_idx, skip_w = saved[:6]
-        hs, idxs, params = saved[6:10], saved[10:14], saved[14:]
+        xn, feat, h1, h2, skip_idx, skip_w, feat_pre = saved[:7]
+        hs, idxs, params = saved[7:11], saved[11:15], saved[15:]
+        if feat_pre is None:
+            feat_pre = feat
         dev = xn.device
         f32 = dict(dtype=torch.float32, device=dev)
         C, Nr = 264, N * r
@@ -172,7 +176,7 @@ class LevelTrainFunction(torch.autograd.Function):
                 pw, pb = prep[blk - 1]
                 cin = C - (s + 60)
                 _lib.launch("pu3_relu_mask_f32", xn, T * 24 * N, dh.data_ptr(), hs[blk].data_ptr())
-                src = feat.data_ptr() + 4 * (s + 60) * N
+                src = feat_pre.data_ptr() + 4 * (s + 60) * N
                 dW(src, fs, dh.data_ptr(), 24 * N, N, cin, 24, pw, pb)
                 _conv(dh, 24 * N, _t(pw), dfeat.data_ptr() + 4 * (s + 60) * N, fs, T, N, 24, cin, acc=True)
         # ---- layer0 (:288) -------------------------------------------------------------------------------------------------------

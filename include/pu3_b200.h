@@ -294,7 +294,7 @@ int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float 
  * Buffers the train-mode forward fills for the backward pass (all caller-allocated): h[blk] (t,24,n) the input of dense block blk
  * (layer0 output, then the three prep outputs after ReLU), idx[blk] (t,n,knn+1) i32 its neighbour lists (column 0 = the dropped
  * rank 0), skip_idx (t,n,fm_knn) i64 and skip_w (t,n,fm_knn) of the skip connection (NULL without a previous level), h1 / h2
- * (t,128,n*r) the activations after up_layer1 / up_layer2.
+ * (t,128,n*r) the activations after up_layer1 / up_layer2, feat_pre see below.
  */
 typedef struct pu3_level_saved {
     float *h[4];
@@ -302,6 +302,8 @@ typedef struct pu3_level_saved {
     int64_t *skip_idx;
     float *skip_w;
     float *h1, *h2;
+    float *feat_pre; /* (t,264,n) copy of the features BEFORE the skip connection's in-place update (what the prep convolutions
+                        read in the forward); NULL without a previous level (feat itself is then unchanged) */
 } pu3_level_saved;
 int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
                                 const int32_t *owner, int groups, int max_group, const float *prev_xyz,

@@ -169,7 +169,8 @@ def test_native_level_backward_matches_the_operator_composition(pu3, cuda, tc):
     operator by operator.  Both run the same kNN kernels, so the neighbourhoods agree; what can still differ discretely is a
     Chamfer nearest-neighbour assignment at a near-tie (the two forwards differ by ~1e-6: fused skip kernel, and for tc=2 the
     3xTF32 tensor-core head against FFMA).  So: every one of the 80 parameter gradients and the input-cloud gradient must agree
-    to 1e-4 of the tensor's scale on >= 99.5 % of their entries, and nowhere be off by more than 5 %."""
+    to 1e-4 of the tensor's scale on >= 99.5 % of their entries (98 % against the tensor-core forward), and nowhere be off by
+    more than 5 %."""
     import ctypes
     levels, ratio, B = 2, 4, 3
     P0 = {k: v for k, v in ref_net.make_params(4, seed=9).items() if int(k.split(".")[1].split("_")[1]) <= levels}
@@ -203,7 +204,8 @@ def test_native_level_backward_matches_the_operator_composition(pu3, cuda, tc):
         scale = float(b.abs().max()) + 1e-12
         err = (a - b).abs()
         frac = float((err <= 1e-4 * scale).float().mean())
-        assert frac >= 0.995 and float(err.max()) <= 5e-2 * scale, \
+        need = 0.995 if tc == 0 else 0.98      # tc=2: activations within ~7e-7 of zero flip their ReLU mask between the two forwards
+        assert frac >= need and float(err.max()) <= 5e-2 * scale, \
             f"{what}: {frac:.4f} of the entries within 1e-4 of scale {scale:.3e}, max err {float(err.max()):.3e}"
     close(xa, xb, "d loss / d input cloud")
     assert set(ga) == set(gb) and len(ga) == 80
@@ -237,3 +239,32 @@ def test_model_optimize_accumulates_into_the_flat_gradient_buffer(pu3, cuda):
         assert lt.accumulate_into_param_grads is False
     for k in res[0]:
         torch.testing.assert_close(res[0][k], res[1][k], rtol=1e-4, atol=1e-6)
+
+
+def test_graphed_train_step_equals_the_eager_one(pu3, cuda):
+    """Model.optimize replays zero_grad -> forward -> Chamfer -> backward from a CUDA graph after two eager steps; with a
+    single level (no random zoom seed) the parameters after 6 steps must be those of 6 eager steps (the backward sums with
+    atomics, so equality is to rounding)."""
+    P0 = {k: v for k, v in ref_net.make_params(4, seed=6).items() if int(k.split(".")[1].split("_")[1]) <= 2}
+    g = torch.Generator().manual_seed(21)
+    xs = [torch.rand(4, 3, 312, generator=g).to(cuda) for _ in range(6)]
+    gts = [torch.rand(4, 3, 624, generator=g).to(cuda) for _ in range(6)]
+    res, losses = [], []
+    for graphed in (True, False):
+        net = pu3.Net(max_up_ratio=4, step_ratio=2, knn=16, growth_rate=12, dense_n=3, fm_knn=5)
+        net.load_state_dict(P0, strict=True)
+        model = pu3.Model(net.to(cuda), "train", lr_init=5e-4)
+        model.use_cuda_graph = graphed
+        ls = []
+        for x, gt in zip(xs, gts):
+            model.set_input(x, 2, label_pc=gt)
+            ls.append(float(model.optimize()))
+        if graphed:
+            assert any("graph" in e for e in model._graphs.values())          # steps 3..6 were replays
+        res.append({k: p.detach().clone() for k, p in net.named_parameters()})
+        losses.append(ls)
+        assert model.step == 6 and abs(model.error_log["cd_loss_x2"] - sum(ls) / 6) < 1e-6
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    for k in res[0]:
+        torch.testing.assert_close(res[0][k], res[1][k], rtol=2e-4, atol=2e-6)

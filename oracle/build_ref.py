@@ -104,7 +104,33 @@ def build(force=False):
             done += have
             continue
         done.append(_build(modname, os.path.join(REF_ROOT, sub), files, patch))
+    stage_python(force)
     return done
+
+
+PY_STAGE = os.path.join(OUT, "py")
+# the reference's DRIVER side, which must keep running unchanged on top of the drop-in modules: main.py, its own Model wrapper,
+# the data set and the numpy / IO helpers.  NOT staged: network/, sampling/, losses/ -- exactly what this repository replaces
+# (3pu_pytorch_b200/shim provides those import names).
+PY_FILES = ["main.py", "model.py", "data.py", "utils/__init__.py", "utils/pc_utils.py", "utils/pytorch_utils.py",
+            "utils/interactive_visualizer.py", "misc/__init__.py", "misc/logger.py"]
+
+
+def stage_python(force=False):
+    """Copy the reference's driver files, byte for byte, into git-ignored oracle/_ref/py (so that the drop-in test can run
+    `python main.py --phase test` on the GPU box, where /root/reference does not exist).  Returns the directory or None."""
+    if not os.path.isfile(os.path.join(REF_ROOT, "main.py")):
+        return PY_STAGE if os.path.isfile(os.path.join(PY_STAGE, "main.py")) else None
+    for rel in PY_FILES:
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(PY_STAGE, rel)
+        if not os.path.isfile(src):
+            if rel.endswith("__init__.py"):          # the reference uses namespace packages where it has no __init__
+                continue
+            raise FileNotFoundError(src)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if force or not os.path.isfile(dst) or open(src, "rb").read() != open(dst, "rb").read():
+            shutil.copyfile(src, dst)
+    return PY_STAGE
 
 
 def load():

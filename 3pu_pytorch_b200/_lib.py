@@ -67,6 +67,7 @@ SIGNATURES = {
     "pu3_relu_mask_f32": (_c_int, [_c_ll, _c_void_p, _c_void_p, _c_void_p]),
     "pu3_iota_i32": (_c_int, [_c_int, _c_void_p, _c_void_p]),
     "pu3_level_set_tc": (None, [_c_int]),
+    "pu3_level_set_knn_override": (None, [_c_void_p] * 5),
     "pu3_normalize_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),
     "pu3_outlier_compact_f32": (_c_int, [_c_int] * 5 + [_c_void_p] * 10),
     "pu3_tile_seeds_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 5),

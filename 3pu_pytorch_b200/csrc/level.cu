@@ -57,6 +57,15 @@ using namespace pu3;
 static int g_level_tc = 2;
 extern "C" void pu3_level_set_tc(int on) { g_level_tc = on; }
 
+// Test hook (teacher forcing): neighbour lists to use INSTEAD of the engine's own searches -- idx[blk] (t,n,knn+1) i32 for the four
+// dense blocks, skip (t,n,fm_knn) i64 for the skip connection; NULL entries keep the search.  With the oracle's lists injected,
+// every continuous stage of a Level can be compared at the full 1e-5 tolerance on every element (no near-tie excuses).
+static const int32_t *g_knn_override[4] = {nullptr, nullptr, nullptr, nullptr};
+static const int64_t *g_skip_override = nullptr;
+extern "C" void pu3_level_set_knn_override(const int32_t *b0, const int32_t *b1, const int32_t *b2, const int32_t *b3, const int64_t *skip) {
+    g_knn_override[0] = b0; g_knn_override[1] = b1; g_knn_override[2] = b2; g_knn_override[3] = b3; g_skip_override = skip;
+}
+
 extern "C" int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream) {
     if (n <= 0) return PU3_OK;
     iota_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(n, out);
@@ -134,7 +143,10 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
         }
         // dynamic graph in feature space (layers.py:33): k+1 nearest, duplicates pushed back, rank 0 dropped by idx_off=1;
         // the edge-conv takes a max over the other k, so they are requested as a set (PU3_KNN_SET_ORDER)
-        if (owner)
+        if (g_knn_override[blk])
+            PU3_TRY(cuda_status(cudaMemcpyAsync(idx, g_knn_override[blk], (size_t)t * n * (K + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                                as_stream(stream)), "level_forward: neighbour-list override"));
+        else if (owner)
             PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_ragged_f32(t, 24, n, n, K + 1, t, groups, me, owner, nullptr, nullptr, h, h, 1 | PU3_KNN_SET_ORDER, nullptr,
                                              nullptr, idx, nullptr, knnws, p.knn_ws, stream));
         else
@@ -145,7 +157,10 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
         lo -= 60;
     }
     if (has_prev) {   // inter-level skip connection (:317-347)
-        if (owner)
+        if (g_skip_override)
+            PU3_TRY(cuda_status(cudaMemcpyAsync(skipidx, g_skip_override, (size_t)t * n * w->fm_knn * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                                as_stream(stream)), "level_forward: skip neighbour-list override"));
+        else if (owner)
             PU3_TRYT(PROF_KNN_SKIP, pu3_group_knn_ragged_f32(t, 3, n, no, w->fm_knn, clouds, groups, owner, owner, prev_n, nullptr, xyz, prev_xyz,
                                              1, nullptr, skipidx, nullptr, nullptr, knnws, p.knn_ws, stream));
         else

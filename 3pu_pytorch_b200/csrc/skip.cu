@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
 // compile time: the 5 neighbour indices are read first and the 5 x 9 row loads of a point are all in flight before
 // the first use.  The generic kernel exposes one row (8-9 loads) at a time and is bound by L2 gather latency
 // (ncu: long-scoreboard 6.3 warps per issue, profiles/r1f_ncu_summary.md).
+// 3 CTAs per SM (ncu, profiles/r2: at 115 registers and the default carve-out only 2 CTAs = 16 warps were resident and the kernel
+// waited on its gathers: long-scoreboard 4.8 warps per issue at 41 % issue-active).
 template <int K, int C>
-__global__ void __launch_bounds__(SK_THREADS) skip_fuse_fixed_kernel(SkipArgs a) {
+__global__ void __launch_bounds__(SK_THREADS, 3) skip_fuse_fixed_kernel(SkipArgs a) {
     extern __shared__ __align__(16) float sm[];
     constexpr int U = (C + 31) / 32;                 // channels per lane
     const int N = a.n;
@@ -383,6 +385,8 @@ extern "C" int pu3_skip_fuse_ex_f32(int t, int n, int c, int k, int p_div, int n
     if (st) return st;
     if (k == 5 && c == 264 && !g_skip_force_generic) {
         st = cuda_status(cudaFuncSetAttribute(skip_fuse_fixed_kernel<5, 264>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_fuse: smem attr");
+        if (st) return st;
+        st = cuda_status(cudaFuncSetAttribute(skip_fuse_fixed_kernel<5, 264>, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "skip_fuse: carve-out");
         if (st) return st;
         skip_fuse_fixed_kernel<5, 264><<<t, SK_THREADS, smem, as_stream(stream)>>>(a);
         PU3_LAUNCH_CHECK("skip_fuse_fixed_kernel");

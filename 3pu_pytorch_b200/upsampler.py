@@ -514,7 +514,7 @@ class Net(torch.nn.Module):
     static_tiles = True
 
     def _eval_level_static(self, level, xyz, old_xyz, old_features, old_n, k, num_output_point, keep_features, bad,
-                           **kwargs):
+                           debug=None, **kwargs):
         """One level past the first for all requests, static shapes, every step a libpu3_b200 kernel (csrc/glue.cu for the
         steps the reference writes as torch expressions): outlier filter + compaction (:63-73), seed FPS (:78), kNN tiles
         (:83-85), normalisation (:138), Level, de-normalise + merge (:144-155), merge FPS (:158).  `bad` is an int32 device
@@ -560,6 +560,8 @@ class Net(torch.nn.Module):
         merged_pm = torch.empty(B, P * kr, 3, **f32)
         L.launch("pu3_denorm_merge_f32", new_xyz, B, P, kr, new_xyz.data_ptr(), centroid.data_ptr(), radius.data_ptr(),
                  merged_pm.data_ptr())
+        if debug is not None:      # tests: intermediate state for stage-wise comparison with the oracle
+            debug.update(patch_xyz=patch_xyz, merged_pm=merged_pm, p_arr=p_arr, n_arr=n_arr)
         # resample to num_output_point (:158)
         oidx = torch.zeros(B, num_output_point, **i32)
         L.launch("pu3_fps_ragged_f32", merged_pm, B, P * kr, num_output_point, pkr_arr.data_ptr(), None, merged_pm.data_ptr(),

@@ -311,6 +311,9 @@ int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, int n, const 
                                 float *out_xyz, void *workspace, size_t workspace_bytes, const pu3_level_saved *saved,
                                 pu3_stream_t stream);
 int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
+/* test hook (teacher forcing): neighbour lists the level engine uses instead of its own searches -- b0..b3 (t,n,knn+1) i32 for the
+ * four dense blocks, skip (t,n,fm_knn) i64; NULL = search as usual.  Global, not thread-safe: tests only. */
+void pu3_level_set_knn_override(const int32_t *b0, const int32_t *b1, const int32_t *b2, const int32_t *b3, const int64_t *skip);
 void pu3_level_set_tc(int mode); /* test / A-B hook: 2 (default) = head + prep convolutions on tcgen05, 1 = head only, 0 = fp32 FFMA kernels */
 
 /*

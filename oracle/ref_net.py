@@ -171,9 +171,12 @@ def _conv(x, w, b):
     return F.conv2d(x, w, b) if w.dim() == 4 else F.conv1d(x, w, b)
 
 
-def dense_edge_conv(P, prefix, x, k, n=3):
-    """layers.py:44-64 DenseEdgeConv.forward with idx=None.  x (B,C,N) -> y (B,C+n*growth,N), idx (B,N,k)."""
+def dense_edge_conv(P, prefix, x, k, n=3, record=None):
+    """layers.py:44-64 DenseEdgeConv.forward with idx=None.  x (B,C,N) -> y (B,C+n*growth,N), idx (B,N,k).
+    record (a list, tests only): receives the full (B,N,k+1) neighbour lists incl. the dropped rank 0 (teacher forcing)."""
     nb, idx, _ = group_knn(k + 1, x, x, unique=True)          # layers.py:33
+    if record is not None:
+        record.append(idx.clone())
     idx = idx[:, :, 1:]                                       # drop rank 0, not "self" (layers.py:34-35)
     nb = nb[:, :, :, 1:]
     centre = x.unsqueeze(-1).expand_as(nb)
@@ -200,16 +203,20 @@ def exponential_distance(points, nbrs):
 
 
 def level_forward(P, prefix, xyz, xyz_normalized, previous_level4=None, knn=32, fm_knn=5,
-                  step_ratio=2, dense_n=3, training=False):
-    """upsampler.py:272-374 Level.forward.  Returns (xyz' (B,3,N*r) normalised frame, features (B,264,N))."""
+                  step_ratio=2, dense_n=3, training=False, record=None):
+    """upsampler.py:272-374 Level.forward.  Returns (xyz' (B,3,N*r) normalised frame, features (B,264,N)).
+    record (a dict, tests only): receives "knn" = the four blocks' neighbour lists and "skip" = the skip connection's."""
+    knn_rec = None
+    if record is not None:
+        knn_rec = record.setdefault("knn", [])
     B, _, N = xyz_normalized.shape
     g = lambda name: (P[f"{prefix}.{name}.weight"], P[f"{prefix}.{name}.bias"])
     x = _conv(xyz_normalized.unsqueeze(-1), *g("layer0.conv")).squeeze(-1)
-    y, _ = dense_edge_conv(P, f"{prefix}.layer1", x, knn, dense_n)
+    y, _ = dense_edge_conv(P, f"{prefix}.layer1", x, knn, dense_n, knn_rec)
     x = torch.cat([y, x], dim=1)
     for li in (2, 3, 4):
         h = F.relu(_conv(x, *g(f"layer{li}_prep.conv")))
-        y, _ = dense_edge_conv(P, f"{prefix}.layer{li}", h, knn, dense_n)
+        y, _ = dense_edge_conv(P, f"{prefix}.layer{li}", h, knn, dense_n, knn_rec)
         x = torch.cat([y, x], dim=1)
 
     if previous_level4 is not None and fm_knn > 0:               # upsampler.py:317-347
@@ -218,6 +225,8 @@ def level_forward(P, prefix, xyz, xyz_normalized, previous_level4=None, knn=32, 
             pxyz = pxyz.expand(B, -1, -1)
             pfeat = pfeat.expand(B, -1, -1)
         nb_xyz, nb_idx, _ = group_knn(fm_knn, xyz, pxyz, unique=True, NCHW=True)
+        if record is not None:
+            record["skip"] = nb_idx.clone()
         pf = pfeat.unsqueeze(2).expand(-1, -1, N, -1)
         nb_feat = torch.gather(pf, 3, nb_idx.unsqueeze(1).expand(-1, pf.size(1), -1, -1))
         _, ws = exponential_distance(xyz, nb_xyz)
@@ -269,9 +278,12 @@ def extract_patches(xyz, k, training, gt_xyz=None, gt_k=None, seed_idx=None):
 
 
 def net_forward(P, xyz, ratio=16, gt=None, training=False, max_up_ratio=16, step_ratio=2, knn=32,
-                fm_knn=5, dense_n=3, max_num_point=312, seed_idx_per_level=None):
+                fm_knn=5, dense_n=3, max_num_point=312, seed_idx_per_level=None, trace=None):
     """upsampler.py:107-189 Net.forward.  Note Net builds Level without fm_knn (upsampler.py:25-26),
-    so the effective fm_knn is Level's default 5 whatever Net was given."""
+    so the effective fm_knn is Level's default 5 whatever Net was given.
+    trace (a dict, tests only): trace[l] receives the state around level l -- the cloud entering it, the previous level's
+    (xyz, features) it reads, its tiles, the neighbour lists its Level used, the merged cloud before and after the
+    resampling FPS -- for stage-wise teacher forcing."""
     B, _, N = xyz.shape
     levels = int(log(ratio, step_ratio))
     cap = min(N, max_num_point)
@@ -291,15 +303,23 @@ def net_forward(P, xyz, ratio=16, gt=None, training=False, max_up_ratio=16, step
         else:
             patch = xyz
         patch_n, centroid, radius = normalize_point_batch(patch, NCHW=True)
+        rec = None
+        if trace is not None:
+            rec = trace[l] = {"xyz_in": xyz.clone(), "old_xyz": old_xyz.clone(), "old_feat": old_feat.clone(),
+                              "patch": patch.clone()}
         xyz, feat = level_forward(P, pre, patch, patch_n, (old_xyz, old_feat), knn, fm_knn, step_ratio,
-                                  dense_n, training)
+                                  dense_n, training, record=rec)
         xyz = xyz * radius + centroid
         old_xyz, old_feat = patch, feat
         if not training and patch.shape[0] != B:                  # merge tiles, resample (upsampler.py:149-159)
             xyz = torch.cat(torch.split(xyz, B, dim=0), dim=2)
             old_xyz = torch.cat(torch.split(old_xyz, B, dim=0), dim=2)
             old_feat = torch.cat(torch.split(old_feat, B, dim=0), dim=2)
+            if rec is not None:
+                rec["merged"] = xyz.clone()
             _, xyz = furthest_point_sample(xyz, N * cur)
+        if rec is not None:
+            rec["xyz_out"] = xyz.clone(); rec["feat"] = old_feat.clone(); rec["next_old_xyz"] = old_xyz.clone()
     return (xyz, gt) if training else xyz
 
 

@@ -26,34 +26,47 @@ def staged():
     return d
 
 
+def _run_main(staged, tmp_path, ckpt, ratio, n_shape, out_name):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "3pu_pytorch_b200", "shim"), ROOT, env.get("PYTHONPATH", "")])
+    cmd = [sys.executable, "main.py", "--phase", "test", "--id", "demo", "--ckpt", ckpt,
+           "--test_data", str(tmp_path / "shapes" / "*.xyz"), "--num_shape_point", str(n_shape), "--num_point", "312",
+           "--up_ratio", str(ratio), "--result_dir", str(tmp_path / out_name)]
+    r = subprocess.run(cmd, cwd=staged, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    out_ply = tmp_path / out_name / "shapes" / "blob.ply"
+    in_ply = tmp_path / out_name / "shapes" / "blob_input.ply"
+    assert out_ply.is_file() and in_ply.is_file(), r.stdout[-1500:]
+    return out_ply, in_ply
+
+
+def _numpy_normalise(data):
+    """utils/pc_utils.py:11-25 normalize_point_cloud on (1,N,3)"""
+    centroid = np.mean(data, axis=1, keepdims=True)
+    data = data - centroid
+    far = np.amax(np.sqrt(np.sum(data ** 2, axis=-1, keepdims=True)), axis=1, keepdims=True)
+    return data / far, centroid, far
+
+
 def test_reference_main_py_runs_unchanged_through_the_shim(pu3, cuda, staged, tmp_path):
-    n_shape, ratio = 624, 16      # 6 overlapping patches
+    n_shape = 624                                              # 6 overlapping patches
     g = torch.Generator().manual_seed(77)
     pts = torch.rand(n_shape, 3, generator=g).numpy().astype(np.float32) * np.float32(2.0) + np.float32(0.5)
     os.makedirs(tmp_path / "shapes")
     np.savetxt(tmp_path / "shapes" / "blob.xyz", pts, fmt="%.8f")
-    params = ref_net.make_params(4, seed=11)
-    torch.save({"states": params, "step": "0"}, str(tmp_path / "final_synth.pth"))
-    env = dict(os.environ)
-    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "3pu_pytorch_b200", "shim"), ROOT, env.get("PYTHONPATH", "")])
-    cmd = [sys.executable, "main.py", "--phase", "test", "--id", "demo", "--ckpt", str(tmp_path / "final_synth.pth"),
-           "--test_data", str(tmp_path / "shapes" / "*.xyz"), "--num_shape_point", str(n_shape), "--num_point", "312",
-           "--up_ratio", str(ratio), "--result_dir", str(tmp_path / "out")]
-    r = subprocess.run(cmd, cwd=staged, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
-    out_ply = tmp_path / "out" / "shapes" / "blob.ply"
-    in_ply = tmp_path / "out" / "shapes" / "blob_input.ply"
-    assert out_ply.is_file() and in_ply.is_file(), r.stdout[-1500:]
+    raw = np.loadtxt(tmp_path / "shapes" / "blob.xyz").astype(np.float32)[np.newaxis]
+    data, centroid, far = _numpy_normalise(raw)
+    pc = torch.from_numpy(data).transpose(2, 1).contiguous()                      # 1x3xN, what main.py feeds pc_prediction
+
+    # ---- (a) 4x (two levels: tiling, skip connection, merge FPS) against the ORACLE's walk through main.py:214-246,346-380.
+    # Deeper ratios cannot be compared cloud against cloud: one neighbour / FPS pick flipped at a near-tie re-tiles the next level
+    # (profiles/debug/dropin_divergence.py); tests/test_gpu_teacher_forced.py covers them stage by stage instead.
+    ratio = 4
+    P4 = {k: v for k, v in ref_net.make_params(4, seed=1).items() if int(k.split(".")[1].split("_")[1]) <= 2}
+    torch.save({"states": P4, "step": "0"}, str(tmp_path / "final_x4.pth"))
+    out_ply, in_ply = _run_main(staged, tmp_path, str(tmp_path / "final_x4.pth"), ratio, n_shape, "out4")
     got = pu3.formats.read_ply(str(out_ply))[:, :3].astype(np.float32)
     assert got.shape == (n_shape * ratio, 3) and np.isfinite(got).all()
-
-    # ---- the same pipeline on the oracle (main.py:346-380 with utils/pc_utils.py:11-25 for the numpy normalisation) -------
-    data = np.loadtxt(tmp_path / "shapes" / "blob.xyz").astype(np.float32)[np.newaxis]
-    centroid = np.mean(data, axis=1, keepdims=True)
-    data = data - centroid
-    far = np.amax(np.sqrt(np.sum(data ** 2, axis=-1, keepdims=True)), axis=1, keepdims=True)
-    data = data / far
-    pc = torch.from_numpy(data).transpose(2, 1)                                    # 1x3xN
     with torch.no_grad():
         num_patches = int(pc.shape[2] / 312 * 3)
         _, seeds = ref_net.furthest_point_sample(pc, num_patches)
@@ -61,12 +74,10 @@ def test_reference_main_py_runs_unchanged_through_the_shim(pu3, cuda, staged, tm
         ups = []
         for k in range(num_patches):
             patch, c, rad = ref_net.normalize_point_batch(patches[:, :, k, :])
-            up = ref_net.net_forward(params, patch, ratio=ratio, max_up_ratio=ratio, knn=32)
-            ups.append(up * rad + c)
-        pred = torch.cat(ups, dim=-1)
-        _, pred = ref_net.furthest_point_sample(pred, n_shape * ratio)
-    want = pred.transpose(2, 1).numpy() * far + centroid
-    frac = cloud_match_fraction(torch.from_numpy(got.T.copy()), torch.from_numpy(want[0].T.astype(np.float32).copy()), tol=2e-4)
+            ups.append(ref_net.net_forward(P4, patch, ratio=ratio, max_up_ratio=ratio, knn=32) * rad + c)
+        _, pred = ref_net.furthest_point_sample(torch.cat(ups, dim=-1), n_shape * ratio)
+    want = (pred.transpose(2, 1).numpy() * far + centroid)[0].astype(np.float32)
+    frac = cloud_match_fraction(torch.from_numpy(got.T.copy()), torch.from_numpy(want.T.copy()), tol=2e-4)
     assert frac > 0.95, frac
 
     # ---- f-4: formats.save_ply against the file the REFERENCE's save_ply (utils/pc_utils.py:246-285) wrote -------------------
@@ -74,3 +85,17 @@ def test_reference_main_py_runs_unchanged_through_the_shim(pu3, cuda, staged, tm
     pu3.formats.save_ply(ref_in, str(tmp_path / "mine_input.ply"))
     assert open(tmp_path / "mine_input.ply", "rb").read() == open(in_ply, "rb").read()        # header and records, byte for byte
     np.testing.assert_allclose(ref_in, (data[0] * far[0] + centroid[0]), rtol=1e-6, atol=1e-6)
+
+    # ---- (b) the full 16x (BASELINE config 5 in small): main.py's per-patch loop equals this package's batched pipeline API ------
+    ratio = 16
+    P16 = ref_net.make_params(4, seed=1)
+    torch.save({"states": P16, "step": "0"}, str(tmp_path / "final_x16.pth"))
+    out_ply, _ = _run_main(staged, tmp_path, str(tmp_path / "final_x16.pth"), ratio, n_shape, "out16")
+    got16 = pu3.formats.read_ply(str(out_ply))[:, :3].astype(np.float32)
+    assert got16.shape == (n_shape * ratio, 3) and np.isfinite(got16).all()
+    net = pu3.Net(max_up_ratio=16, step_ratio=2, knn=32, growth_rate=12, dense_n=3, fm_knn=5)
+    net.load_state_dict(P16, strict=True)
+    net = net.to(cuda).eval()
+    mine = pu3.pipeline.upsample_shape(net, pc.to(cuda), num_point=312, patch_num_ratio=3, up_ratio=16)
+    mine = (mine.transpose(2, 1).cpu().numpy() * far + centroid)[0].astype(np.float32)
+    np.testing.assert_allclose(got16, mine, rtol=1e-5, atol=1e-5)        # every patch gets the result of its own B=1 call

@@ -27,10 +27,15 @@ def _net(pu3, params, cuda):
 class _Override:
     """inject the oracle's neighbour lists into the level engine for the duration of a with-block"""
 
-    def __init__(self, pu3, cuda, rec):
+    def __init__(self, pu3, cuda, rec, slots=None):
         self.lib = pu3._lib.lib()
-        self.knn = [t.to(torch.int32).contiguous().to(cuda) for t in rec["knn"]]
-        self.skip = rec["skip"].to(torch.int64).contiguous().to(cuda) if "skip" in rec else None
+
+        def pad(t):     # static tile slots past the request's own tile count repeat its first tile (Net.static_tiles)
+            if slots is not None and t.shape[0] < slots:
+                t = torch.cat([t, t[:1].expand(slots - t.shape[0], -1, -1)], dim=0)
+            return t
+        self.knn = [pad(t).to(torch.int32).contiguous().to(cuda) for t in rec["knn"]]
+        self.skip = pad(rec["skip"]).to(torch.int64).contiguous().to(cuda) if "skip" in rec else None
 
     def __enter__(self):
         self.lib.pu3_level_set_knn_override(*[t.data_ptr() for t in self.knn], self.skip.data_ptr() if self.skip is not None else None)
@@ -91,18 +96,19 @@ def test_net_eval_stage_by_stage_from_the_oracle_state(pu3, cuda, params):
         old_n = torch.full((1,), No, dtype=torch.int32, device=cuda)
         bad = torch.zeros((), dtype=torch.int32, device=cuda)
         dbg = {}
-        with torch.no_grad(), _Override(pu3, cuda, st):
+        slots = int(n_in / 312 * 5)
+        with torch.no_grad(), _Override(pu3, cuda, st, slots=slots):
             out, prev_xyz, feat_pm, pk = net._eval_level_static(
                 net.levels[f"level_{l}"], st["xyz_in"].to(cuda), st["old_xyz"].to(cuda),
                 st["old_feat"].transpose(1, 2).contiguous().to(cuda), old_n, 312, 312 * 2 ** l, True, bad, debug=dbg)
             torch.cuda.synchronize()
         assert int(bad) == 0
         P = st["patch"].shape[0]
-        assert int(dbg["p_arr"][0]) == P == dbg["patch_xyz"].shape[0]                 # same number of tiles (:76)
-        assert torch.equal(dbg["patch_xyz"].cpu(), st["patch"]), f"level {l}: tiles differ from the oracle's"
-        merged = dbg["merged_pm"].transpose(1, 2)                                     # (1,3,P*624)
+        assert int(dbg["p_arr"][0]) == P <= slots == dbg["patch_xyz"].shape[0]        # same number of tiles (:76)
+        assert torch.equal(dbg["patch_xyz"][:P].cpu(), st["patch"]), f"level {l}: tiles differ from the oracle's"
+        merged = dbg["merged_pm"].transpose(1, 2)[:, :, :P * 624]                     # (1,3,P*624) valid part
         _assert_all_close(merged, st["merged"], f"level {l} merged cloud")
-        _assert_all_close(feat_pm.transpose(1, 2), st["feat"], f"level {l} features for the next level")
-        assert torch.equal(prev_xyz.cpu(), st["next_old_xyz"])
+        _assert_all_close(feat_pm.transpose(1, 2)[:, :, :P * 312], st["feat"], f"level {l} features for the next level")
+        assert torch.equal(prev_xyz[:, :, :P * 312].cpu(), st["next_old_xyz"])
         assert int(pk[0]) == P * 312
         assert cloud_match_fraction(out[0].cpu(), st["xyz_out"][0], tol=1e-5) > 0.99, f"level {l} resampled cloud"

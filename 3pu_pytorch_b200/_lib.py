@@ -199,13 +199,24 @@ def set_profiler(p):
     return prev
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)     # (device index) -> cudaStream_t as int, no Stream object
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def launch(name, tensor, *args, extra_kernels=0, tag=None):
     """Call entry point `name` with `args` (+ the current stream of `tensor`'s device appended), on that device,
-    and raise on a non-zero status."""
-    fn = getattr(lib(), name)
+    and raise on a non-zero status.  The common case (no profiler, tensor on the current device) is kept short: this is the
+    per-launch host cost of every eager call (a 5 us kernel was taking 16 us to issue through the torch.cuda wrappers)."""
+    fn = getattr(_lib or lib(), name)
+    prof = _profiler
+    idx = tensor.device.index
+    if prof is None and _raw_stream is not None and (idx is None or idx == _raw_device()):
+        status = fn(*args, _raw_stream(idx if idx is not None else _raw_device()))
+        if status != 0:
+            check(status, name)
+        return
     with on_device(tensor):
         stream = torch.cuda.current_stream(tensor.device)
-        prof = _profiler
         if prof is not None and prof.timing:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)

@@ -8,6 +8,7 @@ dev = torch.device("cuda:0")
 net = pu3.Net(max_up_ratio=16, step_ratio=2, knn=32, growth_rate=12, dense_n=3, fm_knn=5)
 net.load_state_dict(ref_net.make_params(4, seed=1), strict=True)
 model = pu3.Model(net.to(dev), "train", lr_init=5e-4, weight_full_ratio=1.0)
+model.use_cuda_graph = os.environ.get("GRAPH", "0") == "1"   # eager launches by default: every kernel is its own ncu result
 g = torch.Generator().manual_seed(7)
 x = torch.rand(32, 3, 312, generator=g).to(dev); gt = torch.rand(32, 3, 4992, generator=g).to(dev)
 for _ in range(3):

@@ -46,6 +46,7 @@ struct KnnArgs {
     int32_t *idx32;       // (b,m,k) or null
     float *dist;          // (b,m,k) or null
     int exact_pops;       // knn_feat_kernel, indices-only mode: 1 = ranks 1..k-1 in exact order too (test hook)
+    int prefilter;        // knn_thread_kernel: exact bounding-sphere candidate pre-filter allowed (queries are not the cloud itself)
 };
 
 __device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.owner ? __ldg(a.owner + bi) : bi / a.p_div; }
@@ -685,17 +686,72 @@ __global__ void __launch_bounds__(KT_THREADS) knn_thread_kernel(KnnArgs a) {
 #pragma unroll
         for (int e = 0; e < KK; ++e) { bd[r][e] = __int_as_float(0x7f800000); bj[r][e] = 0; }
     }
+    // ---- exact candidate pre-filter (skip connection: the 256 queries of a CTA are one tile's points, a small region of the
+    // previous level's cloud).  Sphere around the CTA's queries: centre c = centre of their bounding box, radius
+    // R = 1.5 max|q - c|.  A candidate p outside it has |p - q| > R - |q - c| for every query q of the CTA, so if q's k-th best
+    // distance (found among the candidates inside) is below that bound -- checked with slack after the pass -- no excluded
+    // candidate can belong to its k nearest and the result is exactly the unfiltered one.  Otherwise the CTA redoes the search
+    // without the filter.  profiles/r2: 1280 x 312 queries x 6240 candidates were 2.5 G pair evaluations, issue bound.
+    __shared__ float sred[6][KT_THREADS / 32];
+    const bool can_filter = a.prefilter != 0 && dmode != 2 && nv >= 1024;
+    float cx = 0.f, cy = 0.f, cz = 0.f, R1 = 0.f, R1sq = 0.f, dq[KT_QPT];
+#pragma unroll
+    for (int r = 0; r < KT_QPT; ++r) dq[r] = 0.f;
+    if (can_filter) {
+        float lo[3] = {qx[0], qy[0], qz[0]}, hi[3] = {qx[0], qy[0], qz[0]};
+#pragma unroll
+        for (int r = 1; r < KT_QPT; ++r) {
+            lo[0] = fminf(lo[0], qx[r]); lo[1] = fminf(lo[1], qy[r]); lo[2] = fminf(lo[2], qz[r]);
+            hi[0] = fmaxf(hi[0], qx[r]); hi[1] = fmaxf(hi[1], qy[r]); hi[2] = fmaxf(hi[2], qz[r]);
+        }
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[c3] = fminf(lo[c3], __shfl_xor_sync(0xffffffffu, lo[c3], o));
+                hi[c3] = fmaxf(hi[c3], __shfl_xor_sync(0xffffffffu, hi[c3], o));
+            }
+            if ((threadIdx.x & 31) == 0) { sred[c3][threadIdx.x >> 5] = lo[c3]; sred[3 + c3][threadIdx.x >> 5] = hi[c3]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < KT_THREADS / 32; ++w) {
+            lo[0] = fminf(lo[0], sred[0][w]); lo[1] = fminf(lo[1], sred[1][w]); lo[2] = fminf(lo[2], sred[2][w]);
+            hi[0] = fmaxf(hi[0], sred[3][w]); hi[1] = fmaxf(hi[1], sred[4][w]); hi[2] = fmaxf(hi[2], sred[5][w]);
+        }
+        cx = 0.5f * (lo[0] + hi[0]); cy = 0.5f * (lo[1] + hi[1]); cz = 0.5f * (lo[2] + hi[2]);
+        // every query lies in the box, so max|q - c| <= half the box diagonal: no second reduction needed
+        const float hx = 0.5f * (hi[0] - lo[0]), hy = 0.5f * (hi[1] - lo[1]), hz = 0.5f * (hi[2] - lo[2]);
+        R1 = 1.5f * sqrtf(hx * hx + hy * hy + hz * hz) + 1e-6f;
+        R1sq = R1 * R1;
+#pragma unroll
+        for (int r = 0; r < KT_QPT; ++r) {
+            const float ex = qx[r] - cx, ey = qy[r] - cy, ez = qz[r] - cz;
+            dq[r] = sqrtf(ex * ex + ey * ey + ez * ez);
+        }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+    const bool filt = can_filter && pass == 0;
     for (int n0 = 0; n0 < nv; n0 += KT_TILE) {
         const int src = min(KT_TILE, nv - n0);
         __syncthreads();
         int cnt;
-        if (dmode == 1) {
-            // stage only first occurrences, in index order (ordered compaction: ballot prefix inside the warp,
-            // warp totals through shared memory).  In the merged previous-level clouds ~4 of 5 points are duplicates.
+        if (dmode == 1 || filt) {
+            // stage only first occurrences (and, with the pre-filter, only candidates inside the sphere), in index order
+            // (ordered compaction: ballot prefix inside the warp, warp totals through shared memory).  In the merged
+            // previous-level clouds ~4 of 5 points are duplicates.
             int base = 0;
             for (int c0 = 0; c0 < src; c0 += KT_THREADS) {
                 const int t = c0 + threadIdx.x;
-                const bool keep = t < src && dupb[n0 + t] == 0;
+                bool keep = t < src && (dmode != 1 || dupb[n0 + t] == 0);
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (keep) {
+                    x = __ldg(pb + n0 + t); y = __ldg(pb + a.n + n0 + t); z = __ldg(pb + 2 * (size_t)a.n + n0 + t);
+                    if (filt) {
+                        const float ex = x - cx, ey = y - cy, ez = z - cz;
+                        keep = ex * ex + ey * ey + ez * ez <= R1sq;
+                    }
+                }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = __popc(bal);
                 __syncthreads();
@@ -705,7 +761,6 @@ __global__ void __launch_bounds__(KT_THREADS) knn_thread_kernel(KnnArgs a) {
                 for (int w = 0; w < KT_THREADS / 32; ++w) total += wtot[w];
                 if (keep) {
                     const int slot = off + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-                    const float x = __ldg(pb + n0 + t), y = __ldg(pb + a.n + n0 + t), z = __ldg(pb + 2 * (size_t)a.n + n0 + t);
                     tile[slot] = make_float4(x, y, z, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
                     tidx[slot] = n0 + t;
                 }
@@ -744,6 +799,21 @@ __global__ void __launch_bounds__(KT_THREADS) knn_thread_kernel(KnnArgs a) {
                 }
             }
         }
+    }
+    if (!filt) break;
+    // ---- verify: every query's k-th best must lie strictly inside what the sphere guarantees (1e-3 relative slack covers the
+    // fp32 rounding of the expanded-form distances); a query that found fewer than k candidates (distance still +inf) fails
+    bool fail = false;
+#pragma unroll
+    for (int r = 0; r < KT_QPT; ++r) {
+        const float lim = (R1 - dq[r]) * (1.f - 1e-3f) - 1e-6f;
+        fail |= !(lim > 0.f && bd[r][KK - 1] <= lim * lim);
+    }
+    if (!__syncthreads_or(fail)) break;
+#pragma unroll
+    for (int r = 0; r < KT_QPT; ++r)
+#pragma unroll
+        for (int e = 0; e < KK; ++e) { bd[r][e] = __int_as_float(0x7f800000); bj[r][e] = 0; }
     }
 #pragma unroll
     for (int r = 0; r < KT_QPT; ++r) {
@@ -973,6 +1043,9 @@ extern "C" void pu3_knn_force_stream(int on) { g_knn_force_stream = on; }
 static int g_knn_exact_pops = 0;
 extern "C" void pu3_knn_exact_pops(int on) { g_knn_exact_pops = on; }
 // Test hook: 1 = duplicate detection by the O(n^2) scans (hash-first in shared memory up to 1024 points) instead of the hash table.
+// Test hook: 1 = knn_thread_kernel never pre-filters its candidates (A/B of the exact bounding-sphere filter).
+static int g_knn_no_prefilter = 0;
+extern "C" void pu3_knn_no_prefilter(int on) { g_knn_no_prefilter = on; }
 static int g_knn_dup_scan = 0;
 extern "C" void pu3_knn_dup_scan(int on) { g_knn_dup_scan = on; }
 
@@ -1043,7 +1116,8 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
               query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist,
-              (unordered && g_knn_exact_pops == 0) ? 0 : 1};
+              (unordered && g_knn_exact_pops == 0) ? 0 : 1,
+              (query != points && g_knn_no_prefilter == 0) ? 1 : 0};
     if (unique) {
         int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
         int *cloud_any = reinterpret_cast<int *>(ws + pl.off_cany);

@@ -52,9 +52,25 @@ __global__ void __launch_bounds__(NMD_THREADS) nmdist_fwd_kernel(NmdDir d0, NmdD
     for (int k2 = 0; k2 < D.np; k2 += NMD_TILE) {
         const int cnt = min(NMD_TILE, D.np - k2);
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += NMD_THREADS) {
-            const float *s = pb + (size_t)(k2 + t) * 3;
-            tile[t] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.f);
+        const float *src = pb + (size_t)k2 * 3;          // the tile's 3*cnt packed floats
+        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            // 128-bit global loads over the packed (x,y,z) stream; every float lands in its point's float4 slot
+            float *tf = reinterpret_cast<float *>(tile);
+            const int nflt = 3 * cnt, nvec = nflt >> 2;
+            for (int t = threadIdx.x; t < nvec; t += NMD_THREADS) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + t);
+                const int f = 4 * t;
+                tf[((f) / 3) * 4 + (f) % 3] = v.x;
+                tf[((f + 1) / 3) * 4 + (f + 1) % 3] = v.y;
+                tf[((f + 2) / 3) * 4 + (f + 2) % 3] = v.z;
+                tf[((f + 3) / 3) * 4 + (f + 3) % 3] = v.w;
+            }
+            for (int f = 4 * nvec + threadIdx.x; f < nflt; f += NMD_THREADS) tf[(f / 3) * 4 + f % 3] = __ldg(src + f);
+        } else {
+            for (int t = threadIdx.x; t < cnt; t += NMD_THREADS) {
+                const float *s = src + (size_t)t * 3;
+                tile[t] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.f);
+            }
         }
         __syncthreads();
 #pragma unroll 4

@@ -255,3 +255,46 @@ def test_set_order_mode_returns_the_same_neighbour_sets(pu3, cuda):
         a = pu3.fused.dense_edge_conv(xc, ws, bs, 32, idx=exact[..., 1:].long())[0]
         b = pu3.fused.dense_edge_conv(xc, ws, bs, 32, idx=fast[..., 1:].long())[0]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", ["tile_in_big_cloud", "queries_spread_out", "cloud_far_away", "ragged"])
+def test_knn_thread_prefilter_is_exact(pu3, cuda, case):
+    """The skip connection's search (c=3, k<=8, thousands of candidates) pre-filters candidates with a bounding sphere around the
+    CTA's queries and verifies the result afterwards (csrc/group_knn.cu); whatever the geometry -- including the ones where the
+    verification must fail and the CTA redoes the search unfiltered -- indices and distances are those of the unfiltered kernel,
+    bit for bit."""
+    import ctypes
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    B, M, N, k = 6, 312, 6240, 5
+    base = torch.rand(B, 3, N // 5, generator=g)
+    pts = base.repeat(1, 1, 5)                                     # 5x duplicated, like the merged previous-level tiles
+    if case == "tile_in_big_cloud":
+        centre = base[:, :, :1]
+        d = ((base - centre) ** 2).sum(1)
+        near = d.argsort(dim=1)[:, :M]                              # the M points nearest to one of the cloud's points: a tile
+        q = torch.gather(base, 2, near.unsqueeze(1).expand(-1, 3, -1)) + 1e-3 * torch.randn(B, 3, M, generator=g)
+    elif case == "queries_spread_out":
+        q = torch.rand(B, 3, M, generator=g)
+    elif case == "cloud_far_away":
+        q = torch.rand(B, 3, M, generator=g) * 0.05 + 5.0            # nothing inside the sphere: every CTA must fall back
+    else:
+        q = torch.rand(B, 3, M, generator=g) * 0.2 + 0.4
+    q, pts = q.contiguous().to(cuda), pts.contiguous().to(cuda)
+    ragged = None
+    if case == "ragged":
+        owner = torch.tensor([0, 0, 1, 1, 2, 2], dtype=torch.int32, device=cuda)
+        n_arr = torch.tensor([6240, 3120, 1248], dtype=torch.int32, device=cuda)
+        ragged = pu3.operations.Ragged(owner, owner, 3, n_arr=n_arr)
+        pts = pts[:3].contiguous()
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    outs = []
+    for off in (0, 1):
+        lib.pu3_knn_no_prefilter(off)
+        try:
+            _, idx, dist = pu3.operations._knn_raw(k, q, pts, True, 1, want_knn=False, ragged=ragged)
+            torch.cuda.synchronize()
+        finally:
+            lib.pu3_knn_no_prefilter(0)
+        outs.append((idx.clone(), dist.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert int(outs[0][0].max()) < N

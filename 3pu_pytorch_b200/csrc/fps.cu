@@ -41,6 +41,24 @@ struct __align__(16) FpsCand {
     uint32_t pad0, pad1;
 };
 
+// Speculative rounds (cluster flavour with <= 64 warps).  FPS is a chain of m-1 dependent arg-max rounds and a round costs one
+// cluster exchange (~1 us) whatever the work, so the only way to go faster is FEWER EXCHANGES.  Every warp publishes its best
+// candidate AND the key (t, rank) of its second best (in the two spare words of the 32-byte slot).  After the exchange all
+// warps know the candidates sorted by key, c1 >= c2 >= ..., and B = the best UNPUBLISHED key.  c1 is this round's sample.
+// c2 is provably the NEXT sample, without another exchange, when (a) key(c2) > B -- it is the true global runner-up -- and
+// (b) its running distance does not change when c1 is added: d(c2, c1) >= t(c2), evaluated with the very expression the update
+// uses, and (c) t(c2) > 0.  Proof: every other point i had key(i) < key(c2); adding c1 can only lower t(i), and a lowered t(i)
+// is strictly below its old value <= t(c2), an unchanged one keeps key(i) < key(c2); c1 itself drops to t = 0 < t(c2): c2 is
+// the lexicographic maximum after the update, which is what the reference's next round selects.  The same argument accepts c3 (unaffected by c1 and c2), c4, ...; the chain stops at
+// the first candidate that fails (a) or (b).  The accepted samples' updates are then applied in ONE pass over the points.
+// Measured on merged tile clouds: ~1.9 samples per exchange at depth 2, ~3.5 at depth 4 (profiles/r2).  Indices and temp stay
+// bit-identical to the reference: the same samples are chosen in the same order.
+constexpr int FPS_SPEC = 4;
+// tuning / test hooks: run-time cap of the speculation depth (1 = one sample per exchange, the round-1 behaviour) and the number
+// of exchanges cloud 0 of the last launch needed (samples per exchange = (m - 1) / exchanges)
+__device__ int g_fps_spec_cap = FPS_SPEC;
+__device__ unsigned int g_fps_exchanges = 0;
+
 constexpr int FPS_MAX_CAND = 256;          // candidates a CTA receives per round: cluster size x warps per CTA
 struct FpsSmem {
     FpsCand cluster_slot[2][FPS_MAX_CAND];     // [round parity][source CTA rank * warps + source warp]
@@ -117,8 +135,12 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
         t[i] = tv;
     }
     if (g == 0 && m > 0) out[0] = 0;                         // :115 first sample is point 0
-    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
-    if (n > 0) { x1 = __ldg(p + 0); y1 = __ldg(p + 1); z1 = __ldg(p + 2); }
+    constexpr int SPEC = DIRECT ? FPS_SPEC : 1;              // samples one exchange may yield
+    float wx[SPEC], wy[SPEC], wz[SPEC];                      // samples chosen by the last exchange, their update still pending
+#pragma unroll
+    for (int a = 0; a < SPEC; ++a) { wx[a] = 0.f; wy[a] = 0.f; wz[a] = 0.f; }
+    int A = 1;                                               // how many of them
+    if (n > 0) { wx[0] = __ldg(p + 0); wy[0] = __ldg(p + 1); wz[0] = __ldg(p + 2); }
     if (S > 1 && threadIdx.x == 0) {
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
@@ -127,22 +149,35 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     __syncthreads();
     if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem + barriers exist before remote stores
 
-    for (int j = 1; j < m; ++j) {
-        const int par = j & 1;
+    const int spec_cap = SPEC > 1 ? min(SPEC, max(1, g_fps_spec_cap)) : 1;
+    int j = 1;                                               // next sample to choose
+    uint32_t e = 1;
+    for (; j < m; ++e) {                                     // e: exchange counter (buffer parity / barrier phase)
+        const int par = (int)(e & 1u);
         fps_mark(j, 0);
-        // ---- 1. update running distances, thread-local arg-max (first strictly greater) -------
-        float best = -1.f;
-        int besti = 0;
+        // ---- 1. apply the pending samples to the running distances (one pass), thread-local best and second best
+        //         (first strictly greater: within a thread a lower i is a lower tie rank) -------
+        float best = -1.f, sec = -1.f;
+        int besti = 0, seci = 0;
+        // (all SPEC distance evaluations are predicated on a < A rather than dispatched on A: measured, profiles/debug/fps_spec_ab.py --
+        // a per-count copy of this loop is faster at depth 1 but slower at depth 4, where ~3.5 of the 4 are live anyway)
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
             float x, y, z;
             if (XYZ_REGS) { x = px[i]; y = py[i]; z = pz[i]; }
             else { const int slot = i * nthreads + threadIdx.x; x = sx[slot]; y = sy[slot]; z = sz[slot]; }
-            const float d = sqdist3(x - x1, y - y1, z - z1);
             // padding slots keep t = -1: fminf(d,-1) = -1
-            const float d2 = fminf(d, t[i]);
+            float d2 = fminf(sqdist3(x - wx[0], y - wy[0], z - wz[0]), t[i]);
+#pragma unroll
+            for (int a = 1; a < SPEC; ++a)
+                if (a < A) d2 = fminf(sqdist3(x - wx[a], y - wy[a], z - wz[a]), d2);
             t[i] = d2;
-            if (d2 > best) { best = d2; besti = i; }
+            if (d2 > best) {
+                if (SPEC > 1) { sec = best; seci = besti; }
+                best = d2; besti = i;
+            } else if (SPEC > 1 && d2 > sec) {
+                sec = d2; seci = i;
+            }
         }
         fps_mark(j, 1);
         // ---- 2. warp arg-max: the winning lane publishes (distance, tie rank, index, coordinates) ----------
@@ -159,7 +194,22 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
         const uint32_t rmin_w = __popc(holders) == 1 ? __shfl_sync(0xffffffffu, rank, __ffs(holders) - 1)
                                                      : __reduce_min_sync(0xffffffffu, rank);
         const bool publisher = rank == rmin_w && (rmin_w != 0xffffffffu || lane == 0);   // the winner, or lane 0 of an empty warp
-        uint4 plo = make_uint4(0u, 0xffffffffu, 0u, 0u), phi = make_uint4(0u, 0u, 0u, 0u);
+        // the warp's SECOND best key: the winner lane offers its second point, every other lane its best
+        uint32_t o_t = 0u, o_r = 0xffffffffu;
+        if (SPEC > 1) {
+            const bool iswin = rank == rmin_w && rmin_w != 0xffffffffu;
+            const float off = iswin ? sec : best;
+            const int offi = iswin ? seci : besti;
+            const uint32_t okey = off >= 0.f ? __float_as_uint(off) : 0u;
+            o_t = __reduce_max_sync(0xffffffffu, okey);
+            uint32_t orank = 0xffffffffu;
+            if (okey == o_t && off >= 0.f) {
+                const int kk = g + offi * GT;
+                orank = (uint32_t)(kk & (t_ref - 1)) * rank_rows + (uint32_t)(kk >> t_shift);
+            }
+            o_r = __reduce_min_sync(0xffffffffu, orank);
+        }
+        uint4 plo = make_uint4(0u, 0xffffffffu, 0u, 0u), phi = make_uint4(0u, 0u, o_t, o_r);
         if (publisher) {
             const int slot = besti * nthreads + threadIdx.x;            // coordinates from the smem copy: no dynamic register indexing
             plo.x = dmax_w; plo.y = rmin_w; plo.z = (uint32_t)kbest; plo.w = __float_as_uint(sx[slot]);
@@ -181,19 +231,20 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             uint32_t dmax, rmin;
             const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
             const int wsrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
-            x1 = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, wsrc));
-            y1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, wsrc));
-            z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, wsrc));
+            wx[0] = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, wsrc));
+            wy[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, wsrc));
+            wz[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, wsrc));
             const int kw = (int)__shfl_sync(0xffffffffu, lo.z, wsrc);
             if (threadIdx.x == 0) out[j] = kw;
+            A = 1; j += 1;
         } else if (DIRECT) {
             // ---- 3b. cluster of <= 64 warps: EVERY warp sends its candidate straight into every CTA's slot array by
             //          async DSMEM stores that complete on the receiver's mbarrier.  No CTA-level reduction, no
             //          __syncthreads, no leader warp: the in-kernel timeline (profiles/r1g) showed those cost ~1000 of the
-            //          ~2400 cycles of a round.  The mbarrier wait is the only synchronisation: a round's slots are complete
-            //          when all S x nwarps candidates have landed, and a warp cannot overwrite a slot of round j+2 before
-            //          every warp of the cluster has read round j (it must first pass the barrier of round j+1, which
-            //          needs their j+1 sends).  The candidate goes through the warp's own slot so that lane r sends it to
+            //          ~2400 cycles of a round.  The mbarrier wait is the only synchronisation: an exchange's slots are complete
+            //          when all S x nwarps candidates have landed, and a warp cannot overwrite a slot of exchange e+2 before
+            //          every warp of the cluster has read exchange e (it must first pass the barrier of exchange e+1, which
+            //          needs their e+1 sends).  The candidate goes through the warp's own slot so that lane r sends it to
             //          CTA r: the S x 2 remote stores are issued by S lanes at once instead of one lane after the other.
             if (publisher) {
                 uint4 *dst = reinterpret_cast<uint4 *>(&sm.warp_slot[par][warp]);
@@ -206,38 +257,72 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 const uint32_t dst = map_to_cta(&sm.cluster_slot[par][0], (uint32_t)lane) + (crank * (uint32_t)nwarps + (uint32_t)warp) * 32u;
                 const uint32_t rbar = map_to_cta(&sm.mbar[par], (uint32_t)lane);
                 st_async_v4(dst, rbar, lo.x, lo.y, lo.z, lo.w);
-                st_async_v4(dst + 16, rbar, hi.x, hi.y, 0u, 0u);
+                st_async_v4(dst + 16, rbar, hi.x, hi.y, hi.z, hi.w);
             }
             if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.mbar[par], S * (uint32_t)nwarps * 32u);
             fps_mark(j, 4);
-            // ---- 4. every warp: wait for the S x nwarps candidates, reduce them, take the winner's coordinates ----------
-            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);   // phase = earlier uses of this buffer
+            // ---- 4. every warp: wait for the S x nwarps candidates, sort out up to SPEC samples (see FPS_SPEC above) ----------
+            mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);   // phase = earlier uses of this buffer
             fps_mark(j, 5);
             const int total = (int)S * nwarps;
-            uint32_t bd = 0u, br = 0xffffffffu;
-            int bc = 0;
+            uint32_t ct[2], cr[2];                                     // total <= 64 in this flavour: at most two candidates per lane
+            uint32_t lbt = 0u, lbr = 0xffffffffu;                      // lane-local best of the (<= 2) second keys
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {                               // total <= 64 in this flavour: at most two per lane
+            for (int u = 0; u < 2; ++u) {
                 const int c = lane + 32 * u;
+                ct[u] = 0u; cr[u] = 0xffffffffu;
                 if (c < total) {
-                    const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);   // (dkey, rank)
-                    if (kr.x > bd || (kr.x == bd && kr.y < br)) { bd = kr.x; br = kr.y; bc = c; }
+                    const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);           // (dkey, rank)
+                    const uint2 s2 = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]) + 3);     // second best key of that warp
+                    ct[u] = kr.x; cr[u] = kr.y;
+                    if (s2.x > lbt || (s2.x == lbt && s2.y < lbr)) { lbt = s2.x; lbr = s2.y; }
                 }
             }
-            const uint32_t dmax = __reduce_max_sync(0xffffffffu, bd);
-            unsigned cands = __ballot_sync(0xffffffffu, bd == dmax && br != 0xffffffffu);
-            if (__popc(cands) > 1) {                                    // tie on the distance: smallest rank wins
-                const uint32_t rmin = __reduce_min_sync(0xffffffffu, bd == dmax ? br : 0xffffffffu);
-                cands = __ballot_sync(0xffffffffu, bd == dmax && br == rmin);
+            // B = best key that was NOT published (the best of the warps' second bests)
+            const uint32_t bt = __reduce_max_sync(0xffffffffu, lbt);
+            const uint32_t br = __reduce_min_sync(0xffffffffu, lbt == bt ? lbr : 0xffffffffu);
+            int taken = 0;
+            A = 0;
+#pragma unroll
+            for (int mth = 0; mth < SPEC; ++mth) {
+                uint32_t lt = 0u, lr = 0xffffffffu;
+                int lc = lane;
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (!((taken >> u) & 1) && (ct[u] > lt || (ct[u] == lt && cr[u] < lr))) { lt = ct[u]; lr = cr[u]; lc = lane + 32 * u; }
+                const uint32_t tmax = __reduce_max_sync(0xffffffffu, lt);
+                unsigned cands = __ballot_sync(0xffffffffu, lt == tmax && lr != 0xffffffffu);
+                if (__popc(cands) > 1) {                                // tie on the distance: smallest rank wins
+                    const uint32_t rmin = __reduce_min_sync(0xffffffffu, lt == tmax ? lr : 0xffffffffu);
+                    cands = __ballot_sync(0xffffffffu, lt == tmax && lr == rmin);
+                }
+                if (mth > 0 && cands == 0u) break;                      // no candidate left (warp-uniform, like every break below)
+                const int csrc = cands ? __ffs(cands) - 1 : 0;
+                const int cwin = __shfl_sync(0xffffffffu, lc, csrc);
+                if (mth > 0) {
+                    const uint32_t rw = __shfl_sync(0xffffffffu, lr, csrc);
+                    if (!(tmax > bt || (tmax == bt && rw < br))) break;  // (a) some unpublished point may rank above it
+                    if (tmax == 0u) break;   // t = 0: the samples already chosen (t = 0 too, selected points stay candidates in the
+                                             // reference) compete on rank alone -- e.g. m > n repeats the lowest-rank point for ever
+                }
+                const uint4 wlo = *reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][cwin]);     // broadcast reads
+                const uint2 whi = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][cwin]) + 2);
+                const float cx = __uint_as_float(wlo.w), cy = __uint_as_float(whi.x), cz = __uint_as_float(whi.y);
+                if (mth > 0) {
+                    const float tm = __uint_as_float(tmax);
+                    bool keep = true;                                    // (b) unchanged by the samples accepted before it
+#pragma unroll
+                    for (int a = 0; a < SPEC; ++a)
+                        if (a < mth) keep = keep && (fminf(sqdist3(cx - wx[a], cy - wy[a], cz - wz[a]), tm) == tm);
+                    if (!keep) break;
+                }
+                wx[mth] = cx; wy[mth] = cy; wz[mth] = cz;
+                if (g == 0) out[j + mth] = (int)wlo.z;
+                A = mth + 1;
+                if (lane == csrc) taken |= 1 << (cwin >> 5);
+                if (j + A >= m || A >= spec_cap) break;
             }
-            const int csrc = cands ? __ffs(cands) - 1 : 0;
-            const int cwin = __shfl_sync(0xffffffffu, bc, csrc);
-            const uint4 wlo = *reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][cwin]);     // broadcast reads
-            const uint2 whi = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][cwin]) + 2);
-            x1 = __uint_as_float(wlo.w);
-            y1 = __uint_as_float(whi.x);
-            z1 = __uint_as_float(whi.y);
-            if (g == 0) out[j] = (int)wlo.z;
+            j += A;
         } else {
             // ---- 3c. wide cluster (> 64 warps: the 16-CTA whole-shape call): scanning S x nwarps candidates in every warp
             //          would cost more than it saves, so the CTA reduces first (warp slots, __syncthreads, leader warp) and
@@ -271,7 +356,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                     st_async_v4(dst + 16, rbar, chi.x, chi.y, 0u, 0u);
                 }
             }
-            mbar_wait_parity(&sm.mbar[par], (uint32_t)((j - 1) >> 1) & 1u);
+            mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);
             uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
             if (lane < (int)S) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][lane]);
@@ -280,17 +365,32 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             uint32_t dmax, rmin;
             const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
             const int csrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
-            x1 = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, csrc));
-            y1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, csrc));
-            z1 = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, csrc));
+            wx[0] = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, csrc));
+            wy[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, csrc));
+            wz[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, csrc));
             const int kw = (int)__shfl_sync(0xffffffffu, lo.z, csrc);
             if (g == 0) out[j] = kw;
+            A = 1; j += 1;
             fps_mark(j, 6);
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_fps_exchanges = e - 1u;
+    // temp is an in/out buffer of the reference ABI: it ends as the running distance to samples 0 .. m-2 (the reference's round
+    // updates BEFORE it selects, so its last sample is never applied, :133-170).  The last exchange may have chosen several
+    // samples (j + A == m, the last of them is sample m-1): apply all but that one.
     if (trow) {
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
+            if (SPEC > 1 && A > 1) {
+                float x, y, z;
+                if (XYZ_REGS) { x = px[i]; y = py[i]; z = pz[i]; }
+                else { const int slot = i * nthreads + threadIdx.x; x = sx[slot]; y = sy[slot]; z = sz[slot]; }
+                float d2 = t[i];
+#pragma unroll
+                for (int a = 0; a < SPEC - 1; ++a)
+                    if (a + 1 < A) d2 = fminf(sqdist3(x - wx[a], y - wy[a], z - wz[a]), d2);
+                t[i] = d2;
+            }
             const int k = g + i * GT;
             if (k < n) trow[k] = t[i];
         }
@@ -424,6 +524,13 @@ extern "C" void pu3_fps_set_threads(int t) { g_fps_force_threads = t; }   // tun
 
 static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, const float *xyz, float *temp,
                         int32_t *idx, pu3_stream_t stream);
+
+extern "C" void pu3_fps_set_spec(int depth) { cudaMemcpyToSymbol(pu3::g_fps_spec_cap, &depth, sizeof(int)); }
+extern "C" unsigned int pu3_fps_last_exchanges(void) {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, pu3::g_fps_exchanges, sizeof(v));
+    return v;
+}
 
 extern "C" int pu3_fps_f32(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
                            pu3_stream_t stream) {

@@ -87,6 +87,73 @@ __device__ __forceinline__ void fps_mark(int j, int phase) {
 __device__ __forceinline__ void fps_mark(int, int) {}
 #endif
 
+// After an exchange: `total` (<= 64) candidates in `slots`, each with the key of the best point its publisher did NOT publish in
+// the two spare words.  Chooses this exchange's samples (see FPS_SPEC): always the best candidate, then up to spec_cap - 1 more
+// while each is (a) above every unpublished key, (b) unchanged by the samples accepted before it, (c) at t > 0.  Every warp runs
+// this on the same data and reaches the same result.  Returns the number of samples; their coordinates go to wx/wy/wz, their
+// indices to out[j ...] (written by the thread for which `writer` is set).
+template <int SPEC>
+__device__ __forceinline__ int fps_select(const FpsCand *slots, int total, int lane, int spec_cap, int j, int m, bool writer,
+                                          int32_t *out, float (&wx)[SPEC], float (&wy)[SPEC], float (&wz)[SPEC]) {
+    uint32_t ct[2], cr[2];                                     // at most two candidates per lane
+    uint32_t lbt = 0u, lbr = 0xffffffffu;                      // lane-local best of the unpublished keys
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int c = lane + 32 * u;
+        ct[u] = 0u; cr[u] = 0xffffffffu;
+        if (c < total) {
+            const uint2 kr = *reinterpret_cast<const uint2 *>(&slots[c]);           // (dkey, rank)
+            const uint2 s2 = *(reinterpret_cast<const uint2 *>(&slots[c]) + 3);     // best unpublished key of that publisher
+            ct[u] = kr.x; cr[u] = kr.y;
+            if (s2.x > lbt || (s2.x == lbt && s2.y < lbr)) { lbt = s2.x; lbr = s2.y; }
+        }
+    }
+    // B = the best key that was NOT published
+    const uint32_t bt = __reduce_max_sync(0xffffffffu, lbt);
+    const uint32_t br = __reduce_min_sync(0xffffffffu, lbt == bt ? lbr : 0xffffffffu);
+    int taken = 0, A = 0;
+#pragma unroll
+    for (int mth = 0; mth < SPEC; ++mth) {
+        uint32_t lt = 0u, lr = 0xffffffffu;
+        int lc = lane;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (!((taken >> u) & 1) && (ct[u] > lt || (ct[u] == lt && cr[u] < lr))) { lt = ct[u]; lr = cr[u]; lc = lane + 32 * u; }
+        const uint32_t tmax = __reduce_max_sync(0xffffffffu, lt);
+        unsigned cands = __ballot_sync(0xffffffffu, lt == tmax && lr != 0xffffffffu);
+        if (__popc(cands) > 1) {                                // tie on the distance: smallest rank wins
+            const uint32_t rmin = __reduce_min_sync(0xffffffffu, lt == tmax ? lr : 0xffffffffu);
+            cands = __ballot_sync(0xffffffffu, lt == tmax && lr == rmin);
+        }
+        if (mth > 0 && cands == 0u) break;                      // no candidate left (warp-uniform, like every break below)
+        const int csrc = cands ? __ffs(cands) - 1 : 0;
+        const int cwin = __shfl_sync(0xffffffffu, lc, csrc);
+        if (mth > 0) {
+            const uint32_t rw = __shfl_sync(0xffffffffu, lr, csrc);
+            if (!(tmax > bt || (tmax == bt && rw < br))) break;  // (a) some unpublished point may rank above it
+            if (tmax == 0u) break;   // (c) t = 0: the samples already chosen (t = 0 too, selected points stay candidates in the
+                                     // reference) compete on rank alone -- e.g. m > n repeats the lowest-rank point for ever
+        }
+        const uint4 wlo = *reinterpret_cast<const uint4 *>(&slots[cwin]);     // broadcast reads
+        const uint2 whi = *(reinterpret_cast<const uint2 *>(&slots[cwin]) + 2);
+        const float cx = __uint_as_float(wlo.w), cy = __uint_as_float(whi.x), cz = __uint_as_float(whi.y);
+        if (mth > 0) {
+            const float tm = __uint_as_float(tmax);
+            bool keep = true;                                    // (b) unchanged by the samples accepted before it
+#pragma unroll
+            for (int a = 0; a < SPEC; ++a)
+                if (a < mth) keep = keep && (fminf(sqdist3(cx - wx[a], cy - wy[a], cz - wz[a]), tm) == tm);
+            if (!keep) break;
+        }
+        wx[mth] = cx; wy[mth] = cy; wz[mth] = cz;
+        if (writer) out[j + mth] = (int)wlo.z;
+        A = mth + 1;
+        if (lane == csrc) taken |= 1 << (cwin >> 5);
+        if (j + A >= m || A >= spec_cap) break;
+    }
+    return A;
+}
+
 // PPT points per thread; XYZ_REGS: coordinates in registers (else read from shared memory each round)
 // DIRECT: flavour of the cluster exchange (host: S x warps <= 64), a template parameter so that each flavour is compiled alone
 template <int PPT, bool XYZ_REGS, int MAX_THREADS, bool DIRECT>
@@ -135,7 +202,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
         t[i] = tv;
     }
     if (g == 0 && m > 0) out[0] = 0;                         // :115 first sample is point 0
-    constexpr int SPEC = DIRECT ? FPS_SPEC : 1;              // samples one exchange may yield
+    constexpr int SPEC = FPS_SPEC;                           // samples one exchange may yield (all three exchange flavours)
     float wx[SPEC], wy[SPEC], wz[SPEC];                      // samples chosen by the last exchange, their update still pending
 #pragma unroll
     for (int a = 0; a < SPEC; ++a) { wx[a] = 0.f; wy[a] = 0.f; wz[a] = 0.f; }
@@ -149,7 +216,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     __syncthreads();
     if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem + barriers exist before remote stores
 
-    const int spec_cap = SPEC > 1 ? min(SPEC, max(1, g_fps_spec_cap)) : 1;
+    const int spec_cap = min(SPEC, max(1, g_fps_spec_cap));
     int j = 1;                                               // next sample to choose
     uint32_t e = 1;
     for (; j < m; ++e) {                                     // e: exchange counter (buffer parity / barrier phase)
@@ -223,20 +290,8 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 dst[0] = plo; dst[1] = phi;
             }
             __syncthreads();
-            uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
-            if (lane < nwarps) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.warp_slot[par][lane]);
-                lo = src[0]; hi = src[1];
-            }
-            uint32_t dmax, rmin;
-            const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
-            const int wsrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
-            wx[0] = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, wsrc));
-            wy[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, wsrc));
-            wz[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, wsrc));
-            const int kw = (int)__shfl_sync(0xffffffffu, lo.z, wsrc);
-            if (threadIdx.x == 0) out[j] = kw;
-            A = 1; j += 1;
+            A = fps_select<SPEC>(&sm.warp_slot[par][0], nwarps, lane, spec_cap, j, m, threadIdx.x == 0, out, wx, wy, wz);
+            j += A;
         } else if (DIRECT) {
             // ---- 3b. cluster of <= 64 warps: EVERY warp sends its candidate straight into every CTA's slot array by
             //          async DSMEM stores that complete on the receiver's mbarrier.  No CTA-level reduction, no
@@ -264,64 +319,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             // ---- 4. every warp: wait for the S x nwarps candidates, sort out up to SPEC samples (see FPS_SPEC above) ----------
             mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);   // phase = earlier uses of this buffer
             fps_mark(j, 5);
-            const int total = (int)S * nwarps;
-            uint32_t ct[2], cr[2];                                     // total <= 64 in this flavour: at most two candidates per lane
-            uint32_t lbt = 0u, lbr = 0xffffffffu;                      // lane-local best of the (<= 2) second keys
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int c = lane + 32 * u;
-                ct[u] = 0u; cr[u] = 0xffffffffu;
-                if (c < total) {
-                    const uint2 kr = *reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]);           // (dkey, rank)
-                    const uint2 s2 = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][c]) + 3);     // second best key of that warp
-                    ct[u] = kr.x; cr[u] = kr.y;
-                    if (s2.x > lbt || (s2.x == lbt && s2.y < lbr)) { lbt = s2.x; lbr = s2.y; }
-                }
-            }
-            // B = best key that was NOT published (the best of the warps' second bests)
-            const uint32_t bt = __reduce_max_sync(0xffffffffu, lbt);
-            const uint32_t br = __reduce_min_sync(0xffffffffu, lbt == bt ? lbr : 0xffffffffu);
-            int taken = 0;
-            A = 0;
-#pragma unroll
-            for (int mth = 0; mth < SPEC; ++mth) {
-                uint32_t lt = 0u, lr = 0xffffffffu;
-                int lc = lane;
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (!((taken >> u) & 1) && (ct[u] > lt || (ct[u] == lt && cr[u] < lr))) { lt = ct[u]; lr = cr[u]; lc = lane + 32 * u; }
-                const uint32_t tmax = __reduce_max_sync(0xffffffffu, lt);
-                unsigned cands = __ballot_sync(0xffffffffu, lt == tmax && lr != 0xffffffffu);
-                if (__popc(cands) > 1) {                                // tie on the distance: smallest rank wins
-                    const uint32_t rmin = __reduce_min_sync(0xffffffffu, lt == tmax ? lr : 0xffffffffu);
-                    cands = __ballot_sync(0xffffffffu, lt == tmax && lr == rmin);
-                }
-                if (mth > 0 && cands == 0u) break;                      // no candidate left (warp-uniform, like every break below)
-                const int csrc = cands ? __ffs(cands) - 1 : 0;
-                const int cwin = __shfl_sync(0xffffffffu, lc, csrc);
-                if (mth > 0) {
-                    const uint32_t rw = __shfl_sync(0xffffffffu, lr, csrc);
-                    if (!(tmax > bt || (tmax == bt && rw < br))) break;  // (a) some unpublished point may rank above it
-                    if (tmax == 0u) break;   // t = 0: the samples already chosen (t = 0 too, selected points stay candidates in the
-                                             // reference) compete on rank alone -- e.g. m > n repeats the lowest-rank point for ever
-                }
-                const uint4 wlo = *reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][cwin]);     // broadcast reads
-                const uint2 whi = *(reinterpret_cast<const uint2 *>(&sm.cluster_slot[par][cwin]) + 2);
-                const float cx = __uint_as_float(wlo.w), cy = __uint_as_float(whi.x), cz = __uint_as_float(whi.y);
-                if (mth > 0) {
-                    const float tm = __uint_as_float(tmax);
-                    bool keep = true;                                    // (b) unchanged by the samples accepted before it
-#pragma unroll
-                    for (int a = 0; a < SPEC; ++a)
-                        if (a < mth) keep = keep && (fminf(sqdist3(cx - wx[a], cy - wy[a], cz - wz[a]), tm) == tm);
-                    if (!keep) break;
-                }
-                wx[mth] = cx; wy[mth] = cy; wz[mth] = cz;
-                if (g == 0) out[j + mth] = (int)wlo.z;
-                A = mth + 1;
-                if (lane == csrc) taken |= 1 << (cwin >> 5);
-                if (j + A >= m || A >= spec_cap) break;
-            }
+            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
             j += A;
         } else {
             // ---- 3c. wide cluster (> 64 warps: the 16-CTA whole-shape call): scanning S x nwarps candidates in every warp
@@ -341,8 +339,13 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 uint32_t dmax, rmin;
                 const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
                 const unsigned wb = __ballot_sync(0xffffffffu, win);
+                // the CTA's best UNPUBLISHED key: the winner warp's second best or another warp's best, whichever is larger
+                const uint32_t ot = win ? hi.z : lo.x, orr = win ? hi.w : lo.y;
+                const uint32_t c_t = __reduce_max_sync(0xffffffffu, ot);
+                const uint32_t c_r = __reduce_min_sync(0xffffffffu, ot == c_t ? orr : 0xffffffffu);
                 if (wb == 0u ? lane == 0 : win) {
                     uint4 *dst = reinterpret_cast<uint4 *>(&sm.cta_slot[par]);
+                    hi.z = c_t; hi.w = c_r;
                     dst[0] = lo; dst[1] = hi;
                     mbar_arrive_expect_tx(&sm.mbar[par], S * 32u);
                 }
@@ -353,24 +356,12 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                     const uint32_t dst = map_to_cta(&sm.cluster_slot[par][crank], (uint32_t)lane);
                     const uint32_t rbar = map_to_cta(&sm.mbar[par], (uint32_t)lane);
                     st_async_v4(dst, rbar, clo.x, clo.y, clo.z, clo.w);
-                    st_async_v4(dst + 16, rbar, chi.x, chi.y, 0u, 0u);
+                    st_async_v4(dst + 16, rbar, chi.x, chi.y, chi.z, chi.w);
                 }
             }
             mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);
-            uint4 lo = make_uint4(0u, 0xffffffffu, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
-            if (lane < (int)S) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(&sm.cluster_slot[par][lane]);
-                lo = src[0]; hi = src[1];
-            }
-            uint32_t dmax, rmin;
-            const bool win = warp_argmax(lo.x, lo.y, dmax, rmin);
-            const int csrc = (__ffs(__ballot_sync(0xffffffffu, win)) - 1) & 31;
-            wx[0] = __uint_as_float(__shfl_sync(0xffffffffu, lo.w, csrc));
-            wy[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.x, csrc));
-            wz[0] = __uint_as_float(__shfl_sync(0xffffffffu, hi.y, csrc));
-            const int kw = (int)__shfl_sync(0xffffffffu, lo.z, csrc);
-            if (g == 0) out[j] = kw;
-            A = 1; j += 1;
+            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
+            j += A;
             fps_mark(j, 6);
         }
     }

@@ -438,10 +438,27 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
     const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
     const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
 
-    for (int t = tid; t < C * KF_NMAX; t += KF_THREADS) {
-        const int ch = t / KF_NMAX, j = t - ch * KF_NMAX;
-        sx[t] = j < nv ? __ldg(pb + (size_t)ch * a.n + j) : 0.f;
+    // ---- stage the cloud: TMA bulk copies (one per channel row, completing on an mbarrier) when the rows are 16-byte aligned
+    // -- n = 312: 1248-byte rows -- with the row tails and the zero padding up to KF_NMAX by ordinary stores
+    __shared__ uint64_t tma_bar;
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(pb) & 15u) == 0) && ((a.n & 3) == 0);
+    const int nb = bulk_ok ? (nv & ~3) : 0;                  // floats per row moved by the copy engine
+    if (nb > 0) {
+        if (tid == 0) { mbar_init(&tma_bar, 1); mbar_fence_init_cluster(); }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(&tma_bar, (uint32_t)(C * nb * 4));
+        if (tid < C) bulk_copy_g2s(sx + tid * KF_NMAX, pb + (size_t)tid * a.n, (uint32_t)(nb * 4), &tma_bar);
+        for (int ch = KF_THREADS + tid; ch < C; ch += KF_THREADS)     // (generic C > 256 only)
+            bulk_copy_g2s(sx + ch * KF_NMAX, pb + (size_t)ch * a.n, (uint32_t)(nb * 4), &tma_bar);
     }
+    {
+        const int rest = KF_NMAX - nb;
+        for (int t = tid; t < C * rest; t += KF_THREADS) {
+            const int ch = t / rest, j = nb + (t - ch * rest);
+            sx[ch * KF_NMAX + j] = j < nv ? __ldg(pb + (size_t)ch * a.n + j) : 0.f;
+        }
+    }
+    if (nb > 0) mbar_wait_parity(&tma_bar, 0u);
     __syncthreads();
     for (int j = tid; j < KF_NMAX; j += KF_THREADS) {
         float r = 0.f;

@@ -134,6 +134,13 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
             "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
 }
+// TMA bulk copy (the copy engine, SASS UBLKCP): `bytes` (multiple of 16) from 16-byte aligned global memory into 16-byte aligned
+// shared memory of this CTA, completing on `bar` (complete_tx::bytes)
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                   "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 // 16-byte store into a peer CTA's shared memory that signals `bytes written` on that peer's mbarrier
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"

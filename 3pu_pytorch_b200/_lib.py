@@ -137,8 +137,8 @@ KERNELS_PER_CALL = {
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
     "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
     # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 6 head kernels (3 weight splits + 3 tcgen05);
-    # + 4 x 3 duplicate kernels; skip adds 2 + 3, iota 1
-    "pu3_level_forward_f32": 33,
+    # the feature kNN finds duplicates itself (no side kernels); the skip connection adds 3 duplicate kernels + kNN + skip, iota 1
+    "pu3_level_forward_f32": 21, "pu3_level_forward_train_f32": 21,
     "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
     "pu3_fps_ragged_f32": 1,
     "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique

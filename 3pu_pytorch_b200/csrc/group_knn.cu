@@ -47,6 +47,7 @@ struct KnnArgs {
     float *dist;          // (b,m,k) or null
     int exact_pops;       // knn_feat_kernel, indices-only mode: 1 = ranks 1..k-1 in exact order too (test hook)
     int prefilter;        // knn_thread_kernel: exact bounding-sphere candidate pre-filter allowed (queries are not the cloud itself)
+    int fused_dup;        // knn_feat_kernel: `unique` requested and NO duplicate pre-pass ran -- the kernel finds the duplicates itself
 };
 
 __device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.owner ? __ldg(a.owner + bi) : bi / a.p_div; }
@@ -433,9 +434,9 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
     const float *qb = a.query + (size_t)bi * C * a.m;
     const float *pb = a.points + (size_t)cloud * C * a.n;
     const bool self = (qb == pb) && (a.m == a.n);                      // DenseEdgeConv: queries are the cloud itself
-    const int dmode = knn_dup_mode(a, cloud, grp);
-    const bool penal = dmode != 0;
-    const float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
+    int dmode = knn_dup_mode(a, cloud, grp);
+    bool penal = dmode != 0;
+    float maxd = dmode == 2 ? ordered_to_float(a.maxd[grp]) : 0.f;
     const uint8_t *dupb = penal ? a.dup + (size_t)cloud * a.n : nullptr;
 
     // ---- stage the cloud: TMA bulk copies (one per channel row, completing on an mbarrier) when the rows are 16-byte aligned
@@ -466,6 +467,84 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
         snorm[j] = r;
     }
     __syncthreads();
+
+    // ---- duplicates (operations.py:192-204), found HERE when no pre-pass ran: the cloud is in shared memory, a 32-bit hash per
+    // point and ~n^2/2 hash compares per CTA replace three side launches per call (hash table + group flags + max(D): 57 launches
+    // and 0.55 ms per eval step, profiles/r2).  A cloud with >= k first occurrences never selects a duplicate: they are dropped
+    // (mode 1).  Only a degenerate cloud (< k distinct points) needs the reference's exact penalty max(D over its group): this CTA
+    // then computes it itself with the arithmetic of knn_maxd_kernel -- slow, correct, and never on the hot path.
+    __shared__ __align__(16) uint32_t s_hash[KF_NMAX];
+    __shared__ uint8_t s_dup[KF_NMAX];
+    __shared__ int s_ndup;
+    __shared__ uint32_t s_maxd;
+    if (a.fused_dup) {
+        if (tid == 0) { s_ndup = 0; s_maxd = 0u; }
+        for (int j = tid; j < nv; j += KF_THREADS) {
+            uint32_t h = 2166136261u;
+            for (int ch = 0; ch < C; ++ch) {
+                uint32_t u = __float_as_uint(sx[ch * KF_NMAX + j]);
+                if ((u << 1) == 0u) u = 0u;                  // -0.0 == +0.0 (np.unique compares values)
+                h = (h ^ u) * 16777619u;
+                h ^= h >> 15;
+            }
+            s_hash[j] = h;
+        }
+        __syncthreads();
+        int mine = 0;
+        for (int j = tid; j < nv; j += KF_THREADS) {
+            const uint32_t hj = s_hash[j];
+            bool found = false;
+            // four hashes per 128-bit load, independent compares: the scan is throughput-, not latency-bound
+            for (int e0 = 0; e0 < j && !found; e0 += 4) {
+                const uint4 h4 = *reinterpret_cast<const uint4 *>(&s_hash[e0]);
+                unsigned hit = (h4.x == hj ? 1u : 0u) | (h4.y == hj ? 2u : 0u) | (h4.z == hj ? 4u : 0u) | (h4.w == hj ? 8u : 0u);
+                while (hit && !found) {                  // rare: equal hashes -> compare the points, earliest first
+                    const int o = __ffs(hit) - 1;
+                    hit &= hit - 1u;
+                    const int e = e0 + o;
+                    if (e >= j) break;
+                    bool same = true;
+                    for (int ch = 0; ch < C && same; ++ch) same = sx[ch * KF_NMAX + e] == sx[ch * KF_NMAX + j];
+                    found = same;
+                }
+            }
+            s_dup[j] = found ? 1 : 0;
+            mine += found ? 1 : 0;
+        }
+        if (mine) atomicAdd(&s_ndup, mine);
+        __syncthreads();
+        const int ndup = s_ndup;
+        dmode = ndup == 0 ? 0 : (nv - ndup >= a.k ? 1 : 2);
+        penal = dmode != 0;
+        dupb = s_dup;
+        if (dmode == 2) {
+            uint32_t best = 0u;
+            for (int b2 = 0; b2 < a.b; ++b2) {
+                if (knn_group(a, b2) != grp) continue;
+                const int c2 = knn_cloud(a, b2);
+                const int nv2 = knn_n(a, c2), mv2 = knn_m(a, b2);
+                const float *q2 = a.query + (size_t)b2 * C * a.m;
+                const float *p2 = a.points + (size_t)c2 * C * a.n;
+                for (int qi = tid; qi < mv2; qi += KF_THREADS) {
+                    float rq2 = 0.f;
+                    for (int ch = 0; ch < C; ++ch) { const float v = q2[(size_t)ch * a.m + qi]; rq2 = __fmaf_rn(v, v, rq2); }
+                    for (int j = 0; j < nv2; ++j) {
+                        float dot = 0.f, rp = 0.f;
+                        for (int ch = 0; ch < C; ++ch) {
+                            const float pv = __ldg(p2 + (size_t)ch * a.n + j);
+                            dot = __fmaf_rn(q2[(size_t)ch * a.m + qi], pv, dot);
+                            rp = __fmaf_rn(pv, pv, rp);
+                        }
+                        best = max(best, float_to_ordered(expanded_dist(rq2, dot, rp)));
+                    }
+                }
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (lane == 0 && best) atomicMax(&s_maxd, best);
+            __syncthreads();
+            maxd = ordered_to_float(s_maxd);
+        }
+    }
 
     const int qg = tid / KF_JG, jg = tid % KF_JG;    // 4 query groups of 8 x 64 candidate groups of 5
     // few clouds (train step, level 1 of eval, single requests): gridDim.y CTAs share a cloud, each takes every gridDim.y-th
@@ -1063,6 +1142,9 @@ extern "C" void pu3_knn_exact_pops(int on) { g_knn_exact_pops = on; }
 // Test hook: 1 = knn_thread_kernel never pre-filters its candidates (A/B of the exact bounding-sphere filter).
 static int g_knn_no_prefilter = 0;
 extern "C" void pu3_knn_no_prefilter(int on) { g_knn_no_prefilter = on; }
+// Test hook: 1 = the feature-space kernel does not look for duplicates itself (the three pre-pass kernels run, as in round 1).
+static int g_knn_no_fused_dup = 0;
+extern "C" void pu3_knn_no_fused_dup(int on) { g_knn_no_fused_dup = on; }
 static int g_knn_dup_scan = 0;
 extern "C" void pu3_knn_dup_scan(int on) { g_knn_dup_scan = on; }
 
@@ -1134,8 +1216,13 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
     KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
               query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist,
               (unordered && g_knn_exact_pops == 0) ? 0 : 1,
-              (query != points && g_knn_no_prefilter == 0) ? 1 : 0};
-    if (unique) {
+              (query != points && g_knn_no_prefilter == 0) ? 1 : 0, 0};
+    // the tiled feature-space kernel (n <= 320, k <= 64) finds duplicates itself: no pre-pass
+    const bool feat_path = !pl.large && !(c == 3 && k <= KT_KMAX && g_knn_force_stream == 0) && n <= KF_NMAX && g_knn_force_stream == 0 &&
+                           ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4 <= (size_t)device_info().smem_optin;
+    if (unique && feat_path && g_knn_no_fused_dup == 0) {
+        a.fused_dup = 1;
+    } else if (unique) {
         int *group_any = reinterpret_cast<int *>(ws + pl.off_any);
         int *cloud_any = reinterpret_cast<int *>(ws + pl.off_cany);
         uint32_t *maxd = reinterpret_cast<uint32_t *>(ws + pl.off_maxd);

@@ -76,7 +76,7 @@ class LevelTrainFunction(torch.autograd.Function):
         _lib.launch("pu3_level_forward_train_f32", xn, ctypes.addressof(W), T, N, _lib.ptr(xyz_c), xn.data_ptr(), None, 0,
                     int(max_group or T), _lib.ptr(prev_xyz_c), _lib.ptr(prev_pm), int(Bp), int(No), None, feat.data_ptr(),
                     out.data_ptr(), ws.data_ptr(), ws_bytes, ctypes.addressof(sv),
-                    extra_kernels=32 + (6 if has_prev else 0))
+                    extra_kernels=5 if has_prev else 0)
         ctx.level, ctx.has_prev, ctx.dims = level, has_prev, (T, N, r, K, fm, Bp, No)
         ctx.save_for_backward(xn, feat, h1, h2, skip_idx, skip_w, feat_pre, *hs, *idxs, *params)
         return out, feat

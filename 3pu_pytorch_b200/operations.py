@@ -56,6 +56,15 @@ class Ragged:
         self.owner, self.group_of, self.groups, self.n_arr, self.m_arr = owner, group_of, int(groups), n_arr, m_arr
 
 
+def _dup_prepass_kernels(unique, C, N, k):
+    """launches of the duplicate pre-pass (hash table, group flags, max D): none when the tiled feature-space kernel runs (it
+    finds duplicates itself, csrc/group_knn.cu) -- n <= 320 and not one of the other specialised kernels"""
+    if not unique:
+        return 0
+    feat_path = N <= 320 and k <= 64 and not (C == 3 and k <= 8)
+    return 0 if feat_path else 3
+
+
 def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtype=torch.int64, ragged=None, set_order=False):
     """q (B,C,M), p (B/p_div,C,N) contiguous f32 on the same device -> (knn|None, idx, dist|None).
     With `ragged`, p is (clouds,C,N) and the mapping comes from the Ragged description; outputs of invalid
@@ -76,7 +85,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
                     _lib.ptr(ragged.group_of), _lib.ptr(ragged.n_arr), _lib.ptr(ragged.m_arr), _lib.ptr(q), _lib.ptr(p),
                     uflag, _lib.ptr(knn), _lib.ptr(idx if idx_dtype == torch.int64 else None),
                     _lib.ptr(idx if idx_dtype == torch.int32 else None), _lib.ptr(dist), _lib.ptr(ws), ws_bytes,
-                    extra_kernels=3 if unique else 0,
+                    extra_kernels=_dup_prepass_kernels(unique, C, N, k),
                     tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")
         return knn, idx, dist
     if Bp == 0 or B % Bp != 0:
@@ -95,7 +104,7 @@ def _knn_raw(k, q, p, unique, max_group, want_knn=True, want_dist=True, idx_dtyp
     # stream goes last in the C signature, after (workspace, workspace_bytes)
     _lib.launch("pu3_group_knn_f32", q, B, C, M, N, k, p_div, _lib.ptr(q), _lib.ptr(p), uflag,
                 int(max_group or B), _lib.ptr(knn), _lib.ptr(idx64), _lib.ptr(idx32), _lib.ptr(dist), _lib.ptr(ws),
-                ws_bytes, extra_kernels=3 if unique else 0,
+                ws_bytes, extra_kernels=_dup_prepass_kernels(unique, C, N, k),
                 tag=f"pu3_group_knn_f32[c={C},k={k},n<={N}]")
     return knn, idx, dist
 

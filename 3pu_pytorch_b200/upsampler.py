@@ -193,7 +193,7 @@ class Level(torch.nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         feat = torch.empty(T, 264, N, dtype=torch.float32, device=dev)
         out = torch.empty(T, 3, N * r, dtype=torch.float32, device=dev)
-        extra = 12 + (6 if has_prev else 0) + (1 if owner is not None else 0)
+        extra = (5 if has_prev else 0) + (1 if owner is not None else 0)
         fused._lib.launch("pu3_level_forward_f32", xn, ctypes.addressof(W), T, N, fused._lib.ptr(xyz_c), xn.data_ptr(),
                           fused._lib.ptr(owner), int(groups), int(group or T), fused._lib.ptr(prev_xyz),
                           fused._lib.ptr(prev_feat_pm), int(clouds), int(No), fused._lib.ptr(prev_n), feat.data_ptr(),

@@ -298,3 +298,49 @@ def test_knn_thread_prefilter_is_exact(pu3, cuda, case):
         outs.append((idx.clone(), dist.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert int(outs[0][0].max()) < N
+
+
+@pytest.mark.parametrize("case", ["no_dups", "some_dups", "degenerate", "all_equal", "ragged_groups"])
+def test_feature_knn_fused_duplicate_detection_equals_the_prepass(pu3, cuda, case):
+    """The tiled feature-space kernel finds duplicates itself (in-kernel hash compare; exact max(D) penalty computed in the
+    kernel for a degenerate cloud); results must be those of the three-kernel pre-pass (hash table, group flags, max D) it
+    replaces -- indices, distances and gathered neighbours, bit for bit -- and the oracle's."""
+    import ctypes
+    g = torch.Generator().manual_seed(len(case))
+    B, C, N, k = 6, 24, 312, 33
+    x = torch.relu(torch.randn(B, C, N, generator=g))            # post-ReLU features: many exact zeros
+    if case == "some_dups":
+        x[:, :, 100:140] = x[:, :, 0:40]                          # 40 duplicated points per cloud
+        x[2, :, 200:260] = x[2, :, 5:6]                           # and a 60-fold copy of one point
+    elif case == "degenerate":
+        x[1, :, 20:] = x[1, :, 3:4]                               # cloud 1: 21 distinct points < k -> exact max(D) penalty
+        x[4, :, 10:] = x[4, :, :10].repeat(1, 31)[:, :N - 10]     # cloud 4: 10 distinct points
+    elif case == "all_equal":
+        x[:] = 0.5
+    x = x.contiguous().to(cuda)
+    ragged = None
+    max_group = 2 if case != "ragged_groups" else None
+    if case == "ragged_groups":
+        x[0, :, 150:] = x[0, :, 7:8]                              # a degenerate cloud inside a three-cloud group
+        me = torch.arange(B, dtype=torch.int32, device=cuda)
+        grp = torch.tensor([0, 0, 0, 1, 1, 1], dtype=torch.int32, device=cuda)
+        ragged = pu3.operations.Ragged(me, grp, 2)
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    outs = []
+    for off in (0, 1):
+        lib.pu3_knn_no_fused_dup(off)
+        try:
+            knn, idx, dist = pu3.operations._knn_raw(k, x, x, True, max_group, ragged=ragged)
+            _, idx32, _ = pu3.operations._knn_raw(k, x, x, True, max_group, want_knn=False, want_dist=False, idx_dtype=torch.int32,
+                                                  ragged=ragged, set_order=True)
+            torch.cuda.synchronize()
+        finally:
+            lib.pu3_knn_no_fused_dup(0)
+        outs.append((knn.clone(), idx.clone(), dist.clone(), idx32.sort(dim=2)[0]))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    if case in ("no_dups", "some_dups") :                         # and against the oracle (whole-batch penalty scope = one group)
+        _, ridx, rdist = ref_net.group_knn(k, x.cpu()[:2], x.cpu()[:2], unique=True)
+        _, gidx, gdist = pu3.operations._knn_raw(k, x[:2].contiguous(), x[:2].contiguous(), True, 2)
+        assert (gidx.cpu() == ridx).float().mean() > 0.999
+        torch.testing.assert_close(gdist.cpu(), rdist, rtol=1e-4, atol=5e-5)   # rank 0 is the self-distance: rounding noise of |x|^2 ~ 12

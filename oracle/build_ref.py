@@ -108,29 +108,44 @@ def build(force=False):
     return done
 
 
-PY_STAGE = os.path.join(OUT, "py")
+PY_ARCHIVE = os.path.join(OUT, "reference_driver.tar.gz")
 # the reference's DRIVER side, which must keep running unchanged on top of the drop-in modules: main.py, its own Model wrapper,
-# the data set and the numpy / IO helpers.  NOT staged: network/, sampling/, losses/ -- exactly what this repository replaces
+# the data set and the numpy / IO helpers.  NOT included: network/, sampling/, losses/ -- exactly what this repository replaces
 # (3pu_pytorch_b200/shim provides those import names).
 PY_FILES = ["main.py", "model.py", "data.py", "utils/__init__.py", "utils/pc_utils.py", "utils/pytorch_utils.py",
             "utils/interactive_visualizer.py", "misc/__init__.py", "misc/logger.py"]
 
 
 def stage_python(force=False):
-    """Copy the reference's driver files, byte for byte, into git-ignored oracle/_ref/py (so that the drop-in test can run
-    `python main.py --phase test` on the GPU box, where /root/reference does not exist).  Returns the directory or None."""
+    """Pack the reference's driver files, byte for byte, into ONE git-ignored archive under oracle/_ref (it travels to the GPU box,
+    where /root/reference does not exist; no reference source file is ever placed in the tree).  Returns the archive or None."""
+    import tarfile
     if not os.path.isfile(os.path.join(REF_ROOT, "main.py")):
-        return PY_STAGE if os.path.isfile(os.path.join(PY_STAGE, "main.py")) else None
-    for rel in PY_FILES:
-        src, dst = os.path.join(REF_ROOT, rel), os.path.join(PY_STAGE, rel)
-        if not os.path.isfile(src):
-            if rel.endswith("__init__.py"):          # the reference uses namespace packages where it has no __init__
-                continue
-            raise FileNotFoundError(src)
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        if force or not os.path.isfile(dst) or open(src, "rb").read() != open(dst, "rb").read():
-            shutil.copyfile(src, dst)
-    return PY_STAGE
+        return PY_ARCHIVE if os.path.isfile(PY_ARCHIVE) else None
+    if os.path.isfile(PY_ARCHIVE) and not force:
+        return PY_ARCHIVE
+    os.makedirs(OUT, exist_ok=True)
+    with tarfile.open(PY_ARCHIVE, "w:gz") as tar:
+        for rel in PY_FILES:
+            src = os.path.join(REF_ROOT, rel)
+            if not os.path.isfile(src):
+                if rel.endswith("__init__.py"):      # the reference uses namespace packages where it has no __init__
+                    continue
+                raise FileNotFoundError(src)
+            tar.add(src, arcname=rel)
+    shutil.rmtree(os.path.join(OUT, "py"), ignore_errors=True)     # an earlier layout staged loose files
+    return PY_ARCHIVE
+
+
+def unpack_python(dest):
+    """Extract the staged driver files into `dest` (a test's temporary directory); returns dest or None when not staged."""
+    import tarfile
+    arc = stage_python()
+    if arc is None:
+        return None
+    with tarfile.open(arc, "r:gz") as tar:
+        tar.extractall(dest, filter="data")
+    return dest
 
 
 def load():

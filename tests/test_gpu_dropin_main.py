@@ -1,5 +1,6 @@
-"""GPU: the drop-in claim, end to end.  The reference's own driver -- main.py, model.py, data.py, utils/, misc/, staged byte for
-byte into git-ignored oracle/_ref/py by oracle/build_ref.py -- runs UNCHANGED (`python main.py --phase test ...`,
+"""GPU: the drop-in claim, end to end.  The reference's own driver -- main.py, model.py, data.py, utils/, misc/, packed byte for
+byte into a git-ignored archive under oracle/_ref by oracle/build_ref.py and unpacked into the test's temporary directory -- runs
+UNCHANGED (`python main.py --phase test ...`,
 main.py:333-389) with 3pu_pytorch_b200/shim first on PYTHONPATH providing `network`, `sampling`, `losses`, `faiss` (and import
 stand-ins for plyfile / matplotlib / h5py / visdom, which this image lacks).  The PLY it writes is compared with the oracle's
 walk through the same pipeline, and pins formats.save_ply against a file written by the reference's own save_ply."""
@@ -19,10 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def staged():
-    d = build_ref.stage_python()
+def staged(tmp_path_factory):
+    d = build_ref.unpack_python(str(tmp_path_factory.mktemp("reference_driver")))
     if d is None:
-        pytest.skip("oracle/_ref/py not staged (needs /root/reference at build time)")
+        pytest.skip("oracle/_ref/reference_driver.tar.gz not staged (needs /root/reference at build time)")
     return d
 
 

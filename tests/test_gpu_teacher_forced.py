@@ -112,3 +112,55 @@ def test_net_eval_stage_by_stage_from_the_oracle_state(pu3, cuda, params):
         assert torch.equal(prev_xyz[:, :, :P * 312].cpu(), st["next_old_xyz"])
         assert int(pk[0]) == P * 312
         assert cloud_match_fraction(out[0].cpu(), st["xyz_out"][0], tol=1e-5) > 0.99, f"level {l} resampled cloud"
+
+
+@pytest.mark.parametrize("with_prev", [False, True])
+def test_level_backward_teacher_forced_against_oracle_autograd(pu3, cuda, params, with_prev):
+    """Train-mode Level as one native autograd node (level_train.py) against torch autograd of the ORACLE's Level (the reference's
+    graph, upsampler.py:272-374), with the oracle's neighbour lists injected so that both differentiate the same graph: the
+    gradient of a random linear functional of (coordinates, features) with respect to all 40 parameters, the normalised input
+    cloud and the previous level's features.  Remaining discrete difference: the ReLU mask of an activation within rounding of
+    zero.  Bar: 99.9 % of the entries of every gradient within 1e-4 of its scale, none off by more than 1 %."""
+    name = "level_3" if with_prev else "level_1"
+    g = torch.Generator().manual_seed(21 + with_prev)
+    T, N = 4, 312
+    xyz = torch.rand(T, 3, N, generator=g) * 0.3 + 0.2
+    xn = ref_net.normalize_point_batch(xyz)[0]
+    prev = None
+    if with_prev:
+        prev = (torch.rand(T, 3, 312, generator=g) * 0.3 + 0.2, torch.randn(T, 264, 312, generator=g))
+    w_xyz = torch.randn(T, 3, 2 * N, generator=g)
+    w_feat = torch.randn(T, 264, N, generator=g) * 0.1
+    # ---- oracle: torch autograd on the reference graph
+    P = {k: v.clone().requires_grad_() for k, v in params.items() if k.startswith(f"levels.{name}.")}
+    xn_r = xn.clone().requires_grad_()
+    prev_r = None if prev is None else (prev[0], prev[1].clone().requires_grad_())
+    rec = {}
+    oxyz, ofeat = ref_net.level_forward(P, f"levels.{name}", xyz, xn_r, prev_r, knn=32, training=True, record=rec)
+    ((oxyz * w_xyz).sum() + (ofeat * w_feat).sum()).backward()
+    # ---- ours: the native node, same neighbour lists
+    net = _net(pu3, params, cuda).train()
+    level = net.levels[name]
+    xn_g = xn.to(cuda).requires_grad_()
+    prev_g = None if prev is None else (prev[0].to(cuda), prev[1].to(cuda).requires_grad_())
+    with _Override(pu3, cuda, rec):
+        gxyz, gfeat = level(xyz.to(cuda), xn_g, previous_level4=prev_g)
+        ((gxyz * w_xyz.to(cuda)).sum() + (gfeat * w_feat.to(cuda)).sum()).backward()
+        torch.cuda.synchronize()
+    _assert_all_close(gxyz, oxyz, f"{name} train forward coordinates")
+    _assert_all_close(gfeat, ofeat, f"{name} train forward features")
+
+    def close(got, want, what):
+        got, want = got.detach().cpu().double(), want.detach().double()
+        scale = float(want.abs().max()) + 1e-30
+        err = (got - want).abs()
+        frac = float((err <= 1e-4 * scale).double().mean())
+        assert frac >= 0.999 and float(err.max()) <= 1e-2 * scale, \
+            f"{what}: {frac:.5f} of the entries within 1e-4 of scale {scale:.3e}, max err {float(err.max()):.3e}"
+    close(xn_g.grad, xn_r.grad, "d / d xyz_normalized")
+    if with_prev:
+        close(prev_g[1].grad, prev_r[1].grad, "d / d previous features")
+    got = dict(net.named_parameters())
+    assert len(P) == 40
+    for k in sorted(P):
+        close(got[k].grad, P[k].grad, k)

@@ -47,6 +47,9 @@ SIGNATURES = {
                                                          _c_void_p, _c_void_p, _c_ll, _c_void_p]),
     "pu3_conv_tc_project_f32": (_c_int, [_c_int] * 5 + [_c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                                           _c_void_p, _c_ll, _c_void_p, _c_ll, _c_int, _c_int, _c_void_p]),
+    "pu3_head_tc_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll] + [_c_void_p] * 4 + [_c_int, _c_int] + [_c_void_p] * 7
+                        + [_c_ll, _c_void_p, _c_ll, _c_void_p]),
+    "pu3_head_tc_set_debug": (None, [_c_void_p]),
     "pu3_skip_fuse_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 7),
     "pu3_skip_force_generic": (None, [_c_int]),
     "pu3_to_point_major_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
@@ -140,6 +143,7 @@ KERNELS_PER_CALL = {
     # the feature kNN finds duplicates itself (no side kernels); the skip connection adds 3 duplicate kernels + kNN + skip, iota 1
     "pu3_level_forward_f32": 21, "pu3_level_forward_train_f32": 21,
     "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
+    "pu3_head_tc_f32": 1,
     "pu3_fps_ragged_f32": 1,
     "pu3_group_knn_f32": 1, "pu3_group_knn_ragged_f32": 1,  # + 3 (duplicate flags, group flags, max D) when unique
 }

@@ -1,0 +1,465 @@
+// The whole expansion head of a Level (network/upsampler.py:349-372) as ONE persistent tcgen05 kernel:
+//
+//     features (t, cin=264, n)  --up_layer1 (+ code column, x2 replication, ReLU)-->  (128, 2n)
+//                               --up_layer2 + ReLU-->  (128, 2n)  --fc_layer1 + ReLU-->  (64, 2n)
+//                               --fc_layer2 + residual-->  out (t, 3, 2n)
+//
+// Three separate launches (csrc/conv_tc.cu) move ~4.1 KB per point through HBM (write 1 KB, read 1 KB, write 1 KB, read 1 KB)
+// and cannot exceed ~55 % tensor-pipe activity even at full HBM speed; chained on chip the head reads the 264 features once
+// (1.06 KB per input point) and writes 24 bytes, so the tensor cores are the bound.
+//
+// Design (sm_100a):
+//   * tile = 128 input points = four TMA boxes of 32 points x 32 channels; the boxes of a tile may belong to different clouds
+//     (312 points = 9.75 boxes: 2.5 % padding instead of the 18 % of 128-point sub-tiles per cloud), and TMEM lane quarter q of an
+//     accumulator = box q, so every epilogue warp owns the 32 points of one box.
+//   * 3xTF32 as in conv_tc.cu.  Three chained GEMMs per tile, all M = 128:
+//       P1  up1   A = features, MN-major straight from channel-major HBM (TMA, 128B swizzle / 32B atoms), converted to hi/lo
+//                 tf32 by 4 converter warps;  D1 = main | correction accumulators (2 x 128 TMEM columns)
+//       P2  up2   A = relu(D1 + b1 + w_code * code[j]) for replica j = 0, 1: epilogue group j (4 warps, one per lane quarter)
+//                 reads D1 from TMEM and WRITES the hi/lo operand tiles (K-major, 128B swizzle) into shared memory, 32 channels
+//                 at a time -- the epilogue of one layer is the operand producer of the next;  D2 = 2 replicas x 128 columns
+//                 (one accumulator per replica: TMEM holds 512 columns and D1 must stay readable while D2 fills)
+//       P3  fc1   A = relu(D2 + b2), produced the same way;  D3 = 2 replicas x (main 64 | correction 64) in D1's columns
+//       E3        relu(D3 + b3) stays in registers, fc_layer2 (64 -> 3) + bias + residual per point, 12 bytes stored.
+//     The two 256-column TMEM regions swap roles every tile (D1/D3 of tile i in region i&1, D2 in the other) so that up1 of
+//     tile i+1 runs while E3 of tile i drains.
+//   * rings (shared memory, 208 KB): raw activations 3 x 16 KB (TMA landing zone), operand tiles 2 x (hi 16 KB | lo 16 KB)
+//     shared by the three producers (converters, epilogue group 0, epilogue group 1) in one global order, weights 3 x 32 KB
+//     (9 + 4 + 4 k-blocks per tile streamed from L2 by bulk copies; the next tile's activations are prefetched into L2).
+//   * 16 warps: 0 activation TMA, 1 MMA issue, 2 weight copies, 4-7 converters, 8-11 / 12-15 epilogue groups 0 / 1.
+//   * mbarrier parity waits are only safe when the waiter is at most one phase behind.  Ring slots alternate between producers,
+//     so a producer that starts a new phase of the tile first waits for an event that implies "everything up to four uses before
+//     mine has been consumed": accumulator-complete commits for the epilogue groups, a dedicated commit (p3_gate) for the
+//     converters' first block of the next tile.
+#include "tc_common.cuh"
+
+namespace pu3 {
+namespace tc {
+namespace head {
+
+constexpr int KB = 32;                         // channels per k-block
+constexpr int NA = 3, NO = 2, NW = 3;          // ring depths: raw activations, operand tiles, weights
+constexpr int RAW_BYTES = 128 * KB * 4;        // 16 KB: 128 points x 32 channels
+constexpr int O_BYTES = 2 * RAW_BYTES;         // hi | lo
+constexpr int W_BYTES = 2 * 128 * 128;         // [W_hi | W_lo], 128 rows of 128 B each
+constexpr int W3_BYTES = 2 * 64 * 128;
+constexpr int SMEM_BYTES = NA * RAW_BYTES + NO * O_BYTES + NW * W_BYTES + 1024;
+constexpr int NUM_THREADS = 512;
+constexpr int CONV_WARP0 = 4, EPI_WARP0 = 8;
+constexpr int C1 = 128, C2 = 128, C3 = 64;     // channels of up1, up2, fc1
+
+// instruction descriptors (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, M = 128, B K-major; bit 15 = A MN-major
+constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC_MN = IDESC_K | (1u << 15);
+constexpr uint32_t idesc_n(uint32_t base, int n) { return base | ((uint32_t)(n >> 3) << 17); }
+
+struct Args {
+    int b, n, cin, bpc;                 // bpc = boxes of 32 points per cloud
+    long long nboxes, ntiles;
+    const unsigned char *w1, *w2, *w3;  // split weight images (pu3_conv_tc_prepare_f32)
+    const float *bias1, *wfull; int w_stride, code_col; const float *code;
+    const float *bias2, *bias3, *w4, *b4;
+    const float *res; long long res_bstride;
+    float *y; long long y_bstride;
+    unsigned int *dbg;
+};
+
+// bring-up / tuning: SM cycle counter of events of CTA 0 (kind-major, 512 slots per kind)
+__device__ __forceinline__ void tl_mark(unsigned int *dbg, int kind, int slot) {
+    if (dbg && blockIdx.x == 0 && slot < 512) dbg[kind * 512 + slot] = (unsigned int)clock64();
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_A[NA], empty_A[NA], full_O[NO], empty_O[NO], full_W[NW], empty_W[NW];
+    __shared__ uint64_t acc_full[3], e2_done, e3_done, p3_gate;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias1_s[C1], wcode_s[C1], bias2_s[C2], bias3_s[C3], w4_s[3 * C3];
+    __shared__ float b4_s[4], code_s[2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t sA = smem0, sO = smem0 + NA * RAW_BYTES, sW = sO + NO * O_BYTES;
+    unsigned char *gA = smem_gen, *gO = smem_gen + NA * RAW_BYTES;
+
+    const int nkb1 = (a.cin + KB - 1) / KB;
+    const int last_ksteps = ((a.cin - (nkb1 - 1) * KB) + 7) / 8;
+    const uint32_t U = (uint32_t)nkb1 + 16u;                 // operand-tile uses per tile: P1 | P2 (4 chunks x 2 replicas) | P3
+
+    for (int i = threadIdx.x; i < C1; i += NUM_THREADS) {
+        bias1_s[i] = a.bias1 ? a.bias1[i] : 0.f;
+        wcode_s[i] = a.wfull[(size_t)i * a.w_stride + a.code_col];
+        bias2_s[i] = a.bias2 ? a.bias2[i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < C3; i += NUM_THREADS) bias3_s[i] = a.bias3 ? a.bias3[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * C3; i += NUM_THREADS) w4_s[i] = a.w4[i];
+    if (threadIdx.x < 4) b4_s[threadIdx.x] = (threadIdx.x < 3 && a.b4) ? a.b4[threadIdx.x] : 0.f;
+    if (threadIdx.x < 2) code_s[threadIdx.x] = a.code[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(&full_A[s], 1); mbar_init(&empty_A[s], 4); }
+        for (int s = 0; s < NO; ++s) { mbar_init(&full_O[s], 4); mbar_init(&empty_O[s], 1); }
+        for (int s = 0; s < NW; ++s) { mbar_init(&full_W[s], 1); mbar_init(&empty_W[s], 1); }
+        for (int s = 0; s < 3; ++s) mbar_init(&acc_full[s], 1);
+        mbar_init(&e2_done, 8);
+        mbar_init(&e3_done, 8);
+        mbar_init(&p3_gate, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== activation TMA: 4 boxes of 32 points x 32 channels per k-block into the raw ring =====
+        uint32_t slot = 0, phase = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            const long long nt = t + gridDim.x;                       // HBM -> L2 for the next tile of this CTA
+            if (nt < a.ntiles)
+                for (int i = lane; i < nkb1 * 4; i += 32) {
+                    const long long box = nt * 4 + (i & 3);
+                    if (box < a.nboxes) tma_prefetch_3d(&xmap, (int)(box % a.bpc) * 32, (i >> 2) * KB, (int)(box / a.bpc));
+                }
+            for (int kb = 0; kb < nkb1; ++kb) {
+                mbar_wait(&empty_A[slot], phase ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_A[slot], (uint32_t)RAW_BYTES);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long box = t * 4 + q;              // box >= nboxes: cloud index >= b, out of bounds, zeros
+                        tma_load_3d(sA + slot * RAW_BYTES + q * 4096, &xmap, (int)(box % a.bpc) * 32, kb * KB, (int)(box / a.bpc), &full_A[slot]);
+                    }
+                }
+                __syncwarp();
+                if (++slot == NA) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== weight k-blocks: W1[0..nkb1), W2[0..4), W3[0..4) per tile, bulk copies from L2 =====
+        uint32_t slot = 0, phase = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            for (int j = 0; j < nkb1 + 8; ++j) {
+                mbar_wait(&empty_W[slot], phase ^ 1u);
+                if (elect_one()) {
+                    const unsigned char *src;
+                    uint32_t bytes = W_BYTES;
+                    if (j < nkb1) src = a.w1 + (size_t)j * W_BYTES;
+                    else if (j < nkb1 + 4) src = a.w2 + (size_t)(j - nkb1) * W_BYTES;
+                    else { src = a.w3 + (size_t)(j - nkb1 - 4) * W3_BYTES; bytes = W3_BYTES; }
+                    mbar_arrive_expect_tx(&full_W[slot], bytes);
+                    bulk_load(sW + slot * W_BYTES, src, bytes, &full_W[slot]);
+                }
+                __syncwarp();
+                if (++slot == NW) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (whole warp waits, one elected lane issues) =====
+        uint32_t u = 0, wslot = 0, wphase = 0, it = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            const uint32_t RX = tmem_base + (it & 1u) * 256u, RY = tmem_base + ((it & 1u) ^ 1u) * 256u;
+            if (it > 0) mbar_wait(&e2_done, (it - 1u) & 1u);          // D2 of the previous tile (this tile's D1 region) has been read
+            tc_fence_after();
+            if (lane == 0) tl_mark(a.dbg, 0, (int)it);
+            // ---- P1: up1, two accumulators (main = hi.hi, correction = hi.lo + lo.hi)
+            for (int kb = 0; kb < nkb1; ++kb, ++u) {
+                const uint32_t os = u & 1u;
+                mbar_wait(&full_W[wslot], wphase);
+                mbar_wait(&full_O[os], (u >> 1) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t oa = sO + os * O_BYTES, wb = sW + wslot * W_BYTES;
+                    const int nks = kb == nkb1 - 1 ? last_ksteps : KB / 8;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t ahi = smem_desc(oa + ks * 1024, 4096, 512, LAYOUT_SW128_32B);
+                        const uint64_t alo = smem_desc(oa + RAW_BYTES + ks * 1024, 4096, 512, LAYOUT_SW128_32B);
+                        const uint64_t bhl = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);     // rows [W_hi; W_lo]
+                        umma_tf32(RX, ahi, bhl, idesc_n(IDESC_MN, 2 * C1), (kb | ks) != 0);
+                        umma_tf32(RX + C1, alo, bhl, idesc_n(IDESC_MN, C1), 1u);
+                    }
+                    tc_commit(&empty_O[os]);
+                    tc_commit(&empty_W[wslot]);
+                    if (kb == nkb1 - 1) tc_commit(&acc_full[0]);
+                }
+                __syncwarp();
+                if (++wslot == NW) { wslot = 0; wphase ^= 1u; }
+            }
+            if (lane == 0) tl_mark(a.dbg, 1, (int)it);
+            if (it > 0) mbar_wait(&e3_done, (it - 1u) & 1u);          // D3 of the previous tile (this tile's D2 region) has been read
+            tc_fence_after();
+            if (lane == 0) tl_mark(a.dbg, 2, (int)it);
+            // ---- P2: up2, one accumulator per replica
+            for (int ch = 0; ch < C1 / KB; ++ch) {
+                mbar_wait(&full_W[wslot], wphase);
+                for (int g = 0; g < 2; ++g, ++u) {
+                    const uint32_t os = u & 1u;
+                    mbar_wait(&full_O[os], (u >> 1) & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t oa = sO + os * O_BYTES, wb = sW + wslot * W_BYTES, d = RY + g * C2;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t ahi = smem_desc(oa + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t alo = smem_desc(oa + RAW_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t blo = smem_desc(wb + C2 * 128 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            umma_tf32(d, ahi, blo, idesc_n(IDESC_K, C2), (ch | ks) != 0);   // small terms first
+                            umma_tf32(d, alo, bhi, idesc_n(IDESC_K, C2), 1u);
+                            umma_tf32(d, ahi, bhi, idesc_n(IDESC_K, C2), 1u);
+                        }
+                        tc_commit(&empty_O[os]);
+                        if (g == 1) {
+                            tc_commit(&empty_W[wslot]);
+                            if (ch == C1 / KB - 1) tc_commit(&acc_full[1]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (++wslot == NW) { wslot = 0; wphase ^= 1u; }
+            }
+            if (lane == 0) tl_mark(a.dbg, 3, (int)it);
+            // ---- P3: fc1, main | correction per replica, in D1's columns (all of D1 was read before D2 completed)
+            for (int ch = 0; ch < C2 / KB; ++ch) {
+                mbar_wait(&full_W[wslot], wphase);
+                for (int g = 0; g < 2; ++g, ++u) {
+                    const uint32_t os = u & 1u;
+                    mbar_wait(&full_O[os], (u >> 1) & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t oa = sO + os * O_BYTES, wb = sW + wslot * W_BYTES, d = RX + g * (2 * C3);
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t ahi = smem_desc(oa + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t alo = smem_desc(oa + RAW_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t bhl = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);   // rows [W_hi (64); W_lo (64)]
+                            umma_tf32(d, ahi, bhl, idesc_n(IDESC_K, 2 * C3), (ch | ks) != 0);
+                            umma_tf32(d + C3, alo, bhl, idesc_n(IDESC_K, C3), 1u);
+                        }
+                        tc_commit(&empty_O[os]);
+                        if (g == 1) {
+                            tc_commit(&empty_W[wslot]);
+                            if (ch == C2 / KB - 2) tc_commit(&p3_gate);       // all but the last two operand tiles of this tile consumed
+                            if (ch == C2 / KB - 1) tc_commit(&acc_full[2]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (++wslot == NW) { wslot = 0; wphase ^= 1u; }
+            }
+            if (lane == 0) tl_mark(a.dbg, 4, (int)it);
+        }
+    } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+        // ===== converters (P1): raw fp32 -> hi = tf32(x), lo = x - hi, same (TMA-swizzled MN-major) layout =====
+        const int ct = threadIdx.x - CONV_WARP0 * 32;        // 0..127
+        uint32_t aslot = 0, aphase = 0, it = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            if (it > 0) mbar_wait(&p3_gate, (it - 1u) & 1u);
+            for (int kb = 0; kb < nkb1; ++kb) {
+                const uint32_t u = it * U + (uint32_t)kb, os = u & 1u;
+                mbar_wait(&full_A[aslot], aphase);
+                const float4 *src = reinterpret_cast<const float4 *>(gA + aslot * RAW_BYTES);
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = src[ct + i * 128];
+                mbar_wait(&empty_O[os], ((u >> 1) & 1u) ^ 1u);
+                float4 *hi = reinterpret_cast<float4 *>(gO + os * O_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(gO + os * O_BYTES + RAW_BYTES);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 h, l;
+                    h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
+                    l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
+                    hi[ct + i * 128] = h;
+                    lo[ct + i * 128] = l;
+                }
+                fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&full_O[os]); mbar_arrive(&empty_A[aslot]); }
+                if (++aslot == NA) { aslot = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue groups: group g = replica g; warp quarter q = TMEM lanes 32q.. = box q of the tile =====
+        const int g = (warp - EPI_WARP0) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const uint32_t swz = (uint32_t)(row & 7);
+        unsigned char *orow_base = gO + row * 128;
+        const float code_g = code_s[g];
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const uint32_t RX = tmem_base + par * 256u + lanebits, RY = tmem_base + (par ^ 1u) * 256u + lanebits;
+            const long long box = t * 4 + q;
+            const long long bi = box / a.bpc;
+            const int p = (int)(box % a.bpc) * 32 + lane;
+            const bool valid = box < a.nboxes && p < a.n;
+            const uint32_t ubase = it * U + (uint32_t)nkb1 + (uint32_t)g;
+            // ---- E1: D1 -> relu(up1 + bias + w_code * code[g]) -> operand tiles of up2
+            mbar_wait(&acc_full[0], par);
+            tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 5, (int)it);
+#pragma unroll 1
+            for (int ch = 0; ch < C1 / KB; ++ch) {
+                uint32_t v[32], vc[32];
+                tmem_ld32(RX + ch * 32, v);
+                tmem_ld32(RX + C1 + ch * 32, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = ch * 32 + j;
+                    const float pre = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) + bias1_s[co];
+                    v[j] = __float_as_uint(fmaxf(__fmaf_rn(wcode_s[co], code_g, pre), 0.f));
+                }
+                const uint32_t u = ubase + 2u * ch, os = u & 1u;
+                mbar_wait(&empty_O[os], ((u >> 1) & 1u) ^ 1u);
+                unsigned char *orow = orow_base + os * O_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 h, l;
+                    const float x0 = __uint_as_float(v[4 * c]), x1 = __uint_as_float(v[4 * c + 1]), x2 = __uint_as_float(v[4 * c + 2]), x3 = __uint_as_float(v[4 * c + 3]);
+                    h.x = to_tf32(x0); h.y = to_tf32(x1); h.z = to_tf32(x2); h.w = to_tf32(x3);
+                    l.x = x0 - h.x; l.y = x1 - h.y; l.z = x2 - h.z; l.w = x3 - h.w;
+                    const uint32_t off = ((uint32_t)c ^ swz) << 4;
+                    *reinterpret_cast<float4 *>(orow + off) = h;
+                    *reinterpret_cast<float4 *>(orow + RAW_BYTES + off) = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_O[os]);
+            }
+            // ---- E2: D2 (replica g) -> relu(up2 + bias) -> operand tiles of fc1
+            mbar_wait(&acc_full[1], par);
+            tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 6, (int)it);
+#pragma unroll 1
+            for (int ch = 0; ch < C2 / KB; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(RY + g * C2 + ch * 32, v);
+                tmem_ld_wait();
+                if (ch == C2 / KB - 1) {                     // D2 fully read: the MMA warp may start up1 of the next tile in this region
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&e2_done);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bias2_s[ch * 32 + j], 0.f));
+                const uint32_t u = ubase + 8u + 2u * ch, os = u & 1u;
+                mbar_wait(&empty_O[os], ((u >> 1) & 1u) ^ 1u);
+                unsigned char *orow = orow_base + os * O_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 h, l;
+                    const float x0 = __uint_as_float(v[4 * c]), x1 = __uint_as_float(v[4 * c + 1]), x2 = __uint_as_float(v[4 * c + 2]), x3 = __uint_as_float(v[4 * c + 3]);
+                    h.x = to_tf32(x0); h.y = to_tf32(x1); h.z = to_tf32(x2); h.w = to_tf32(x3);
+                    l.x = x0 - h.x; l.y = x1 - h.y; l.z = x2 - h.z; l.w = x3 - h.w;
+                    const uint32_t off = ((uint32_t)c ^ swz) << 4;
+                    *reinterpret_cast<float4 *>(orow + off) = h;
+                    *reinterpret_cast<float4 *>(orow + RAW_BYTES + off) = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_O[os]);
+            }
+            // ---- E3: D3 (replica g) -> relu(fc1 + bias) in registers -> fc_layer2 + bias + residual
+            mbar_wait(&acc_full[2], par);
+            tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 7, (int)it);
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C3 / 32; ++ch) {
+                uint32_t v[32], vc[32];
+                tmem_ld32(RX + g * (2 * C3) + ch * 32, v);
+                tmem_ld32(RX + g * (2 * C3) + C3 + ch * 32, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = ch * 32 + j;
+                    const float h = fmaxf((__uint_as_float(v[j]) + __uint_as_float(vc[j])) + bias3_s[co], 0.f);
+                    o0 = __fmaf_rn(w4_s[co], h, o0);
+                    o1 = __fmaf_rn(w4_s[C3 + co], h, o1);
+                    o2 = __fmaf_rn(w4_s[2 * C3 + co], h, o2);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e3_done);
+            if (valid) {
+                const float o[3] = {o0 + b4_s[0], o1 + b4_s[1], o2 + b4_s[2]};
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    float r = o[c3];
+                    if (a.res) r += __ldg(a.res + bi * a.res_bstride + (size_t)c3 * a.n + p);
+                    a.y[bi * a.y_bstride + (size_t)c3 * (2 * a.n) + 2 * p + g] = r;
+                }
+            }
+            if (warp == EPI_WARP0 && lane == 0) tl_mark(a.dbg, 8, (int)it);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static unsigned int *g_dbg = nullptr;
+
+}  // namespace head
+}  // namespace tc
+}  // namespace pu3
+
+using namespace pu3;
+
+extern "C" void pu3_head_tc_set_debug(void *buf) { tc::head::g_dbg = static_cast<unsigned int *>(buf); }
+
+extern "C" int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long x_bstride, const void *ws1, const void *ws2,
+                               const void *ws3, const float *w1, int w1_stride, int code_col, const float *b1, const float *code,
+                               const float *b2, const float *b3, const float *w4, const float *b4, const float *res,
+                               long long res_bstride, float *y, long long y_bstride, pu3_stream_t stream) {
+    namespace H = tc::head;
+    PU3_ARG_CHECK(b >= 0 && n >= 0 && cin > 0, "head_tc: bad size b=%d n=%d cin=%d", b, n, cin);
+    if (b == 0 || n == 0) return PU3_OK;
+    PU3_ARG_CHECK(x && ws1 && ws2 && ws3 && w1 && code && w4 && y, "head_tc: null pointer");
+    PU3_ARG_CHECK(n % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                  "head_tc: the TMA path needs n %% 4 == 0 and 16-byte aligned slices (n=%d)", n);
+    PU3_ARG_CHECK(((reinterpret_cast<uintptr_t>(ws1) | reinterpret_cast<uintptr_t>(ws2) | reinterpret_cast<uintptr_t>(ws3)) & 15) == 0,
+                  "head_tc: split weights must be 16-byte aligned");
+    tc::EncodeTiledFn enc = tc::encode_fn();
+    if (!enc) { set_error("head_tc: cuTensorMapEncodeTiled not available"); return PU3_E_ARG; }
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)cin, (cuuint64_t)b};
+    const cuuint64_t gstride[2] = {(cuuint64_t)n * 4, (cuuint64_t)x_bstride * 4};
+    const cuuint32_t box[3] = {32, H::KB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("head_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return PU3_E_ARG; }
+    H::Args a{};
+    a.b = b; a.n = n; a.cin = cin; a.bpc = (n + 31) / 32;
+    a.nboxes = (long long)b * a.bpc;
+    a.ntiles = (a.nboxes + 3) / 4;
+    a.w1 = static_cast<const unsigned char *>(ws1); a.w2 = static_cast<const unsigned char *>(ws2); a.w3 = static_cast<const unsigned char *>(ws3);
+    a.bias1 = b1; a.wfull = w1; a.w_stride = w1_stride; a.code_col = code_col; a.code = code;
+    a.bias2 = b2; a.bias3 = b3; a.w4 = w4; a.b4 = b4;
+    a.res = res; a.res_bstride = res_bstride; a.y = y; a.y_bstride = y_bstride;
+    a.dbg = H::g_dbg;
+    {
+        int st = cuda_status(cudaFuncSetAttribute(H::head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H::SMEM_BYTES),
+                             "head_tc: shared memory opt-in");
+        if (st) return st;
+    }
+    const int grid = (int)(a.ntiles < device_info().sm_count ? a.ntiles : device_info().sm_count);
+    H::head_tc_kernel<<<grid, H::NUM_THREADS, H::SMEM_BYTES, as_stream(stream)>>>(map, a);
+    PU3_LAUNCH_CHECK("head_tc_kernel");
+    return PU3_OK;
+}

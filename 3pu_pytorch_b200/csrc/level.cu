@@ -52,9 +52,10 @@ static LevelPlan plan_level(int t, int n, int r, int knn, int fm_knn, int clouds
 
 using namespace pu3;
 
-// Test / A-B hook: 2 (default) = expansion head and the three 24-channel prep convolutions on the tcgen05 kernels,
-// 1 = head only, 0 = everything on the fp32 FFMA SGEMM.
-static int g_level_tc = 2;
+// Test / A-B hook: 3 (default) = the expansion head as one fused tcgen05 kernel (eval) + the three 24-channel prep convolutions
+// on the tcgen05 conv kernel, 2 = head as three tcgen05 kernels + prep convolutions, 1 = three-kernel head only,
+// 0 = everything on the fp32 FFMA SGEMM.
+static int g_level_tc = 3;
 extern "C" void pu3_level_set_tc(int on) { g_level_tc = on; }
 
 // Test hook (teacher forcing): neighbour lists to use INSTEAD of the engine's own searches -- idx[blk] (t,n,knn+1) i32 for the four
@@ -173,7 +174,16 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
                                   owner, saved ? saved->skip_w : nullptr, stream));
     }
     // expansion head (:349-372)
-    if (g_level_tc >= 1 && n % 4 == 0 && r <= 8) {
+    if (g_level_tc >= 3 && n % 4 == 0 && r == 2 && !saved) {
+        // the whole head as ONE persistent tcgen05 kernel (csrc/head_tc.cu): activations chained on chip, HBM sees the
+        // features once and the 3-channel result (the train-mode forward keeps the 3-kernel path: its backward needs h1, h2)
+        void *ws1 = ws + p.off_wsplit[0], *ws2 = ws + p.off_wsplit[1], *ws3 = ws + p.off_wsplit[2];
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(C, 128, w->up1_w, C + 1, ws1, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(128, 128, w->up2_w, 128, ws2, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_conv_tc_prepare_f32(128, 64, w->fc1_w, 128, ws3, stream));
+        PU3_TRYT(PROF_CONV_TC, pu3_head_tc_f32(t, n, C, feat, fs, ws1, ws2, ws3, w->up1_w, C + 1, C, w->up1_b, w->code, w->up2_b, w->fc1_b,
+                                               w->fc2_w, w->fc2_b, xyz_norm, 3LL * n, out_xyz, 3LL * n * r, stream));
+    } else if (g_level_tc >= 1 && n % 4 == 0 && r <= 8) {
         // tensor cores (tcgen05, 3xTF32): up1 + code column + replication | up2 | fc1 + fc2 + residual -- 3 kernels, the
         // (t,265,n*r) input, the 128-channel "pre" tensor and the 64-channel activation never exist
         void *ws1 = ws + p.off_wsplit[0], *ws2 = ws + p.off_wsplit[1], *ws3 = ws + p.off_wsplit[2];

@@ -266,3 +266,24 @@ def tc_project(x, w_mid, b_mid, w_out, b_out, residual=None, res_div=1, wsplit=N
                 x.stride(0) if B > 1 else Cin * N, ws.data_ptr(), _lib.ptr(b_mid), wo.data_ptr(), _lib.ptr(b_out),
                 out.data_ptr(), wo.shape[0] * N, rp, rbs, rn, res_div)
     return out
+
+
+def tc_head(x, w1_full, b1, code, w2, b2, w3, b3, w4, b4, residual=None, wsplits=None):
+    """The whole expansion head (upsampler.py:349-372) as one persistent tcgen05 kernel (csrc/head_tc.cu): x (B,Cin,N) features,
+    w1_full (128, Cin+1) = up_layer1 incl. its code column, w2 (128,128), w3 (64,128), w4 (3,64), residual (B,3,N) -> (B,3,2N).
+    Step ratio 2 only (code has two entries)."""
+    B, Cin, N = x.shape
+    m = lambda w: w.reshape(w.shape[0], w.shape[1]).contiguous()
+    w1, w2, w3, w4 = m(w1_full), m(w2), m(w3), m(w4)
+    assert w1.shape == (128, Cin + 1) and w2.shape == (128, 128) and w3.shape == (64, 128) and w4.shape == (3, 64)
+    assert code.numel() == 2 and x.stride(2) == 1 and x.stride(1) == N
+    ws = wsplits if wsplits is not None else (tc_prepare(w1, cin=Cin), tc_prepare(w2), tc_prepare(w3))
+    out = torch.empty(B, 3, 2 * N, dtype=torch.float32, device=x.device)
+    rp, rbs = None, 0
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == (B, 3, N)
+        rp, rbs = residual.data_ptr(), 3 * N
+    _lib.launch("pu3_head_tc_f32", x, B, N, Cin, x.data_ptr(), x.stride(0) if B > 1 else Cin * N, ws[0].data_ptr(),
+                ws[1].data_ptr(), ws[2].data_ptr(), w1.data_ptr(), Cin + 1, Cin, _lib.ptr(b1), code.data_ptr(), _lib.ptr(b2),
+                _lib.ptr(b3), w4.data_ptr(), _lib.ptr(b4), rp, rbs, out.data_ptr(), 3 * 2 * N)
+    return out

@@ -213,6 +213,22 @@ int pu3_conv_tc_project_f32(int b, int n, int cin, int cmid, int cout, const flo
                             int res_div, pu3_stream_t stream);
 
 /*
+ * The whole expansion head (network/upsampler.py:349-372: replicate x2 + 1-D code, up_layer1, up_layer2, fc_layer1,
+ * fc_layer2, residual) as ONE persistent tcgen05 kernel: the 128/128/64-channel activations never leave the SM (the epilogue
+ * of a layer writes the tf32 hi/lo operand tiles of the next one into shared memory), HBM sees the (b,cin,n) features once
+ * and the (b,3,2n) result.  Step ratio 2 and the reference's head widths (128, 128, 64, 3) only; other configurations use
+ * the three pu3_conv_tc_* calls.  x: channel slice (pointer + batch stride, channel stride n); ws1/ws2/ws3: split images of
+ * up_layer1 (cin feature columns of its (128, >= cin+1) weight w1, code column code_col), up_layer2 (128,128), fc_layer1
+ * (64,128) from pu3_conv_tc_prepare_f32; code (2); w4 (3,64) / b4 (3) = fc_layer2; res (b,3,n) or NULL; y (b,3,2n) with
+ * y[b,c,2p+j] = fc2(relu(fc1(relu(up2(relu(up1([x[b,:,p]; code[j]])))))))[c] + res[b,c,p].
+ */
+int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long x_bstride, const void *ws1, const void *ws2,
+                    const void *ws3, const float *w1, int w1_stride, int code_col, const float *b1, const float *code,
+                    const float *b2, const float *b3, const float *w4, const float *b4, const float *res,
+                    long long res_bstride, float *y, long long y_bstride, pu3_stream_t stream);
+void pu3_head_tc_set_debug(void *buf); /* test hook: device buffer (9 x 512 u32) receiving CTA 0's event timeline; NULL = off */
+
+/*
  * Fused DenseEdgeConv forward for the reference configuration (24 input channels, growth 12, 3 layers):
  * replaces network/layers.py:22-64 (neighbour gather, edge feature [c, n-c], three 1x1 convolutions with dense
  * concatenation, max over the k edges).  x (b,24,n) slice (batch stride x_bstride), idx (b,n,idx_stride) i32 of which
@@ -314,7 +330,7 @@ int pu3_iota_i32(int n, int32_t *out, pu3_stream_t stream); /* out[i] = i */
 /* test hook (teacher forcing): neighbour lists the level engine uses instead of its own searches -- b0..b3 (t,n,knn+1) i32 for the
  * four dense blocks, skip (t,n,fm_knn) i64; NULL = search as usual.  Global, not thread-safe: tests only. */
 void pu3_level_set_knn_override(const int32_t *b0, const int32_t *b1, const int32_t *b2, const int32_t *b3, const int64_t *skip);
-void pu3_level_set_tc(int mode); /* test / A-B hook: 2 (default) = head + prep convolutions on tcgen05, 1 = head only, 0 = fp32 FFMA kernels */
+void pu3_level_set_tc(int mode); /* test / A-B hook: 3 (default) = fused tcgen05 head (pu3_head_tc_f32) + prep convolutions on tcgen05, 2 = three-kernel tcgen05 head + prep convolutions, 1 = three-kernel head only, 0 = fp32 FFMA kernels */
 
 /*
  * Weight / bias gradient of the 1x1 convolution: dw[co,ci] += sum_{b,p} dy[b,co,p] x[b,ci,p], db[co] += sum dy

@@ -1,0 +1,69 @@
+"""Fused tcgen05 head (csrc/head_tc.cu) against the three-kernel tcgen05 head at the four level shapes of the B=32 eval step,
+plus the in-kernel event timeline of CTA 0 (cycles per tile phase).  Usage: python profiles/head_time.py [--timeline] [--only=T]"""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+pu3 = importlib.import_module("3pu_pytorch_b200")
+F = pu3.fused
+dev = torch.device("cuda:0")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=7):
+    ts = []
+    for _ in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts[2:])[len(ts[2:]) // 2]
+
+
+g = torch.Generator().manual_seed(0)
+cin, n = 264, 312
+w1 = (torch.randn(128, cin + 1, generator=g) * 0.08).to(dev); b1 = torch.randn(128, generator=g).mul(0.1).to(dev)
+w2 = (torch.randn(128, 128, generator=g) * 0.12).to(dev); b2 = torch.randn(128, generator=g).mul(0.1).to(dev)
+w3 = (torch.randn(64, 128, generator=g) * 0.12).to(dev); b3 = torch.randn(64, generator=g).mul(0.1).to(dev)
+w4 = (torch.randn(3, 64, generator=g) * 0.2).to(dev); b4 = torch.randn(3, generator=g).mul(0.1).to(dev)
+code = torch.tensor([-1.0, 1.0], device=dev)
+ws = (F.tc_prepare(w1, cin=cin), F.tc_prepare(w2), F.tc_prepare(w3))
+total_f = total_3 = 0.0
+only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]
+for T in (only or (32, 160, 640, 1275)):
+    x = torch.randn(T, cin, n, device=dev)
+    res = torch.randn(T, 3, n, device=dev)
+    h1 = torch.empty(T, 128, 2 * n, device=dev); h2 = torch.empty_like(h1)
+
+    def three():
+        F.tc_expand(x, w1, b1, code, 2, wsplit=ws[0], out=h1)
+        F.tc_conv_into(h1, w2, b2, h2, relu=True, wsplit=ws[1])
+        return F.tc_project(h2, w3, b3, w4, b4, residual=res, res_div=2, wsplit=ws[2])
+
+    fused = lambda: F.tc_head(x, w1, b1, code, w2, b2, w3, b3, w4, b4, residual=res, wsplits=ws)
+    a, b = fused(), three()
+    tf, t3 = timed(fused), timed(three)
+    total_f += tf; total_3 += t3
+    tiles = -(-T * 10 // 4)
+    per_sm = -(-tiles // 148)
+    mma_cycles = 33 * 192 + 16 * 2 * 192 + 16 * 2 * 96            # tensor-pipe cycles per tile at the nominal tf32 rate
+    print(f"T={T:5d}: fused {tf:.4f} ms, three kernels {t3:.4f} ms ({t3 / tf:.2f}x); {tiles} tiles, {per_sm} per SM, "
+          f"{tf * 1e3 / per_sm:.2f} us per tile (tensor work {mma_cycles} cycles); max |fused - three| {float((a - b).abs().max()):.2e}")
+print(f"sum over the four levels: fused {total_f:.3f} ms, three kernels {total_3:.3f} ms")
+
+if "--timeline" in sys.argv:
+    T = 1275
+    x = torch.randn(T, cin, n, device=dev); res = torch.randn(T, 3, n, device=dev)
+    buf = torch.zeros(9 * 512, dtype=torch.int32, device=dev)
+    lib = pu3._lib.lib()
+    lib.pu3_head_tc_set_debug(buf.data_ptr())
+    F.tc_head(x, w1, b1, code, w2, b2, w3, b3, w4, b4, residual=res, wsplits=ws)
+    torch.cuda.synchronize()
+    lib.pu3_head_tc_set_debug(None)
+    ev = buf.cpu().view(9, 512).numpy().astype("int64") & 0xffffffff
+    names = ["P1 start", "P1 issued", "P2 start (E3 of previous tile done)", "P2 issued", "P3 issued", "E1 start (D1 complete)",
+             "E2 start (D2 complete)", "E3 start (D3 complete)", "E3 done"]
+    t0 = ev[0, 2]
+    for it in range(2, 8):
+        print(f"tile {it}: " + " | ".join(f"{names[k]} {int((ev[k, it] - t0) & 0xffffffff)}" for k in range(9)))
+    per = [(ev[0, it + 1] - ev[0, it]) & 0xffffffff for it in range(2, 18)]
+    print("cycles per tile (P1 start to P1 start):", [int(v) for v in per])

@@ -91,8 +91,51 @@ def test_conv_tc_rejects_what_tma_cannot_address(pu3, cuda):
         pu3.fused.tc_prepare(torch.zeros(130, 8, device=cuda))   # cout > 128
 
 
+def _head_reference(x, w1, b1, code, w2, b2, w3, b3, w4, b4, res):
+    """float64 evaluation of upsampler.py:349-372 for step ratio 2: replicate, append the code, four 1x1 convolutions, residual."""
+    B, C, N = x.shape
+    xr = x.double().repeat_interleave(2, dim=2)                                  # (B,C,2N): point p -> 2p, 2p+1
+    cd = code.double().repeat(N).view(1, 1, 2 * N).expand(B, 1, 2 * N)
+    h = F.relu(F.conv1d(torch.cat([xr, cd], 1), w1.double().unsqueeze(-1), b1.double()))
+    h = F.relu(F.conv1d(h, w2.double().unsqueeze(-1), b2.double()))
+    h = F.relu(F.conv1d(h, w3.double().unsqueeze(-1), b3.double()))
+    y = F.conv1d(h, w4.double().unsqueeze(-1), b4.double())
+    return y + res.double().repeat_interleave(2, dim=2) if res is not None else y
+
+
+# one tile on one CTA; ragged clouds (box tails, clouds smaller than a TMA box, boxes of different clouds in one tile); cin that
+# is not a multiple of the 32-channel k-block; more tiles than SMs (every CTA runs several tiles: TMEM regions swap roles, the
+# operand ring changes hands between the converters and the epilogue groups)
+@pytest.mark.parametrize("b,n,cin,res", [(1, 128, 264, True), (3, 312, 264, True), (5, 100, 264, False), (7, 36, 72, True),
+                                         (2, 4, 264, True), (40, 312, 264, True), (700, 312, 264, True)])
+def test_head_tc_fused_chain(pu3, cuda, b, n, cin, res):
+    g = torch.Generator().manual_seed(b * 1000 + n + cin)
+    x = _rand(g, b, cin, n)
+    w1, b1 = _rand(g, 128, cin + 1, scale=(2.0 / cin) ** 0.5), _rand(g, 128, scale=0.1)
+    w2, b2 = _rand(g, 128, 128, scale=0.125), _rand(g, 128, scale=0.1)
+    w3, b3 = _rand(g, 64, 128, scale=0.125), _rand(g, 64, scale=0.1)
+    w4, b4 = _rand(g, 3, 64, scale=0.2), _rand(g, 3, scale=0.1)
+    code = torch.tensor([-1.0, 1.0])
+    r = _rand(g, b, 3, n) if res else None
+    nref = min(b, 48)                                                            # float64 reference on a subset of the clouds
+    pick = torch.linspace(0, b - 1, nref).round().long().unique()
+    want = _head_reference(x[pick], w1, b1, code, w2, b2, w3, b3, w4, b4, None if r is None else r[pick])
+    c = lambda t: None if t is None else t.to(cuda)
+    out = pu3.fused.tc_head(c(x), c(w1), c(b1), c(code), c(w2), c(b2), c(w3), c(b3), c(w4), c(b4), residual=c(r))
+    torch.cuda.synchronize()
+    assert out.shape == (b, 3, 2 * n) and bool(torch.isfinite(out).all())
+    assert_close_frac(out[pick.to(cuda)], want, rtol=1e-5, atol=1e-5, what="fused tcgen05 head")
+    # and against the three-kernel tensor-core head (same 3xTF32 arithmetic up to the accumulator layout of up2)
+    h1 = pu3.fused.tc_expand(c(x), c(w1), c(b1), c(code), 2)
+    h2 = torch.empty_like(h1)
+    pu3.fused.tc_conv_into(h1, c(w2), c(b2), h2, relu=True)
+    three = pu3.fused.tc_project(h2, c(w3), c(b3), c(w4), c(b4), residual=c(r), res_div=2)
+    assert float((out - three).abs().max()) <= 1e-5 * (1.0 + float(three.abs().max()))
+
+
 def test_level_head_on_tensor_cores_matches_ffma_head_and_oracle(pu3, cuda):
-    """The level engine with the tcgen05 head against (a) the same engine with the FFMA head and (b) the oracle."""
+    """The level engine with the tcgen05 head (fused and three-kernel) against (a) the same engine with the FFMA head and
+    (b) the oracle."""
     params = ref_net.make_params(1, seed=1)
     net = pu3.Net(max_up_ratio=2, step_ratio=2, knn=32, growth_rate=12, dense_n=3, fm_knn=5)
     net.load_state_dict(params, strict=True)
@@ -102,16 +145,20 @@ def test_level_head_on_tensor_cores_matches_ffma_head_and_oracle(pu3, cuda):
     lib = pu3._lib.lib()
     try:
         with torch.no_grad():
-            lib.pu3_level_set_tc(2)          # default: head and prep convolutions on tensor cores
+            lib.pu3_level_set_tc(3)          # default: fused head, prep convolutions on tensor cores
             all_xyz, all_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
-            lib.pu3_level_set_tc(1)          # head only
+            lib.pu3_level_set_tc(2)          # three-kernel head, prep convolutions on tensor cores
+            k3_xyz, k3_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
+            lib.pu3_level_set_tc(1)          # three-kernel head only
             tc_xyz, tc_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
             lib.pu3_level_set_tc(0)
             ff_xyz, ff_feat = net.levels["level_1"](xyz.to(cuda), xyz.to(cuda))
     finally:
-        lib.pu3_level_set_tc(2)
+        lib.pu3_level_set_tc(3)
     assert torch.equal(tc_feat, ff_feat)                                # the head does not touch the features
+    assert torch.equal(all_feat, k3_feat)
     assert_close_frac(tc_xyz, ff_xyz, rtol=1e-5, atol=2e-6, what="tcgen05 head vs FFMA head")
+    assert_close_frac(all_xyz, k3_xyz, rtol=1e-5, atol=2e-6, what="fused tcgen05 head vs three-kernel tcgen05 head")
     want_xyz, _ = ref_net.level_forward(params, "levels.level_1", xyz, xyz, None, knn=32)
     assert_close_frac(tc_xyz, want_xyz, rtol=1e-5, atol=2e-6, frac=0.99, what="tcgen05 head vs oracle")
     # prep convolutions on tensor cores feed the feature kNN: near-tie flips may move a small share of the features

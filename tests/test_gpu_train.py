@@ -137,7 +137,7 @@ def test_eval_after_train_steps_sees_the_updated_weights(pu3, cuda):
     x = ref_net.normalize_point_batch(torch.rand(2, 3, 312, generator=g))[0].to(cuda)
     gt = torch.rand(2, 3, 624, generator=g).to(cuda)
     lib = ctypes.CDLL(pu3._lib.LIB_PATH)
-    for tc in (2, 0):
+    for tc in (3, 2, 0):
         lib.pu3_level_set_tc(tc)
         try:
             net.eval()
@@ -158,7 +158,7 @@ def test_eval_after_train_steps_sees_the_updated_weights(pu3, cuda):
             with torch.no_grad():
                 want = fresh(x, ratio=2)
         finally:
-            lib.pu3_level_set_tc(2)
+            lib.pu3_level_set_tc(3)
         assert (after - before).abs().max() > 1e-4                     # the weights did move
         assert torch.equal(after, want), f"tc={tc}: stale weight image after FlatAdam steps"
 
@@ -194,7 +194,7 @@ def test_native_level_backward_matches_the_operator_composition(pu3, cuda, tc):
             loss.backward()
             outs[native] = (pc.detach(), float(loss), xin.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
     finally:
-        lib.pu3_level_set_tc(2)
+        lib.pu3_level_set_tc(3)
     pa, la, xa, ga = outs[True]
     pb, lb, xb, gb = outs[False]
     assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6)             # forward: level engine vs per-layer composition

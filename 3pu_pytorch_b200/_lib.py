@@ -50,6 +50,7 @@ SIGNATURES = {
     "pu3_head_tc_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll] + [_c_void_p] * 4 + [_c_int, _c_int] + [_c_void_p] * 7
                         + [_c_ll, _c_void_p, _c_ll, _c_void_p]),
     "pu3_head_tc_set_debug": (None, [_c_void_p]),
+    "pu3_head_tc_set_mode": (None, [_c_int]),
     "pu3_skip_fuse_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 7),
     "pu3_skip_force_generic": (None, [_c_int]),
     "pu3_to_point_major_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
@@ -139,9 +140,10 @@ KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
     "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
-    # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 6 head kernels (3 weight splits + 3 tcgen05);
+    # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 4 head kernels (3 weight splits + 1 fused tcgen05; the
+    # train-mode forward keeps the three-kernel head: 21);
     # the feature kNN finds duplicates itself (no side kernels); the skip connection adds 3 duplicate kernels + kNN + skip, iota 1
-    "pu3_level_forward_f32": 21, "pu3_level_forward_train_f32": 21,
+    "pu3_level_forward_f32": 19, "pu3_level_forward_train_f32": 21,
     "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
     "pu3_head_tc_f32": 1,
     "pu3_fps_ragged_f32": 1,
@@ -167,7 +169,7 @@ class Profiler:
 
     ENGINE_TAGS = ["pu3_pointwise_conv_f32", "pu3_group_knn_f32[c=24,k=33,n<=312]", "pu3_edgeconv_f32",
                    "pu3_group_knn_f32[c=3,k=5,skip]", "pu3_skip_fuse_f32", "pu3_expand_code_f32", "misc",
-                   "pu3_conv_tc_f32[tcgen05 head: 3 weight splits + expand + conv + project]",
+                   "pu3_head_tc_f32[tcgen05 head: 3 weight splits + ONE fused up1/up2/fc1/fc2 kernel]",
                    "pu3_conv_tc_f32[tcgen05 prep convs 84/144/204->24: 3 weight splits + 3 convs]"]
 
     def summary(self):

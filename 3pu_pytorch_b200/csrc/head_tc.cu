@@ -66,7 +66,7 @@ struct Args {
 
 // bring-up / tuning: SM cycle counter of events of CTA 0 (kind-major, 512 slots per kind)
 __device__ __forceinline__ void tl_mark(unsigned int *dbg, int kind, int slot) {
-    if (dbg && blockIdx.x == 0 && slot < 512) dbg[kind * 512 + slot] = (unsigned int)clock64();
+    if (dbg && blockIdx.x == 0 && slot < 512) dbg[kind * 512 + slot] = (unsigned int)clock64();   // 16 kinds
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
@@ -411,6 +411,443 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_tc_kernel(const __grid_co
     }
 }
 
+
+// =====================================================================================================================
+// Version 2 (default): activation operands in TENSOR MEMORY (tcgen05.mma "TS" form: A from TMEM, B = weights from smem).
+//
+// ncu of version 1 (profiles/r2/ncu_summary.md): 4.2 MB of shared-memory traffic per 128-point tile (tensor-core operand
+// reads 1.9 MB, converter / epilogue loads and stores 1.7 MB, TMA writes 0.6 MB) at 128 B/clk = the measured 32.5 K cycles per
+// tile: shared-memory-bandwidth bound at 48 % tensor-pipe activity.  Here the hi/lo activation tiles are written with
+// tcgen05.st into tensor memory (lane = point, one column per channel) and read by the MMA from there, so shared memory only
+// carries the raw TMA landing zone (read once by the converters) and the weight k-blocks: ~2.0 MB per tile.
+//
+// TMEM (512 columns) cannot hold both replicas' accumulators plus operands, so the replicas run one after the other (the
+// weights of up2 / fc1 are streamed twice per tile) and every operand tile is written over columns that have just died:
+//     tile parity p:  R = columns [256p, 256p+256),  O = the other half,  S = O[128:256)
+//       up1      A: converters -> ring of 2 slots x (hi 32 | lo 32) in S            D1 = R[0:128) main | R[128:256) correction
+//       E1(0)    group 0 reads main + correction chunk by chunk: pre = main + corr + bias -> over main (replica 1 needs it),
+//                h = relu(pre + w_code code[0]): hi -> over the correction chunk just read, lo -> S[32 ch ..]
+//       up2(0)   A = R[128:256) | S                                                  D2 = O[0:128)   (one accumulator)
+//       E2(0)    relu(D2 + bias): hi -> over D2 in place, lo -> S
+//       fc1(0)   A = O[0:128) | S                                                    D3 = R[128:256) (main 64 | correction 64)
+//       E1(1)    group 1 reads pre: hi -> over pre in place, lo -> S chunk by chunk as fc1(0) releases it (lo_free)
+//       up2(1)   A = R[0:128) | S                                                    D2 = O[0:128)
+//       E2(1), fc1(1) as for replica 0                                               D3 = R[0:128)
+//       E3(g)    relu(D3 + bias) in registers, fc_layer2 + bias + residual, 12 bytes per point stored
+//     The tensor pipe executes MMAs in issue order, so "operand consumed before its columns are overwritten by a later MMA's
+//     accumulator" needs no barrier; epilogue writes are ordered by the accumulator-complete commits.  up1 of the next tile
+//     (D1 in O) overlaps E3 of replica 1; no operand production ever waits for a ring slot except the converters'.
+// =====================================================================================================================
+// L2 -> SM delivery (~30-38 B/clk per SM measured) bounds the kernel once the operands are out of shared memory, so fc_layer1's
+// split image (64 KB, used twice per tile) stays resident; up_layer1 / up_layer2 k-blocks stream through a 3-slot ring.
+constexpr int TS_NA = 3, TS_NW = 3;
+constexpr int TS_W3_BYTES = 4 * W3_BYTES;
+constexpr int TS_SMEM_BYTES = TS_NA * RAW_BYTES + TS_NW * W_BYTES + TS_W3_BYTES + 1024;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 activations of this thread's point -> tf32 hi part to 32 columns at hi_addr, remainder to 32 columns at lo_addr
+__device__ __forceinline__ void stage_hi_lo(uint32_t hi_addr, uint32_t lo_addr, const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float x = __uint_as_float(v[half * 16 + j]);
+            const float h = to_tf32(x);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(x - h);
+        }
+        tmem_st16(hi_addr + half * 16, hi);
+        tmem_st16(lo_addr + half * 16, lo);
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) head_ts_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_A[TS_NA], empty_A[TS_NA], full_W[TS_NW], empty_W[TS_NW], full_S[2], empty_S[2];
+    __shared__ uint64_t full_C[4][4];                       // [production phase E1(0), E2(0), E1(1), E2(1)][32-channel chunk]
+    __shared__ uint64_t lo_free[4];                         // fc1(0) has consumed chunk ch: its lo columns may take replica 1's
+    __shared__ uint64_t acc1_full, acc2_full[2], acc3_full[2], e3_done[2], w3_full;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias1_s[C1], wcode_s[C1], bias2_s[C2], bias3_s[C3], w4_s[3 * C3];
+    __shared__ float b4_s[4], code_s[2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t sA = smem0, sW = smem0 + TS_NA * RAW_BYTES, sW3 = sW + TS_NW * W_BYTES;
+
+    const int nkb1 = (a.cin + KB - 1) / KB;
+    const int last_ksteps = ((a.cin - (nkb1 - 1) * KB) + 7) / 8;
+
+    for (int i = threadIdx.x; i < C1; i += NUM_THREADS) {
+        bias1_s[i] = a.bias1 ? a.bias1[i] : 0.f;
+        wcode_s[i] = a.wfull[(size_t)i * a.w_stride + a.code_col];
+        bias2_s[i] = a.bias2 ? a.bias2[i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < C3; i += NUM_THREADS) bias3_s[i] = a.bias3 ? a.bias3[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * C3; i += NUM_THREADS) w4_s[i] = a.w4[i];
+    if (threadIdx.x < 4) b4_s[threadIdx.x] = (threadIdx.x < 3 && a.b4) ? a.b4[threadIdx.x] : 0.f;
+    if (threadIdx.x < 2) code_s[threadIdx.x] = a.code[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_NA; ++s) { mbar_init(&full_A[s], 1); mbar_init(&empty_A[s], 4); }
+        for (int s = 0; s < TS_NW; ++s) { mbar_init(&full_W[s], 1); mbar_init(&empty_W[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_S[s], 4); mbar_init(&empty_S[s], 1);
+            mbar_init(&acc2_full[s], 1); mbar_init(&acc3_full[s], 1);
+            mbar_init(&e3_done[s], 4);
+        }
+        for (int p = 0; p < 4; ++p) {
+            for (int c = 0; c < 4; ++c) mbar_init(&full_C[p][c], 4);
+            mbar_init(&lo_free[p], 1);
+        }
+        mbar_init(&acc1_full, 1);
+        mbar_init(&w3_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== activation TMA (no swizzle: the converters, not the tensor core, read this): [box q][channel][32 points] =====
+        uint32_t slot = 0, phase = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            const long long nt = t + gridDim.x;
+            if (nt < a.ntiles)
+                for (int i = lane; i < nkb1 * 4; i += 32) {
+                    const long long box = nt * 4 + (i & 3);
+                    if (box < a.nboxes) tma_prefetch_3d(&xmap, (int)(box % a.bpc) * 32, (i >> 2) * KB, (int)(box / a.bpc));
+                }
+            for (int kb = 0; kb < nkb1; ++kb) {
+                mbar_wait(&empty_A[slot], phase ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_A[slot], (uint32_t)RAW_BYTES);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long box = t * 4 + q;
+                        tma_load_3d(sA + slot * RAW_BYTES + q * 4096, &xmap, (int)(box % a.bpc) * 32, kb * KB, (int)(box / a.bpc), &full_A[slot]);
+                    }
+                }
+                __syncwarp();
+                if (++slot == TS_NA) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== weights: fc_layer1's image once (resident); per tile the k-blocks W1[0..nkb1) | W2[0..4) | W2[0..4) =====
+        uint32_t slot = 0, phase = 0;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&w3_full, (uint32_t)TS_W3_BYTES);
+            for (int j = 0; j < 4; ++j) bulk_load(sW3 + j * W3_BYTES, a.w3 + (size_t)j * W3_BYTES, W3_BYTES, &w3_full);
+        }
+        __syncwarp();
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            for (int j = 0; j < nkb1 + 8; ++j) {
+                mbar_wait(&empty_W[slot], phase ^ 1u);
+                if (elect_one()) {
+                    const unsigned char *src = j < nkb1 ? a.w1 + (size_t)j * W_BYTES : a.w2 + (size_t)((j - nkb1) & 3) * W_BYTES;
+                    mbar_arrive_expect_tx(&full_W[slot], (uint32_t)W_BYTES);
+                    bulk_load(sW + slot * W_BYTES, src, W_BYTES, &full_W[slot]);
+                }
+                __syncwarp();
+                if (++slot == TS_NW) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        uint32_t u = 0, wslot = 0, wphase = 0, it = 0;
+        const bool tl = a.dbg != nullptr && blockIdx.x == 0;            // tuning: cycles this warp waits for weights / operands / epilogues
+#define TL_WAIT(acc, bar, parity) do { if (tl) { const long long c0_ = clock64(); mbar_wait(bar, parity); acc += (unsigned int)(clock64() - c0_); } else mbar_wait(bar, parity); } while (0)
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u, prev = (it - 1u) & 1u;
+            const uint32_t R = tmem_base + par * 256u, O = tmem_base + (par ^ 1u) * 256u, S = O + 128u;
+            unsigned int wait_w = 0, wait_s = 0, wait_e = 0, wait_s1 = 0;
+            if (lane == 0) tl_mark(a.dbg, 0, (int)it);
+            // D1 columns R = last tile's O: its operands (h2 hi | lo) were consumed by MMAs issued before these
+            for (int kb = 0; kb < nkb1; ++kb, ++u) {                    // ---- up1: main = hi.hi, correction = hi.lo + lo.hi
+                const uint32_t ss = u & 1u;
+                TL_WAIT(wait_w, &full_W[wslot], wphase);
+                TL_WAIT(wait_s1, &full_S[ss], (u >> 1) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = S + ss * 64u, wb = sW + wslot * W_BYTES;
+                    const int nks = kb == nkb1 - 1 ? last_ksteps : KB / 8;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t bhl = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);     // rows [W_hi; W_lo]
+                        umma_tf32_ts(R, sa + ks * 8, bhl, idesc_n(IDESC_K, 2 * C1), (kb | ks) != 0);
+                        umma_tf32_ts(R + C1, sa + 32 + ks * 8, bhl, idesc_n(IDESC_K, C1), 1u);
+                    }
+                    tc_commit(&empty_S[ss]);
+                    tc_commit(&empty_W[wslot]);
+                    if (kb == nkb1 - 1) tc_commit(&acc1_full);
+                }
+                __syncwarp();
+                if (++wslot == TS_NW) { wslot = 0; wphase ^= 1u; }
+            }
+            if (lane == 0) tl_mark(a.dbg, 1, (int)it);
+            if (it > 0) TL_WAIT(wait_e, &e3_done[1], prev);           // D2 columns O[0:128) = D3(1) of the previous tile: has been read
+            else mbar_wait(&w3_full, 0);                              // fc_layer1's weights have landed (once)
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t Ahi1 = g == 0 ? R + 128u : R;            // up2 operand: hi over D1's correction (g = 0) / over pre (g = 1)
+                if (lane == 0) tl_mark(a.dbg, 2 + 3 * g, (int)it);
+                for (int ch = 0; ch < C1 / KB; ++ch) {                  // ---- up2(g): one accumulator in O[0:128)
+                    TL_WAIT(wait_w, &full_W[wslot], wphase);
+                    TL_WAIT(wait_s, &full_C[2 * g][ch], par);
+                    if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + ch] = (unsigned int)clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t ahi = Ahi1 + ch * 32, alo = S + ch * 32, wb = sW + wslot * W_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t blo = smem_desc(wb + C2 * 128 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            umma_tf32_ts(O, ahi + ks * 8, blo, idesc_n(IDESC_K, C2), (ch | ks) != 0);
+                            umma_tf32_ts(O, alo + ks * 8, bhi, idesc_n(IDESC_K, C2), 1u);
+                            umma_tf32_ts(O, ahi + ks * 8, bhi, idesc_n(IDESC_K, C2), 1u);
+                        }
+                        tc_commit(&empty_W[wslot]);
+                        if (ch == C1 / KB - 1) tc_commit(&acc2_full[g]);
+                    }
+                    __syncwarp();
+                    if (++wslot == TS_NW) { wslot = 0; wphase ^= 1u; }
+                }
+                if (lane == 0) tl_mark(a.dbg, 3 + 3 * g, (int)it);
+                const uint32_t D3 = g == 0 ? R + 128u : R;              // over the up2 operand of this replica (consumed: issue order)
+                for (int ch = 0; ch < C2 / KB; ++ch) {                  // ---- fc1(g): main | correction; weights resident
+                    TL_WAIT(wait_s, &full_C[2 * g + 1][ch], par);
+                    if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + 4 + ch] = (unsigned int)clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t ahi = O + ch * 32, alo = S + ch * 32, wb = sW3 + ch * W3_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t bhl = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);   // rows [W_hi (64); W_lo (64)]
+                            umma_tf32_ts(D3, ahi + ks * 8, bhl, idesc_n(IDESC_K, 2 * C3), (ch | ks) != 0);
+                            umma_tf32_ts(D3 + C3, alo + ks * 8, bhl, idesc_n(IDESC_K, C3), 1u);
+                        }
+                        if (g == 0) tc_commit(&lo_free[ch]);
+                        if (ch == C2 / KB - 1) tc_commit(&acc3_full[g]);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) tl_mark(a.dbg, 4 + 3 * g, (int)it);
+            }
+            if (tl && lane == 0 && it < 512) {
+                a.dbg[16 * 512 + it] = wait_w; a.dbg[17 * 512 + it] = wait_s1; a.dbg[18 * 512 + it] = wait_s; a.dbg[19 * 512 + it] = wait_e;
+            }
+        }
+#undef TL_WAIT
+    } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+        // ===== converters (up1): this thread's point, 32 channels: raw fp32 -> hi / lo -> staging slot in TMEM =====
+        const int q = warp & 3;
+        const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        uint32_t aslot = 0, aphase = 0, it = 0, u = 0;
+        const bool tl = a.dbg != nullptr && blockIdx.x == 0 && warp == CONV_WARP0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            const uint32_t S = tmem_base + ((it & 1u) ^ 1u) * 256u + 128u + lanebits;
+            unsigned int wait_a = 0, wait_slot = 0;
+            if (it > 0) {
+                mbar_wait(&e3_done[0], (it - 1u) & 1u);                // this tile's staging columns = D3(0) of the previous tile
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < nkb1; ++kb, ++u) {
+                const uint32_t ss = u & 1u;
+                { const long long c0 = tl ? clock64() : 0; mbar_wait(&full_A[aslot], aphase); if (tl) wait_a += (unsigned int)(clock64() - c0); }
+                const float *src = reinterpret_cast<const float *>(smem_gen + aslot * RAW_BYTES + q * 4096) + lane;
+                uint32_t v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(src[c * 32]);
+                { const long long c0 = tl ? clock64() : 0; mbar_wait(&empty_S[ss], ((u >> 1) & 1u) ^ 1u); if (tl) wait_slot += (unsigned int)(clock64() - c0); }
+                tc_fence_after();
+                stage_hi_lo(S + ss * 64u, S + ss * 64u + 32u, v);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&full_S[ss]); mbar_arrive(&empty_A[aslot]); }
+                if (++aslot == TS_NA) { aslot = 0; aphase ^= 1u; }
+            }
+            if (tl && lane == 0 && it < 512) { a.dbg[20 * 512 + it] = wait_a; a.dbg[21 * 512 + it] = wait_slot; }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue groups: group g = replica g (E1, E2, E3 of that replica); warp quarter q = box q of the tile =====
+        const int g = (warp - EPI_WARP0) >> 2, q = warp & 3;
+        const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const float code_g = code_s[g];
+        const float4 *bias1_4 = reinterpret_cast<const float4 *>(bias1_s), *wcode_4 = reinterpret_cast<const float4 *>(wcode_s);
+        const float4 *bias2_4 = reinterpret_cast<const float4 *>(bias2_s), *bias3_4 = reinterpret_cast<const float4 *>(bias3_s);
+        const float4 *w4_4 = reinterpret_cast<const float4 *>(w4_s);
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const uint32_t R = tmem_base + par * 256u + lanebits, O = tmem_base + (par ^ 1u) * 256u + lanebits, S = O + 128u;
+            const long long box = t * 4 + q;
+            const long long bi = box / a.bpc;
+            const int p = (int)(box % a.bpc) * 32 + lane;
+            const bool valid = box < a.nboxes && p < a.n;
+            const bool fine = a.dbg != nullptr && blockIdx.x == 0 && g == 0 && q == 0 && lane == 0 && it == 3;
+#define FINE_MARK(idx) do { if (fine) a.dbg[22 * 512 + (idx)] = (unsigned int)clock64(); } while (0)
+            // ---- E1(g): relu(pre + w_code * code[g]) -> operand of up2(g)
+            if (g == 0) {
+                mbar_wait(&acc1_full, par);
+                tc_fence_after();
+            }
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 8 + 3 * g, (int)it);
+#pragma unroll 1
+            for (int ch = 0; ch < C1 / KB; ++ch) {
+                uint32_t v[32];
+                FINE_MARK(ch * 5 + 0);
+                if (g == 0) {
+                    uint32_t vc[32];
+                    tmem_ld32(R + ch * 32, v);
+                    tmem_ld32(R + C1 + ch * 32, vc);
+                    tmem_ld_wait();
+                    FINE_MARK(ch * 5 + 1);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = bias1_4[ch * 8 + j4];
+                        v[4 * j4 + 0] = __float_as_uint((__uint_as_float(v[4 * j4 + 0]) + __uint_as_float(vc[4 * j4 + 0])) + b.x);
+                        v[4 * j4 + 1] = __float_as_uint((__uint_as_float(v[4 * j4 + 1]) + __uint_as_float(vc[4 * j4 + 1])) + b.y);
+                        v[4 * j4 + 2] = __float_as_uint((__uint_as_float(v[4 * j4 + 2]) + __uint_as_float(vc[4 * j4 + 2])) + b.z);
+                        v[4 * j4 + 3] = __float_as_uint((__uint_as_float(v[4 * j4 + 3]) + __uint_as_float(vc[4 * j4 + 3])) + b.w);
+                    }
+                    {   // pre replaces D1's main columns: replica 1 reads it from there
+                        uint32_t lo16[16], hi16[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { lo16[j] = v[j]; hi16[j] = v[16 + j]; }
+                        tmem_st16(R + ch * 32, lo16);
+                        tmem_st16(R + ch * 32 + 16, hi16);
+                    }
+                } else {
+                    mbar_wait(&full_C[0][ch], par);           // group 0 has written pre chunk ch
+                    tc_fence_after();
+                    tmem_ld32(R + ch * 32, v);
+                    tmem_ld_wait();
+                }
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 w = wcode_4[ch * 8 + j4];
+                    v[4 * j4 + 0] = __float_as_uint(fmaxf(__fmaf_rn(w.x, code_g, __uint_as_float(v[4 * j4 + 0])), 0.f));
+                    v[4 * j4 + 1] = __float_as_uint(fmaxf(__fmaf_rn(w.y, code_g, __uint_as_float(v[4 * j4 + 1])), 0.f));
+                    v[4 * j4 + 2] = __float_as_uint(fmaxf(__fmaf_rn(w.z, code_g, __uint_as_float(v[4 * j4 + 2])), 0.f));
+                    v[4 * j4 + 3] = __float_as_uint(fmaxf(__fmaf_rn(w.w, code_g, __uint_as_float(v[4 * j4 + 3])), 0.f));
+                }
+                if (g == 1) {
+                    mbar_wait(&lo_free[ch], par);             // fc1(0) has consumed the lo columns of chunk ch
+                    tc_fence_after();
+                }
+                // g = 0: hi over the correction chunk just read; g = 1: hi over the pre chunk just read; lo -> S
+                FINE_MARK(ch * 5 + 2);
+                stage_hi_lo((g == 0 ? R + C1 : R) + ch * 32, S + ch * 32, v);
+                FINE_MARK(ch * 5 + 3);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_C[2 * g][ch]);
+                FINE_MARK(ch * 5 + 4);
+            }
+            // ---- E2(g): relu(D2 + bias): hi over D2 in place, lo -> S (up2(g) is complete: its operands are dead)
+            mbar_wait(&acc2_full[g], par);
+            tc_fence_after();
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 9 + 3 * g, (int)it);
+#pragma unroll 1
+            for (int ch = 0; ch < C2 / KB; ++ch) {
+                uint32_t v[32];
+                FINE_MARK(20 + ch * 5 + 0);
+                tmem_ld32(O + ch * 32, v);
+                tmem_ld_wait();
+                FINE_MARK(20 + ch * 5 + 1);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = bias2_4[ch * 8 + j4];
+                    v[4 * j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 0]) + b.x, 0.f));
+                    v[4 * j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 1]) + b.y, 0.f));
+                    v[4 * j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 2]) + b.z, 0.f));
+                    v[4 * j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 3]) + b.w, 0.f));
+                }
+                FINE_MARK(20 + ch * 5 + 2);
+                stage_hi_lo(O + ch * 32, S + ch * 32, v);
+                FINE_MARK(20 + ch * 5 + 3);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_C[2 * g + 1][ch]);
+                FINE_MARK(20 + ch * 5 + 4);
+            }
+            // ---- E3(g): relu(D3 + bias) in registers -> fc_layer2 + bias + residual
+            mbar_wait(&acc3_full[g], par);
+            tc_fence_after();
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 10 + 3 * g, (int)it);
+            const uint32_t D3 = g == 0 ? R + 128u : R;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C3 / 32; ++ch) {
+                uint32_t v[32], vc[32];
+                tmem_ld32(D3 + ch * 32, v);
+                tmem_ld32(D3 + C3 + ch * 32, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = bias3_4[ch * 8 + j4];
+                    const float4 wa = w4_4[ch * 8 + j4], wb = w4_4[C3 / 4 + ch * 8 + j4], wc = w4_4[2 * (C3 / 4) + ch * 8 + j4];
+                    const float bb[4] = {b.x, b.y, b.z, b.w}, w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h = fmaxf((__uint_as_float(v[4 * j4 + e]) + __uint_as_float(vc[4 * j4 + e])) + bb[e], 0.f);
+                        o0 = __fmaf_rn(w0[e], h, o0);
+                        o1 = __fmaf_rn(w1[e], h, o1);
+                        o2 = __fmaf_rn(w2[e], h, o2);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e3_done[g]);
+            if (valid) {
+                const float o[3] = {o0 + b4_s[0], o1 + b4_s[1], o2 + b4_s[2]};
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    float r = o[c3];
+                    if (a.res) r += __ldg(a.res + bi * a.res_bstride + (size_t)c3 * a.n + p);
+                    a.y[bi * a.y_bstride + (size_t)c3 * (2 * a.n) + 2 * p + g] = r;
+                }
+            }
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 14 + g, (int)it);
+#undef FINE_MARK
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+static int g_mode = 1;    // 1 = activation operands in TMEM (head_ts_kernel), 0 = in shared memory (head_tc_kernel)
 static unsigned int *g_dbg = nullptr;
 
 }  // namespace head
@@ -420,6 +857,7 @@ static unsigned int *g_dbg = nullptr;
 using namespace pu3;
 
 extern "C" void pu3_head_tc_set_debug(void *buf) { tc::head::g_dbg = static_cast<unsigned int *>(buf); }
+extern "C" void pu3_head_tc_set_mode(int mode) { tc::head::g_mode = mode; }
 
 extern "C" int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long x_bstride, const void *ws1, const void *ws2,
                                const void *ws3, const float *w1, int w1_stride, int code_col, const float *b1, const float *code,
@@ -440,9 +878,10 @@ extern "C" int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long 
     const cuuint64_t gstride[2] = {(cuuint64_t)n * 4, (cuuint64_t)x_bstride * 4};
     const cuuint32_t box[3] = {32, H::KB, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    const bool ts = H::g_mode != 0;     // TS form: the converters read the landing zone, so it needs no swizzle
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, ts ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("head_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return PU3_E_ARG; }
     H::Args a{};
     a.b = b; a.n = n; a.cin = cin; a.bpc = (n + 31) / 32;
@@ -453,12 +892,20 @@ extern "C" int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long 
     a.bias2 = b2; a.bias3 = b3; a.w4 = w4; a.b4 = b4;
     a.res = res; a.res_bstride = res_bstride; a.y = y; a.y_bstride = y_bstride;
     a.dbg = H::g_dbg;
+    const int grid = (int)(a.ntiles < device_info().sm_count ? a.ntiles : device_info().sm_count);
+    if (ts) {
+        int st = cuda_status(cudaFuncSetAttribute(H::head_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H::TS_SMEM_BYTES),
+                             "head_tc: shared memory opt-in");
+        if (st) return st;
+        H::head_ts_kernel<<<grid, H::NUM_THREADS, H::TS_SMEM_BYTES, as_stream(stream)>>>(map, a);
+        PU3_LAUNCH_CHECK("head_ts_kernel");
+        return PU3_OK;
+    }
     {
         int st = cuda_status(cudaFuncSetAttribute(H::head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H::SMEM_BYTES),
                              "head_tc: shared memory opt-in");
         if (st) return st;
     }
-    const int grid = (int)(a.ntiles < device_info().sm_count ? a.ntiles : device_info().sm_count);
     H::head_tc_kernel<<<grid, H::NUM_THREADS, H::SMEM_BYTES, as_stream(stream)>>>(map, a);
     PU3_LAUNCH_CHECK("head_tc_kernel");
     return PU3_OK;

@@ -48,7 +48,7 @@ def _tensor_peak():
     return 1400.0, "fallback (B200_PROFILING.md)"
 
 
-TC_TAG = "pu3_conv_tc_f32[tcgen05 head"
+TC_TAG = "pu3_head_tc_f32[tcgen05 head"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from the ncu --set full
 # captures summarised in profiles/r2/ncu_summary.md; None = not captured
@@ -80,28 +80,31 @@ NCU_METRICS = {
 
 
 def _mlp_roofline(summ, steps):
-    """Secondary roofline object for the tensor-core expansion head (csrc/conv_tc.cu): per step 4 levels x
-    {up1 264->128 on N points, up2 128->128 and fc1 128->64 on 2N points}; every product runs as 3 tf32 tensor-core
-    passes (hi.hi, hi.lo, lo.hi), so executed tensor FLOPs are 3x the fp32-equivalent ones."""
+    """Secondary roofline object for the tensor-core expansion head (csrc/head_tc.cu, one fused kernel per level): per step
+    4 levels x {up1 264->128 on N points, up2 128->128 and fc1 128->64 on 2N points}; every product runs as 3 tf32 tensor-core
+    passes (hi.hi, hi.lo, lo.hi), so executed tensor FLOPs are 3x the fp32-equivalent ones.  HBM side: the 264 features and the
+    residual are read once, 3 coordinates per up-sampled point written (the 128/128/64-channel activations stay on chip)."""
     hit = [(k, v) for k, v in summ.items() if k.startswith(TC_TAG)]
     if not hit:
         return None
     _, (calls, ms) = hit[0]
     pts = sum(B_PATCHES * p * NUM_POINT for p in (1, 10, 20, 40))            # points entering the head per step
     flops = pts * 2 * 264 * 128 + 2 * pts * 2 * (128 * 128 + 128 * 64)        # fp32-equivalent, per step
-    alg_bytes = pts * 4 * (264 + 2 * 128) + 2 * pts * 4 * (128 + 128) + 2 * pts * 4 * (128 + 3 + 1.5)
+    alg_bytes = pts * 4 * (264 + 3) + 2 * pts * 4 * 3
     s_per_step = ms / 1e3 / steps
     bf16, src = _tensor_peak()
     hbm, _ = _peaks()
     tf32_peak = bf16 / 2
     executed = 3 * flops / s_per_step / 1e12
-    return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 3xTF32 expansion head, 3 launches + 3 weight splits per level)",
+    return {"bound": "tensor", "kernel": "head_ts_kernel (tcgen05 3xTF32 expansion head: up1 -> up2 -> fc1 -> fc2 in one kernel, operands in TMEM; "
+                                         "+ 3 weight-split launches per level)",
             "achieved": round(executed, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(executed / tf32_peak, 4),
             "fp32_equivalent_tflops": round(flops / s_per_step / 1e12, 1),
             "peak_source": src + " / 2 for tf32", "ms_per_step": round(s_per_step * 1e3, 3),
             "hbm_achieved_gbs": round(alg_bytes / s_per_step / 1e9, 1), "hbm_frac": round(alg_bytes / s_per_step / 1e9 / hbm, 4),
             "alg_bytes_per_step": int(alg_bytes), "flops_per_step": int(flops),
-            "note": "times include the small levels (32 and 320 tiles) that cannot fill 148 SMs; level-4 launches alone: profiles/r1g"}
+            "note": "times include the small levels (32 and 320 tiles) that cannot fill 148 SMs and the weight splits; the level-4 launch "
+                    "alone and its ncu tensor-pipe figure: profiles/r2/ncu_summary.md"}
 
 
 class ClockSampler(threading.Thread):

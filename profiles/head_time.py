@@ -28,6 +28,9 @@ w4 = (torch.randn(3, 64, generator=g) * 0.2).to(dev); b4 = torch.randn(3, genera
 code = torch.tensor([-1.0, 1.0], device=dev)
 ws = (F.tc_prepare(w1, cin=cin), F.tc_prepare(w2), F.tc_prepare(w3))
 total_f = total_3 = 0.0
+mode = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--mode=")]
+pu3._lib.lib().pu3_head_tc_set_mode(mode[0] if mode else 1)
+print("activation operands in", "tensor memory (TS)" if not mode or mode[0] else "shared memory (SS)")
 only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]
 for T in (only or (32, 160, 640, 1275)):
     x = torch.randn(T, cin, n, device=dev)
@@ -53,17 +56,33 @@ print(f"sum over the four levels: fused {total_f:.3f} ms, three kernels {total_3
 if "--timeline" in sys.argv:
     T = 1275
     x = torch.randn(T, cin, n, device=dev); res = torch.randn(T, 3, n, device=dev)
-    buf = torch.zeros(9 * 512, dtype=torch.int32, device=dev)
+    buf = torch.zeros(24 * 512, dtype=torch.int32, device=dev)
     lib = pu3._lib.lib()
     lib.pu3_head_tc_set_debug(buf.data_ptr())
     F.tc_head(x, w1, b1, code, w2, b2, w3, b3, w4, b4, residual=res, wsplits=ws)
     torch.cuda.synchronize()
     lib.pu3_head_tc_set_debug(None)
-    ev = buf.cpu().view(9, 512).numpy().astype("int64") & 0xffffffff
-    names = ["P1 start", "P1 issued", "P2 start (E3 of previous tile done)", "P2 issued", "P3 issued", "E1 start (D1 complete)",
-             "E2 start (D2 complete)", "E3 start (D3 complete)", "E3 done"]
+    ev = buf.cpu().view(24, 512).numpy().astype("int64") & 0xffffffff
+    if mode and mode[0] == 0:
+        names = {0: "P1 start", 1: "P1 issued", 2: "P2 start", 3: "P2 issued", 4: "P3 issued", 5: "E1 start", 6: "E2 start", 7: "E3 start", 8: "E3 done"}
+    else:
+        names = {0: "up1 start", 1: "up1 issued", 2: "up2(0) start", 3: "up2(0) issued", 4: "fc1(0) issued", 5: "up2(1) start",
+                 6: "up2(1) issued", 7: "fc1(1) issued", 8: "E1(0) start", 9: "E2(0) start", 10: "E3(0) start", 11: "E1(1) start",
+                 12: "E2(1) start", 13: "E3(1) start", 14: "E3(0) done", 15: "E3(1) done"}
     t0 = ev[0, 2]
-    for it in range(2, 8):
-        print(f"tile {it}: " + " | ".join(f"{names[k]} {int((ev[k, it] - t0) & 0xffffffff)}" for k in range(9)))
+    for it in range(2, 6):
+        print(f"tile {it}: " + " | ".join(f"{names[k]} {int((ev[k, it] - t0) & 0xffffffff)}" for k in sorted(names)))
     per = [(ev[0, it + 1] - ev[0, it]) & 0xffffffff for it in range(2, 18)]
-    print("cycles per tile (P1 start to P1 start):", [int(v) for v in per])
+    print("cycles per tile (up1 start to up1 start):", [int(v) for v in per])
+    if not (mode and mode[0] == 0):
+        for k, nm in ((16, "MMA warp waits for weights"), (17, "MMA warp waits for staged up1 operands"), (18, "MMA warp waits for staged up2/fc1 operands"),
+                      (19, "MMA warp waits for epilogue events"), (20, "converter waits for the raw TMA block"), (21, "converter waits for a staging slot")):
+            print(f"{nm}: cycles per tile", [int(v) for v in ev[k, 2:10]])
+        base = ev[0, 3]
+        rel = lambda v: int((v - base) & 0xffffffff)
+        print("tile 3, epilogue group 0 / quarter 0, cycles after up1 start; per chunk: start | TMEM loaded | math done | stores issued | arrived")
+        for ph, nm in ((0, "E1(0)"), (20, "E2(0)")):
+            for ch in range(4):
+                print(f"  {nm} chunk {ch}: " + " | ".join(str(rel(ev[22, ph + ch * 5 + k])) for k in range(5)))
+        print("  MMA warp saw operands ready: up2(0)", [rel(ev[23, c]) for c in range(4)], "fc1(0)", [rel(ev[23, 4 + c]) for c in range(4)],
+              "up2(1)", [rel(ev[23, 8 + c]) for c in range(4)], "fc1(1)", [rel(ev[23, 12 + c]) for c in range(4)])

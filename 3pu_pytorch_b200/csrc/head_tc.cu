@@ -847,7 +847,530 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts_kernel(const __grid_co
 }
 
 
-static int g_mode = 1;    // 1 = activation operands in TMEM (head_ts_kernel), 0 = in shared memory (head_tc_kernel)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Version 3: the same dataflow on CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 = two 128-point tiles, one per SM).
+// What bounds version 2 is the delivery of weight k-blocks (L2 -> SM at ~25-38 B/clk per SM, profiles/r2/ncu_summary.md): every SM
+// streams 676 KB per tile.  In a pair each CTA holds the weight rows of HALF of the output channels and the tensor cores of
+// both SMs read both halves, so weight bytes per SM (L2 traffic, TMA writes and tensor-core operand reads) are halved.  The
+// leader CTA (rank 0) issues every MMA and commits with a multicast arrive to both CTAs' barriers; everything a producer of
+// either CTA has to tell the MMA warp is an arrive on the LEADER's barrier (remote arrive from the peer).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TS2_NA = 5;                      // raw activation ring: 5 x 16 KB (what is in flight bounds the L2 -> SM rate)
+constexpr int TS2_NW = 6;                      // weight ring: 6 slots x [hi 64 rows | lo 64 rows] = 16 KB
+constexpr int W2H_BYTES = W_BYTES / 2;         // this CTA's half of a 128-channel k-block
+constexpr int W3H_BYTES = W3_BYTES / 2;        // ... of a fc_layer1 k-block: [hi 32 rows | lo 32 rows] = 8 KB
+constexpr int TS2_SMEM_BYTES = TS2_NA * RAW_BYTES + TS2_NW * W2H_BYTES + 4 * W3H_BYTES + 1024;
+constexpr uint32_t IDESC2_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 4) << 24);   // M = 256 over the pair
+
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+// completion of all MMAs issued so far -> arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrive on `bar` of CTA `cta` of the cluster (local fast path)
+__device__ __forceinline__ void arrive_at(uint64_t *bar, uint32_t cta, bool local) {
+    if (local) { mbar_arrive(bar); return; }
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// wait on a barrier that also receives arrivals from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && (spins & 255u) == 255u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+
+// One 32-channel chunk of E1 for replica 0, straight from the up1 accumulators: pre = main + correction + bias -> over the main
+// columns (replica 1 reads it there), relu(pre + w_code code[0]): hi -> over the correction columns just read, lo -> S.
+// Ends with the stores complete and fenced; the caller arrives on the barriers.
+__device__ __forceinline__ void e1_chunk_from_d1(uint32_t R, uint32_t S, int ch, float code0, const float4 *bias1_4, const float4 *wcode_4) {
+    uint32_t v[32];
+    {
+        uint32_t vc[32];
+        tmem_ld32(R + ch * 32, v);
+        tmem_ld32(R + C1 + ch * 32, vc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bias1_4[ch * 8 + j4];
+            v[4 * j4 + 0] = __float_as_uint((__uint_as_float(v[4 * j4 + 0]) + __uint_as_float(vc[4 * j4 + 0])) + b.x);
+            v[4 * j4 + 1] = __float_as_uint((__uint_as_float(v[4 * j4 + 1]) + __uint_as_float(vc[4 * j4 + 1])) + b.y);
+            v[4 * j4 + 2] = __float_as_uint((__uint_as_float(v[4 * j4 + 2]) + __uint_as_float(vc[4 * j4 + 2])) + b.z);
+            v[4 * j4 + 3] = __float_as_uint((__uint_as_float(v[4 * j4 + 3]) + __uint_as_float(vc[4 * j4 + 3])) + b.w);
+        }
+    }
+    {
+        uint32_t lo16[16], hi16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { lo16[j] = v[j]; hi16[j] = v[16 + j]; }
+        tmem_st16(R + ch * 32, lo16);
+        tmem_st16(R + ch * 32 + 16, hi16);
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 w = wcode_4[ch * 8 + j4];
+        v[4 * j4 + 0] = __float_as_uint(fmaxf(__fmaf_rn(w.x, code0, __uint_as_float(v[4 * j4 + 0])), 0.f));
+        v[4 * j4 + 1] = __float_as_uint(fmaxf(__fmaf_rn(w.y, code0, __uint_as_float(v[4 * j4 + 1])), 0.f));
+        v[4 * j4 + 2] = __float_as_uint(fmaxf(__fmaf_rn(w.z, code0, __uint_as_float(v[4 * j4 + 2])), 0.f));
+        v[4 * j4 + 3] = __float_as_uint(fmaxf(__fmaf_rn(w.w, code0, __uint_as_float(v[4 * j4 + 3])), 0.f));
+    }
+    stage_hi_lo(R + C1 + ch * 32, S + ch * 32, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+}
+// E1 values of replica 1 for one chunk: relu(pre + w_code code[1]) into registers (staged later, when the columns are free)
+__device__ __forceinline__ void e1_values_from_pre(uint32_t R, int ch, float code1, const float4 *wcode_4, uint32_t (&v)[32]) {
+    tmem_ld32(R + ch * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 w = wcode_4[ch * 8 + j4];
+        v[4 * j4 + 0] = __float_as_uint(fmaxf(__fmaf_rn(w.x, code1, __uint_as_float(v[4 * j4 + 0])), 0.f));
+        v[4 * j4 + 1] = __float_as_uint(fmaxf(__fmaf_rn(w.y, code1, __uint_as_float(v[4 * j4 + 1])), 0.f));
+        v[4 * j4 + 2] = __float_as_uint(fmaxf(__fmaf_rn(w.z, code1, __uint_as_float(v[4 * j4 + 2])), 0.f));
+        v[4 * j4 + 3] = __float_as_uint(fmaxf(__fmaf_rn(w.w, code1, __uint_as_float(v[4 * j4 + 3])), 0.f));
+    }
+}
+// One chunk of E2: relu(D2 + bias): hi over the D2 chunk in place, lo -> S
+__device__ __forceinline__ void e2_chunk(uint32_t O, uint32_t S, int ch, const float4 *bias2_4) {
+    uint32_t v[32];
+    tmem_ld32(O + ch * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = bias2_4[ch * 8 + j4];
+        v[4 * j4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 0]) + b.x, 0.f));
+        v[4 * j4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 1]) + b.y, 0.f));
+        v[4 * j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 2]) + b.z, 0.f));
+        v[4 * j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 3]) + b.w, 0.f));
+    }
+    stage_hi_lo(O + ch * 32, S + ch * 32, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_A[TS2_NA], empty_A[TS2_NA], full_W[TS2_NW], empty_W[TS2_NW], full_S[2], empty_S[2];
+    __shared__ uint64_t full_C[4][4];                       // [production phase E1(0), E2(0), E1(1), E2(1)][32-channel chunk]
+    __shared__ uint64_t lo_free[4];                         // fc1(0) has consumed chunk ch: its lo columns may take replica 1's
+    __shared__ uint64_t acc1_full, acc2_full[2], acc3_full[2], e3_done[2], w3_full;
+    __shared__ uint64_t full_Wl[TS2_NW], w3l_full, pre_ok[4];   // local: this CTA's weight copies have landed; pre chunk written
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias1_s[C1], wcode_s[C1], bias2_s[C2], bias3_s[C3], w4_s[3 * C3];
+    __shared__ float b4_s[4], code_s[2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t sA = smem0, sW = smem0 + TS2_NA * RAW_BYTES, sW3 = sW + TS2_NW * W2H_BYTES;
+    const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues every MMA of the pair), 1 = peer
+    const bool leader = rank == 0;
+
+    const int nkb1 = (a.cin + KB - 1) / KB;
+    const int last_ksteps = ((a.cin - (nkb1 - 1) * KB) + 7) / 8;
+    // both CTAs of a pair run the same number of tiles (the leader issues the MMAs of both): tiles >= ntiles are all padding
+    const long long tiles_end = (a.ntiles + gridDim.x - 1) / gridDim.x * gridDim.x;
+
+    for (int i = threadIdx.x; i < C1; i += NUM_THREADS) {
+        bias1_s[i] = a.bias1 ? a.bias1[i] : 0.f;
+        wcode_s[i] = a.wfull[(size_t)i * a.w_stride + a.code_col];
+        bias2_s[i] = a.bias2 ? a.bias2[i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < C3; i += NUM_THREADS) bias3_s[i] = a.bias3 ? a.bias3[i] : 0.f;
+    for (int i = threadIdx.x; i < 3 * C3; i += NUM_THREADS) w4_s[i] = a.w4[i];
+    if (threadIdx.x < 4) b4_s[threadIdx.x] = (threadIdx.x < 3 && a.b4) ? a.b4[threadIdx.x] : 0.f;
+    if (threadIdx.x < 2) code_s[threadIdx.x] = a.code[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS2_NA; ++s) { mbar_init(&full_A[s], 1); mbar_init(&empty_A[s], 4); }
+        for (int s = 0; s < TS2_NW; ++s) { mbar_init(&full_W[s], 2); mbar_init(&empty_W[s], 1); mbar_init(&full_Wl[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_S[s], 8); mbar_init(&empty_S[s], 1);
+            mbar_init(&acc2_full[s], 1); mbar_init(&acc3_full[s], 1);
+            mbar_init(&e3_done[s], s == 0 ? 4 : 8);          // [0]: this CTA's converters wait for it; [1]: the leader's MMA warp (both CTAs arrive)
+        }
+        for (int p = 0; p < 4; ++p) {
+            for (int c = 0; c < 4; ++c) mbar_init(&full_C[p][c], 8);
+            mbar_init(&lo_free[p], 1);
+            mbar_init(&pre_ok[p], 4);
+        }
+        mbar_init(&acc1_full, 1);
+        mbar_init(&w3_full, 2);
+        mbar_init(&w3l_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive_release();                                // both CTAs' barriers are initialised before anything arrives remotely
+    cluster_wait_acquire();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== activation TMA (no swizzle: the converters, not the tensor core, read this): [box q][channel][32 points] =====
+        uint32_t slot = 0, phase = 0;
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x) {
+            const long long nt = t + gridDim.x;
+            if (nt < a.ntiles)
+                for (int i = lane; i < nkb1 * 4; i += 32) {
+                    const long long box = nt * 4 + (i & 3);
+                    if (box < a.nboxes) tma_prefetch_3d(&xmap, (int)(box % a.bpc) * 32, (i >> 2) * KB, (int)(box / a.bpc));
+                }
+            for (int kb = 0; kb < nkb1; ++kb) {
+                mbar_wait(&empty_A[slot], phase ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_A[slot], (uint32_t)RAW_BYTES);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long box = t * 4 + q;
+                        tma_load_3d(sA + slot * RAW_BYTES + q * 4096, &xmap, (int)(box % a.bpc) * 32, kb * KB, (int)(box / a.bpc), &full_A[slot]);
+                    }
+                }
+                __syncwarp();
+                if (++slot == TS2_NA) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== weights, this CTA's half of the output channels (rows 64 rank .. of the hi and of the lo image): fc_layer1 once
+        // (resident, [k-block][hi 32 rows | lo 32 rows]); per tile the k-blocks W1[0..nkb1) | W2[0..4) | W2[0..4) as [hi 64 | lo 64] =====
+        uint32_t slot = 0, phase = 0;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&w3l_full, (uint32_t)(4 * W3H_BYTES));
+            for (int j = 0; j < 4; ++j) {
+                bulk_load(sW3 + j * W3H_BYTES, a.w3 + (size_t)j * W3_BYTES + rank * (W3H_BYTES / 2), W3H_BYTES / 2, &w3l_full);
+                bulk_load(sW3 + j * W3H_BYTES + W3H_BYTES / 2, a.w3 + (size_t)j * W3_BYTES + W3_BYTES / 2 + rank * (W3H_BYTES / 2), W3H_BYTES / 2, &w3l_full);
+            }
+        }
+        __syncwarp();
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x) {
+            for (int j = 0; j < nkb1 + 8; ++j) {
+                mbar_wait(&empty_W[slot], phase ^ 1u);
+                if (elect_one()) {
+                    const unsigned char *src = j < nkb1 ? a.w1 + (size_t)j * W_BYTES : a.w2 + (size_t)((j - nkb1) & 3) * W_BYTES;
+                    mbar_arrive_expect_tx(&full_Wl[slot], (uint32_t)W2H_BYTES);
+                    bulk_load(sW + slot * W2H_BYTES, src + rank * (W2H_BYTES / 2), W2H_BYTES / 2, &full_Wl[slot]);
+                    bulk_load(sW + slot * W2H_BYTES + W2H_BYTES / 2, src + W_BYTES / 2 + rank * (W2H_BYTES / 2), W2H_BYTES / 2, &full_Wl[slot]);
+                }
+                __syncwarp();
+                if (++slot == TS2_NW) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== forwarder: "this CTA's copy of weight block j has landed" -> the leader's full_W (the MMA needs both halves) =====
+        uint32_t slot = 0, phase = 0;
+        mbar_wait(&w3l_full, 0);
+        if (lane == 0) arrive_at(&w3_full, 0u, leader);
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x) {
+            for (int j = 0; j < nkb1 + 8; ++j) {
+                mbar_wait(&full_Wl[slot], phase);
+                if (lane == 0) arrive_at(&full_W[slot], 0u, leader);
+                __syncwarp();
+                if (++slot == TS2_NW) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer =====
+        uint32_t u = 0, wslot = 0, wphase = 0, it = 0;
+        const bool tl = a.dbg != nullptr && blockIdx.x == 0;            // tuning: cycles this warp waits for weights / operands / epilogues
+#define TL_WAIT(acc, bar, parity) do { if (tl) { const long long c0_ = clock64(); mbar_wait_cluster(bar, parity); acc += (unsigned int)(clock64() - c0_); } else mbar_wait_cluster(bar, parity); } while (0)
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u, prev = (it - 1u) & 1u;
+            const uint32_t R = tmem_base + par * 256u, O = tmem_base + (par ^ 1u) * 256u, S = O + 128u;
+            unsigned int wait_w = 0, wait_s = 0, wait_e = 0, wait_s1 = 0;
+            if (lane == 0) tl_mark(a.dbg, 0, (int)it);
+            // D1 columns R = last tile's O: its operands (h2 hi | lo) were consumed by MMAs issued before these
+            for (int kb = 0; kb < nkb1; ++kb, ++u) {                    // ---- up1: main = hi.hi, correction = hi.lo + lo.hi
+                const uint32_t ss = u & 1u;
+                TL_WAIT(wait_w, &full_W[wslot], wphase);
+                TL_WAIT(wait_s1, &full_S[ss], (u >> 1) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = S + ss * 64u, wb = sW + wslot * W2H_BYTES;
+                    const int nks = kb == nkb1 - 1 ? last_ksteps : KB / 8;
+                    for (int ks = 0; ks < nks; ++ks) {    // each CTA supplies its 64 rows of W_hi / W_lo: N = 128 per instruction
+                        const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t blo = smem_desc(wb + W2H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
+                        umma2_tf32_ts(R, sa + ks * 8, bhi, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
+                        umma2_tf32_ts(R + C1, sa + ks * 8, blo, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
+                        umma2_tf32_ts(R + C1, sa + 32 + ks * 8, bhi, idesc_n(IDESC2_K, C1), 1u);
+                    }
+                    tc_commit2(&empty_S[ss]);
+                    tc_commit2(&empty_W[wslot]);
+                    if (kb == nkb1 - 1) tc_commit2(&acc1_full);
+                }
+                __syncwarp();
+                if (++wslot == TS2_NW) { wslot = 0; wphase ^= 1u; }
+            }
+            if (lane == 0) tl_mark(a.dbg, 1, (int)it);
+            if (it > 0) TL_WAIT(wait_e, &e3_done[1], prev);           // D2 columns O[0:128) = D3(1) of the previous tile: has been read
+            else mbar_wait_cluster(&w3_full, 0);                      // fc_layer1's weights have landed in both CTAs (once)
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t Ahi1 = g == 0 ? R + 128u : R;            // up2 operand: hi over D1's correction (g = 0) / over pre (g = 1)
+                if (lane == 0) tl_mark(a.dbg, 2 + 3 * g, (int)it);
+                for (int ch = 0; ch < C1 / KB; ++ch) {                  // ---- up2(g): one accumulator in O[0:128)
+                    TL_WAIT(wait_w, &full_W[wslot], wphase);
+                    TL_WAIT(wait_s, &full_C[2 * g][ch], par);
+                    if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + ch] = (unsigned int)clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t ahi = Ahi1 + ch * 32, alo = S + ch * 32, wb = sW + wslot * W2H_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t blo = smem_desc(wb + W2H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            umma2_tf32_ts(O, ahi + ks * 8, blo, idesc_n(IDESC2_K, C2), (ch | ks) != 0);
+                            umma2_tf32_ts(O, alo + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
+                            umma2_tf32_ts(O, ahi + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
+                        }
+                        tc_commit2(&empty_W[wslot]);
+                        if (ch == C1 / KB - 1) tc_commit2(&acc2_full[g]);
+                    }
+                    __syncwarp();
+                    if (++wslot == TS2_NW) { wslot = 0; wphase ^= 1u; }
+                }
+                if (lane == 0) tl_mark(a.dbg, 3 + 3 * g, (int)it);
+                const uint32_t D3 = g == 0 ? R + 128u : R;              // over the up2 operand of this replica (consumed: issue order)
+                for (int ch = 0; ch < C2 / KB; ++ch) {                  // ---- fc1(g): main | correction; weights resident
+                    TL_WAIT(wait_s, &full_C[2 * g + 1][ch], par);
+                    if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + 4 + ch] = (unsigned int)clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t ahi = O + ch * 32, alo = S + ch * 32, wb = sW3 + ch * W3H_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 8; ++ks) {
+                            const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);            // this CTA's 32 rows of W_hi
+                            const uint64_t blo = smem_desc(wb + W3H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            umma2_tf32_ts(D3, ahi + ks * 8, bhi, idesc_n(IDESC2_K, C3), (ch | ks) != 0);
+                            umma2_tf32_ts(D3 + C3, ahi + ks * 8, blo, idesc_n(IDESC2_K, C3), (ch | ks) != 0);
+                            umma2_tf32_ts(D3 + C3, alo + ks * 8, bhi, idesc_n(IDESC2_K, C3), 1u);
+                        }
+                        if (g == 0) tc_commit2(&lo_free[ch]);
+                        if (ch == C2 / KB - 1) tc_commit2(&acc3_full[g]);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) tl_mark(a.dbg, 4 + 3 * g, (int)it);
+            }
+            if (tl && lane == 0 && it < 512) {
+                a.dbg[16 * 512 + it] = wait_w; a.dbg[17 * 512 + it] = wait_s1; a.dbg[18 * 512 + it] = wait_s; a.dbg[19 * 512 + it] = wait_e;
+            }
+        }
+#undef TL_WAIT
+    } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+        // ===== converters (up1): this thread's point, 32 channels: raw fp32 -> hi / lo -> staging slot in TMEM; afterwards
+        // they help epilogue group 0 (chunks 1 and 3 of E1(0) and E2(0)): one warp alone needs ~1000 cycles per chunk, the MMAs of
+        // a chunk 768 (up2) / 384 (fc1) =====
+        const int q = warp & 3;
+        const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const float4 *bias1_4 = reinterpret_cast<const float4 *>(bias1_s), *wcode_4 = reinterpret_cast<const float4 *>(wcode_s);
+        const float4 *bias2_4 = reinterpret_cast<const float4 *>(bias2_s);
+        const float code0 = code_s[0];
+        uint32_t aslot = 0, aphase = 0, it = 0, u = 0;
+        const bool tl = a.dbg != nullptr && blockIdx.x == 0 && warp == CONV_WARP0;
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const uint32_t R = tmem_base + par * 256u + lanebits, O = tmem_base + (par ^ 1u) * 256u + lanebits, S = O + 128u;
+            unsigned int wait_a = 0, wait_slot = 0;
+            if (it > 0) {
+                mbar_wait(&e3_done[0], (it - 1u) & 1u);                // this tile's staging columns = D3(0) of the previous tile
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < nkb1; ++kb, ++u) {
+                const uint32_t ss = u & 1u;
+                { const long long c0 = tl ? clock64() : 0; mbar_wait(&full_A[aslot], aphase); if (tl) wait_a += (unsigned int)(clock64() - c0); }
+                const float *src = reinterpret_cast<const float *>(smem_gen + aslot * RAW_BYTES + q * 4096) + lane;
+                uint32_t v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(src[c * 32]);
+                { const long long c0 = tl ? clock64() : 0; mbar_wait(&empty_S[ss], ((u >> 1) & 1u) ^ 1u); if (tl) wait_slot += (unsigned int)(clock64() - c0); }
+                tc_fence_after();
+                stage_hi_lo(S + ss * 64u, S + ss * 64u + 32u, v);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { arrive_at(&full_S[ss], 0u, leader); mbar_arrive(&empty_A[aslot]); }
+                if (++aslot == TS2_NA) { aslot = 0; aphase ^= 1u; }
+            }
+            if (tl && lane == 0 && it < 512) { a.dbg[20 * 512 + it] = wait_a; a.dbg[21 * 512 + it] = wait_slot; }
+            mbar_wait(&acc1_full, par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 1; ch < C1 / KB; ch += 2) {
+                e1_chunk_from_d1(R, S, ch, code0, bias1_4, wcode_4);
+                if (lane == 0) { mbar_arrive(&pre_ok[ch]); arrive_at(&full_C[0][ch], 0u, leader); }
+            }
+            mbar_wait(&acc2_full[0], par);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 1; ch < C2 / KB; ch += 2) {
+                e2_chunk(O, S, ch, bias2_4);
+                if (lane == 0) arrive_at(&full_C[1][ch], 0u, leader);
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue groups: group g = replica g (E1, E2, E3 of that replica); warp quarter q = box q of the tile.
+        // Chunks 1 and 3 of E1(0) / E2(0) are done by the converter warps, of E2(1) by group 0 (idle after E3(0)). =====
+        const int g = (warp - EPI_WARP0) >> 2, q = warp & 3;
+        const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const float code_g = code_s[g];
+        const float4 *bias1_4 = reinterpret_cast<const float4 *>(bias1_s), *wcode_4 = reinterpret_cast<const float4 *>(wcode_s);
+        const float4 *bias2_4 = reinterpret_cast<const float4 *>(bias2_s), *bias3_4 = reinterpret_cast<const float4 *>(bias3_s);
+        const float4 *w4_4 = reinterpret_cast<const float4 *>(w4_s);
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const uint32_t R = tmem_base + par * 256u + lanebits, O = tmem_base + (par ^ 1u) * 256u + lanebits, S = O + 128u;
+            const long long box = t * 4 + q;
+            const long long bi = box / a.bpc;
+            const int p = (int)(box % a.bpc) * 32 + lane;
+            const bool valid = box < a.nboxes && p < a.n;
+            if (g == 0) {
+                // ---- E1(0), chunks 0 and 2: pre over D1's main columns, hi over the correction columns, lo -> S
+                mbar_wait(&acc1_full, par);
+                tc_fence_after();
+                if (q == 0 && lane == 0) tl_mark(a.dbg, 8, (int)it);
+#pragma unroll 1
+                for (int ch = 0; ch < C1 / KB; ch += 2) {
+                    e1_chunk_from_d1(R, S, ch, code_g, bias1_4, wcode_4);
+                    if (lane == 0) { mbar_arrive(&pre_ok[ch]); arrive_at(&full_C[0][ch], 0u, leader); }
+                }
+            } else {
+                // ---- E1(1): values from pre one chunk ahead; hi over pre in place, lo -> S as fc1(0) releases the columns
+                if (q == 0 && lane == 0) tl_mark(a.dbg, 11, (int)it);
+                uint32_t v[32];
+                mbar_wait(&pre_ok[0], par);
+                tc_fence_after();
+                e1_values_from_pre(R, 0, code_g, wcode_4, v);
+#pragma unroll
+                for (int ch = 0; ch < C1 / KB; ++ch) {
+                    uint32_t vn[32];
+                    if (ch + 1 < C1 / KB) {
+                        mbar_wait(&pre_ok[ch + 1], par);
+                        tc_fence_after();
+                        e1_values_from_pre(R, ch + 1, code_g, wcode_4, vn);
+                    }
+                    mbar_wait(&lo_free[ch], par);             // fc1(0) has consumed the lo columns of chunk ch
+                    tc_fence_after();
+                    stage_hi_lo(R + ch * 32, S + ch * 32, v);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_at(&full_C[2][ch], 0u, leader);
+                    if (ch + 1 < C1 / KB) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = vn[j];
+                    }
+                }
+            }
+            // ---- E2(g), chunks 0 and 2: relu(D2 + bias): hi over D2 in place, lo -> S (up2(g) is complete: its operands are dead)
+            mbar_wait(&acc2_full[g], par);
+            tc_fence_after();
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 9 + 3 * g, (int)it);
+#pragma unroll 1
+            for (int ch = 0; ch < C2 / KB; ch += 2) {
+                e2_chunk(O, S, ch, bias2_4);
+                if (lane == 0) arrive_at(&full_C[2 * g + 1][ch], 0u, leader);
+            }
+            // ---- E3(g): relu(D3 + bias) in registers -> fc_layer2 + bias + residual
+            mbar_wait(&acc3_full[g], par);
+            tc_fence_after();
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 10 + 3 * g, (int)it);
+            const uint32_t D3 = g == 0 ? R + 128u : R;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C3 / 32; ++ch) {
+                uint32_t v[32], vc[32];
+                tmem_ld32(D3 + ch * 32, v);
+                tmem_ld32(D3 + C3 + ch * 32, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = bias3_4[ch * 8 + j4];
+                    const float4 wa = w4_4[ch * 8 + j4], wb = w4_4[C3 / 4 + ch * 8 + j4], wc = w4_4[2 * (C3 / 4) + ch * 8 + j4];
+                    const float bb[4] = {b.x, b.y, b.z, b.w}, w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h = fmaxf((__uint_as_float(v[4 * j4 + e]) + __uint_as_float(vc[4 * j4 + e])) + bb[e], 0.f);
+                        o0 = __fmaf_rn(w0[e], h, o0);
+                        o1 = __fmaf_rn(w1[e], h, o1);
+                        o2 = __fmaf_rn(w2[e], h, o2);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (g == 0) mbar_arrive(&e3_done[0]); else arrive_at(&e3_done[1], 0u, leader); }
+            if (valid) {
+                const float o[3] = {o0 + b4_s[0], o1 + b4_s[1], o2 + b4_s[2]};
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    float r = o[c3];
+                    if (a.res) r += __ldg(a.res + bi * a.res_bstride + (size_t)c3 * a.n + p);
+                    a.y[bi * a.y_bstride + (size_t)c3 * (2 * a.n) + 2 * p + g] = r;
+                }
+            }
+            if (q == 0 && lane == 0) tl_mark(a.dbg, 14 + g, (int)it);
+            if (g == 0) {
+                // ---- group 0 is idle now: chunks 1 and 3 of E2(1)
+                mbar_wait(&acc2_full[1], par);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 1; ch < C2 / KB; ch += 2) {
+                    e2_chunk(O, S, ch, bias2_4);
+                    if (lane == 0) arrive_at(&full_C[3][ch], 0u, leader);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive_release();                                // no CTA leaves while its partner may still signal it or read its shared memory
+    cluster_wait_acquire();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+static int g_mode = 2;    // 2 = CTA pairs (head_ts2_kernel), 1 = activation operands in TMEM (head_ts_kernel), 0 = in shared memory (head_tc_kernel)
 static unsigned int *g_dbg = nullptr;
 
 }  // namespace head
@@ -893,6 +1416,24 @@ extern "C" int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long 
     a.res = res; a.res_bstride = res_bstride; a.y = y; a.y_bstride = y_bstride;
     a.dbg = H::g_dbg;
     const int grid = (int)(a.ntiles < device_info().sm_count ? a.ntiles : device_info().sm_count);
+    if (H::g_mode == 2) {
+        int st = cuda_status(cudaFuncSetAttribute(H::head_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H::TS2_SMEM_BYTES),
+                             "head_tc: shared memory opt-in");
+        if (st) return st;
+        const int sms = device_info().sm_count & ~1;
+        const long long want = (a.ntiles + 1) & ~1LL;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(want < sms ? want : sms));
+        cfg.blockDim = dim3((unsigned)H::NUM_THREADS);
+        cfg.dynamicSmemBytes = H::TS2_SMEM_BYTES;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cuda_status(cudaLaunchKernelEx(&cfg, H::head_ts2_kernel, map, a), "head_ts2_kernel launch");
+    }
     if (ts) {
         int st = cuda_status(cudaFuncSetAttribute(H::head_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H::TS_SMEM_BYTES),
                              "head_tc: shared memory opt-in");

@@ -227,7 +227,7 @@ int pu3_head_tc_f32(int b, int n, int cin, const float *x, long long x_bstride, 
                     const float *b2, const float *b3, const float *w4, const float *b4, const float *res,
                     long long res_bstride, float *y, long long y_bstride, pu3_stream_t stream);
 void pu3_head_tc_set_debug(void *buf); /* test hook: device buffer (24 x 512 u32) receiving CTA 0's event timeline; NULL = off */
-void pu3_head_tc_set_mode(int mode);   /* A/B hook: 1 (default) = activation operands in tensor memory (tcgen05.mma TS form), 0 = in shared memory */
+void pu3_head_tc_set_mode(int mode);   /* A/B hook: 2 (default) = CTA pairs (tcgen05.mma.cta_group::2), operands in tensor memory; 1 = single CTAs, operands in tensor memory (TS form); 0 = operands in shared memory */
 
 /*
  * Fused DenseEdgeConv forward for the reference configuration (24 input channels, growth 12, 3 layers):

@@ -29,8 +29,8 @@ code = torch.tensor([-1.0, 1.0], device=dev)
 ws = (F.tc_prepare(w1, cin=cin), F.tc_prepare(w2), F.tc_prepare(w3))
 total_f = total_3 = 0.0
 mode = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--mode=")]
-pu3._lib.lib().pu3_head_tc_set_mode(mode[0] if mode else 1)
-print("activation operands in", "tensor memory (TS)" if not mode or mode[0] else "shared memory (SS)")
+pu3._lib.lib().pu3_head_tc_set_mode(mode[0] if mode else 2)
+print("mode:", {0: "operands in shared memory (SS)", 1: "operands in tensor memory (TS)", 2: "CTA pairs, operands in tensor memory (cta_group::2, TS)"}[mode[0] if mode else 2])
 only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]
 for T in (only or (32, 160, 640, 1275)):
     x = torch.randn(T, cin, n, device=dev)

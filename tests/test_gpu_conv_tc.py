@@ -108,14 +108,15 @@ def _head_reference(x, w1, b1, code, w2, b2, w3, b3, w4, b4, res):
 # operand ring changes hands between the converters and the epilogue groups)
 @pytest.mark.parametrize("b,n,cin,res", [(1, 128, 264, True), (3, 312, 264, True), (5, 100, 264, False), (7, 36, 72, True),
                                          (2, 4, 264, True), (40, 312, 264, True), (700, 312, 264, True)])
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [2, 1, 0])
 def test_head_tc_fused_chain(pu3, cuda, b, n, cin, res, mode):
-    """mode 1: activation operands staged in tensor memory (tcgen05.mma TS form, the default); mode 0: in shared memory."""
+    """mode 2 (default): CTA pairs (tcgen05.mma.cta_group::2), operands in tensor memory; mode 1: single CTAs, operands in tensor
+    memory (TS form); mode 0: operands in shared memory."""
     pu3._lib.lib().pu3_head_tc_set_mode(mode)
     try:
         _head_case(pu3, cuda, b, n, cin, res)
     finally:
-        pu3._lib.lib().pu3_head_tc_set_mode(1)
+        pu3._lib.lib().pu3_head_tc_set_mode(2)
 
 
 def _head_case(pu3, cuda, b, n, cin, res):

@@ -857,10 +857,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts_kernel(const __grid_co
 // either CTA has to tell the MMA warp is an arrive on the LEADER's barrier (remote arrive from the peer).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TS2_NA = 5;                      // raw activation ring: 5 x 16 KB (what is in flight bounds the L2 -> SM rate)
-constexpr int TS2_NW = 6;                      // weight ring: 6 slots x [hi 64 rows | lo 64 rows] = 16 KB
+constexpr int TS2_NW = 5;                      // weight ring: 5 slots x [hi 64 rows | lo 64 rows] = 16 KB
 constexpr int W2H_BYTES = W_BYTES / 2;         // this CTA's half of a 128-channel k-block
 constexpr int W3H_BYTES = W3_BYTES / 2;        // ... of a fc_layer1 k-block: [hi 32 rows | lo 32 rows] = 8 KB
-constexpr int TS2_SMEM_BYTES = TS2_NA * RAW_BYTES + TS2_NW * W2H_BYTES + 4 * W3H_BYTES + 1024;
+constexpr int W3R_BYTES = W3_BYTES / 2 + W3_BYTES / 4;   // resident fc_layer1 k-block of one CTA: 64 + 32 rows = 12 KB
+constexpr int TS2_SMEM_BYTES = TS2_NA * RAW_BYTES + TS2_NW * W2H_BYTES + 4 * W3R_BYTES + 1024;
 constexpr uint32_t IDESC2_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 4) << 24);   // M = 256 over the pair
 
 __device__ __forceinline__ void umma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -912,12 +913,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 // One 32-channel chunk of E1 for replica 0, straight from the up1 accumulators: pre = main + correction + bias -> over the main
 // columns (replica 1 reads it there), relu(pre + w_code code[0]): hi -> over the correction columns just read, lo -> S.
 // Ends with the stores complete and fenced; the caller arrives on the barriers.
-__device__ __forceinline__ void e1_chunk_from_d1(uint32_t R, uint32_t S, int ch, float code0, const float4 *bias1_4, const float4 *wcode_4) {
+__device__ __forceinline__ void e1_chunk_from_d1(uint32_t R0, uint32_t R1, uint32_t S, int ch, float code0, const float4 *bias1_4, const float4 *wcode_4) {
     uint32_t v[32];
     {
         uint32_t vc[32];
-        tmem_ld32(R + ch * 32, v);
-        tmem_ld32(R + C1 + ch * 32, vc);
+        tmem_ld32(R0 + ch * 32, v);
+        tmem_ld32(R1 + ch * 32, vc);
         tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -932,8 +933,8 @@ __device__ __forceinline__ void e1_chunk_from_d1(uint32_t R, uint32_t S, int ch,
         uint32_t lo16[16], hi16[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { lo16[j] = v[j]; hi16[j] = v[16 + j]; }
-        tmem_st16(R + ch * 32, lo16);
-        tmem_st16(R + ch * 32 + 16, hi16);
+        tmem_st16(R0 + ch * 32, lo16);
+        tmem_st16(R0 + ch * 32 + 16, hi16);
     }
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -943,7 +944,7 @@ __device__ __forceinline__ void e1_chunk_from_d1(uint32_t R, uint32_t S, int ch,
         v[4 * j4 + 2] = __float_as_uint(fmaxf(__fmaf_rn(w.z, code0, __uint_as_float(v[4 * j4 + 2])), 0.f));
         v[4 * j4 + 3] = __float_as_uint(fmaxf(__fmaf_rn(w.w, code0, __uint_as_float(v[4 * j4 + 3])), 0.f));
     }
-    stage_hi_lo(R + C1 + ch * 32, S + ch * 32, v);
+    stage_hi_lo(R1 + ch * 32, S + ch * 32, v);
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
@@ -961,10 +962,11 @@ __device__ __forceinline__ void e1_values_from_pre(uint32_t R, int ch, float cod
         v[4 * j4 + 3] = __float_as_uint(fmaxf(__fmaf_rn(w.w, code1, __uint_as_float(v[4 * j4 + 3])), 0.f));
     }
 }
-// One chunk of E2: relu(D2 + bias): hi over the D2 chunk in place, lo -> S
-__device__ __forceinline__ void e2_chunk(uint32_t O, uint32_t S, int ch, const float4 *bias2_4) {
+// One chunk of E2: relu(D2 + bias): hi over the D2 chunk in place, lo -> S once `free_bar` says the MMAs that read the previous
+// content of those columns have completed
+__device__ __forceinline__ void e2_chunk(uint32_t D2, uint32_t S, int ch, const float4 *bias2_4, uint64_t *free_bar, uint32_t parity) {
     uint32_t v[32];
-    tmem_ld32(O + ch * 32, v);
+    tmem_ld32(D2 + ch * 32, v);
     tmem_ld_wait();
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -974,7 +976,9 @@ __device__ __forceinline__ void e2_chunk(uint32_t O, uint32_t S, int ch, const f
         v[4 * j4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 2]) + b.z, 0.f));
         v[4 * j4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j4 + 3]) + b.w, 0.f));
     }
-    stage_hi_lo(O + ch * 32, S + ch * 32, v);
+    mbar_wait(free_bar, parity);
+    tc_fence_after();
+    stage_hi_lo(D2 + ch * 32, S + ch * 32, v);
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
@@ -984,7 +988,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_A[TS2_NA], empty_A[TS2_NA], full_W[TS2_NW], empty_W[TS2_NW], full_S[2], empty_S[2];
     __shared__ uint64_t full_C[4][4];                       // [production phase E1(0), E2(0), E1(1), E2(1)][32-channel chunk]
-    __shared__ uint64_t lo_free[4];                         // fc1(0) has consumed chunk ch: its lo columns may take replica 1's
+    __shared__ uint64_t s_free[4][4];                       // [up2(0), up2(1), fc1(0), fc1(1)][chunk]: consumed, its lo columns may be rewritten
     __shared__ uint64_t acc1_full, acc2_full[2], acc3_full[2], e3_done[2], w3_full;
     __shared__ uint64_t full_Wl[TS2_NW], w3l_full, pre_ok[4];   // local: this CTA's weight copies have landed; pre chunk written
     __shared__ uint32_t tmem_base_s;
@@ -1018,11 +1022,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
         for (int s = 0; s < 2; ++s) {
             mbar_init(&full_S[s], 8); mbar_init(&empty_S[s], 1);
             mbar_init(&acc2_full[s], 1); mbar_init(&acc3_full[s], 1);
-            mbar_init(&e3_done[s], s == 0 ? 4 : 8);          // [0]: this CTA's converters wait for it; [1]: the leader's MMA warp (both CTAs arrive)
+            mbar_init(&e3_done[s], 8);                       // the leader's MMA warp waits for both CTAs' E3 of replica s
         }
         for (int p = 0; p < 4; ++p) {
             for (int c = 0; c < 4; ++c) mbar_init(&full_C[p][c], 8);
-            mbar_init(&lo_free[p], 1);
+            for (int c = 0; c < 4; ++c) mbar_init(&s_free[p][c], 1);
             mbar_init(&pre_ok[p], 4);
         }
         mbar_init(&acc1_full, 1);
@@ -1071,10 +1075,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
         // (resident, [k-block][hi 32 rows | lo 32 rows]); per tile the k-blocks W1[0..nkb1) | W2[0..4) | W2[0..4) as [hi 64 | lo 64] =====
         uint32_t slot = 0, phase = 0;
         if (elect_one()) {
-            mbar_arrive_expect_tx(&w3l_full, (uint32_t)(4 * W3H_BYTES));
+            // fc_layer1 (64 output channels), per k-block: X0 = 64 rows: W_hi in the leader, W_lo in the peer -> ONE N = 128 instruction
+            // A_hi . [W_hi; W_lo] fills main | correction; X1 = 32 rows: W_hi(0:32) in the leader, W_hi(32:64) in the peer -> N = 64 for A_lo . W_hi
+            mbar_arrive_expect_tx(&w3l_full, (uint32_t)(4 * W3R_BYTES));
             for (int j = 0; j < 4; ++j) {
-                bulk_load(sW3 + j * W3H_BYTES, a.w3 + (size_t)j * W3_BYTES + rank * (W3H_BYTES / 2), W3H_BYTES / 2, &w3l_full);
-                bulk_load(sW3 + j * W3H_BYTES + W3H_BYTES / 2, a.w3 + (size_t)j * W3_BYTES + W3_BYTES / 2 + rank * (W3H_BYTES / 2), W3H_BYTES / 2, &w3l_full);
+                bulk_load(sW3 + j * W3R_BYTES, a.w3 + (size_t)j * W3_BYTES + rank * (W3_BYTES / 2), W3_BYTES / 2, &w3l_full);
+                bulk_load(sW3 + j * W3R_BYTES + W3_BYTES / 2, a.w3 + (size_t)j * W3_BYTES + rank * (W3_BYTES / 4), W3_BYTES / 4, &w3l_full);
             }
         }
         __syncwarp();
@@ -1105,20 +1111,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
             }
         }
     } else if (warp == 1 && leader) {
-        // ===== MMA issuer =====
-        uint32_t u = 0, wslot = 0, wphase = 0, it = 0;
+        // ===== MMA issuer (leader CTA only).  Order per tile: up1 | up2(0) | up2(1) | fc1(0) | fc1(1): the epilogue that turns an
+        // accumulator into the next operand (E2 of replica 0 / 1) runs while the MMAs of the OTHER replica execute =====
+        uint32_t wslot = 0, wphase = 0, it = 0, cnt[2] = {0, 0};
+        const uint32_t R0 = tmem_base, R1 = tmem_base + 128u, O0 = tmem_base + 256u, S = tmem_base + 384u;
         const bool tl = a.dbg != nullptr && blockIdx.x == 0;            // tuning: cycles this warp waits for weights / operands / epilogues
 #define TL_WAIT(acc, bar, parity) do { if (tl) { const long long c0_ = clock64(); mbar_wait_cluster(bar, parity); acc += (unsigned int)(clock64() - c0_); } else mbar_wait_cluster(bar, parity); } while (0)
         for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
             const uint32_t par = it & 1u, prev = (it - 1u) & 1u;
-            const uint32_t R = tmem_base + par * 256u, O = tmem_base + (par ^ 1u) * 256u, S = O + 128u;
             unsigned int wait_w = 0, wait_s = 0, wait_e = 0, wait_s1 = 0;
+            if (it > 0) TL_WAIT(wait_e, &e3_done[0], prev);           // R0 = D3(0) of the previous tile: has been read
             if (lane == 0) tl_mark(a.dbg, 0, (int)it);
-            // D1 columns R = last tile's O: its operands (h2 hi | lo) were consumed by MMAs issued before these
-            for (int kb = 0; kb < nkb1; ++kb, ++u) {                    // ---- up1: main = hi.hi, correction = hi.lo + lo.hi
-                const uint32_t ss = u & 1u;
+            for (int kb = 0; kb < nkb1; ++kb) {                         // ---- up1: main (R0) = hi.hi, correction (R1) = hi.lo + lo.hi
+                const uint32_t ss = kb & 1u;
                 TL_WAIT(wait_w, &full_W[wslot], wphase);
-                TL_WAIT(wait_s1, &full_S[ss], (u >> 1) & 1u);
+                TL_WAIT(wait_s1, &full_S[ss], cnt[ss] & 1u);
+                ++cnt[ss];
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = S + ss * 64u, wb = sW + wslot * W2H_BYTES;
@@ -1126,9 +1134,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
                     for (int ks = 0; ks < nks; ++ks) {    // each CTA supplies its 64 rows of W_hi / W_lo: N = 128 per instruction
                         const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
                         const uint64_t blo = smem_desc(wb + W2H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
-                        umma2_tf32_ts(R, sa + ks * 8, bhi, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
-                        umma2_tf32_ts(R + C1, sa + ks * 8, blo, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
-                        umma2_tf32_ts(R + C1, sa + 32 + ks * 8, bhi, idesc_n(IDESC2_K, C1), 1u);
+                        umma2_tf32_ts(R0, sa + ks * 8, bhi, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
+                        umma2_tf32_ts(R1, sa + ks * 8, blo, idesc_n(IDESC2_K, C1), (kb | ks) != 0);
+                        umma2_tf32_ts(R1, sa + 32 + ks * 8, bhi, idesc_n(IDESC2_K, C1), 1u);
                     }
                     tc_commit2(&empty_S[ss]);
                     tc_commit2(&empty_W[wslot]);
@@ -1138,54 +1146,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
                 if (++wslot == TS2_NW) { wslot = 0; wphase ^= 1u; }
             }
             if (lane == 0) tl_mark(a.dbg, 1, (int)it);
-            if (it > 0) TL_WAIT(wait_e, &e3_done[1], prev);           // D2 columns O[0:128) = D3(1) of the previous tile: has been read
+            if (it > 0) TL_WAIT(wait_e, &e3_done[1], prev);           // O0 = D3(1) of the previous tile: has been read
             else mbar_wait_cluster(&w3_full, 0);                      // fc_layer1's weights have landed in both CTAs (once)
-            for (int g = 0; g < 2; ++g) {
-                const uint32_t Ahi1 = g == 0 ? R + 128u : R;            // up2 operand: hi over D1's correction (g = 0) / over pre (g = 1)
-                if (lane == 0) tl_mark(a.dbg, 2 + 3 * g, (int)it);
-                for (int ch = 0; ch < C1 / KB; ++ch) {                  // ---- up2(g): one accumulator in O[0:128)
+            for (int g = 0; g < 2; ++g) {                               // ---- up2(g): one accumulator; g = 0 -> O0, g = 1 -> R1 (hi1(0) consumed)
+                const uint32_t Ahi = g == 0 ? R1 : R0, D2 = g == 0 ? O0 : R1;
+                if (lane == 0) tl_mark(a.dbg, 2 + 2 * g, (int)it);
+                for (int ch = 0; ch < C1 / KB; ++ch) {
                     TL_WAIT(wait_w, &full_W[wslot], wphase);
                     TL_WAIT(wait_s, &full_C[2 * g][ch], par);
                     if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + ch] = (unsigned int)clock64();
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t ahi = Ahi1 + ch * 32, alo = S + ch * 32, wb = sW + wslot * W2H_BYTES;
+                        const uint32_t ahi = Ahi + ch * 32, alo = S + ch * 32, wb = sW + wslot * W2H_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < KB / 8; ++ks) {
                             const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);
                             const uint64_t blo = smem_desc(wb + W2H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
-                            umma2_tf32_ts(O, ahi + ks * 8, blo, idesc_n(IDESC2_K, C2), (ch | ks) != 0);
-                            umma2_tf32_ts(O, alo + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
-                            umma2_tf32_ts(O, ahi + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
+                            umma2_tf32_ts(D2, ahi + ks * 8, blo, idesc_n(IDESC2_K, C2), (ch | ks) != 0);
+                            umma2_tf32_ts(D2, alo + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
+                            umma2_tf32_ts(D2, ahi + ks * 8, bhi, idesc_n(IDESC2_K, C2), 1u);
                         }
                         tc_commit2(&empty_W[wslot]);
+                        tc_commit2(&s_free[g][ch]);                  // the lo columns of chunk ch may take the next operand
                         if (ch == C1 / KB - 1) tc_commit2(&acc2_full[g]);
                     }
                     __syncwarp();
                     if (++wslot == TS2_NW) { wslot = 0; wphase ^= 1u; }
                 }
-                if (lane == 0) tl_mark(a.dbg, 3 + 3 * g, (int)it);
-                const uint32_t D3 = g == 0 ? R + 128u : R;              // over the up2 operand of this replica (consumed: issue order)
-                for (int ch = 0; ch < C2 / KB; ++ch) {                  // ---- fc1(g): main | correction; weights resident
+                if (lane == 0) tl_mark(a.dbg, 3 + 2 * g, (int)it);
+            }
+            for (int g = 0; g < 2; ++g) {                               // ---- fc1(g): main | correction; weights resident
+                // g = 0: operand hi over D2(0) in O0, D3 -> R0 (hi1(1) consumed); g = 1: operand hi over D2(1) in R1, D3 -> O0 (hi2(0) consumed)
+                const uint32_t Ahi = g == 0 ? O0 : R1, D3 = g == 0 ? R0 : O0;
+                for (int ch = 0; ch < C2 / KB; ++ch) {
                     TL_WAIT(wait_s, &full_C[2 * g + 1][ch], par);
                     if (tl && lane == 0 && it == 3) a.dbg[23 * 512 + g * 8 + 4 + ch] = (unsigned int)clock64();
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t ahi = O + ch * 32, alo = S + ch * 32, wb = sW3 + ch * W3H_BYTES;
+                        const uint32_t ahi = Ahi + ch * 32, alo = S + ch * 32, wb = sW3 + ch * W3R_BYTES;
 #pragma unroll
-                        for (int ks = 0; ks < KB / 8; ++ks) {
-                            const uint64_t bhi = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);            // this CTA's 32 rows of W_hi
-                            const uint64_t blo = smem_desc(wb + W3H_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);
-                            umma2_tf32_ts(D3, ahi + ks * 8, bhi, idesc_n(IDESC2_K, C3), (ch | ks) != 0);
-                            umma2_tf32_ts(D3 + C3, ahi + ks * 8, blo, idesc_n(IDESC2_K, C3), (ch | ks) != 0);
-                            umma2_tf32_ts(D3 + C3, alo + ks * 8, bhi, idesc_n(IDESC2_K, C3), 1u);
+                        for (int ks = 0; ks < KB / 8; ++ks) {   // an MMA costs >= ~70 cycles whatever its N (A read from TMEM): 2 instead of 3 per k-step
+                            const uint64_t bhl = smem_desc(wb + ks * 32, 16, 1024, LAYOUT_SW128);                    // pair: [W_hi (64); W_lo (64)]
+                            const uint64_t bh2 = smem_desc(wb + W3_BYTES / 2 + ks * 32, 16, 1024, LAYOUT_SW128);     // pair: W_hi (32 + 32)
+                            umma2_tf32_ts(D3, ahi + ks * 8, bhl, idesc_n(IDESC2_K, 2 * C3), (ch | ks) != 0);
+                            umma2_tf32_ts(D3 + C3, alo + ks * 8, bh2, idesc_n(IDESC2_K, C3), 1u);
                         }
-                        if (g == 0) tc_commit2(&lo_free[ch]);
+                        tc_commit2(&s_free[2 + g][ch]);
                         if (ch == C2 / KB - 1) tc_commit2(&acc3_full[g]);
                     }
                     __syncwarp();
                 }
-                if (lane == 0) tl_mark(a.dbg, 4 + 3 * g, (int)it);
+                if (lane == 0) tl_mark(a.dbg, 6 + g, (int)it);
             }
             if (tl && lane == 0 && it < 512) {
                 a.dbg[16 * 512 + it] = wait_w; a.dbg[17 * 512 + it] = wait_s1; a.dbg[18 * 512 + it] = wait_s; a.dbg[19 * 512 + it] = wait_e;
@@ -1193,32 +1204,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
         }
 #undef TL_WAIT
     } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
-        // ===== converters (up1): this thread's point, 32 channels: raw fp32 -> hi / lo -> staging slot in TMEM; afterwards
-        // they help epilogue group 0 (chunks 1 and 3 of E1(0) and E2(0)): one warp alone needs ~1000 cycles per chunk, the MMAs of
-        // a chunk 768 (up2) / 384 (fc1) =====
+        // ===== converters (up1): this thread's point, 32 channels: raw fp32 -> hi / lo -> staging slot in TMEM (slot = k-block & 1:
+        // columns S[0:64) / S[64:128), i.e. the lo columns of chunks 0-1 / 2-3).  Afterwards they help the epilogue groups where one
+        // warp per lane quarter is too slow for the MMAs it feeds: chunks 1 and 3 of E1(0) and of E2(1) =====
         const int q = warp & 3;
         const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const uint32_t R0 = tmem_base + lanebits, R1 = R0 + 128u, S = R0 + 384u;
         const float4 *bias1_4 = reinterpret_cast<const float4 *>(bias1_s), *wcode_4 = reinterpret_cast<const float4 *>(wcode_s);
         const float4 *bias2_4 = reinterpret_cast<const float4 *>(bias2_s);
         const float code0 = code_s[0];
-        uint32_t aslot = 0, aphase = 0, it = 0, u = 0;
+        uint32_t aslot = 0, aphase = 0, it = 0, cnt[2] = {0, 0};
         const bool tl = a.dbg != nullptr && blockIdx.x == 0 && warp == CONV_WARP0;
         for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
             const uint32_t par = it & 1u;
-            const uint32_t R = tmem_base + par * 256u + lanebits, O = tmem_base + (par ^ 1u) * 256u + lanebits, S = O + 128u;
             unsigned int wait_a = 0, wait_slot = 0;
-            if (it > 0) {
-                mbar_wait(&e3_done[0], (it - 1u) & 1u);                // this tile's staging columns = D3(0) of the previous tile
-                tc_fence_after();
-            }
-            for (int kb = 0; kb < nkb1; ++kb, ++u) {
-                const uint32_t ss = u & 1u;
+            for (int kb = 0; kb < nkb1; ++kb) {
+                const uint32_t ss = kb & 1u;
                 { const long long c0 = tl ? clock64() : 0; mbar_wait(&full_A[aslot], aphase); if (tl) wait_a += (unsigned int)(clock64() - c0); }
                 const float *src = reinterpret_cast<const float *>(smem_gen + aslot * RAW_BYTES + q * 4096) + lane;
                 uint32_t v[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(src[c * 32]);
-                { const long long c0 = tl ? clock64() : 0; mbar_wait(&empty_S[ss], ((u >> 1) & 1u) ^ 1u); if (tl) wait_slot += (unsigned int)(clock64() - c0); }
+                { const long long c0 = tl ? clock64() : 0;
+                  if (it > 0 && kb < 2) mbar_wait(&s_free[3][2 * kb + 1], (it - 1u) & 1u);   // fc1(1) of the previous tile has consumed these lo columns
+                  mbar_wait(&empty_S[ss], (cnt[ss] & 1u) ^ 1u);
+                  if (tl) wait_slot += (unsigned int)(clock64() - c0); }
+                ++cnt[ss];
                 tc_fence_after();
                 stage_hi_lo(S + ss * 64u, S + ss * 64u + 32u, v);
                 tmem_st_wait();
@@ -1232,22 +1243,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 1; ch < C1 / KB; ch += 2) {
-                e1_chunk_from_d1(R, S, ch, code0, bias1_4, wcode_4);
+                e1_chunk_from_d1(R0, R1, S, ch, code0, bias1_4, wcode_4);
                 if (lane == 0) { mbar_arrive(&pre_ok[ch]); arrive_at(&full_C[0][ch], 0u, leader); }
             }
-            mbar_wait(&acc2_full[0], par);
+            mbar_wait(&acc2_full[1], par);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 1; ch < C2 / KB; ch += 2) {
-                e2_chunk(O, S, ch, bias2_4);
-                if (lane == 0) arrive_at(&full_C[1][ch], 0u, leader);
+                e2_chunk(R1, S, ch, bias2_4, &s_free[2][ch], par);
+                if (lane == 0) arrive_at(&full_C[3][ch], 0u, leader);
             }
         }
     } else if (warp >= EPI_WARP0) {
-        // ===== epilogue groups: group g = replica g (E1, E2, E3 of that replica); warp quarter q = box q of the tile.
-        // Chunks 1 and 3 of E1(0) / E2(0) are done by the converter warps, of E2(1) by group 0 (idle after E3(0)). =====
+        // ===== epilogue groups: group g = replica g (E1, E2, E3 of that replica); warp quarter q = box q of the tile =====
         const int g = (warp - EPI_WARP0) >> 2, q = warp & 3;
         const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+        const uint32_t R0 = tmem_base + lanebits, R1 = R0 + 128u, O0 = R0 + 256u, S = R0 + 384u;
         const float code_g = code_s[g];
         const float4 *bias1_4 = reinterpret_cast<const float4 *>(bias1_s), *wcode_4 = reinterpret_cast<const float4 *>(wcode_s);
         const float4 *bias2_4 = reinterpret_cast<const float4 *>(bias2_s), *bias3_4 = reinterpret_cast<const float4 *>(bias3_s);
@@ -1255,39 +1266,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
         uint32_t it = 0;
         for (long long t = blockIdx.x; t < tiles_end; t += gridDim.x, ++it) {
             const uint32_t par = it & 1u;
-            const uint32_t R = tmem_base + par * 256u + lanebits, O = tmem_base + (par ^ 1u) * 256u + lanebits, S = O + 128u;
             const long long box = t * 4 + q;
             const long long bi = box / a.bpc;
             const int p = (int)(box % a.bpc) * 32 + lane;
             const bool valid = box < a.nboxes && p < a.n;
             if (g == 0) {
-                // ---- E1(0), chunks 0 and 2: pre over D1's main columns, hi over the correction columns, lo -> S
+                // ---- E1(0), chunks 0 and 2 (1 and 3: converter warps): pre over D1's main columns, hi over the correction columns, lo -> S
                 mbar_wait(&acc1_full, par);
                 tc_fence_after();
                 if (q == 0 && lane == 0) tl_mark(a.dbg, 8, (int)it);
 #pragma unroll 1
                 for (int ch = 0; ch < C1 / KB; ch += 2) {
-                    e1_chunk_from_d1(R, S, ch, code_g, bias1_4, wcode_4);
+                    e1_chunk_from_d1(R0, R1, S, ch, code_g, bias1_4, wcode_4);
                     if (lane == 0) { mbar_arrive(&pre_ok[ch]); arrive_at(&full_C[0][ch], 0u, leader); }
                 }
+                // ---- E2(0) (while up2(1) runs): relu(D2(0) + bias): hi over D2(0) in place, lo -> S as up2(1) releases the columns
+                mbar_wait(&acc2_full[0], par);
+                tc_fence_after();
+                if (q == 0 && lane == 0) tl_mark(a.dbg, 9, (int)it);
+#pragma unroll 1
+                for (int ch = 0; ch < C2 / KB; ++ch) {
+                    e2_chunk(O0, S, ch, bias2_4, &s_free[1][ch], par);
+                    if (lane == 0) arrive_at(&full_C[1][ch], 0u, leader);
+                }
             } else {
-                // ---- E1(1): values from pre one chunk ahead; hi over pre in place, lo -> S as fc1(0) releases the columns
+                // ---- E1(1) (while up2(0) runs): values from pre one chunk ahead; hi over pre in place, lo -> S as up2(0) releases the columns
                 if (q == 0 && lane == 0) tl_mark(a.dbg, 11, (int)it);
                 uint32_t v[32];
                 mbar_wait(&pre_ok[0], par);
                 tc_fence_after();
-                e1_values_from_pre(R, 0, code_g, wcode_4, v);
+                e1_values_from_pre(R0, 0, code_g, wcode_4, v);
 #pragma unroll
                 for (int ch = 0; ch < C1 / KB; ++ch) {
                     uint32_t vn[32];
                     if (ch + 1 < C1 / KB) {
                         mbar_wait(&pre_ok[ch + 1], par);
                         tc_fence_after();
-                        e1_values_from_pre(R, ch + 1, code_g, wcode_4, vn);
+                        e1_values_from_pre(R0, ch + 1, code_g, wcode_4, vn);
                     }
-                    mbar_wait(&lo_free[ch], par);             // fc1(0) has consumed the lo columns of chunk ch
+                    mbar_wait(&s_free[0][ch], par);           // up2(0) has consumed the lo columns of chunk ch
                     tc_fence_after();
-                    stage_hi_lo(R + ch * 32, S + ch * 32, v);
+                    stage_hi_lo(R0 + ch * 32, S + ch * 32, v);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -1297,21 +1316,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
                         for (int j = 0; j < 32; ++j) v[j] = vn[j];
                     }
                 }
-            }
-            // ---- E2(g), chunks 0 and 2: relu(D2 + bias): hi over D2 in place, lo -> S (up2(g) is complete: its operands are dead)
-            mbar_wait(&acc2_full[g], par);
-            tc_fence_after();
-            if (q == 0 && lane == 0) tl_mark(a.dbg, 9 + 3 * g, (int)it);
+                // ---- E2(1), chunks 0 and 2 (1 and 3: converter warps; while fc1(0) runs): hi over D2(1) in place (R1), lo -> S
+                mbar_wait(&acc2_full[1], par);
+                tc_fence_after();
+                if (q == 0 && lane == 0) tl_mark(a.dbg, 12, (int)it);
 #pragma unroll 1
-            for (int ch = 0; ch < C2 / KB; ch += 2) {
-                e2_chunk(O, S, ch, bias2_4);
-                if (lane == 0) arrive_at(&full_C[2 * g + 1][ch], 0u, leader);
+                for (int ch = 0; ch < C2 / KB; ch += 2) {
+                    e2_chunk(R1, S, ch, bias2_4, &s_free[2][ch], par);
+                    if (lane == 0) arrive_at(&full_C[3][ch], 0u, leader);
+                }
             }
             // ---- E3(g): relu(D3 + bias) in registers -> fc_layer2 + bias + residual
             mbar_wait(&acc3_full[g], par);
             tc_fence_after();
             if (q == 0 && lane == 0) tl_mark(a.dbg, 10 + 3 * g, (int)it);
-            const uint32_t D3 = g == 0 ? R + 128u : R;
+            const uint32_t D3 = g == 0 ? R0 : O0;
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
             for (int ch = 0; ch < C3 / 32; ++ch) {
@@ -1335,7 +1354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (g == 0) mbar_arrive(&e3_done[0]); else arrive_at(&e3_done[1], 0u, leader); }
+            if (lane == 0) arrive_at(&e3_done[g], 0u, leader);
             if (valid) {
                 const float o[3] = {o0 + b4_s[0], o1 + b4_s[1], o2 + b4_s[2]};
 #pragma unroll
@@ -1346,16 +1365,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts2_kernel(const __grid_c
                 }
             }
             if (q == 0 && lane == 0) tl_mark(a.dbg, 14 + g, (int)it);
-            if (g == 0) {
-                // ---- group 0 is idle now: chunks 1 and 3 of E2(1)
-                mbar_wait(&acc2_full[1], par);
-                tc_fence_after();
-#pragma unroll 1
-                for (int ch = 1; ch < C2 / KB; ch += 2) {
-                    e2_chunk(O, S, ch, bias2_4);
-                    if (lane == 0) arrive_at(&full_C[3][ch], 0u, leader);
-                }
-            }
         }
     }
 

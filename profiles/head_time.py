@@ -63,11 +63,16 @@ if "--timeline" in sys.argv:
     torch.cuda.synchronize()
     lib.pu3_head_tc_set_debug(None)
     ev = buf.cpu().view(24, 512).numpy().astype("int64") & 0xffffffff
-    if mode and mode[0] == 0:
+    m = mode[0] if mode else 2
+    if m == 0:
         names = {0: "P1 start", 1: "P1 issued", 2: "P2 start", 3: "P2 issued", 4: "P3 issued", 5: "E1 start", 6: "E2 start", 7: "E3 start", 8: "E3 done"}
-    else:
+    elif m == 1:
         names = {0: "up1 start", 1: "up1 issued", 2: "up2(0) start", 3: "up2(0) issued", 4: "fc1(0) issued", 5: "up2(1) start",
                  6: "up2(1) issued", 7: "fc1(1) issued", 8: "E1(0) start", 9: "E2(0) start", 10: "E3(0) start", 11: "E1(1) start",
+                 12: "E2(1) start", 13: "E3(1) start", 14: "E3(0) done", 15: "E3(1) done"}
+    else:
+        names = {0: "up1 start", 1: "up1 issued", 2: "up2(0) start", 3: "up2(0) issued", 4: "up2(1) start", 5: "up2(1) issued",
+                 6: "fc1(0) issued", 7: "fc1(1) issued", 8: "E1(0) start", 9: "E2(0) start", 10: "E3(0) start", 11: "E1(1) start",
                  12: "E2(1) start", 13: "E3(1) start", 14: "E3(0) done", 15: "E3(1) done"}
     t0 = ev[0, 2]
     for it in range(2, 6):
@@ -80,9 +85,10 @@ if "--timeline" in sys.argv:
             print(f"{nm}: cycles per tile", [int(v) for v in ev[k, 2:10]])
         base = ev[0, 3]
         rel = lambda v: int((v - base) & 0xffffffff)
-        print("tile 3, epilogue group 0 / quarter 0, cycles after up1 start; per chunk: start | TMEM loaded | math done | stores issued | arrived")
-        for ph, nm in ((0, "E1(0)"), (20, "E2(0)")):
-            for ch in range(4):
-                print(f"  {nm} chunk {ch}: " + " | ".join(str(rel(ev[22, ph + ch * 5 + k])) for k in range(5)))
+        if m == 1:
+            print("tile 3, epilogue group 0 / quarter 0, cycles after up1 start; per chunk: start | TMEM loaded | math done | stores issued | arrived")
+            for ph, nm in ((0, "E1(0)"), (20, "E2(0)")):
+                for ch in range(4):
+                    print(f"  {nm} chunk {ch}: " + " | ".join(str(rel(ev[22, ph + ch * 5 + k])) for k in range(5)))
         print("  MMA warp saw operands ready: up2(0)", [rel(ev[23, c]) for c in range(4)], "fc1(0)", [rel(ev[23, 4 + c]) for c in range(4)],
               "up2(1)", [rel(ev[23, 8 + c]) for c in range(4)], "fc1(1)", [rel(ev[23, 12 + c]) for c in range(4)])

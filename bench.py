@@ -69,8 +69,12 @@ NCU_METRICS = {
     "skip_fuse_fixed_kernel": {"ms": 0.945, "issue_active_pct": 52.2, "warps_active_pct": 35.1, "dram_mb": 1362.8,
                                "long_scoreboard_per_issue": 5.0, "bound": "L2 gather latency", "source": "profiles/r2/ncu_fps_skip_raw.csv"},
     "knn_thread_kernel<5>": {"ms": 0.691, "issue_active_pct": 79.0, "bound": "fp32 issue", "source": "profiles/r2/ncu_skip_knnthread_raw.csv"},
+    "head_ts2_kernel": {"ms": 0.352, "ms_under_ncu": 0.382, "tensor_pipe_pct": 55.5, "issue_active_pct": 38.9, "dram_mb": 438.3,
+                        "smem_pipe_pct": {"lsu": 13.6, "tensor_core": 13.3},
+                        "bound": "tensor pipe at 55 %: per-instruction cost of the K = 8 tf32 MMA with A from TMEM, L2 -> SM weight delivery in the up1 phase",
+                        "source": "profiles/r2/ncu_head_ts2_raw.csv"},
     "conv_tc_kernel": {"ms": [0.255, 0.218, 0.135], "tensor_pipe_pct": [34.8, 28.3, 29.5], "dram_pct": [33.5, 33.2, 37.0],
-                       "bound": "pipeline depth (two 96 KB stages) and, for cout = 128, the single TMEM accumulator stage",
+                       "bound": "three-kernel head (now only the train-mode forward): HBM round trips of the 128-channel activations, pipeline depth",
                        "source": "profiles/r1g/ncu_summary.md"},
     "nmdist_fwd_kernel": {"ms_train_shape": 0.021, "ms_b32_n4992": 0.574, "issue_active_pct": 86.9, "fma_pipe_pct": 52.1,
                           "bound": "fp32 issue (all-pairs), launch latency at the train shape", "source": "profiles/r2/ncu_chamfer_gather_raw.csv"},

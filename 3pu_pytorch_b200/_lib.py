@@ -30,6 +30,8 @@ SIGNATURES = {
     "pu3_nmdist_fwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 7),
     "pu3_nmdist_bwd_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 9),
     "pu3_group_knn_workspace": (_c_size_t, [_c_int] * 7),
+    "pu3_knn_set_grid": (None, [_c_int]),
+    "pu3_knn_no_prefilter": (None, [_c_int]),
     "pu3_group_knn_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "pu3_group_knn_ragged_f32": (_c_int, [_c_int] * 7 + [_c_void_p] * 6 + [_c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "pu3_group_gather_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 4),

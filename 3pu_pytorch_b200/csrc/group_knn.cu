@@ -48,6 +48,7 @@ struct KnnArgs {
     int exact_pops;       // knn_feat_kernel, indices-only mode: 1 = ranks 1..k-1 in exact order too (test hook)
     int prefilter;        // knn_thread_kernel: exact bounding-sphere candidate pre-filter allowed (queries are not the cloud itself)
     int fused_dup;        // knn_feat_kernel: `unique` requested and NO duplicate pre-pass ran -- the kernel finds the duplicates itself
+    int grid_target;      // knn_grid_kernel: candidates per cell the grid is sized for
 };
 
 __device__ __forceinline__ int knn_cloud(const KnnArgs &a, int bi) { return a.owner ? __ldg(a.owner + bi) : bi / a.p_div; }
@@ -933,6 +934,308 @@ __global__ void __launch_bounds__(KT_THREADS) knn_thread_kernel(KnnArgs a) {
 }
 
 // --------------------------------------------------------------------------------------------
+// k <= 8, 3 channels, >= 1024 candidates: uniform-grid search (inter-level skip at levels 3 and 4, outlier filter of the
+// merged clouds).  knn_thread_kernel evaluates every (query, candidate) pair: 0.5 G pairs for the level-4 skip search even
+// after dropping the duplicates and the bounding-sphere pre-filter, fp32-issue bound.  Here a CTA
+//   1. stages the cloud's candidates (first occurrences only when the cloud has duplicates) into shared memory SORTED BY CELL
+//      of a G^3 grid over their bounding box (~6 per cell: count, histogram, scan, scatter -- ~1 k instructions per thread,
+//      paid once per CTA and amortised over several tiles of queries: gridDim.x CTAs share a cloud's query blocks),
+//   2. answers a query from the 27 cells around it (a few hundred candidates instead of thousands), with the SAME distance
+//      expression and the same (distance, index) order as the exhaustive kernel, and
+//   3. verifies the result: every candidate outside the scanned block is farther than the distance to the block's faces, so
+//      if the k-th best distance (plus slack for the fp32 rounding of the expanded-form distances and of the cell
+//      assignment) is below that bound the answer is exactly the exhaustive one; otherwise the query is redone over all cells.
+// Batch elements in duplicate mode 2 (fewer than k distinct points: exact max(D) penalty) take the exhaustive path from
+// global memory.  Results are bit-identical to knn_thread_kernel (tests/test_gpu_group_knn.py, A/B hook pu3_knn_set_grid).
+// --------------------------------------------------------------------------------------------
+constexpr int KG_TEAM = 320;      // threads of a team: one tile of 312 queries = one pass
+constexpr int KG_TEAMS = 2;       // teams per CTA (the staged cloud fills shared memory: one CTA per SM, so two tiles at a time)
+constexpr int KG_THREADS = KG_TEAM * KG_TEAMS;
+constexpr int KG_GMAX = 12;       // cells per axis (<= 1728 cells)
+constexpr int KG_MIN_N = 1024;
+
+template <int KK>
+__device__ __forceinline__ void kg_insert(float (&bd)[KK], int (&bj)[KK], float d, int j) {
+    // (distance, index) lexicographic: the exhaustive kernel visits candidates in index order with a strict compare
+    if (d < bd[KK - 1] || (d == bd[KK - 1] && j < bj[KK - 1])) {
+        bd[KK - 1] = d; bj[KK - 1] = j;
+#pragma unroll
+        for (int e = KK - 1; e > 0; --e) {
+            if (bd[e] < bd[e - 1] || (bd[e] == bd[e - 1] && bj[e] < bj[e - 1])) {
+                const float td = bd[e]; bd[e] = bd[e - 1]; bd[e - 1] = td;
+                const int tj = bj[e]; bj[e] = bj[e - 1]; bj[e - 1] = tj;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(KG_TEAM) : "memory"); }
+
+template <int KK>
+__global__ void __launch_bounds__(KG_THREADS) knn_grid_kernel(KnnArgs a) {
+    extern __shared__ __align__(16) unsigned char kg_raw[];
+    float4 *pts = reinterpret_cast<float4 *>(kg_raw);                      // [n] (x, y, z, |p|^2), sorted by cell
+    int *pidx = reinterpret_cast<int *>(pts + a.n);                          // [n] original index
+    int *cstart = pidx + a.n;                                                // [G^3 + 1]
+    int *qh_all = cstart + (KG_GMAX * KG_GMAX * KG_GMAX + 1);                // per team: [G^3 + 1] cell histogram of its queries
+    int *qord_all = qh_all + KG_TEAMS * (KG_GMAX * KG_GMAX * KG_GMAX + 1);   // per team: [KG_TEAM] queries sorted by cell
+    __shared__ float s_red[8][KG_THREADS / 32];
+    __shared__ int s_cnt;
+    __shared__ float s_box[8];                                               // lo xyz, cell xyz, max |p|^2, -
+    __shared__ int s_g;
+    const int cloud = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nv = knn_n(a, cloud);
+    const float *pb = a.points + (size_t)cloud * 3 * a.n;
+    const bool drop_dups = a.dup != nullptr && a.cloud_dups[cloud] > 0;     // duplicate mode 1 (mode 2 elements: exhaustive path below)
+    const uint8_t *dupb = a.dup ? a.dup + (size_t)cloud * a.n : nullptr;
+
+    // ---- 1a. bounding box, count and max |p|^2 of the candidates that take part
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, rmax = 0.f;
+    int mine = 0;
+    for (int j = tid; j < nv; j += KG_THREADS) {
+        if (drop_dups && dupb[j]) continue;
+        const float x = __ldg(pb + j), y = __ldg(pb + a.n + j), z = __ldg(pb + 2 * (size_t)a.n + j);
+        lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+        hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+        rmax = fmaxf(rmax, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+        ++mine;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+            lo[c3] = fminf(lo[c3], __shfl_xor_sync(0xffffffffu, lo[c3], o));
+            hi[c3] = fmaxf(hi[c3], __shfl_xor_sync(0xffffffffu, hi[c3], o));
+        }
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    }
+    if (tid == 0) s_cnt = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) { s_red[c3][warp] = lo[c3]; s_red[3 + c3][warp] = hi[c3]; }
+        s_red[6][warp] = rmax;
+    }
+    __syncthreads();
+    if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+    if (tid == 0) {
+        for (int w = 1; w < KG_THREADS / 32; ++w) {
+#pragma unroll
+            for (int c3 = 0; c3 < 3; ++c3) { s_red[c3][0] = fminf(s_red[c3][0], s_red[c3][w]); s_red[3 + c3][0] = fmaxf(s_red[3 + c3][0], s_red[3 + c3][w]); }
+            s_red[6][0] = fmaxf(s_red[6][0], s_red[6][w]);
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (tid == 0) {
+        int g = (int)cbrtf((float)cnt / (float)a.grid_target);
+        g = g < 1 ? 1 : (g > KG_GMAX ? KG_GMAX : g);
+        s_g = g;
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+            const float ext = fmaxf(s_red[3 + c3][0] - s_red[c3][0], 1e-12f);
+            s_box[c3] = s_red[c3][0];
+            s_box[3 + c3] = ext / (float)g;
+        }
+        s_box[6] = s_red[6][0];
+    }
+    __syncthreads();
+    const int G = s_g, GC = G * G * G;
+    const float blo[3] = {s_box[0], s_box[1], s_box[2]}, cell[3] = {s_box[3], s_box[4], s_box[5]};
+    const float inv[3] = {1.0f / cell[0], 1.0f / cell[1], 1.0f / cell[2]};
+    const float rp_max = s_box[6];
+    const float ext_max = fmaxf(fmaxf(cell[0], cell[1]), cell[2]) * (float)G;
+    auto cell_of = [&](float v, int c3) { int c = (int)floorf((v - blo[c3]) * inv[c3]); return c < 0 ? 0 : (c >= G ? G - 1 : c); };
+
+    // ---- 1b. histogram, exclusive scan, scatter
+    for (int c = tid; c <= GC; c += KG_THREADS) cstart[c] = 0;
+    __syncthreads();
+    for (int j = tid; j < nv; j += KG_THREADS) {
+        if (drop_dups && dupb[j]) continue;
+        const float x = __ldg(pb + j), y = __ldg(pb + a.n + j), z = __ldg(pb + 2 * (size_t)a.n + j);
+        atomicAdd(&cstart[(cell_of(z, 2) * G + cell_of(y, 1)) * G + cell_of(x, 0) + 1], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // inclusive scan of cstart[1..GC] by one warp, 32 cells at a time
+        int carry = 0;
+        for (int c0 = 1; c0 <= GC; c0 += 32) {
+            const int c = c0 + lane;
+            int v = c <= GC ? cstart[c] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += up;
+            }
+            if (c <= GC) cstart[c] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    // scatter: cstart[c] = first slot of cell c; a per-cell fill counter lives in pidx's tail?  No spare room in general: use a
+    // second pass with atomics on a copy of the starts kept in the (not yet written) pidx array's upper... -> simplest: cursor array
+    // in registers is impossible, so cstart[] doubles as the cursor and is restored afterwards by a shift.
+    for (int j = tid; j < nv; j += KG_THREADS) {
+        if (drop_dups && dupb[j]) continue;
+        const float x = __ldg(pb + j), y = __ldg(pb + a.n + j), z = __ldg(pb + 2 * (size_t)a.n + j);
+        const int c = (cell_of(z, 2) * G + cell_of(y, 1)) * G + cell_of(x, 0);
+        const int slot = atomicAdd(&cstart[c], 1);     // cursor of cell c runs from its start to the start of cell c+1
+        pts[slot] = make_float4(x, y, z, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+        pidx[slot] = j;
+    }
+    __syncthreads();
+    // after the scatter cstart[c] holds the END of cell c = the start of cell c+1: shift by one cell to restore the starts
+    {
+        int keep[(KG_GMAX * KG_GMAX * KG_GMAX + KG_THREADS) / KG_THREADS];
+        int e = 0;
+        for (int c = tid; c < GC; c += KG_THREADS) keep[e++] = cstart[c];
+        __syncthreads();
+        e = 0;
+        for (int c = tid; c < GC; c += KG_THREADS) cstart[c + 1] = keep[e++];
+        if (tid == 0) cstart[0] = 0;
+    }
+    __syncthreads();
+
+    // ---- 2. queries: batch elements that read this cloud, their query blocks dealt round-robin to the gridDim.x CTAs of the cloud
+    const int team = tid / KG_TEAM, tt = tid - team * KG_TEAM;
+    int *qh = qh_all + team * (KG_GMAX * KG_GMAX * KG_GMAX + 1), *qord = qord_all + team * KG_TEAM;
+    int item = 0;
+    const int bi_lo = a.owner ? 0 : cloud * a.p_div, bi_hi = a.owner ? a.b : (cloud + 1) * a.p_div;
+    for (int bi0 = bi_lo; bi0 < bi_hi; bi0 += 32) {
+      // which of the next 32 batch elements read this cloud (one owner load per lane instead of a dependent load per element)
+      unsigned todo = __ballot_sync(0xffffffffu, bi0 + lane < bi_hi && (a.owner == nullptr || __ldg(a.owner + bi0 + lane) == cloud));
+      while (todo) {                                                         // block-uniform: every warp sees the same mask
+        const int bi = bi0 + __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const int mv = knn_m(a, bi);
+        const int grp = knn_group(a, bi);
+        const bool mode2 = a.dup != nullptr && a.group_any[grp] != 0;
+        const float maxd = mode2 ? ordered_to_float(a.maxd[grp]) : 0.f;
+        const float *qb = a.query + (size_t)bi * 3 * a.m;
+        for (int q0 = 0; q0 < mv; q0 += KG_TEAM, ++item) {
+            if (item % ((int)gridDim.x * KG_TEAMS) != (int)blockIdx.x * KG_TEAMS + team) continue;   // team-uniform
+            // threads of a warp should look at the same cells (candidate loads become broadcasts instead of 32 different
+            // addresses): the team's queries are sorted by cell first (counting sort, ~100 instructions per thread)
+            int qs = tt;                                                   // the query (offset in this block) this thread answers
+            const int nq = min(KG_TEAM, mv - q0);
+            if (!mode2) {
+                for (int c = tt; c <= GC; c += KG_TEAM) qh[c] = 0;
+                team_sync(team);
+                int mycell = 0;
+                if (tt < nq) {
+                    const float x = __ldg(qb + q0 + tt), y = __ldg(qb + a.m + q0 + tt), z = __ldg(qb + 2 * (size_t)a.m + q0 + tt);
+                    mycell = (cell_of(z, 2) * G + cell_of(y, 1)) * G + cell_of(x, 0);
+                    atomicAdd(&qh[mycell + 1], 1);
+                }
+                team_sync(team);
+                if (tt < 32) {
+                    int carry = 0;
+                    for (int c0 = 1; c0 <= GC; c0 += 32) {
+                        const int c = c0 + tt;
+                        int v = c <= GC ? qh[c] : 0;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, v, d);
+                            if (tt >= d) v += up;
+                        }
+                        if (c <= GC) qh[c] = v + carry;
+                        carry += __shfl_sync(0xffffffffu, v, 31);
+                    }
+                }
+                team_sync(team);
+                if (tt < nq) qord[atomicAdd(&qh[mycell], 1)] = tt;
+                team_sync(team);
+                if (tt < nq) qs = qord[tt];
+            }
+            const int qi = q0 + qs;
+            if (tt >= nq) continue;
+            const float qx = __ldg(qb + qi), qy = __ldg(qb + a.m + qi), qz = __ldg(qb + 2 * (size_t)a.m + qi);
+            const float rq = __fmaf_rn(qz, qz, __fmaf_rn(qy, qy, __fmul_rn(qx, qx)));
+            float bd[KK];
+            int bj[KK];
+#pragma unroll
+            for (int e = 0; e < KK; ++e) { bd[e] = __int_as_float(0x7f800000); bj[e] = 0; }
+            if (mode2) {
+                // degenerate cloud: all candidates in index order from global memory, duplicates penalised by max(D)
+                for (int j = 0; j < nv; ++j) {
+                    const float x = __ldg(pb + j), y = __ldg(pb + a.n + j), z = __ldg(pb + 2 * (size_t)a.n + j);
+                    const float rp = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                    const float dot = __fmaf_rn(qz, z, __fmaf_rn(qy, y, __fmul_rn(qx, x)));
+                    float d = expanded_dist(rq, dot, rp);
+                    if (dupb[j]) d = __fadd_rn(d, maxd);
+                    kg_insert<KK>(bd, bj, d, j);
+                }
+            } else {
+                const int cx = cell_of(qx, 0), cy = cell_of(qy, 1), cz = cell_of(qz, 2);
+                const float slack = 8e-6f * (rq + rp_max) + 1e-9f;        // fp32 rounding of two expanded-form distances
+                bool done = false;
+                // the 3x3x3 block around the query's cell, then -- if the verification fails -- the shell up to 5x5x5
+                int px0 = 0, px1 = -1, py0 = 0, py1 = -1, pz0 = 0, pz1 = -1;   // block scanned so far (empty)
+#pragma unroll 1
+                for (int ring = 1; ring <= 2 && !done; ++ring) {
+                    const int x0 = max(cx - ring, 0), x1 = min(cx + ring, G - 1), y0 = max(cy - ring, 0), y1 = min(cy + ring, G - 1);
+                    const int z0 = max(cz - ring, 0), z1 = min(cz + ring, G - 1);
+                    for (int zz = z0; zz <= z1; ++zz)
+                        for (int yy = y0; yy <= y1; ++yy) {
+                            // the cells x0..x1 of a row are contiguous in the sorted array; rows inside the previous block only
+                            // contribute their two ends
+                            const bool inner = zz >= pz0 && zz <= pz1 && yy >= py0 && yy <= py1;
+                            const int rowc = (zz * G + yy) * G;
+                            int s0 = cstart[rowc + x0], s1 = cstart[rowc + x1 + 1];
+                            int h0 = s1, h1 = s1;                           // hole [h0, h1) = what the previous block already covered
+                            if (inner) { h0 = cstart[rowc + px0]; h1 = cstart[rowc + px1 + 1]; }
+                            for (int sl = s0; sl < s1; ++sl) {
+                                if (sl == h0) { sl = h1; if (sl >= s1) break; }
+                                const float4 p = pts[sl];
+                                const float dot = __fmaf_rn(qz, p.z, __fmaf_rn(qy, p.y, __fmul_rn(qx, p.x)));
+                                kg_insert<KK>(bd, bj, expanded_dist(rq, dot, p.w), pidx[sl]);
+                            }
+                        }
+                    px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+                    // verify: distance from the query to the nearest face of the scanned block that has cells behind it
+                    float lim = INFINITY;
+                    if (x0 > 0) lim = fminf(lim, qx - (blo[0] + (float)x0 * cell[0]));
+                    if (x1 < G - 1) lim = fminf(lim, (blo[0] + (float)(x1 + 1) * cell[0]) - qx);
+                    if (y0 > 0) lim = fminf(lim, qy - (blo[1] + (float)y0 * cell[1]));
+                    if (y1 < G - 1) lim = fminf(lim, (blo[1] + (float)(y1 + 1) * cell[1]) - qy);
+                    if (z0 > 0) lim = fminf(lim, qz - (blo[2] + (float)z0 * cell[2]));
+                    if (z1 < G - 1) lim = fminf(lim, (blo[2] + (float)(z1 + 1) * cell[2]) - qz);
+                    // slack: a candidate may sit in the neighbouring cell of where exact arithmetic would put it (1e-4 of the box)
+                    const float lim_eff = lim * (1.f - 1e-3f) - 1e-4f * ext_max - 1e-6f;
+                    float dk = bd[0];                             // the k-th best decides (k <= KK)
+#pragma unroll
+                    for (int e = 1; e < KK; ++e) if (e < a.k) dk = bd[e];
+                    done = dk < __int_as_float(0x7f800000) && (lim == INFINITY || (lim_eff > 0.f && dk + slack <= lim_eff * lim_eff));
+                }
+                if (!done) {                                      // exhaustive over the staged candidates (any order: (d, j) insert)
+#pragma unroll
+                    for (int e = 0; e < KK; ++e) { bd[e] = __int_as_float(0x7f800000); bj[e] = 0; }
+                    for (int sl = 0; sl < cnt; ++sl) {
+                        const float4 p = pts[sl];
+                        const float dot = __fmaf_rn(qz, p.z, __fmaf_rn(qy, p.y, __fmul_rn(qx, p.x)));
+                        kg_insert<KK>(bd, bj, expanded_dist(rq, dot, p.w), pidx[sl]);
+                    }
+                }
+            }
+            const size_t row = ((size_t)bi * a.m + qi) * a.k;
+#pragma unroll
+            for (int e = 0; e < KK; ++e) {
+                if (e < a.k) {
+                    if (a.idx64) a.idx64[row + e] = bj[e];
+                    if (a.idx32) a.idx32[row + e] = bj[e];
+                    if (a.dist) a.dist[row + e] = bd[e];
+                    if (a.knn) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            a.knn[(((size_t)bi * 3 + ch) * a.m + qi) * a.k + e] = __ldg(pb + (size_t)ch * a.n + bj[e]);
+                    }
+                }
+            }
+        }
+      }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // k > 64: CTA per query
 // --------------------------------------------------------------------------------------------
 constexpr int KL_THREADS = 256;
@@ -1142,6 +1445,15 @@ extern "C" void pu3_knn_exact_pops(int on) { g_knn_exact_pops = on; }
 // Test hook: 1 = knn_thread_kernel never pre-filters its candidates (A/B of the exact bounding-sphere filter).
 static int g_knn_no_prefilter = 0;
 extern "C" void pu3_knn_no_prefilter(int on) { g_knn_no_prefilter = on; }
+// Test / A-B hook: 0 = the xyz searches (c = 3, k <= 8) always run the exhaustive knn_thread_kernel, 1 (default) = clouds of
+// >= 1024 points go through the uniform-grid kernel (bit-identical results).
+static int g_knn_grid = 1;
+extern "C" void pu3_knn_set_grid(int on) { g_knn_grid = on; }
+static int knn_grid_target() {
+    static int t = 0;
+    if (t == 0) { const char *e = getenv("PU3_KNN_GRID_TARGET"); t = e ? atoi(e) : 3; if (t < 1) t = 1; }
+    return t;
+}
 // Test hook: 1 = the feature-space kernel does not look for duplicates itself (the three pre-pass kernels run, as in round 1).
 static int g_knn_no_fused_dup = 0;
 extern "C" void pu3_knn_no_fused_dup(int on) { g_knn_no_fused_dup = on; }
@@ -1216,7 +1528,7 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
     KnnArgs a{b, c, m, n, k, p_div, max_group, owner, group_of, n_arr, m_arr,
               query, points, nullptr, nullptr, nullptr, nullptr, knn, idx64, idx32, dist,
               (unordered && g_knn_exact_pops == 0) ? 0 : 1,
-              (query != points && g_knn_no_prefilter == 0) ? 1 : 0, 0};
+              (query != points && g_knn_no_prefilter == 0) ? 1 : 0, 0, knn_grid_target()};
     // the tiled feature-space kernel (n <= 320, k <= 64) finds duplicates itself: no pre-pass
     const bool feat_path = !pl.large && !(c == 3 && k <= KT_KMAX && g_knn_force_stream == 0) && n <= KF_NMAX && g_knn_force_stream == 0 &&
                            ((size_t)(c + 1) * KF_NMAX) * 4 + (size_t)KF_QB * KF_NMAX * 4 <= (size_t)device_info().smem_optin;
@@ -1253,6 +1565,31 @@ static int group_knn_impl(int b, int c, int m, int n, int k, int p_div, int clou
         knn_large_kernel<<<dim3(m, b), KL_THREADS, pl.smem, s>>>(a, pl.k2, gkeys);
         PU3_LAUNCH_CHECK("knn_large_kernel");
         return PU3_OK;
+    }
+    if (c == 3 && k <= KT_KMAX && g_knn_force_stream == 0 && g_knn_grid != 0 && n >= KG_MIN_N) {
+        // uniform-grid search: the cloud's candidates sorted by cell in shared memory (20 bytes per point + the cell starts)
+        const size_t smem = (size_t)n * 20 + (size_t)(KG_GMAX * KG_GMAX * KG_GMAX + 1) * 4 * (1 + KG_TEAMS) + (size_t)KG_TEAMS * KG_TEAM * 4 + 16;
+        if (smem <= (size_t)device_info().smem_optin) {
+            // CTAs per cloud: enough to cover the chip, never more than there are query blocks
+            const long long blocks_per_cloud = ((long long)((m + KG_TEAM - 1) / KG_TEAM) * (b / clouds > 0 ? b / clouds : 1) + KG_TEAMS - 1) / KG_TEAMS;
+            long long parts = (device_info().sm_count + clouds - 1) / clouds;
+            if (parts > blocks_per_cloud) parts = blocks_per_cloud;
+            if (parts < 1) parts = 1;
+#define PU3_KG_LAUNCH(KKV)                                                                                              \
+    do {                                                                                                                \
+        auto kern = knn_grid_kernel<KKV>;                                                                                \
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),        \
+                             "group_knn: smem attr");                                                                   \
+        if (st) return st;                                                                                              \
+        kern<<<dim3((unsigned)parts, clouds), KG_THREADS, smem, s>>>(a);                                                \
+    } while (0)
+            if (k <= 2) PU3_KG_LAUNCH(2);
+            else if (k <= 5) PU3_KG_LAUNCH(5);
+            else PU3_KG_LAUNCH(8);
+#undef PU3_KG_LAUNCH
+            PU3_LAUNCH_CHECK("knn_grid_kernel");
+            return PU3_OK;
+        }
     }
     if (c == 3 && k <= KT_KMAX && g_knn_force_stream == 0) {
         dim3 grid((m + KT_THREADS * KT_QPT - 1) / (KT_THREADS * KT_QPT), b);

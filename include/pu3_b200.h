@@ -130,6 +130,8 @@ int pu3_nmdist_bwd_f32(int b, int n, int m, const float *xyz1, const float *xyz2
  */
 #define PU3_KNN_SET_ORDER 2
 size_t pu3_group_knn_workspace(int b, int c, int m, int n, int k, int p_div, int unique);
+void pu3_knn_set_grid(int on);     /* test / A-B hook: 1 (default) = xyz searches (c = 3, k <= 8) over >= 1024 points use the uniform-grid kernel, 0 = always the exhaustive kernel; results are bit-identical */
+void pu3_knn_no_prefilter(int on); /* test / A-B hook: 1 = the exhaustive xyz kernel without its bounding-sphere pre-filter */
 int pu3_group_knn_f32(int b, int c, int m, int n, int k, int p_div, const float *query, const float *points,
                       int unique, int max_group, float *knn, int64_t *idx64, int32_t *idx32, float *dist,
                       void *workspace, size_t workspace_bytes, pu3_stream_t stream);

@@ -300,6 +300,71 @@ def test_knn_thread_prefilter_is_exact(pu3, cuda, case):
     assert int(outs[0][0].max()) < N
 
 
+@pytest.mark.parametrize("case", ["uniform", "tiles_in_merged_cloud", "queries_outside", "clustered", "surface", "ragged", "self_k2",
+                                  "degenerate", "k8_with_dist"])
+def test_knn_grid_search_is_exact(pu3, cuda, case):
+    """xyz searches over >= 1024 candidates (skip connection at levels 3 / 4, outlier filter of the merged clouds) sort the
+    candidates into a uniform grid and look at the 27 cells around a query, verify the k-th distance against the distance to the
+    unscanned cells, widen to 5x5x5 and fall back to all cells otherwise (csrc/group_knn.cu: knn_grid_kernel).  Whatever the
+    geometry -- uniform volumes, 5x duplicated merged clouds, queries outside the candidates' box (every query falls back), one
+    dense cluster plus far outliers (most points in one cell), a thin surface, ragged clouds, the self search of the outlier
+    filter, a degenerate cloud with fewer than k distinct points (exact max(D) penalty) -- indices, distances and gathered
+    neighbours are those of the exhaustive kernel, bit for bit."""
+    import ctypes
+    g = torch.Generator().manual_seed(sum(map(ord, case)))
+    B, M, N, k = 4, 312, 6240, 5
+    unique, ragged, want_knn = True, None, False
+    if case == "uniform":
+        pts = torch.rand(B, 3, N, generator=g); q = torch.rand(B, 3, M, generator=g)
+    elif case == "tiles_in_merged_cloud":
+        base = torch.rand(B, 3, N // 5, generator=g)
+        pts = base.repeat(1, 1, 5)[:, :, torch.randperm(N, generator=g)]
+        d = ((base - base[:, :, :1]) ** 2).sum(1)
+        near = d.argsort(dim=1)[:, :M]
+        q = torch.gather(base, 2, near.unsqueeze(1).expand(-1, 3, -1)) + 1e-3 * torch.randn(B, 3, M, generator=g)
+    elif case == "queries_outside":
+        pts = torch.rand(B, 3, N, generator=g); q = torch.rand(B, 3, M, generator=g) * 0.1 + 3.0
+    elif case == "clustered":
+        pts = torch.cat([torch.randn(B, 3, N - 40, generator=g) * 0.01, torch.rand(B, 3, 40, generator=g) * 10 - 5], 2)
+        q = torch.cat([torch.randn(B, 3, M - 12, generator=g) * 0.01, torch.rand(B, 3, 12, generator=g) * 10 - 5], 2)
+    elif case == "surface":
+        uv = torch.rand(B, 2, N, generator=g)
+        pts = torch.stack([uv[:, 0], uv[:, 1], 0.2 * torch.sin(6 * uv[:, 0]) * torch.cos(5 * uv[:, 1])], 1)
+        q = pts[:, :, :M] + 2e-3 * torch.randn(B, 3, M, generator=g)
+    elif case == "ragged":
+        pts = torch.rand(3, 3, N, generator=g); q = torch.rand(6, 3, M, generator=g)
+        owner = torch.tensor([0, 0, 1, 2, 2, 2], dtype=torch.int32, device=cuda)
+        ragged = pu3.operations.Ragged(owner, owner, 3, n_arr=torch.tensor([6240, 3000, 1100], dtype=torch.int32, device=cuda))
+    elif case == "self_k2":
+        N, k = 2496, 2
+        pts = torch.rand(B, 3, N, generator=g); pts[:, :, 100:110] = pts[:, :, :10]          # a few exact duplicates
+        q = None
+    elif case == "degenerate":
+        N = 1024
+        pts = torch.rand(B, 3, 3, generator=g).repeat(1, 1, 342)[:, :, :N].contiguous()      # 3 distinct points < k
+        q = torch.rand(B, 3, M, generator=g)
+    else:
+        k, want_knn, unique = 8, True, False
+        pts = torch.rand(B, 3, N, generator=g); q = torch.rand(B, 3, 700, generator=g)
+    pts = pts.contiguous().to(cuda)
+    q = pts if q is None else q.contiguous().to(cuda)
+    lib = ctypes.CDLL(pu3._lib.LIB_PATH)
+    outs = []
+    for on in (1, 0):
+        lib.pu3_knn_set_grid(on)
+        try:
+            nb, idx, dist = pu3.operations._knn_raw(k, q, pts, unique, 1, want_knn=want_knn, ragged=ragged)
+            torch.cuda.synchronize()
+        finally:
+            lib.pu3_knn_set_grid(1)
+        outs.append((idx.clone(), dist.clone(), None if nb is None else nb.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]), f"{case}: {(outs[0][0] != outs[1][0]).sum().item()} indices differ"
+    assert torch.equal(outs[0][1], outs[1][1])
+    if want_knn:
+        assert torch.equal(outs[0][2], outs[1][2])
+    assert int(outs[0][0].max()) < pts.shape[2]
+
+
 @pytest.mark.parametrize("case", ["no_dups", "some_dups", "degenerate", "all_equal", "ragged_groups"])
 def test_feature_knn_fused_duplicate_detection_equals_the_prepass(pu3, cuda, case):
     """The tiled feature-space kernel finds duplicates itself (in-kernel hash compare; exact max(D) penalty computed in the

@@ -123,7 +123,8 @@ def test_level_backward_teacher_forced_against_oracle_autograd(pu3, cuda, params
     zero (more of them after the skip connection, whose exp() weights move the features by ~1e-6).  ONE flipped unit at one of the
     ~2500 points moves a whole row of that layer's weight gradient and one entry of its bias gradient by that point's share,
     ~4e-4 .. 1e-3 of the tensor's scale -- that is the quantum below which a per-entry bound says nothing.  Bar for every
-    gradient: relative L2 error <= 1e-3, 99.9 % of the entries within 1e-3 of scale, none off by more than 1 % of scale."""
+    gradient: relative L2 error <= 1e-3, 99.9 % of the entries within 1e-3 of scale (a bias-sized tensor: at most one entry
+    beyond), none off by more than 1 % of scale."""
     name = "level_3" if with_prev else "level_1"
     g = torch.Generator().manual_seed(21 + with_prev)
     T, N = 4, 312
@@ -158,8 +159,9 @@ def test_level_backward_teacher_forced_against_oracle_autograd(pu3, cuda, params
         scale = float(want.abs().max()) + 1e-30
         err = (got - want).abs()
         frac = float((err <= 1e-3 * scale).double().mean())
+        n_off = int((err > 1e-3 * scale).sum())
         l2 = float(err.norm() / (want.norm() + 1e-30))
-        assert frac >= 0.999 and float(err.max()) <= 1e-2 * scale and l2 <= 1e-3, \
+        assert (frac >= 0.999 or n_off <= 1) and float(err.max()) <= 1e-2 * scale and l2 <= 1e-3, \
             f"{what}: {frac:.5f} of the entries within 1e-3 of scale {scale:.3e}, max err {float(err.max()):.3e}, rel L2 {l2:.2e}"
     close(xn_g.grad, xn_r.grad, "d / d xyz_normalized")
     if with_prev:

@@ -58,6 +58,7 @@ constexpr int FPS_SPEC = 4;
 // of exchanges cloud 0 of the last launch needed (samples per exchange = (m - 1) / exchanges)
 __device__ int g_fps_spec_cap = FPS_SPEC;
 __device__ unsigned int g_fps_exchanges = 0;
+__device__ int g_fps_select_all = 0;        // tuning: 1 = every warp runs the selection itself (no hand-over through shared memory)
 
 constexpr int FPS_MAX_CAND = 256;          // candidates a CTA receives per round: cluster size x warps per CTA
 struct FpsSmem {
@@ -65,6 +66,9 @@ struct FpsSmem {
     FpsCand warp_slot[2][32];                  // [round parity][warp]: the warp's winner, coordinates included
     FpsCand cta_slot[2];                       // [round parity] the CTA's winner (wide clusters: leader-warp exchange)
     uint64_t mbar[2];                          // [round parity] "all S candidates of the round have landed"
+    int top[32][4];                            // [warp] fps_select scratch: slots of the FPS_SPEC best candidates
+    float res_w[2][FPS_SPEC][4];               // [round parity] samples chosen by warp 0 (x, y, z, -) ...
+    int res_a[2];                              // ... and how many
 };
 
 // lexicographic arg-max over the full warp; returns true in exactly one lane (the winner)
@@ -94,8 +98,15 @@ __device__ __forceinline__ void fps_mark(int, int) {}
 // indices to out[j ...] (written by the thread for which `writer` is set).
 template <int SPEC>
 __device__ __forceinline__ int fps_select(const FpsCand *slots, int total, int lane, int spec_cap, int j, int m, bool writer,
-                                          int32_t *out, float (&wx)[SPEC], float (&wy)[SPEC], float (&wz)[SPEC]) {
-    uint32_t ct[2], cr[2];                                     // at most two candidates per lane
+                                          int32_t *out, float (&wx)[SPEC], float (&wy)[SPEC], float (&wz)[SPEC], int *top) {
+    // Round 2, second version.  The first one popped the candidates one after the other with the slot read, the distance tests
+    // and the break conditions of a sample on the chain before the next reduce-max: ~650 cycles per accepted sample, 2 600 of an
+    // exchange's 5 600 cycles at depth 4 (in-kernel timeline, profiles/r2) -- latency, not issue slots: running it in one warp
+    // instead of all changed nothing, and ranking every candidate against all others (no collectives, but ~900 instructions in
+    // one warp) was slower still.  Now the SPEC best candidates are found first by SPEC rounds of {reduce-max, ballot, shuffle}
+    // and nothing else; their slots are then read and all acceptance tests evaluated side by side.  Same candidates, same order,
+    // same tests as before: results are bit-identical.
+    uint32_t ct[2], cr[2];
     uint32_t lbt = 0u, lbr = 0xffffffffu;                      // lane-local best of the unpublished keys
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -111,45 +122,61 @@ __device__ __forceinline__ int fps_select(const FpsCand *slots, int total, int l
     // B = the best key that was NOT published
     const uint32_t bt = __reduce_max_sync(0xffffffffu, lbt);
     const uint32_t br = __reduce_min_sync(0xffffffffu, lbt == bt ? lbr : 0xffffffffu);
-    int taken = 0, A = 0;
+    // the SPEC best candidates in order: SPEC rounds of {reduce-max, ballot, shuffle}, NOTHING else on the chain (the slot reads
+    // and the acceptance tests of all of them follow side by side)
+    int cwin[SPEC];
+    bool cvalid[SPEC];
+    int taken = 0;
 #pragma unroll
     for (int mth = 0; mth < SPEC; ++mth) {
         uint32_t lt = 0u, lr = 0xffffffffu;
         int lc = lane;
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (!((taken >> u) & 1) && (ct[u] > lt || (ct[u] == lt && cr[u] < lr))) { lt = ct[u]; lr = cr[u]; lc = lane + 32 * u; }
+        for (int u = 0; u < 2; ++u) {
+            const bool free_u = !((taken >> u) & 1);
+            const bool take = free_u & ((ct[u] > lt) | ((ct[u] == lt) & (cr[u] < lr)));
+            lt = take ? ct[u] : lt; lr = take ? cr[u] : lr; lc = take ? lane + 32 * u : lc;
+        }
         const uint32_t tmax = __reduce_max_sync(0xffffffffu, lt);
         unsigned cands = __ballot_sync(0xffffffffu, lt == tmax && lr != 0xffffffffu);
-        if (__popc(cands) > 1) {                                // tie on the distance: smallest rank wins
+        if (__popc(cands) > 1) {                                // tie on the distance (rare): smallest rank wins
             const uint32_t rmin = __reduce_min_sync(0xffffffffu, lt == tmax ? lr : 0xffffffffu);
             cands = __ballot_sync(0xffffffffu, lt == tmax && lr == rmin);
         }
-        if (mth > 0 && cands == 0u) break;                      // no candidate left (warp-uniform, like every break below)
+        cvalid[mth] = cands != 0u;
         const int csrc = cands ? __ffs(cands) - 1 : 0;
-        const int cwin = __shfl_sync(0xffffffffu, lc, csrc);
-        if (mth > 0) {
-            const uint32_t rw = __shfl_sync(0xffffffffu, lr, csrc);
-            if (!(tmax > bt || (tmax == bt && rw < br))) break;  // (a) some unpublished point may rank above it
-            if (tmax == 0u) break;   // (c) t = 0: the samples already chosen (t = 0 too, selected points stay candidates in the
-                                     // reference) compete on rank alone -- e.g. m > n repeats the lowest-rank point for ever
-        }
-        const uint4 wlo = *reinterpret_cast<const uint4 *>(&slots[cwin]);     // broadcast reads
-        const uint2 whi = *(reinterpret_cast<const uint2 *>(&slots[cwin]) + 2);
-        const float cx = __uint_as_float(wlo.w), cy = __uint_as_float(whi.x), cz = __uint_as_float(whi.y);
-        if (mth > 0) {
-            const float tm = __uint_as_float(tmax);
-            bool keep = true;                                    // (b) unchanged by the samples accepted before it
+        cwin[mth] = __shfl_sync(0xffffffffu, lc, csrc);
+        if (lane == csrc) taken |= 1 << (cwin[mth] >> 5);
+    }
+    uint32_t kt[SPEC], krk[SPEC];
+    int kidx[SPEC];
+    float cx[SPEC], cy[SPEC], cz[SPEC];
 #pragma unroll
-            for (int a = 0; a < SPEC; ++a)
-                if (a < mth) keep = keep && (fminf(sqdist3(cx - wx[a], cy - wy[a], cz - wz[a]), tm) == tm);
-            if (!keep) break;
+    for (int mth = 0; mth < SPEC; ++mth) {
+        const uint4 wlo = *reinterpret_cast<const uint4 *>(&slots[cwin[mth]]);      // broadcast reads, independent of each other
+        const uint2 whi = *(reinterpret_cast<const uint2 *>(&slots[cwin[mth]]) + 2);
+        kt[mth] = wlo.x; krk[mth] = cvalid[mth] ? wlo.y : 0xffffffffu; kidx[mth] = (int)wlo.z;
+        cx[mth] = __uint_as_float(wlo.w); cy[mth] = __uint_as_float(whi.x); cz[mth] = __uint_as_float(whi.y);
+    }
+    int A = 0;
+    bool go = true;
+#pragma unroll
+    for (int mth = 0; mth < SPEC; ++mth) {
+        if (mth > 0) {
+            go = go && krk[mth] != 0xffffffffu;                                             // a candidate is left
+            go = go && (kt[mth] > bt || (kt[mth] == bt && krk[mth] < br));                  // (a) above every unpublished key
+            go = go && kt[mth] != 0u;                                                       // (c) t > 0
+            const float tm = __uint_as_float(kt[mth]);
+#pragma unroll
+            for (int a2 = 0; a2 < SPEC; ++a2)                                               // (b) unchanged by the samples before it
+                if (a2 < mth) go = go && (fminf(sqdist3(cx[mth] - cx[a2], cy[mth] - cy[a2], cz[mth] - cz[a2]), tm) == tm);
         }
-        wx[mth] = cx; wy[mth] = cy; wz[mth] = cz;
-        if (writer) out[j + mth] = (int)wlo.z;
-        A = mth + 1;
-        if (lane == csrc) taken |= 1 << (cwin >> 5);
-        if (j + A >= m || A >= spec_cap) break;
+        if (go) {
+            wx[mth] = cx[mth]; wy[mth] = cy[mth]; wz[mth] = cz[mth];
+            if (writer) out[j + mth] = kidx[mth];
+            A = mth + 1;
+            if (j + A >= m || A >= spec_cap) go = false;
+        }
     }
     return A;
 }
@@ -217,6 +244,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem + barriers exist before remote stores
 
     const int spec_cap = min(SPEC, max(1, g_fps_spec_cap));
+    const bool select_all = g_fps_select_all != 0;
     int j = 1;                                               // next sample to choose
     uint32_t e = 1;
     for (; j < m; ++e) {                                     // e: exchange counter (buffer parity / barrier phase)
@@ -290,7 +318,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 dst[0] = plo; dst[1] = phi;
             }
             __syncthreads();
-            A = fps_select<SPEC>(&sm.warp_slot[par][0], nwarps, lane, spec_cap, j, m, threadIdx.x == 0, out, wx, wy, wz);
+            A = fps_select<SPEC>(&sm.warp_slot[par][0], nwarps, lane, spec_cap, j, m, threadIdx.x == 0, out, wx, wy, wz, sm.top[warp]);
             j += A;
         } else if (DIRECT) {
             // ---- 3b. cluster of <= 64 warps: EVERY warp sends its candidate straight into every CTA's slot array by
@@ -319,7 +347,34 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             // ---- 4. every warp: wait for the S x nwarps candidates, sort out up to SPEC samples (see FPS_SPEC above) ----------
             mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);   // phase = earlier uses of this buffer
             fps_mark(j, 5);
-            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
+            // The selection is a chain of warp-wide reductions (~650 cycles per accepted sample when all 16 warps of an SM run it
+            // at the same time, in-kernel timeline profiles/r2: 2 600 of an exchange's 5 600 cycles).  Every warp would reach the same
+            // result, so warp 0 alone computes it and hands it over through shared memory: one __syncthreads instead of 7
+            // redundant copies competing for the issue slots.
+            if (select_all) {
+                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
+                fps_mark(j, 6);
+                j += A;
+                continue;
+            }
+            if (warp == 0) {
+                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
+                if (lane == 0) {
+                    sm.res_a[par] = A;
+#pragma unroll
+                    for (int a = 0; a < SPEC; ++a) *reinterpret_cast<float4 *>(&sm.res_w[par][a][0]) = make_float4(wx[a], wy[a], wz[a], 0.f);
+                }
+            }
+            __syncthreads();
+            if (warp != 0) {
+                A = sm.res_a[par];
+#pragma unroll
+                for (int a = 0; a < SPEC; ++a) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(&sm.res_w[par][a][0]);
+                    wx[a] = w4.x; wy[a] = w4.y; wz[a] = w4.z;
+                }
+            }
+            fps_mark(j, 6);
             j += A;
         } else {
             // ---- 3c. wide cluster (> 64 warps: the 16-CTA whole-shape call): scanning S x nwarps candidates in every warp
@@ -360,7 +415,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 }
             }
             mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);
-            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
+            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
             j += A;
             fps_mark(j, 6);
         }
@@ -516,6 +571,7 @@ extern "C" void pu3_fps_set_threads(int t) { g_fps_force_threads = t; }   // tun
 static int fps_dispatch(int b, int n, int m, const int32_t *n_arr, const int32_t *m_arr, const float *xyz, float *temp,
                         int32_t *idx, pu3_stream_t stream);
 
+extern "C" void pu3_fps_set_select_all(int on) { cudaMemcpyToSymbol(pu3::g_fps_select_all, &on, sizeof(int)); }
 extern "C" void pu3_fps_set_spec(int depth) { cudaMemcpyToSymbol(pu3::g_fps_spec_cap, &depth, sizeof(int)); }
 extern "C" unsigned int pu3_fps_last_exchanges(void) {
     unsigned int v = 0;

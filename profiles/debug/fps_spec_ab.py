@@ -9,6 +9,8 @@ pu3 = importlib.import_module("3pu_pytorch_b200")
 dev = torch.device("cuda:0")
 lib = ctypes.CDLL(pu3._lib.LIB_PATH)
 lib.pu3_fps_last_exchanges.restype = ctypes.c_uint
+if '--select-all' in sys.argv:
+    lib.pu3_fps_set_select_all(1)
 g = torch.Generator().manual_seed(0)
 clouds = {}
 # (a) what the network actually produces at level 4 (xavier weights: volumetric blobs) -- capture the merged cloud via the debug hook

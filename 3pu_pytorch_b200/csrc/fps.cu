@@ -58,7 +58,7 @@ constexpr int FPS_SPEC = 4;
 // of exchanges cloud 0 of the last launch needed (samples per exchange = (m - 1) / exchanges)
 __device__ int g_fps_spec_cap = FPS_SPEC;
 __device__ unsigned int g_fps_exchanges = 0;
-__device__ int g_fps_select_all = 0;        // tuning: 1 = every warp runs the selection itself (no hand-over through shared memory)
+__device__ int g_fps_select_all = -1;       // tuning: 1 = every warp runs the selection itself, 0 = warp 0 + hand-over through shared memory, -1 = by cloud size
 
 constexpr int FPS_MAX_CAND = 256;          // candidates a CTA receives per round: cluster size x warps per CTA
 struct FpsSmem {
@@ -244,7 +244,9 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
     if (S > 1) { cluster_arrive_release(); cluster_wait_acquire(); }  // peers' smem + barriers exist before remote stores
 
     const int spec_cap = min(SPEC, max(1, g_fps_spec_cap));
-    const bool select_all = g_fps_select_all != 0;
+    // measured (profiles/debug/fps_spec_ab.py): the hand-over wins on the 24 960-point clouds (3.57 against 3.74 ms), the redundant
+    // selection on the smaller ones (0.70 / 1.38 against 0.76 / 1.46 ms)
+    const bool select_all = g_fps_select_all < 0 ? n < 20000 : g_fps_select_all != 0;
     int j = 1;                                               // next sample to choose
     uint32_t e = 1;
     for (; j < m; ++e) {                                     // e: exchange counter (buffer parity / barrier phase)

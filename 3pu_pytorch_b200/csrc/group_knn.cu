@@ -620,6 +620,122 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
         }
         __syncthreads();
         // ---- phase 2: selection, one warp per query ----------------------------------------------------
+        if (HOT && a.exact_pops == 0) {
+            // Indices-only calls of the fused DenseEdgeConv (rank 0 exact, ranks 1..k-1 as a set, see below): a warp works on TWO
+            // queries at once (ql and ql + 8).  The k-1 rounds are a dependent chain of {reduce-min, compare, shared-memory load}
+            // per query -- ~60 cycles of latency per round against ~7 instructions -- so independent chains interleaved in the
+            // same warp fill each other's bubbles (two at once: 5.08 -> 4.85 ms per step) (the per-lane sorting networks of the two queries interleave the same way).
+            constexpr int NZ = 2;                                     // queries a warp works on at once (4: 4.89 ms, 2: 4.85 ms, 1: 5.08 ms per step)
+            for (int base = 0; base < KF_QB && q0 + base + warp < mv; base += NZ * (KF_THREADS / 32)) {
+                int qlz[NZ];
+                uint32_t *krowz[NZ];
+                int nz = 0;
+#pragma unroll
+                for (int z = 0; z < NZ; ++z) {
+                    qlz[z] = base + warp + z * (KF_THREADS / 32);
+                    krowz[z] = skeys + qlz[z] * KF_NMAX;
+                    if (q0 + qlz[z] < mv) nz = z + 1;
+                }
+                uint32_t hk[NZ], perm_lo[NZ], perm_hi[NZ];
+#pragma unroll
+                for (int z = 0; z < NZ; ++z) {
+                    hk[z] = 0xffffffffu; perm_lo[z] = 0; perm_hi[z] = 0;
+                    if (z < nz) {
+                        uint32_t *krow = krowz[z];
+                        unsigned long long v[KF_S];
+#pragma unroll
+                        for (int s2 = 0; s2 < KF_S; ++s2) v[s2] = ((unsigned long long)krow[s2 * 32 + lane] << 32) | (uint32_t)s2;
+                        cex(v[4], v[9]); cex(v[3], v[8]); cex(v[2], v[7]); cex(v[1], v[6]); cex(v[0], v[5]);
+                        cex(v[1], v[4]); cex(v[6], v[9]); cex(v[0], v[3]); cex(v[5], v[8]);
+                        cex(v[0], v[2]); cex(v[3], v[6]); cex(v[7], v[9]);
+                        cex(v[0], v[1]); cex(v[2], v[4]); cex(v[5], v[7]); cex(v[8], v[9]);
+                        cex(v[1], v[2]); cex(v[4], v[6]); cex(v[7], v[8]); cex(v[3], v[5]);
+                        cex(v[2], v[5]); cex(v[6], v[8]); cex(v[1], v[3]); cex(v[4], v[7]);
+                        cex(v[2], v[3]); cex(v[6], v[7]);
+                        cex(v[3], v[4]); cex(v[5], v[6]);
+                        cex(v[4], v[5]);
+#pragma unroll
+                        for (int s2 = 0; s2 < KF_S; ++s2) {
+                            const uint32_t tag = (uint32_t)v[s2] & 15u;
+                            if (s2 < 8) perm_lo[z] |= tag << (4 * s2); else perm_hi[z] |= tag << (4 * (s2 - 8));
+                            if (s2 > 0) krow[s2 * 32 + lane] = (uint32_t)(v[s2] >> 32);
+                        }
+                        hk[z] = (uint32_t)(v[0] >> 32);
+                    }
+                }
+                uint32_t hk_first[NZ];
+#pragma unroll
+                for (int z = 0; z < NZ; ++z) hk_first[z] = hk[z];
+                __syncwarp();
+                // rank 0 exactly (key, then lowest index); then k-1 cheap rounds: every lane whose head equals the warp minimum advances
+                bool first[NZ];
+                int cnt[NZ];
+#pragma unroll
+                for (int z = 0; z < NZ; ++z) {
+                    const uint32_t hj = (perm_lo[z] & 15u) * 32u + lane;
+                    const uint32_t kmin0 = __reduce_min_sync(0xffffffffu, hk[z]);
+                    const uint32_t jmin0 = __reduce_min_sync(0xffffffffu, hk[z] == kmin0 ? hj : 0xffffffffu);
+                    first[z] = (hj == jmin0 && hk[z] == kmin0);
+                    cnt[z] = 0;
+                    if (first[z]) { hk[z] = krowz[z][32 + lane]; cnt[z] = 1; }
+                }
+                for (int r = 1; r < a.k; ++r) {
+#pragma unroll
+                    for (int z = 0; z < NZ; ++z) {
+                        const uint32_t kmin = __reduce_min_sync(0xffffffffu, hk[z]);
+                        if (hk[z] == kmin) {
+                            ++cnt[z];                             // index clamped: a lane that runs out of keys (or massive ties)
+                            hk[z] = krowz[z][min(cnt[z], KF_S - 1) * 32 + lane];   // re-reads its last key; that case is caught below
+                        }
+                    }
+                }
+#pragma unroll
+                for (int z = 0; z < NZ; ++z) {
+                    if (z >= nz) continue;                            // warp-uniform
+                    uint32_t *krow = krowz[z];
+                    uint16_t *stage = reinterpret_cast<uint16_t *>(krow);   // stripe 0 of the row is free: heads live in registers
+                    const int total = __reduce_add_sync(0xffffffffu, cnt[z]);
+                    const int most = __reduce_max_sync(0xffffffffu, cnt[z]);
+                    if (total == a.k && most < KF_S) {        // exactly k pops, and no lane exhausted its 10 keys
+                        const int mine = cnt[z] - (first[z] ? 1 : 0);
+                        int incl = mine;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += up;
+                        }
+                        int pos = 1 + incl - mine;
+                        unsigned long long perm = ((unsigned long long)perm_hi[z] << 32) | perm_lo[z];
+                        if (first[z]) { stage[0] = (uint16_t)(((uint32_t)perm & 15u) * 32u + lane); perm >>= 4; }
+                        for (int e = 0; e < mine; ++e) {
+                            stage[pos + e] = (uint16_t)(((uint32_t)perm & 15u) * 32u + lane);
+                            perm >>= 4;
+                        }
+                    } else {
+                        // ties straddling rank k-1 (duplicates, clamped distances) or an exhausted lane: exact pops
+                        uint32_t hkx = hk_first[z], plo = perm_lo[z], phi = perm_hi[z];
+                        uint32_t hjx = (plo & 15u) * 32u + lane;
+                        int h = 1;
+                        for (int r = 0; r < a.k; ++r) {
+                            const uint32_t kmin = __reduce_min_sync(0xffffffffu, hkx);
+                            const uint32_t jmin = __reduce_min_sync(0xffffffffu, hkx == kmin ? hjx : 0xffffffffu);
+                            if (hjx == jmin && hkx == kmin) {       // exactly one lane (indices are unique)
+                                stage[r] = (uint16_t)hjx;
+                                hkx = h < KF_S ? krow[h * 32 + lane] : 0xffffffffu;
+                                plo = __funnelshift_r(plo, phi, 4);
+                                phi >>= 4;
+                                hjx = (plo & 15u) * 32u + lane;
+                                ++h;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    int32_t *o = a.idx32 + ((size_t)bi * a.m + q0 + qlz[z]) * a.k;
+                    for (int r = lane; r < a.k; r += 32) o[r] = stage[r];
+                    __syncwarp();
+                }
+            }
+        } else
         for (int ql = warp; ql < KF_QB; ql += KF_THREADS / 32) {
             const int qi = q0 + ql;
             if (qi >= mv) break;  // warp-uniform

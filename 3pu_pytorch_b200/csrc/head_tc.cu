@@ -856,8 +856,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_ts_kernel(const __grid_co
 // leader CTA (rank 0) issues every MMA and commits with a multicast arrive to both CTAs' barriers; everything a producer of
 // either CTA has to tell the MMA warp is an arrive on the LEADER's barrier (remote arrive from the peer).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TS2_NA = 5;                      // raw activation ring: 5 x 16 KB (what is in flight bounds the L2 -> SM rate)
-constexpr int TS2_NW = 5;                      // weight ring: 5 slots x [hi 64 rows | lo 64 rows] = 16 KB
+#ifndef PU3_TS2_NA
+#define PU3_TS2_NA 5
+#endif
+#ifndef PU3_TS2_NW
+#define PU3_TS2_NW 5
+#endif
+constexpr int TS2_NA = PU3_TS2_NA;                      // raw activation ring: 5 x 16 KB (what is in flight bounds the L2 -> SM rate)
+constexpr int TS2_NW = PU3_TS2_NW;                      // weight ring: 5 slots x [hi 64 rows | lo 64 rows] = 16 KB
 constexpr int W2H_BYTES = W_BYTES / 2;         // this CTA's half of a 128-channel k-block
 constexpr int W3H_BYTES = W3_BYTES / 2;        // ... of a fc_layer1 k-block: [hi 32 rows | lo 32 rows] = 8 KB
 constexpr int W3R_BYTES = W3_BYTES / 2 + W3_BYTES / 4;   // resident fc_layer1 k-block of one CTA: 64 + 32 rows = 12 KB

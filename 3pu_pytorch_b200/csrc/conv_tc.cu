@@ -118,8 +118,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
 
-    const int spc = (a.n + SUBM - 1) / SUBM;                 // sub-tiles per cloud
-    const long long nsub = (long long)a.b * spc;
+    // A 128-point sub-tile is four TMA boxes of 32 points, and the boxes of a sub-tile may belong to different clouds: the
+    // (cloud, point) list is cut into boxes, not into 128-point pieces per cloud (312 points = 9.75 boxes: 2.5 % padding
+    // instead of 18 %).  TMEM lane quarter q of a sub-tile = its box q = one epilogue warp.
+    const int bpc = (a.n + 31) / 32;                         // boxes per cloud
+    const long long nboxes = (long long)a.b * bpc;
+    const long long nsub = (nboxes + 3) / 4;
     const long long ntiles = (nsub + SUB - 1) / SUB;
     const int nkb = (a.cin + KB - 1) / KB;
     const int last_ksteps = ((a.cin - (nkb - 1) * KB) + 7) / 8;
@@ -167,21 +171,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         uint32_t stage = 0, phase = 0;
         long long li = 0;                                    // this CTA's tile counter
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++li) {
-            int cb[SUB], cp[SUB];
+            int cb[SUB][4], cp[SUB][4];
 #pragma unroll
-            for (int s = 0; s < SUB; ++s) {
-                const long long sid = t * SUB + s;       // sid >= nsub: cloud index b -> fully out of bounds -> zeros
-                cb[s] = (int)(sid / spc);
-                cp[s] = (int)(sid % spc) * SUBM;
-            }
+            for (int s = 0; s < SUB; ++s)
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) {
+                    const long long box = (t * SUB + s) * 4 + mb;   // box >= nboxes: cloud index >= b -> fully out of bounds -> zeros
+                    cb[s][mb] = (int)(box / bpc);
+                    cp[s][mb] = (int)(box % bpc) * 32;
+                }
             for (int kb = 0; kb < nkb; ++kb) {
                 if (lane < SUB * 4 && !(a.variant & 64)) {
                     const long long f = li * nkb + kb + PREFETCH;
                     const long long lt = f / nkb, tt = blockIdx.x + lt * gridDim.x;
                     if (tt < ntiles) {
-                        const long long sid = tt * SUB + (lane >> 2);
-                        if (sid < nsub)
-                            tma_prefetch_3d(&xmap, (int)(sid % spc) * SUBM + (lane & 3) * 32, (int)(f - lt * nkb) * KB, (int)(sid / spc));
+                        const long long box = tt * SUB * 4 + lane;      // lanes 0..7: the eight boxes of that tile
+                        if (box < nboxes)
+                            tma_prefetch_3d(&xmap, (int)(box % bpc) * 32, (int)(f - lt * nkb) * KB, (int)(box / bpc));
                     }
                 }
                 mbar_wait(&bar_empty[stage], phase ^ 1u);
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         for (int s = 0; s < SUB; ++s)
 #pragma unroll
                             for (int mb = 0; mb < 4; ++mb)
-                                tma_load_3d(sa + s * A_SUB_BYTES + mb * 4096, &xmap, cp[s] + mb * 32, kb * KB, cb[s], &bar_full[stage]);
+                                tma_load_3d(sa + s * A_SUB_BYTES + mb * 4096, &xmap, cp[s][mb], kb * KB, cb[s][mb], &bar_full[stage]);
                     }
                     if (!no_w) bulk_load(sa + 2 * C::A_BYTES, a.wsplit + (size_t)kb * (2 * C::B_HALF), 2 * C::B_HALF, &bar_full[stage]);
                 }
@@ -297,10 +303,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             {
-                const long long sid = t * SUB + s;
-                const long long bi = sid / spc;
-                const int p = (int)(sid % spc) * SUBM + q * 32 + lane;
-                const bool valid = sid < nsub && p < a.n && !(a.variant & 16);   // 16: timing without stores
+                const long long box = (t * SUB + s) * 4 + q;
+                const long long bi = box / bpc;
+                const int p = (int)(box % bpc) * 32 + lane;
+                const bool valid = box < nboxes && p < a.n && !(a.variant & 16);   // 16: timing without stores
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + s * 2 * NC;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll(MODE == MODE_PROJECT ? NC / 32 : 1)
@@ -433,8 +439,8 @@ static int launch(const CUtensorMap &map, const Args &a, cudaStream_t s) {
                              "conv_tc: shared memory opt-in");
         if (st) return st;
     }
-    const int spc = (a.n + SUBM - 1) / SUBM;
-    const long long ntiles = ((long long)a.b * spc + SUB - 1) / SUB;
+    const long long nsubs = ((long long)a.b * ((a.n + 31) / 32) + 3) / 4;
+    const long long ntiles = (nsubs + SUB - 1) / SUB;
     const int grid = (int)(ntiles < device_info().sm_count ? ntiles : device_info().sm_count);
     conv_tc_kernel<NC, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, a);
     PU3_LAUNCH_CHECK("conv_tc_kernel");

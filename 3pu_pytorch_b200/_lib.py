@@ -63,10 +63,14 @@ SIGNATURES = {
     "pu3_level_workspace": (_c_size_t, [_c_int] * 8),
     "pu3_level_forward_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "pu3_level_forward_pm_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                          _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
+                                          _c_void_p]),
     "pu3_level_forward_train_f32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                              _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
                                              _c_void_p, _c_void_p]),
     "pu3_skip_fuse_ex_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 8),
+    "pu3_skip_fuse_pm_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 9),
     "pu3_skip_bwd_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 6),
     "pu3_pointwise_conv_bwd_w_ex_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_ll, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "pu3_replica_sum_f32": (_c_int, [_c_ll, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
@@ -145,7 +149,7 @@ KERNELS_PER_CALL = {
     # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 4 head kernels (3 weight splits + 1 fused tcgen05; the
     # train-mode forward keeps the three-kernel head: 21);
     # the feature kNN finds duplicates itself (no side kernels); the skip connection adds 3 duplicate kernels + kNN + skip, iota 1
-    "pu3_level_forward_f32": 19, "pu3_level_forward_train_f32": 21,
+    "pu3_level_forward_f32": 19, "pu3_level_forward_pm_f32": 19, "pu3_level_forward_train_f32": 21,
     "pu3_conv_tc_prepare_f32": 1, "pu3_conv_tc_f32": 1, "pu3_conv_tc_expand_f32": 1, "pu3_conv_tc_project_f32": 1,
     "pu3_head_tc_f32": 1,
     "pu3_fps_ragged_f32": 1,

@@ -79,13 +79,30 @@ extern "C" size_t pu3_level_workspace(int t, int n, int r, int knn, int fm_knn, 
     return plan_level(t, n, r, knn, fm_knn, clouds, no, has_prev != 0).total;
 }
 
+static int level_forward_impl(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                              const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                              const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
+                              float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
+                              const pu3_level_saved *saved, float *feat_pm_out, pu3_stream_t stream);
+
 extern "C" int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
                                      const int32_t *owner, int groups, int max_group, const float *prev_xyz,
                                      const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
                                      float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
                                      pu3_stream_t stream) {
-    return pu3_level_forward_train_f32(w, t, n, xyz, xyz_norm, owner, groups, max_group, prev_xyz, prev_feat_pm, clouds, no, prev_n,
-                                       feat, out_xyz, workspace, workspace_bytes, nullptr, stream);
+    return level_forward_impl(w, t, n, xyz, xyz_norm, owner, groups, max_group, prev_xyz, prev_feat_pm, clouds, no, prev_n,
+                              feat, out_xyz, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+// ... and the features once more point-major (t,n,264) for the next level's skip connection: written by the skip kernel of THIS
+// level while the rows are in registers (levels without a previous level: a transposing pass)
+extern "C" int pu3_level_forward_pm_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                                        const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                                        const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
+                                        float *feat, float *out_xyz, float *feat_pm_out, void *workspace, size_t workspace_bytes,
+                                        pu3_stream_t stream) {
+    return level_forward_impl(w, t, n, xyz, xyz_norm, owner, groups, max_group, prev_xyz, prev_feat_pm, clouds, no, prev_n,
+                              feat, out_xyz, workspace, workspace_bytes, nullptr, feat_pm_out, stream);
 }
 
 // The same forward keeping what the backward pass needs (train step, model.py:53-66): the 24-channel input of every dense
@@ -96,6 +113,15 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
                                            const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
                                            float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
                                            const pu3_level_saved *saved, pu3_stream_t stream) {
+    return level_forward_impl(w, t, n, xyz, xyz_norm, owner, groups, max_group, prev_xyz, prev_feat_pm, clouds, no, prev_n,
+                              feat, out_xyz, workspace, workspace_bytes, saved, nullptr, stream);
+}
+
+static int level_forward_impl(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                              const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                              const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n,
+                              float *feat, float *out_xyz, void *workspace, size_t workspace_bytes,
+                              const pu3_level_saved *saved, float *feat_pm_out, pu3_stream_t stream) {
     PU3_ARG_CHECK(w && t >= 0 && n > 0, "level_forward: bad arguments");
     if (t == 0) return PU3_OK;
     PU3_ARG_CHECK(xyz_norm && feat && out_xyz, "level_forward: null pointer");
@@ -170,8 +196,10 @@ extern "C" int pu3_level_forward_train_f32(const pu3_level_weights *w, int t, in
         if (saved && saved->feat_pre)
             PU3_TRY(cuda_status(cudaMemcpyAsync(saved->feat_pre, feat, (size_t)t * C * n * sizeof(float), cudaMemcpyDeviceToDevice,
                                                 as_stream(stream)), "level_forward: copy of the pre-skip features"));
-        PU3_TRYT(PROF_SKIP_FUSE, pu3_skip_fuse_ex_f32(t, n, C, w->fm_knn, owner ? 1 : t / clouds, no, feat, xyz, skipidx, prev_xyz, prev_feat_pm,
-                                  owner, saved ? saved->skip_w : nullptr, stream));
+        PU3_TRYT(PROF_SKIP_FUSE, pu3_skip_fuse_pm_f32(t, n, C, w->fm_knn, owner ? 1 : t / clouds, no, feat, xyz, skipidx, prev_xyz, prev_feat_pm,
+                                  owner, saved ? saved->skip_w : nullptr, feat_pm_out, stream));
+    } else if (feat_pm_out) {
+        PU3_TRYT(PROF_MISC, pu3_to_point_major_f32(t, C, n, feat, nullptr, feat_pm_out, stream));
     }
     // expansion head (:349-372)
     if (g_level_tc >= 3 && n % 4 == 0 && r == 2 && !saved) {

@@ -29,6 +29,7 @@ struct SkipArgs {
     const float *prev_feat;    // (clouds,no,c) POINT-major
     const int32_t *owner;      // (t) or null -> t / p_div
     float *w_out;              // (t,n,k) or null: the normalised interpolation weights (saved for the backward pass)
+    float *pm_out;             // (t,n,c) or null: the updated features once more, POINT-major (what the next level gathers from)
 };
 
 __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
@@ -132,7 +133,9 @@ __global__ void __launch_bounds__(SK_THREADS) skip_fuse_kernel(SkipArgs a) {
                     }
                 }
                 float *cell = &xt[ch * (SK_PT + 1) + pl];
-                *cell = __fmaf_rn(0.2f, acc, *cell);   // x = 0.2 * knnIdx_feats + x (:347)
+                const float nv = __fmaf_rn(0.2f, acc, *cell);   // x = 0.2 * knnIdx_feats + x (:347)
+                *cell = nv;
+                if (a.pm_out) a.pm_out[((size_t)ti * N + i) * C + ch] = nv;
             }
         }
         __syncthreads();
@@ -277,7 +280,11 @@ __global__ void __launch_bounds__(SK_THREADS, 3) skip_fuse_fixed_kernel(SkipArgs
 #pragma unroll
                     for (int kk = 0; kk < K; ++kk) acc = __fmaf_rn(w[kk], nb[kk][u], acc);
                     float *cell = &xt[ch * (SK_PT + 1) + pl];
-                    *cell = __fmaf_rn(0.2f, acc, *cell);
+                    const float nv = __fmaf_rn(0.2f, acc, *cell);
+                    *cell = nv;
+                    // the warp holds the point's whole updated row, channel = lane + 32 u: the point-major copy the next level's skip
+                    // connection gathers from is written from here (coalesced), instead of by a transposing pass over x afterwards
+                    if (a.pm_out) a.pm_out[((size_t)ti * N + i) * C + ch] = nv;
                 }
             }
         }
@@ -373,12 +380,18 @@ extern "C" int pu3_skip_bwd_f32(int t, int n, int c, int k, int p_div, int no, c
 extern "C" int pu3_skip_fuse_ex_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz,
                                     const int64_t *idx, const float *prev_xyz, const float *prev_feat_pm,
                                     const int32_t *owner, float *w_out, pu3_stream_t stream) {
+    return pu3_skip_fuse_pm_f32(t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner, w_out, nullptr, stream);
+}
+
+extern "C" int pu3_skip_fuse_pm_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz,
+                                    const int64_t *idx, const float *prev_xyz, const float *prev_feat_pm,
+                                    const int32_t *owner, float *w_out, float *x_pm_out, pu3_stream_t stream) {
     PU3_ARG_CHECK(t >= 0 && n > 0 && c > 0 && k > 0 && no > 0, "skip_fuse: bad size t=%d n=%d c=%d k=%d no=%d", t, n, c, k, no);
     if (t == 0) return PU3_OK;
     PU3_ARG_CHECK(k <= SK_KMAX, "skip_fuse: k=%d exceeds %d", k, SK_KMAX);
     PU3_ARG_CHECK(owner || p_div >= 1, "skip_fuse: need owner or p_div");
     PU3_ARG_CHECK(x && xyz && idx && prev_xyz && prev_feat_pm, "skip_fuse: null pointer");
-    SkipArgs a{t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner, w_out};
+    SkipArgs a{t, n, c, k, p_div, no, x, xyz, idx, prev_xyz, prev_feat_pm, owner, w_out, x_pm_out};
     const size_t smem = ((size_t)c * (SK_PT + 1) + 2 * (size_t)n * k + 2 * SK_WARPS) * sizeof(float);
     PU3_ARG_CHECK(smem <= (size_t)device_info().smem_optin, "skip_fuse: c=%d n=%d k=%d needs %zu bytes of shared memory", c, n, k, smem);
     int st = cuda_status(cudaFuncSetAttribute(skip_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "skip_fuse: smem attr");

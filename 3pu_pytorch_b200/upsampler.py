@@ -169,7 +169,7 @@ class Level(torch.nn.Module):
         return (self.feat_channels == 264 and all(b.k == self.knn for b in (self.layer1, self.layer2, self.layer3, self.layer4))
                 and self.up_layer.up_layer1.conv.weight.shape[1] == 265)
 
-    def _forward_engine(self, xyz, xyz_normalized, previous_level4, group, ragged):
+    def _forward_engine(self, xyz, xyz_normalized, previous_level4, group, ragged, feat_pm_out=None):
         import ctypes
         T, _, N = xyz_normalized.shape
         dev = xyz_normalized.device
@@ -194,6 +194,16 @@ class Level(torch.nn.Module):
         feat = torch.empty(T, 264, N, dtype=torch.float32, device=dev)
         out = torch.empty(T, 3, N * r, dtype=torch.float32, device=dev)
         extra = (5 if has_prev else 0) + (1 if owner is not None else 0)
+        if feat_pm_out is not None:
+            # the features once more point-major (T,N,264) for the next level's skip connection: written by this level's skip
+            # kernel while the rows are in registers (level 1: by a transposing pass inside the engine)
+            assert feat_pm_out.is_contiguous() and feat_pm_out.numel() == T * N * 264
+            fused._lib.launch("pu3_level_forward_pm_f32", xn, ctypes.addressof(W), T, N, fused._lib.ptr(xyz_c), xn.data_ptr(),
+                              fused._lib.ptr(owner), int(groups), int(group or T), fused._lib.ptr(prev_xyz),
+                              fused._lib.ptr(prev_feat_pm), int(clouds), int(No), fused._lib.ptr(prev_n), feat.data_ptr(),
+                              out.data_ptr(), feat_pm_out.data_ptr(), ws.data_ptr(), ws_bytes,
+                              extra_kernels=extra + (0 if has_prev else 1), tag="pu3_level_forward_f32")
+            return out, feat
         fused._lib.launch("pu3_level_forward_f32", xn, ctypes.addressof(W), T, N, fused._lib.ptr(xyz_c), xn.data_ptr(),
                           fused._lib.ptr(owner), int(groups), int(group or T), fused._lib.ptr(prev_xyz),
                           fused._lib.ptr(prev_feat_pm), int(clouds), int(No), fused._lib.ptr(prev_n), feat.data_ptr(),
@@ -316,8 +326,11 @@ class Level(torch.nn.Module):
         fast = self._fast_path_ok(xyz_normalized)
         if ragged is not None and not fast:
             raise RuntimeError("ragged batches are an eval-mode (no-grad, CUDA fp32) feature")
+        feat_pm_out = kwargs.pop("feat_pm_out", None)     # (extension, eval) buffer receiving the features point-major
         if fast and self.use_engine and self._engine_ok() and (previous_level4 is None or prev_point_major or self.fm_knn <= 0):
-            return self._forward_engine(xyz, xyz_normalized, previous_level4, group, ragged)
+            return self._forward_engine(xyz, xyz_normalized, previous_level4, group, ragged, feat_pm_out)
+        if feat_pm_out is not None:
+            raise RuntimeError("feat_pm_out needs the level engine (eval mode, CUDA fp32, reference configuration)")
         if not fast and self.native_train and torch.is_grad_enabled() and not prev_point_major and ragged is None \
                 and self._native_train_ok(xyz_normalized, previous_level4):
             prev_xyz, prev_feat = previous_level4 if (previous_level4 is not None and self.fm_knn > 0) else (None, None)
@@ -554,6 +567,10 @@ class Net(torch.nn.Module):
         L.launch("pu3_tiles_normalize_f32", tiles, B, P, k, tiles.data_ptr(), patch_xyz.data_ptr(), patch_norm.data_ptr(),
                  centroid.data_ptr(), radius.data_ptr(), L.ptr(prev_xyz))
         ragged = operations.Ragged(owner, owner, B, n_arr=old_n)
+        feat_pm = None
+        if keep_features and level.use_engine and level._engine_ok():
+            feat_pm = torch.empty(B, P * k, 264, **f32)     # filled by the level itself (skip kernel / engine)
+            kwargs = dict(kwargs, feat_pm_out=feat_pm)
         new_xyz, features = level(patch_xyz, patch_norm, previous_level4=(old_xyz, old_features), ragged=ragged,
                                   prev_point_major=True, **kwargs)                    # (T,3,k*r) normalised frame
         kr = new_xyz.shape[2]
@@ -570,9 +587,10 @@ class Net(torch.nn.Module):
         L.launch("pu3_gather_pm_f32", merged_pm, B, P * kr, num_output_point, merged_pm.data_ptr(), oidx.data_ptr(),
                  out_xyz.data_ptr())
         if keep_features:
-            Cf = features.shape[1]
-            feat_pm = torch.empty(B, P * k, Cf, **f32)
-            L.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(), None, feat_pm.data_ptr())
+            if feat_pm is None:
+                Cf = features.shape[1]
+                feat_pm = torch.empty(B, P * k, Cf, **f32)
+                L.launch("pu3_to_point_major_f32", features, features.shape[0], Cf, k, features.data_ptr(), None, feat_pm.data_ptr())
             return out_xyz, prev_xyz, feat_pm, pk_arr
         return out_xyz, None, None, None
 

@@ -255,6 +255,11 @@ int pu3_skip_fuse_f32(int t, int n, int c, int k, int p_div, int no, float *x, c
 /* ... the same, also writing the normalised weights w (t,n,k) (NULL = not wanted): what the backward pass needs. */
 int pu3_skip_fuse_ex_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
                          const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, float *w_out, pu3_stream_t stream);
+/* the same, also writing the updated features point-major, x_pm_out (t,n,c) (NULL = not wanted): what the NEXT level's skip
+ * connection gathers from, produced while the rows are in registers instead of by pu3_to_point_major_f32 afterwards */
+int pu3_skip_fuse_pm_f32(int t, int n, int c, int k, int p_div, int no, float *x, const float *xyz, const int64_t *idx,
+                         const float *prev_xyz, const float *prev_feat_pm, const int32_t *owner, float *w_out, float *x_pm_out,
+                         pu3_stream_t stream);
 /*
  * Backward of the skip connection (autograd of network/upsampler.py:334-347 in the train step; the weights are detached there,
  * :243,249): dprev_feat_pm[cloud, idx[i,kk], :] += 0.2 * w[i,kk] * dx[:, i] with fp32 atomics into a caller-zeroed POINT-major
@@ -309,6 +314,11 @@ int pu3_level_forward_f32(const pu3_level_weights *w, int t, int n, const float 
                           const int32_t *owner, int groups, int max_group, const float *prev_xyz,
                           const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
                           float *out_xyz, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
+/* the same, also handing the level's features over point-major for the next level: feat_pm_out (t,n,264) or NULL */
+int pu3_level_forward_pm_f32(const pu3_level_weights *w, int t, int n, const float *xyz, const float *xyz_norm,
+                             const int32_t *owner, int groups, int max_group, const float *prev_xyz,
+                             const float *prev_feat_pm, int clouds, int no, const int32_t *prev_n, float *feat,
+                             float *out_xyz, float *feat_pm_out, void *workspace, size_t workspace_bytes, pu3_stream_t stream);
 /*
  * Buffers the train-mode forward fills for the backward pass (all caller-allocated): h[blk] (t,24,n) the input of dense block blk
  * (layer0 output, then the three prep outputs after ReLU), idx[blk] (t,n,knn+1) i32 its neighbour lists (column 0 = the dropped

@@ -66,7 +66,6 @@ struct FpsSmem {
     FpsCand warp_slot[2][32];                  // [round parity][warp]: the warp's winner, coordinates included
     FpsCand cta_slot[2];                       // [round parity] the CTA's winner (wide clusters: leader-warp exchange)
     uint64_t mbar[2];                          // [round parity] "all S candidates of the round have landed"
-    int top[32][4];                            // [warp] fps_select scratch: slots of the FPS_SPEC best candidates
     float res_w[2][FPS_SPEC][4];               // [round parity] samples chosen by warp 0 (x, y, z, -) ...
     int res_a[2];                              // ... and how many
 };
@@ -98,7 +97,7 @@ __device__ __forceinline__ void fps_mark(int, int) {}
 // indices to out[j ...] (written by the thread for which `writer` is set).
 template <int SPEC>
 __device__ __forceinline__ int fps_select(const FpsCand *slots, int total, int lane, int spec_cap, int j, int m, bool writer,
-                                          int32_t *out, float (&wx)[SPEC], float (&wy)[SPEC], float (&wz)[SPEC], int *top) {
+                                          int32_t *out, float (&wx)[SPEC], float (&wy)[SPEC], float (&wz)[SPEC]) {
     // Round 2, second version.  The first one popped the candidates one after the other with the slot read, the distance tests
     // and the break conditions of a sample on the chain before the next reduce-max: ~650 cycles per accepted sample, 2 600 of an
     // exchange's 5 600 cycles at depth 4 (in-kernel timeline, profiles/r2) -- latency, not issue slots: running it in one warp
@@ -320,7 +319,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 dst[0] = plo; dst[1] = phi;
             }
             __syncthreads();
-            A = fps_select<SPEC>(&sm.warp_slot[par][0], nwarps, lane, spec_cap, j, m, threadIdx.x == 0, out, wx, wy, wz, sm.top[warp]);
+            A = fps_select<SPEC>(&sm.warp_slot[par][0], nwarps, lane, spec_cap, j, m, threadIdx.x == 0, out, wx, wy, wz);
             j += A;
         } else if (DIRECT) {
             // ---- 3b. cluster of <= 64 warps: EVERY warp sends its candidate straight into every CTA's slot array by
@@ -354,13 +353,13 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
             // result, so warp 0 alone computes it and hands it over through shared memory: one __syncthreads instead of 7
             // redundant copies competing for the issue slots.
             if (select_all) {
-                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
+                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
                 fps_mark(j, 6);
                 j += A;
                 continue;
             }
             if (warp == 0) {
-                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
+                A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S * nwarps, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
                 if (lane == 0) {
                     sm.res_a[par] = A;
 #pragma unroll
@@ -417,7 +416,7 @@ fps_kernel(int n_stride, int m_stride, const int32_t *__restrict__ n_arr, const 
                 }
             }
             mbar_wait_parity(&sm.mbar[par], ((e - 1u) >> 1) & 1u);
-            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S, lane, spec_cap, j, m, g == 0, out, wx, wy, wz, sm.top[warp]);
+            A = fps_select<SPEC>(&sm.cluster_slot[par][0], (int)S, lane, spec_cap, j, m, g == 0, out, wx, wy, wz);
             j += A;
             fps_mark(j, 6);
         }

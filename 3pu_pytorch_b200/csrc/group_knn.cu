@@ -642,25 +642,60 @@ __global__ void __launch_bounds__(KF_THREADS, KF_MINB) knn_feat_kernel(KnnArgs a
                     hk[z] = 0xffffffffu; perm_lo[z] = 0; perm_hi[z] = 0;
                     if (z < nz) {
                         uint32_t *krow = krowz[z];
-                        unsigned long long v[KF_S];
+                        // The lane's 10 keys are first sorted on 32-bit words (key with its low 4 bits replaced by the stripe: a
+                        // compare-exchange is one IMNMX pair instead of a 64-bit compare and two 64-bit selects), the exact keys are
+                        // fetched in that order and checked; a lane with two keys closer than 16 ulp may come out in the wrong
+                        // order, and then (any lane of the warp) the query is sorted again on the packed 64-bit words.
+                        uint32_t w[KF_S];
 #pragma unroll
-                        for (int s2 = 0; s2 < KF_S; ++s2) v[s2] = ((unsigned long long)krow[s2 * 32 + lane] << 32) | (uint32_t)s2;
-                        cex(v[4], v[9]); cex(v[3], v[8]); cex(v[2], v[7]); cex(v[1], v[6]); cex(v[0], v[5]);
-                        cex(v[1], v[4]); cex(v[6], v[9]); cex(v[0], v[3]); cex(v[5], v[8]);
-                        cex(v[0], v[2]); cex(v[3], v[6]); cex(v[7], v[9]);
-                        cex(v[0], v[1]); cex(v[2], v[4]); cex(v[5], v[7]); cex(v[8], v[9]);
-                        cex(v[1], v[2]); cex(v[4], v[6]); cex(v[7], v[8]); cex(v[3], v[5]);
-                        cex(v[2], v[5]); cex(v[6], v[8]); cex(v[1], v[3]); cex(v[4], v[7]);
-                        cex(v[2], v[3]); cex(v[6], v[7]);
-                        cex(v[3], v[4]); cex(v[5], v[6]);
-                        cex(v[4], v[5]);
+                        for (int s2 = 0; s2 < KF_S; ++s2) w[s2] = (krow[s2 * 32 + lane] & ~15u) | (uint32_t)s2;
+#define PU3_CEX32(a_, b_) do { const uint32_t lo_ = min(a_, b_), hi_ = max(a_, b_); a_ = lo_; b_ = hi_; } while (0)
+                        PU3_CEX32(w[4], w[9]); PU3_CEX32(w[3], w[8]); PU3_CEX32(w[2], w[7]); PU3_CEX32(w[1], w[6]); PU3_CEX32(w[0], w[5]);
+                        PU3_CEX32(w[1], w[4]); PU3_CEX32(w[6], w[9]); PU3_CEX32(w[0], w[3]); PU3_CEX32(w[5], w[8]);
+                        PU3_CEX32(w[0], w[2]); PU3_CEX32(w[3], w[6]); PU3_CEX32(w[7], w[9]);
+                        PU3_CEX32(w[0], w[1]); PU3_CEX32(w[2], w[4]); PU3_CEX32(w[5], w[7]); PU3_CEX32(w[8], w[9]);
+                        PU3_CEX32(w[1], w[2]); PU3_CEX32(w[4], w[6]); PU3_CEX32(w[7], w[8]); PU3_CEX32(w[3], w[5]);
+                        PU3_CEX32(w[2], w[5]); PU3_CEX32(w[6], w[8]); PU3_CEX32(w[1], w[3]); PU3_CEX32(w[4], w[7]);
+                        PU3_CEX32(w[2], w[3]); PU3_CEX32(w[6], w[7]);
+                        PU3_CEX32(w[3], w[4]); PU3_CEX32(w[5], w[6]);
+                        PU3_CEX32(w[4], w[5]);
+#undef PU3_CEX32
+                        uint32_t ex[KF_S];
 #pragma unroll
-                        for (int s2 = 0; s2 < KF_S; ++s2) {
-                            const uint32_t tag = (uint32_t)v[s2] & 15u;
-                            if (s2 < 8) perm_lo[z] |= tag << (4 * s2); else perm_hi[z] |= tag << (4 * (s2 - 8));
-                            if (s2 > 0) krow[s2 * 32 + lane] = (uint32_t)(v[s2] >> 32);
+                        for (int s2 = 0; s2 < KF_S; ++s2) ex[s2] = krow[(w[s2] & 15u) * 32 + lane];
+                        bool ok = true;
+#pragma unroll
+                        for (int s2 = 0; s2 + 1 < KF_S; ++s2)
+                            ok = ok & ((ex[s2] < ex[s2 + 1]) | ((ex[s2] == ex[s2 + 1]) & ((w[s2] & 15u) < (w[s2 + 1] & 15u))));
+                        if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+                            for (int s2 = 0; s2 < KF_S; ++s2) {
+                                const uint32_t tag = w[s2] & 15u;
+                                if (s2 < 8) perm_lo[z] |= tag << (4 * s2); else perm_hi[z] |= tag << (4 * (s2 - 8));
+                                if (s2 > 0) krow[s2 * 32 + lane] = ex[s2];
+                            }
+                            hk[z] = ex[0];
+                        } else {
+                            unsigned long long v[KF_S];
+#pragma unroll
+                            for (int s2 = 0; s2 < KF_S; ++s2) v[s2] = ((unsigned long long)krow[s2 * 32 + lane] << 32) | (uint32_t)s2;
+                            cex(v[4], v[9]); cex(v[3], v[8]); cex(v[2], v[7]); cex(v[1], v[6]); cex(v[0], v[5]);
+                            cex(v[1], v[4]); cex(v[6], v[9]); cex(v[0], v[3]); cex(v[5], v[8]);
+                            cex(v[0], v[2]); cex(v[3], v[6]); cex(v[7], v[9]);
+                            cex(v[0], v[1]); cex(v[2], v[4]); cex(v[5], v[7]); cex(v[8], v[9]);
+                            cex(v[1], v[2]); cex(v[4], v[6]); cex(v[7], v[8]); cex(v[3], v[5]);
+                            cex(v[2], v[5]); cex(v[6], v[8]); cex(v[1], v[3]); cex(v[4], v[7]);
+                            cex(v[2], v[3]); cex(v[6], v[7]);
+                            cex(v[3], v[4]); cex(v[5], v[6]);
+                            cex(v[4], v[5]);
+#pragma unroll
+                            for (int s2 = 0; s2 < KF_S; ++s2) {
+                                const uint32_t tag = (uint32_t)v[s2] & 15u;
+                                if (s2 < 8) perm_lo[z] |= tag << (4 * s2); else perm_hi[z] |= tag << (4 * (s2 - 8));
+                                if (s2 > 0) krow[s2 * 32 + lane] = (uint32_t)(v[s2] >> 32);
+                            }
+                            hk[z] = (uint32_t)(v[0] >> 32);
                         }
-                        hk[z] = (uint32_t)(v[0] >> 32);
                     }
                 }
                 uint32_t hk_first[NZ];

@@ -54,8 +54,9 @@ __device__ __forceinline__ float sqdist3(float dx, float dy, float dz) {
 
 // Monotone map float -> uint32 (total order, -0 < +0, NaNs at the ends).
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const uint32_t u = __float_as_uint(f);
+    // negative: ~u, else u | 0x80000000 -- both are u ^ (sign-extension | 0x80000000): a shift and one LOP3, no select
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float ordered_to_float(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pu3_head_tc_set_mode": (None, [_c_int]),
     "pu3_skip_fuse_f32": (_c_int, [_c_int] * 6 + [_c_void_p] * 7),
     "pu3_skip_force_generic": (None, [_c_int]),
+    "pu3_edgeconv_set_tc": (None, [_c_int]),
     "pu3_to_point_major_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
     "pu3_clip_adam_f32": (_c_int, [_c_ll] + [_c_void_p] * 4 + [_c_float] * 6 + [_c_int, _c_void_p]),
     "pu3_pointwise_conv_bwd_w_f32": (_c_int, [_c_int] * 4 + [_c_void_p, _c_ll, _c_void_p, _c_ll, _c_void_p, _c_void_p, _c_void_p]),

@@ -456,6 +456,14 @@ using namespace pu3;
 // Test hook: force the generic kernel.
 static int g_ec_force_generic = 0;
 extern "C" void pu3_edgeconv_force_generic(int on) { g_ec_force_generic = on; }
+// A/B hook (0 until the tensor-core kernel is the faster one): 1 = k == 32 runs the per-edge layers on the tensor cores (edgeconv_tc.cu), 0 = FFMA kernels only
+static int g_ec_tc = 0;
+extern "C" void pu3_edgeconv_set_tc(int on) { g_ec_tc = on; }
+namespace pu3 {
+bool edgeconv_tc_launch(int b, int n, const float *x, long long x_bstride, const int32_t *idx, int idx_stride, int idx_off,
+                        const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
+                        float *y, long long y_bstride, cudaStream_t s, int *status);
+}
 
 extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
                                 int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
@@ -482,6 +490,13 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     dim3 grid((n + pts - 1) / pts, b);
     cudaStream_t s = as_stream(stream);
     int st;
+    if (k == 32 && g_ec_tc && !g_ec_force_generic) {
+        if (edgeconv_tc_launch(b, n, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, s, &st)) {
+            if (st) return st;
+            PU3_LAUNCH_CHECK("edgeconv_tc_kernel");
+            return PU3_OK;
+        }
+    }
     const size_t fast_smem = sizeof(EfSmemW) + (size_t)(EC_OUT * (EC_PT + 1) + EC_WARPS * 2 * 36 + EC_WARPS * 2 * EF_PS + (size_t)n * (EF_XS + EF_PS0)) * sizeof(float);
     if (k <= 32 && fast_smem <= 110 * 1024 && g_ec_force_generic == 0) {
         auto kern = k == 32 ? edgeconv_fast_kernel<true> : edgeconv_fast_kernel<false>;

@@ -87,6 +87,8 @@ SIGNATURES = {
     "pu3_gather_pm_f32": (_c_int, [_c_int] * 3 + [_c_void_p] * 4),
     "pu3_edgeconv_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
                          [_c_void_p, _c_ll, _c_void_p]),
+    "pu3_edgeconv_ffma_f32": (_c_int, [_c_int] * 3 + [_c_void_p, _c_ll, _c_void_p, _c_int, _c_int] + [_c_void_p] * 6 +
+                         [_c_void_p, _c_ll, _c_void_p]),
 }
 
 class LevelWeights(ctypes.Structure):
@@ -146,7 +148,7 @@ def check(status, what):
 KERNELS_PER_CALL = {
     "pu3_fps_f32": 1, "pu3_gather_fwd": 1, "pu3_gather_bwd": 1, "pu3_ball_query_f32": 1, "pu3_nmdist_fwd_f32": 1,
     "pu3_nmdist_bwd_f32": 1, "pu3_group_gather_bwd_f32": 1, "pu3_pointwise_conv_f32": 1, "pu3_expand_code_f32": 1,
-    "pu3_edgeconv_f32": 1, "pu3_iota_i32": 1,
+    "pu3_edgeconv_f32": 1, "pu3_edgeconv_ffma_f32": 1, "pu3_iota_i32": 1,
     # layer0 + 4 x (kNN + edge-conv) + 3 x (prep weight split + prep conv) + 4 head kernels (3 weight splits + 1 fused tcgen05; the
     # train-mode forward keeps the three-kernel head: 21);
     # the feature kNN finds duplicates itself (no side kernels); the skip connection adds 3 duplicate kernels + kNN + skip, iota 1

@@ -456,8 +456,8 @@ using namespace pu3;
 // Test hook: force the generic kernel.
 static int g_ec_force_generic = 0;
 extern "C" void pu3_edgeconv_force_generic(int on) { g_ec_force_generic = on; }
-// A/B hook (0 until the tensor-core kernel is the faster one): 1 = k == 32 runs the per-edge layers on the tensor cores (edgeconv_tc.cu), 0 = FFMA kernels only
-static int g_ec_tc = 0;
+// A/B hook: 1 (default) = k == 32 runs the per-edge layers on the tensor cores (edgeconv_tc.cu), 0 = FFMA kernels only
+static int g_ec_tc = 1;
 extern "C" void pu3_edgeconv_set_tc(int on) { g_ec_tc = on; }
 namespace pu3 {
 bool edgeconv_tc_launch(int b, int n, const float *x, long long x_bstride, const int32_t *idx, int idx_stride, int idx_off,
@@ -465,10 +465,10 @@ bool edgeconv_tc_launch(int b, int n, const float *x, long long x_bstride, const
                         float *y, long long y_bstride, cudaStream_t s, int *status);
 }
 
-extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
-                                int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
-                                const float *b1, const float *w2, const float *b2, float *y, long long y_bstride,
-                                pu3_stream_t stream) {
+static int edgeconv_forward(bool allow_tc, int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
+                            int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
+                            const float *b1, const float *w2, const float *b2, float *y, long long y_bstride,
+                            pu3_stream_t stream) {
     PU3_ARG_CHECK(b >= 0 && n >= 0 && k > 0, "edgeconv: bad size b=%d n=%d k=%d", b, n, k);
     if (b == 0 || n == 0) return PU3_OK;
     PU3_ARG_CHECK(b <= 65535, "edgeconv: b=%d exceeds 65535", b);
@@ -490,7 +490,7 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     dim3 grid((n + pts - 1) / pts, b);
     cudaStream_t s = as_stream(stream);
     int st;
-    if (k == 32 && g_ec_tc && !g_ec_force_generic) {
+    if (k == 32 && allow_tc && g_ec_tc && !g_ec_force_generic) {
         if (edgeconv_tc_launch(b, n, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, s, &st)) {
             if (st) return st;
             PU3_LAUNCH_CHECK("edgeconv_tc_kernel");
@@ -517,6 +517,21 @@ extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x
     }
     PU3_LAUNCH_CHECK("edgeconv_kernel");
     return PU3_OK;
+}
+
+extern "C" int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
+                                int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
+                                const float *b1, const float *w2, const float *b2, float *y, long long y_bstride,
+                                pu3_stream_t stream) {
+    return edgeconv_forward(true, b, n, k, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, stream);
+}
+// the FFMA kernels only: the arithmetic pu3_edgeconv_bwd_f32 recomputes, so a train-mode forward returns exactly the function its
+// backward differentiates
+extern "C" int pu3_edgeconv_ffma_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx,
+                                     int idx_stride, int idx_off, const float *w0, const float *b0, const float *w1,
+                                     const float *b1, const float *w2, const float *b2, float *y, long long y_bstride,
+                                     pu3_stream_t stream) {
+    return edgeconv_forward(false, b, n, k, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

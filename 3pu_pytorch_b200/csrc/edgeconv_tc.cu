@@ -21,25 +21,27 @@ namespace pu3 {
 using namespace tc;
 
 constexpr int ET_C = 24, ET_G = 12;
-constexpr int ET_WGS = 2;                 // warpgroups per CTA
-constexpr int ET_THREADS = ET_WGS * 128;
-constexpr int ET_BLK = 32;                // points per output staging block
-constexpr int ET_XS = 25;                 // row stride of the staged cloud (prolog only)
-constexpr int ET_IMG = 8192;              // one operand image: 2 k-steps x (128 rows x 8 tf32)
-constexpr int ET_KSTEP = 4096;
-constexpr int ET_SO = 36 * (ET_BLK + 1);  // floats of one warpgroup's output block
-constexpr int ET_TMEM_WG = 128;           // tensor-memory columns per warpgroup (96 used)
-constexpr int ET_WB = 8192;               // weight images: B1 (64 rows) 4096 | Bc1 (32 rows) 2048 | B2 (32 rows) 2048
+constexpr int ET_WGS = 2;                      // warpgroups of edge threads per CTA
+constexpr int ET_SIMT = ET_WGS * 128;
+constexpr int ET_THREADS = ET_SIMT + 32 * ET_WGS;   // + one MMA-issuing warp per warpgroup
+constexpr int ET_BLK = 16;                     // points per output staging block (4 tiles)
+constexpr int ET_TILE_IMG = 128 * 96;          // operand image of one tile: 128 rows x [hi(12) | lo(12)] tf32, K-major, no swizzle
+constexpr int ET_SBO = 768;                    // 8-row group: 6 chunks (16 B per row each) of 128 B
+constexpr int ET_OPER = ET_WGS * 2 * ET_TILE_IMG;   // two tiles in flight per warpgroup; the prolog keeps its [hi(24) | lo(24)] images here
+constexpr int ET_XSBO = 1536;                  // prolog image: 12 chunks per 8-row group
+constexpr int ET_WB1 = 64 * 24 * 4, ET_WB2 = 32 * 24 * 4, ET_WB = ET_WB1 + ET_WB2;
+constexpr int ET_BP = 96 * 24 * 4;             // prolog weights [Wp_hi ; Wp_lo] (48 + 48 rows) x 24
+constexpr int ET_SO = 36 * (ET_BLK + 1);       // floats of one output block
+constexpr int ET_SOUT = ET_WGS * ET_SO * 4;         // one block per warpgroup (bytes)
+constexpr int ET_TMEM_WG = 128;                // tensor-memory columns per warpgroup: 2 tiles x 64 (prolog: 96)
+constexpr int ET_RAW = 576 + 432 + 576 + 36;   // floats of the raw weights staged by the prolog
 
 struct EtWeights { const float *w0, *b0, *w1, *b1, *w2, *b2; };   // (12,48) (12,36) (12,48), row-major as in the state_dict
 
-__host__ __device__ inline size_t et_oper_bytes(int n) {
-    const size_t xs = ((size_t)n * ET_XS * sizeof(float) + 127) & ~(size_t)127;
-    const size_t op = (size_t)ET_WGS * 2 * ET_IMG;
-    return xs > op ? xs : op;
-}
+static_assert(ET_RAW * 4 <= ET_OPER, "raw weights are staged in the operand region");
+
 __host__ inline size_t et_smem_bytes(int n, int pts) {
-    return 128 + et_oper_bytes(n) + ET_WB + (size_t)n * ET_G * 4 + (size_t)pts * 36 * 4 + (size_t)ET_WGS * ET_SO * 4 + 64;
+    return 128 + ET_OPER + ET_WB + ET_BP + (size_t)n * ET_G * 4 + (size_t)pts * 36 * 4 + ET_SOUT + 48 * 4 + 8 * 8 + 16;
 }
 
 __device__ __forceinline__ constexpr uint32_t et_idesc(uint32_t ncols) {
@@ -55,304 +57,430 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// mbarrier wait that parks the thread in hardware (suspend-time hint, CUTLASS' ClusterBarrier::wait form) instead of polling: the
+// polling loop of tc::mbar_wait costs issue slots -- ncu counted 644 warp instructions per point with it, the MMA lanes spinning all
+// the time on two of the four schedulers.  Still bounded: traps after ~4 s.
+__device__ __forceinline__ void et_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity), "r"(10000000u) : "memory");
+        if (!done && spins > 400u) __trap();
+    }
+}
 __device__ __forceinline__ float warp_max_f32(float v) {
     float r;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
     return r;
+}
+// lane o (< 12) keeps m[o]: a select tree on the lane's bits (11 selects, 4 predicates) instead of 12 compare-and-select pairs
+__device__ __forceinline__ float et_pick12(const float (&m)[ET_G], int lane) {
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+    const float a0 = b0 ? m[1] : m[0], a1 = b0 ? m[3] : m[2], a2 = b0 ? m[5] : m[4], a3 = b0 ? m[7] : m[6], a4 = b0 ? m[9] : m[8], a5 = b0 ? m[11] : m[10];
+    const float c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2, c2 = b1 ? a5 : a4;
+    const float d0 = b2 ? c1 : c0;
+    return b3 ? c2 : d0;
+}
+__device__ __forceinline__ float et_max12(const float (&r)[ET_G], int lane) {
+    float m[ET_G];
+#pragma unroll
+    for (int o = 0; o < ET_G; ++o) m[o] = warp_max_f32(r[o]);
+    return et_pick12(m, lane);
 }
 __device__ __forceinline__ void wg_sync(int wg) {
     if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
-// bring-up timeline (build with `make -B EXTRA=-DPU3_ET_TIMELINE`, then profiles/edgeconv_tc_timeline.py): SM cycle counter at the
-// phases of tiles [8, 16) of CTA (0,0), warpgroup 0, thread 0.  Compiled out by default.
+// bring-up timeline (build with `make -B EXTRA=-DPU3_ET_TIMELINE`, then profiles/edgeconv_tc_timeline.py): SM cycle counter of
+// CTA (0,0), thread 0 at the phases of the CTA and at the start of its warpgroup-0 tiles.  Compiled out by default.
 #ifdef PU3_ET_TIMELINE
 __device__ unsigned int *g_et_timeline = nullptr;
-__device__ __forceinline__ void et_mark(int tile, int phase) {
-    if (g_et_timeline && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tile >= 8 && tile < 16)
-        g_et_timeline[(tile - 8) * 16 + phase] = (unsigned int)clock64();
+__device__ __forceinline__ void et_mark(int slot) {
+    if (g_et_timeline && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 256) && slot >= 0 && slot < 160) g_et_timeline[slot] = (unsigned int)clock64();
 }
-__device__ __forceinline__ void et_mark_cta(int slot) {
-    if (g_et_timeline && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_et_timeline[128 + slot] = (unsigned int)clock64();
-}
+__device__ __forceinline__ int et_tslot(int q, int ph) { return (q >= 8 && q < 16) ? 8 + (q - 8) * 8 + ph : -1; }       // edge thread 0
+__device__ __forceinline__ int et_mslot(int q, int ph) { return (q >= 8 && q < 16) ? 80 + (q - 8) * 4 + ph : -1; }     // MMA lane of warpgroup 0
 #else
-__device__ __forceinline__ void et_mark(int, int) {}
-__device__ __forceinline__ void et_mark_cta(int) {}
+__device__ __forceinline__ void et_mark(int) {}
+__device__ __forceinline__ int et_tslot(int, int) { return -1; }
+__device__ __forceinline__ int et_mslot(int, int) { return -1; }
 #endif
 
-// the row's 12 values as hi / lo tf32 chunks of the K-major operand images (chunk 3 = K 12..15 stays zero)
-__device__ __forceinline__ void et_store_split(unsigned char *img_hi, unsigned char *img_lo, uint32_t row_off, const float (&r)[ET_G]) {
+// element (row r, k) of a weight image with 8 k per k-step: k-step stride rows * 32 B, 8-row groups 256 B apart, the two 4-k halves 128 B apart
+__device__ __forceinline__ int et_w_off(int rows, int r, int kk) {
+    return (kk >> 3) * (rows * 32) + (r >> 3) * 256 + ((kk & 7) >> 2) * 128 + (r & 7) * 16 + (kk & 3) * 4;
+}
+__device__ __forceinline__ float et_hi_or_lo(float w, bool lo) {
+    const float hi = to_tf32(w);
+    return lo ? to_tf32(w - hi) : hi;
+}
+
+// the row's 12 values as [hi | lo] tf32 chunks of the tile's K-major operand image
+__device__ __forceinline__ void et_store_split(unsigned char *img, uint32_t row_off, const float (&r)[ET_G]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float4 hi, lo;
         hi.x = to_tf32(r[4 * c + 0]); hi.y = to_tf32(r[4 * c + 1]); hi.z = to_tf32(r[4 * c + 2]); hi.w = to_tf32(r[4 * c + 3]);
         lo.x = r[4 * c + 0] - hi.x; lo.y = r[4 * c + 1] - hi.y; lo.z = r[4 * c + 2] - hi.z; lo.w = r[4 * c + 3] - hi.w;
-        const uint32_t off = (uint32_t)(c >> 1) * ET_KSTEP + (uint32_t)(c & 1) * 128u + row_off;
-        *reinterpret_cast<float4 *>(img_hi + off) = hi;
-        *reinterpret_cast<float4 *>(img_lo + off) = lo;
+        *reinterpret_cast<float4 *>(img + row_off + c * 128) = hi;
+        *reinterpret_cast<float4 *>(img + row_off + (3 + c) * 128) = lo;
     }
 }
 
-__global__ void __launch_bounds__(ET_THREADS, 2) edgeconv_tc_kernel(int n, int pts_per_cta, const float *__restrict__ x, long long x_bstride,
+struct EtSlot {            // what an edge thread carries for a tile in flight
+    int j;                 // neighbour index of the thread's edge (fetched one round ahead)
+    float k0, k1;          // lanes 0..11: max over the point's edges of h0[lane], h1[lane]
+    uint32_t phase;        // parity of the slot's `done` barrier
+    const float4 *ai;      // the point's centre terms A0 | A1 | A2 (9 float4)
+    int lp;                // the point's column in the output block, -1 beyond the item's last point
+};
+
+__global__ void __launch_bounds__(ET_THREADS, 2) edgeconv_tc_kernel(int n, int pts_per_cta, int splits, int items, const float *__restrict__ x, long long x_bstride,
                                                                     const int32_t *__restrict__ idx, int idx_stride, int idx_off,
                                                                     EtWeights W, float *__restrict__ y, long long y_bstride) {
     extern __shared__ unsigned char raw_[];
     unsigned char *sm = raw_ + ((128u - (smem_u32(raw_) & 127u)) & 127u);
-    unsigned char *oper = sm;                                                    // [wg][hi|lo][ET_IMG]; the prolog keeps the cloud here
-    unsigned char *wb = oper + et_oper_bytes(n);
-    float *sP = reinterpret_cast<float *>(wb + ET_WB);                           // [n][12]
+    unsigned char *oper = sm;                                                    // [wg][slot][ET_TILE_IMG]
+    unsigned char *wb = oper + ET_OPER;                                          // B1 (64 rows x 24) | B2 (32 rows x 24)
+    unsigned char *bp = wb + ET_WB;                                              // prolog weights [Wp_hi ; Wp_lo] x 24
+    float *sP = reinterpret_cast<float *>(bp + ET_BP);                           // [n][12]
     float *sA = sP + (size_t)n * ET_G;                                           // [pts][36]: A0 | A1 | A2
-    float *s_out = sA + (size_t)pts_per_cta * 36;                                // [wg][36][33]; the prolog keeps wcat | bias here
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_out + ET_WGS * ET_SO);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + ET_WGS);
+    float *s_out = sA + (size_t)pts_per_cta * 36;                                // [wg][36][17]
+    float *bias = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(s_out) + ET_SOUT);   // [48]: 0 | b0 | b1 | b2
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias + 48);                    // ready[wg][slot] (128 arrivals), done[wg][slot] (commit)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wg = warp >> 2, wq = warp & 3;
-    const int bi = blockIdx.y;
-    const float *xb = x + bi * x_bstride;
-    float *yb = y + bi * y_bstride;
-    const int32_t *ib = idx + (size_t)bi * n * idx_stride + idx_off;
-    const int p_begin = blockIdx.x * pts_per_cta, p_end = min(n, p_begin + pts_per_cta);
+    const bool mma_warp = warp >= ET_SIMT / 32;
+    const int wg = mma_warp ? warp - ET_SIMT / 32 : warp >> 2, wq = warp & 3;
+    uint64_t *ready = bars + wg * 2, *done = bars + 4 + wg * 2;
 
-    // ---------------- prolog: cloud, weights, per-point terms ----------------------------------------------------------
-    et_mark_cta(0);
+    et_mark(0);
     if (tid == 0) {
-        for (int g = 0; g < ET_WGS; ++g) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[g])) : "memory");
+        for (int g = 0; g < 4; ++g) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&bars[g])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[4 + g])) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ET_WGS * ET_TMEM_WG)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    et_mark_cta(1);
-    float *xs = reinterpret_cast<float *>(oper);
-    float *wcat = s_out;                 // [24][48]: W0b | W0a - W0b | W1[:, 12:] | W2[:, 24:]   (in-major)
-    float *bias = s_out + ET_C * 48;     // [48]: 0 | b0 | b1 | b2
-    for (int t = tid; t < ET_C * n; t += ET_THREADS) {
-        const int c = t / n, p = t - c * n;
-        xs[p * ET_XS + c] = __ldg(xb + (size_t)c * n + p);
-    }
-    for (int t = tid; t < ET_C * 48; t += ET_THREADS) {
-        const int ch = t / 48, o = t - ch * 48;
+    // ---------------- prolog 1: raw weights -> shared memory -> the tf32 weight images ------------------------------------------
+    float *rw = reinterpret_cast<float *>(oper);         // w0 (576) | w1 (432) | w2 (576) | b0 b1 b2 (36)
+    for (int t = tid; t < ET_RAW; t += ET_THREADS) {
         float v;
-        if (o < 12) v = __ldg(W.w0 + o * 48 + 24 + ch);
-        else if (o < 24) v = __ldg(W.w0 + (o - 12) * 48 + ch) - __ldg(W.w0 + (o - 12) * 48 + 24 + ch);
-        else if (o < 36) v = __ldg(W.w1 + (o - 24) * 36 + 12 + ch);
-        else v = __ldg(W.w2 + (o - 36) * 48 + 24 + ch);
-        wcat[t] = v;
+        if (t < 576) v = __ldg(W.w0 + t);
+        else if (t < 1008) v = __ldg(W.w1 + t - 576);
+        else if (t < 1584) v = __ldg(W.w2 + t - 1008);
+        else if (t < 1596) v = __ldg(W.b0 + t - 1584);
+        else if (t < 1608) v = __ldg(W.b1 + t - 1596);
+        else v = __ldg(W.b2 + t - 1608);
+        rw[t] = v;
     }
-    if (tid < 48) bias[tid] = tid < 12 ? 0.f : (tid < 24 ? __ldg(W.b0 + tid - 12) : (tid < 36 ? __ldg(W.b1 + tid - 24) : __ldg(W.b2 + tid - 36)));
-    et_mark_cta(2);
-    // weight images, K-major without swizzle: element (row r, k) of a k-step at (r / 8) * 256 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4
-    for (int t = tid; t < 128 * 16; t += ET_THREADS) {
-        const int rr = t >> 4, kk = t & 15;                  // rr: 0..63 B1, 64..95 Bc1, 96..127 B2
-        int img_off, nr, r;
-        if (rr < 64) { img_off = 0; nr = 64; r = rr; }
-        else if (rr < 96) { img_off = 4096; nr = 32; r = rr - 64; }
-        else { img_off = 6144; nr = 32; r = rr - 96; }
-        const int blk = r >> 4, o = r & 15;
-        float w = 0.f;
-        bool lo = false;
-        if (o < ET_G && kk < ET_G) {
-            if (rr < 64) { w = blk < 2 ? __ldg(W.w1 + o * 36 + kk) : __ldg(W.w2 + o * 48 + 12 + kk); lo = blk & 1; }
-            else if (rr < 96) { w = blk == 0 ? __ldg(W.w1 + o * 36 + kk) : __ldg(W.w2 + o * 48 + 12 + kk); }
-            else { w = __ldg(W.w2 + o * 48 + kk); lo = blk & 1; }
-        }
-        const float hi = to_tf32(w);
-        const float v = lo ? to_tf32(w - hi) : hi;
-        const int off = img_off + (kk >> 3) * (nr * 32) + (r >> 3) * 256 + ((kk & 7) >> 2) * 128 + (r & 7) * 16 + (kk & 3) * 4;
-        *reinterpret_cast<float *>(wb + off) = v;
-    }
-    et_mark_cta(3);
-    __syncthreads();
-    et_mark_cta(4);
-    for (int t = tid; t < n * 3; t += ET_THREADS) {          // P_j for the whole cloud (any point can be a neighbour)
-        const int p = t / 3, q = t - p * 3;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float *row = xs + p * ET_XS;
-#pragma unroll
-        for (int ch = 0; ch < ET_C; ++ch) {
-            const float4 w = *reinterpret_cast<const float4 *>(wcat + ch * 48 + q * 4);
-            const float v = row[ch];
-            acc.x = __fmaf_rn(w.x, v, acc.x); acc.y = __fmaf_rn(w.y, v, acc.y); acc.z = __fmaf_rn(w.z, v, acc.z); acc.w = __fmaf_rn(w.w, v, acc.w);
-        }
-        *reinterpret_cast<float4 *>(sP + p * ET_G + q * 4) = acc;
-    }
-    const int pcnt = p_end - p_begin;
-    et_mark_cta(5);
-    for (int t = tid; t < pcnt * 9; t += ET_THREADS) {       // centre terms of the CTA's own points
-        const int p = t / 9, q = t - p * 9;
-        float4 acc = *reinterpret_cast<const float4 *>(bias + 12 + q * 4);
-        const float *row = xs + (p_begin + p) * ET_XS;
-#pragma unroll
-        for (int ch = 0; ch < ET_C; ++ch) {
-            const float4 w = *reinterpret_cast<const float4 *>(wcat + ch * 48 + 12 + q * 4);
-            const float v = row[ch];
-            acc.x = __fmaf_rn(w.x, v, acc.x); acc.y = __fmaf_rn(w.y, v, acc.y); acc.z = __fmaf_rn(w.z, v, acc.z); acc.w = __fmaf_rn(w.w, v, acc.w);
-        }
-        *reinterpret_cast<float4 *>(sA + p * 36 + q * 4) = acc;
-    }
-    et_mark_cta(6);
-    for (int t = tid; t < ET_C * pcnt; t += ET_THREADS) {    // y[36..59] = the centre itself
-        const int c = t / pcnt, p = t - c * pcnt;
-        yb[(size_t)(36 + c) * n + p_begin + p] = xs[(p_begin + p) * ET_XS + c];
-    }
-    et_mark_cta(7);
-    __syncthreads();
-    et_mark_cta(8);
-    for (int t = tid; t < ET_WGS * 2 * ET_IMG / 16; t += ET_THREADS) reinterpret_cast<float4 *>(oper)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_proxy_async();
+    const int row = wq * 32 + lane;                       // row of the warpgroup's tile = lane of tensor memory
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    et_mark_cta(9);
+    const float *rw0 = rw, *rw1 = rw + 576, *rw2 = rw + 1008;
+    for (int t = tid; t < 96 * 24; t += ET_THREADS) {     // Bp: rows 0..47 hi, 48..95 lo of Wp[o][ch] = W0b | W0a - W0b | W1[:, 12:] | W2[:, 24:]
+        const int r = t / 24, ch = t - r * 24, o = r % 48;
+        float v;
+        if (o < 12) v = rw0[o * 48 + 24 + ch];
+        else if (o < 24) v = rw0[(o - 12) * 48 + ch] - rw0[(o - 12) * 48 + 24 + ch];
+        else if (o < 36) v = rw1[(o - 24) * 36 + 12 + ch];
+        else v = rw2[(o - 36) * 48 + 24 + ch];
+        *reinterpret_cast<float *>(bp + et_w_off(96, r, ch)) = et_hi_or_lo(v, r >= 48);
+    }
+    for (int t = tid; t < 64 * 24; t += ET_THREADS) {     // B1: K 0..11 against h0_hi: W1a_hi | W1a_lo | W2b_hi | W2b_lo; K 12..23 against h0_lo: 0 | W1a_hi | 0 | W2b_hi
+        const int r = t / 24, kk = t - r * 24, blk = r >> 4, o = r & 15, in = kk % 12;
+        float v = 0.f;
+        if (o < ET_G) {
+            const float w = blk < 2 ? rw1[o * 36 + in] : rw2[o * 48 + 12 + in];
+            if (kk < 12) v = et_hi_or_lo(w, blk & 1);
+            else if (blk & 1) v = to_tf32(w);
+        }
+        *reinterpret_cast<float *>(wb + et_w_off(64, r, kk)) = v;
+    }
+    for (int t = tid; t < 32 * 24; t += ET_THREADS) {     // B2: K 0..11 against h1_hi: W2a_hi | W2a_lo; K 12..23 against h1_lo: 0 | W2a_hi
+        const int r = t / 24, kk = t - r * 24, blk = r >> 4, o = r & 15, in = kk % 12;
+        float v = 0.f;
+        if (o < ET_G) {
+            const float w = rw2[o * 48 + in];
+            if (kk < 12) v = et_hi_or_lo(w, blk & 1);
+            else if (blk & 1) v = to_tf32(w);
+        }
+        *reinterpret_cast<float *>(wb + ET_WB1 + et_w_off(32, r, kk)) = v;
+    }
+    if (tid < 48) bias[tid] = tid < 12 ? 0.f : rw[1584 + tid - 12];
+    fence_proxy_async();
+    __syncthreads();          // the raw weights are dead: the operand region is free
+    et_mark(1);
 
-    // ---------------- main loop: a warpgroup walks its blocks of 32 points, 4 points (128 edges) per tile -----------------
     const uint32_t tmem_wg = *tmem_slot + (uint32_t)wg * ET_TMEM_WG;
-    const uint32_t tmem_rd = tmem_wg + ((uint32_t)(wq * 32) << 16);
-    unsigned char *img_hi = oper + (size_t)wg * 2 * ET_IMG, *img_lo = img_hi + ET_IMG;
-    const uint32_t row = (uint32_t)(wq * 32 + lane);
-    const uint32_t row_off = (row >> 3) * 256u + (row & 7u) * 16u;
-    const uint64_t d_ah = smem_desc(smem_u32(img_hi), 128, 256, 0), d_al = smem_desc(smem_u32(img_lo), 128, 256, 0);
-    const uint64_t d_b1 = smem_desc(smem_u32(wb), 128, 256, 0), d_bc1 = smem_desc(smem_u32(wb + 4096), 128, 256, 0),
-                   d_b2 = smem_desc(smem_u32(wb + 6144), 128, 256, 0);
-    uint64_t *bar = &bars[wg];
-    uint32_t phase = 0;
-    float *so = s_out + wg * ET_SO;
-    const bool issuer = (wq == 0 && lane == 0);
-    // the prolog's wcat | bias live where the output blocks go: every thread is past its reads (barriers above)
+    unsigned char *img_wg = oper + (size_t)wg * 2 * ET_TILE_IMG;
+    const uint64_t d_b1 = smem_desc(smem_u32(wb), 128, 256, 0), d_b2 = smem_desc(smem_u32(wb + ET_WB1), 128, 256, 0);
+    const int m_tiles = (n + 127) >> 7;
 
-    const int nblk = (pcnt + ET_BLK - 1) / ET_BLK;
-    int jn = 0, tile_no = 0;
-    if (wg < nblk) jn = __ldg(ib + (size_t)min(p_begin + wg * ET_BLK + wq, p_end - 1) * idx_stride + lane);
-    for (int blk = wg; blk < nblk; blk += ET_WGS) {
-        const int b0p = p_begin + blk * ET_BLK;
-        const int bcnt = min(ET_BLK, p_end - b0p);
-        const int ntile = (bcnt + 3) >> 2;
-        for (int t = 0; t < ntile; ++t) {
-            const int lp = t * 4 + wq;
-            const bool pv = lp < bcnt;
-            const int i = pv ? b0p + lp : p_end - 1;
-            const int j = jn;
-            {   // the neighbour index of this thread's next edge, one tile ahead
-                int nb = blk, nt = t + 1;
-                if (nt >= ntile) { nb = blk + ET_WGS; nt = 0; }
-                if (nb < nblk) jn = __ldg(ib + (size_t)min(p_begin + nb * ET_BLK + nt * 4 + wq, p_end - 1) * idx_stride + lane);
-            }
-            const float4 *ai = reinterpret_cast<const float4 *>(sA + (size_t)(i - p_begin) * 36);
-            float k0 = 0.f, k1 = 0.f, k2 = 0.f;
-            et_mark(tile_no, 0);
-            float r[ET_G];
-            // ---- layer 0: gather + add + ReLU -------------------------------------------------------------------------------
-            {
-                const float4 *pj = reinterpret_cast<const float4 *>(sP + (size_t)j * ET_G);
+    if (mma_warp) {
+        // =============================== MMA issuer of warpgroup `wg` (one lane) ===============================================
+        uint32_t rph[2] = {0u, 0u};
+        const uint64_t d_bp = smem_desc(smem_u32(bp), 128, 256, 0);
+        const uint64_t d_x = smem_desc(smem_u32(img_wg), 128, ET_XSBO, 0);
+        const uint64_t d_a[2] = {smem_desc(smem_u32(img_wg), 128, ET_SBO, 0), smem_desc(smem_u32(img_wg + ET_TILE_IMG), 128, ET_SBO, 0)};
+        auto tile_of = [&](int q) { return (q >> 2) * 8 + wg * 4 + (q & 3); };
+        // stage 1: [h1 | h2 part] = [h0_hi | h0_lo] (operand image in shared memory) . B1^T;  stage 2: h2 += [h1_hi | h1_lo] (24 columns of
+        // tensor memory, written over the dead h1 accumulator) . B2^T
+        auto issue = [&](int sl, bool second, int q) {
+            et_wait(&ready[sl], rph[sl]); rph[sl] ^= 1u;
+            et_mark(et_mslot(q, second ? 2 : 0));
+            tc_fence_after();
+            if (!second) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float4 p = pj[q], a = ai[q];
-                    r[4 * q + 0] = fmaxf(p.x + a.x, 0.f); r[4 * q + 1] = fmaxf(p.y + a.y, 0.f);
-                    r[4 * q + 2] = fmaxf(p.z + a.z, 0.f); r[4 * q + 3] = fmaxf(p.w + a.w, 0.f);
+                for (uint32_t s = 0; s < 3; ++s) umma_tf32(tmem_wg + sl * 64, d_a[sl] + s * 16, d_b1 + s * 128, et_idesc(64), s);
+            } else {
+#pragma unroll
+                for (uint32_t s = 0; s < 3; ++s) umma_tf32_ts(tmem_wg + sl * 64 + 32, tmem_wg + sl * 64 + s * 8, d_b2 + s * 64, et_idesc(32), 1u);
+            }
+            tc_commit(&done[sl]);
+            et_mark(et_mslot(q, second ? 3 : 1));
+        };
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int p_begin = (item % splits) * pts_per_cta, pcnt = min(n, p_begin + pts_per_cta) - p_begin;
+            if (lane == 0) {
+                for (int mt = wg; mt < m_tiles; mt += ET_WGS) {      // prolog: [P | A] = x . Wp^T per 128 points
+                    et_wait(&ready[0], rph[0]); rph[0] ^= 1u;
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t s = 0; s < 3; ++s) umma_tf32(tmem_wg, d_x + s * 16, d_bp + s * 192, et_idesc(96), s);
+#pragma unroll
+                    for (uint32_t s = 0; s < 3; ++s) umma_tf32(tmem_wg + 48, d_x + 48 + s * 16, d_bp + s * 192, et_idesc(48), 1u);
+                    tc_commit(&done[0]);
+                }
+            }
+            __syncwarp();
+            asm volatile("bar.sync 3, %0;" ::"r"(ET_THREADS) : "memory");      // with every thread of the CTA: P of the whole cloud is in place
+            if (lane == 0) {
+                const int tiles_total = (pcnt + 3) >> 2;
+                for (int q = 0; tile_of(q) < tiles_total; q += 2) {
+                    const bool two = tile_of(q + 1) < tiles_total;
+                    issue(0, false, q); if (two) issue(1, false, q + 1);
+                    issue(0, true, q); if (two) issue(1, true, q + 1);
+                }
+            }
+            __syncwarp();
+            asm volatile("bar.sync 3, %0;" ::"r"(ET_THREADS) : "memory");      // the item is finished: P | A may be overwritten
+        }
+    } else {
+        // =============================== edge threads ==========================================================================
+        EtSlot S[2];
+        S[0].phase = S[1].phase = 0u;
+        const uint32_t xrow_off = (uint32_t)(row >> 3) * ET_XSBO + (uint32_t)(row & 7) * 16u;
+        const uint32_t row_off = (uint32_t)(row >> 3) * ET_SBO + (uint32_t)(row & 7) * 16u;
+        const uint32_t tmem_rd = tmem_wg + ((uint32_t)(wq * 32) << 16);
+        float *so = s_out + (size_t)wg * ET_SO;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int bi = item / splits;
+            const float *xb = x + bi * x_bstride;
+            float *yb = y + bi * y_bstride;
+            const int32_t *ib = idx + (size_t)bi * n * idx_stride + idx_off;
+            const int p_begin = (item - bi * splits) * pts_per_cta, p_end = min(n, p_begin + pts_per_cta);
+            const int pcnt = p_end - p_begin;
+            // ---- prolog: the thread's point of every 128-point tile of this warpgroup: centre copy, [hi | lo] image row, P | A row
+            for (int mt = wg; mt < m_tiles; mt += ET_WGS) {
+                const int p = mt * 128 + row;
+                float xv[ET_C];
+#pragma unroll
+                for (int c = 0; c < ET_C; ++c) xv[c] = p < n ? __ldg(xb + (size_t)c * n + p) : 0.f;
+                const bool own = p >= p_begin && p < p_end;
+                if (own) {
+#pragma unroll
+                    for (int c = 0; c < ET_C; ++c) yb[(size_t)(36 + c) * n + p] = xv[c];
                 }
 #pragma unroll
-                for (int o = 0; o < ET_G; ++o) { const float m = warp_max_f32(r[o]); if (lane == o) k0 = m; }
-                et_store_split(img_hi, img_lo, row_off, r);
-            }
-            et_mark(tile_no, 1);
-            fence_proxy_async();
-            tc_fence_before();
-            wg_sync(wg);
-            et_mark(tile_no, 2);
-            if (issuer) {
+                for (int c = 0; c < 6; ++c) {
+                    float4 hi, lo;
+                    hi.x = to_tf32(xv[4 * c + 0]); hi.y = to_tf32(xv[4 * c + 1]); hi.z = to_tf32(xv[4 * c + 2]); hi.w = to_tf32(xv[4 * c + 3]);
+                    lo.x = xv[4 * c + 0] - hi.x; lo.y = xv[4 * c + 1] - hi.y; lo.z = xv[4 * c + 2] - hi.z; lo.w = xv[4 * c + 3] - hi.w;
+                    *reinterpret_cast<float4 *>(img_wg + xrow_off + c * 128) = hi;
+                    *reinterpret_cast<float4 *>(img_wg + xrow_off + (6 + c) * 128) = lo;
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&ready[0]);
+                et_wait(&done[0], S[0].phase); S[0].phase ^= 1u;
                 tc_fence_after();
 #pragma unroll
-                for (uint32_t ks = 0; ks < 2; ++ks) {
-                    umma_tf32(tmem_wg + 0, d_ah + ks * (ET_KSTEP >> 4), d_b1 + ks * (2048 >> 4), et_idesc(64), ks);
-                    umma_tf32(tmem_wg + 64, d_al + ks * (ET_KSTEP >> 4), d_bc1 + ks * (1024 >> 4), et_idesc(32), ks);
-                }
-                tc_commit(bar);
-            }
-            et_mark(tile_no, 3);
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
-            et_mark(tile_no, 4);
-            // ---- layer 1 epilogue: + A1, ReLU, max, next operand ----------------------------------------------------------------
-            {
-                float a[16], b[16], c[16];
-                tmem_ld16(tmem_rd + 0, a); tmem_ld16(tmem_rd + 16, b); tmem_ld16(tmem_rd + 64, c);
-                tmem_ld_wait();
-                et_mark(tile_no, 5);
+                for (int ch = 0; ch < 3; ++ch) {
+                    float a[16], b[16];
+                    tmem_ld16(tmem_rd + ch * 16, a); tmem_ld16(tmem_rd + 48 + ch * 16, b);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float4 a1 = ai[3 + q];
-                    r[4 * q + 0] = fmaxf((a[4 * q + 0] + a1.x) + (b[4 * q + 0] + c[4 * q + 0]), 0.f);
-                    r[4 * q + 1] = fmaxf((a[4 * q + 1] + a1.y) + (b[4 * q + 1] + c[4 * q + 1]), 0.f);
-                    r[4 * q + 2] = fmaxf((a[4 * q + 2] + a1.z) + (b[4 * q + 2] + c[4 * q + 2]), 0.f);
-                    r[4 * q + 3] = fmaxf((a[4 * q + 3] + a1.w) + (b[4 * q + 3] + c[4 * q + 3]), 0.f);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int o = ch * 16 + q4 * 4;          // outputs o..o+3: P for o < 12, A[o - 12] above
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias + o);
+                        float4 v;
+                        v.x = (a[q4 * 4 + 0] + bb.x) + b[q4 * 4 + 0]; v.y = (a[q4 * 4 + 1] + bb.y) + b[q4 * 4 + 1];
+                        v.z = (a[q4 * 4 + 2] + bb.z) + b[q4 * 4 + 2]; v.w = (a[q4 * 4 + 3] + bb.w) + b[q4 * 4 + 3];
+                        if (o < 12) { if (p < n) *reinterpret_cast<float4 *>(sP + (size_t)p * ET_G + o) = v; }
+                        else if (own) *reinterpret_cast<float4 *>(sA + (size_t)(p - p_begin) * 36 + (o - 12)) = v;
+                    }
                 }
-#pragma unroll
-                for (int o = 0; o < ET_G; ++o) { const float m = warp_max_f32(r[o]); if (lane == o) k1 = m; }
-                et_store_split(img_hi, img_lo, row_off, r);     // stage 1 has completed: its operand images are free
+                tc_fence_before();
             }
-            et_mark(tile_no, 6);
-            fence_proxy_async();
-            tc_fence_before();
-            wg_sync(wg);
-            et_mark(tile_no, 7);
-            if (issuer) {
+            asm volatile("bar.sync 3, %0;" ::"r"(ET_THREADS) : "memory");
+            if (item == blockIdx.x) et_mark(2);
+
+            // ---- main loop: two tiles (4 points x 32 edges each) in flight per warpgroup ---------------------------------------------
+            const int tiles_total = (pcnt + 3) >> 2;
+            auto tile_of = [&](int q) { return (q >> 2) * 8 + wg * 4 + (q & 3); };
+            auto point_of = [&](int q) { return min(p_begin + tile_of(q) * 4 + wq, p_end - 1); };
+            auto fetch = [&](int q) { return __ldg(ib + (size_t)point_of(q) * idx_stride + lane); };
+            // layer 0 of tile q: gather + add + ReLU, max, operand image, hand-over to the MMA warp
+            auto layer0 = [&](int q, int sl) {
+                et_mark(et_tslot(q, 0));
+                const float4 *ai = reinterpret_cast<const float4 *>(sA + (size_t)(point_of(q) - p_begin) * 36);
+                S[sl].ai = ai;
+                S[sl].lp = p_begin + tile_of(q) * 4 + wq < p_end ? (q & 3) * 4 + wq : -1;
+                const float4 *pj = reinterpret_cast<const float4 *>(sP + (size_t)S[sl].j * ET_G);
+                if (tile_of(q + 2) < tiles_total) S[sl].j = fetch(q + 2);
+                float r[ET_G];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 p = pj[c], a = ai[c];
+                    r[4 * c + 0] = fmaxf(p.x + a.x, 0.f); r[4 * c + 1] = fmaxf(p.y + a.y, 0.f);
+                    r[4 * c + 2] = fmaxf(p.z + a.z, 0.f); r[4 * c + 3] = fmaxf(p.w + a.w, 0.f);
+                }
+                S[sl].k0 = et_max12(r, lane);
+                et_store_split(img_wg + sl * ET_TILE_IMG, row_off, r);
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&ready[sl]);
+                et_mark(et_tslot(q, 1));
+            };
+            // layer 1 of tile q: accumulator + A1, ReLU, max; [hi | lo] go back into tensor memory as the operand of layer 2
+            auto layer1 = [&](int q, int sl) {
+                const float4 *ai = S[sl].ai + 3;
+                et_mark(et_tslot(q, 2));
+                et_wait(&done[sl], S[sl].phase); S[sl].phase ^= 1u;
                 tc_fence_after();
-#pragma unroll
-                for (uint32_t ks = 0; ks < 2; ++ks) {
-                    umma_tf32(tmem_wg + 32, d_ah + ks * (ET_KSTEP >> 4), d_b2 + ks * (1024 >> 4), et_idesc(32), 1u);
-                    umma_tf32(tmem_wg + 80, d_al + ks * (ET_KSTEP >> 4), d_b2 + ks * (1024 >> 4), et_idesc(16), 1u);
-                }
-                tc_commit(bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
-            et_mark(tile_no, 8);
-            // ---- layer 2 epilogue: + A2, max (no ReLU: layers.py:58-59) -------------------------------------------------------
-            {
-                float a[16], b[16], c[16];
-                tmem_ld16(tmem_rd + 32, a); tmem_ld16(tmem_rd + 48, b); tmem_ld16(tmem_rd + 80, c);
+                et_mark(et_tslot(q, 3));
+                float a[16], b[16], r[ET_G];
+                tmem_ld16(tmem_rd + sl * 64, a); tmem_ld16(tmem_rd + sl * 64 + 16, b);
                 tmem_ld_wait();
-                et_mark(tile_no, 9);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float4 a2 = ai[6 + q];
-                    r[4 * q + 0] = (a[4 * q + 0] + a2.x) + (b[4 * q + 0] + c[4 * q + 0]);
-                    r[4 * q + 1] = (a[4 * q + 1] + a2.y) + (b[4 * q + 1] + c[4 * q + 1]);
-                    r[4 * q + 2] = (a[4 * q + 2] + a2.z) + (b[4 * q + 2] + c[4 * q + 2]);
-                    r[4 * q + 3] = (a[4 * q + 3] + a2.w) + (b[4 * q + 3] + c[4 * q + 3]);
+                for (int c = 0; c < 3; ++c) {
+                    const float4 a1 = ai[c];
+                    r[4 * c + 0] = fmaxf((a[4 * c + 0] + a1.x) + b[4 * c + 0], 0.f); r[4 * c + 1] = fmaxf((a[4 * c + 1] + a1.y) + b[4 * c + 1], 0.f);
+                    r[4 * c + 2] = fmaxf((a[4 * c + 2] + a1.z) + b[4 * c + 2], 0.f); r[4 * c + 3] = fmaxf((a[4 * c + 3] + a1.w) + b[4 * c + 3], 0.f);
                 }
+                S[sl].k1 = et_max12(r, lane);
+                uint32_t w0[16], w1[8];      // columns 0..11 hi, 12..23 lo (the K order of B2)
 #pragma unroll
-                for (int o = 0; o < ET_G; ++o) { const float m = warp_max_f32(r[o]); if (lane == o) k2 = m; }
+                for (int o = 0; o < ET_G; ++o) {
+                    const float h = to_tf32(r[o]);
+                    w0[o] = __float_as_uint(h);
+                    const uint32_t l = __float_as_uint(r[o] - h);
+                    if (o < 4) w0[12 + o] = l; else w1[o - 4] = l;
+                }
+                tmem_st16(tmem_rd + sl * 64, w0);
+                tmem_st8(tmem_rd + sl * 64 + 16, w1);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&ready[sl]);
+                et_mark(et_tslot(q, 4));
+            };
+            // layer 2 of tile q: accumulator + A2 (no ReLU: layers.py:58-59), max, the point's 36 values into the output block
+            auto layer2 = [&](int q, int sl) {
+                const int g = tile_of(q);
+                const float4 *ai = S[sl].ai + 6;
+                et_mark(et_tslot(q, 5));
+                et_wait(&done[sl], S[sl].phase); S[sl].phase ^= 1u;
+                tc_fence_after();
+                et_mark(et_tslot(q, 6));
+                float a[16], b[16];
+                tmem_ld16(tmem_rd + sl * 64 + 32, a); tmem_ld16(tmem_rd + sl * 64 + 48, b);
+                tmem_ld_wait();
+                tc_fence_before();
+                float r[ET_G];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 a2 = ai[c];
+                    r[4 * c + 0] = (a[4 * c + 0] + a2.x) + b[4 * c + 0]; r[4 * c + 1] = (a[4 * c + 1] + a2.y) + b[4 * c + 1];
+                    r[4 * c + 2] = (a[4 * c + 2] + a2.z) + b[4 * c + 2]; r[4 * c + 3] = (a[4 * c + 3] + a2.w) + b[4 * c + 3];
+                }
+                const float k = et_max12(r, lane);
+                const int lp = S[sl].lp;
+                if (lane < ET_G && lp >= 0) {
+                    so[lane * (ET_BLK + 1) + lp] = k;
+                    so[(12 + lane) * (ET_BLK + 1) + lp] = S[sl].k1;
+                    so[(24 + lane) * (ET_BLK + 1) + lp] = S[sl].k0;
+                }
+                if ((q & 3) == 3 || tile_of(q + 1) >= tiles_total) {       // the block is complete: 36 rows of up to 16 points
+                    wg_sync(wg);
+                    const int b0p = p_begin + (g >> 2) * ET_BLK, bcnt = min(ET_BLK, p_end - b0p);
+                    for (int e = (tid & 127); e < 36 * ET_BLK; e += 128) {
+                        const int ch = e >> 4, c = e & 15;
+                        if (c < bcnt) yb[(size_t)ch * n + b0p + c] = so[ch * (ET_BLK + 1) + c];
+                    }
+                    wg_sync(wg);
+                }
+                et_mark(et_tslot(q, 7));
+            };
+            if (tile_of(0) < tiles_total) S[0].j = fetch(0);
+            if (tile_of(1) < tiles_total) S[1].j = fetch(1);
+            if (tile_of(0) < tiles_total) layer0(0, 0);
+            if (tile_of(1) < tiles_total) layer0(1, 1);
+            for (int q = 0; tile_of(q) < tiles_total; q += 2) {
+                const bool two = tile_of(q + 1) < tiles_total;
+                layer1(q, 0);
+                if (two) layer1(q + 1, 1);
+                layer2(q, 0);
+                if (tile_of(q + 2) < tiles_total) layer0(q + 2, 0);
+                if (two) {
+                    layer2(q + 1, 1);
+                    if (tile_of(q + 3) < tiles_total) layer0(q + 3, 1);
+                }
             }
-            if (pv && lane < ET_G) {
-                so[lane * (ET_BLK + 1) + lp] = k2;
-                so[(12 + lane) * (ET_BLK + 1) + lp] = k1;
-                so[(24 + lane) * (ET_BLK + 1) + lp] = k0;
-            }
-            et_mark(tile_no, 10);
-            ++tile_no;
+            if (item == blockIdx.x) et_mark(3);
+            asm volatile("bar.sync 3, %0;" ::"r"(ET_THREADS) : "memory");      // every warp is done with P | A of this item
         }
-        wg_sync(wg);
-        for (int e = (tid & 127); e < 36 * ET_BLK; e += 128) {
-            const int ch = e >> 5, c = e & 31;
-            if (c < bcnt) yb[(size_t)ch * n + b0p + c] = so[ch * (ET_BLK + 1) + c];
-        }
-        // the next block's first write to `so` comes after two more warpgroup barriers: no barrier needed here
     }
 
-    et_mark_cta(10);
     tc_fence_before();
     __syncthreads();
-    et_mark_cta(11);
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)(ET_WGS * ET_TMEM_WG)) : "memory");
     }
+    et_mark(4);
 }
 
 // launched by pu3_edgeconv_f32 (edgeconv.cu) for k == 32; returns false when the shape does not fit (caller falls back)
@@ -360,24 +488,35 @@ bool edgeconv_tc_launch(int b, int n, const float *x, long long x_bstride, const
                         const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
                         float *y, long long y_bstride, cudaStream_t s, int *status) {
     const int sms = device_info().sm_count;
-    int pts = n;
-    if ((long long)b < 2LL * sms) {                     // few clouds: several CTAs per cloud, each at least two blocks per warpgroup pair
-        const int split = (int)((2LL * sms + b - 1) / b);
-        pts = (n + split - 1) / split;
-        pts = ((pts + 2 * ET_BLK - 1) / (2 * ET_BLK)) * (2 * ET_BLK);
-        if (pts > n) pts = n;
+    // at least two work items per cloud (the centre terms of half a cloud fit next to the operand images at two CTAs per SM), more when
+    // there are few clouds; an item's points come in blocks of 16 shared out between the two warpgroups.  CTAs are persistent: the
+    // weight images are built once per CTA, two CTAs per SM.
+    // points per item: a multiple of 16 up to 160, chosen by a small cost model -- rounds of the persistent grid x (prolog + the busier
+    // warpgroup's blocks); the prolog (P | A of the whole cloud) costs about as much as a 16-point block per warpgroup
+    int pts = 160;
+    {
+        double best = 1e30;
+        const long long slots = 2LL * sms;
+        for (int cand = 32; cand <= 160; cand += 16) {
+            const long long its = (long long)((n + cand - 1) / cand) * b;
+            const long long rounds = (its + slots - 1) / slots;
+            const double cost = (double)rounds * (1.0 + (double)(((cand + 15) / 16 + 1) / 2));
+            if (cost < best - 1e-9 || (cost < best + 1e-9 && cand > pts)) { best = cost; pts = cand; }
+        }
     }
+    const int splits = (n + pts - 1) / pts;
     const size_t smem = et_smem_bytes(n, pts);
-    if (smem > 112 * 1024) return false;
+    if (smem > 113 * 1024 || n < 32) return false;
     static bool attr_done = false;
     if (!attr_done) {
-        *status = cuda_status(cudaFuncSetAttribute(edgeconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), "edgeconv_tc: smem attr");
+        *status = cuda_status(cudaFuncSetAttribute(edgeconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024), "edgeconv_tc: smem attr");
         if (*status) return true;
         attr_done = true;
     }
     EtWeights W{w0, b0, w1, b1, w2, b2};
-    dim3 grid((n + pts - 1) / pts, b);
-    edgeconv_tc_kernel<<<grid, ET_THREADS, smem, s>>>(n, pts, x, x_bstride, idx, idx_stride, idx_off, W, y, y_bstride);
+    const long long items = (long long)splits * b;
+    const int grid = (int)(items < 2LL * sms ? items : 2LL * sms);
+    edgeconv_tc_kernel<<<grid, ET_THREADS, smem, s>>>(n, pts, splits, (int)items, x, x_bstride, idx, idx_stride, idx_off, W, y, y_bstride);
     *status = PU3_OK;
     return true;
 }

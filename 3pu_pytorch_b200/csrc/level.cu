@@ -179,7 +179,7 @@ static int level_forward_impl(const pu3_level_weights *w, int t, int n, const fl
         else
             PU3_TRYT(PROF_KNN_FEAT, pu3_group_knn_f32(t, 24, n, n, K + 1, 1, h, h, 1 | PU3_KNN_SET_ORDER, max_group, nullptr, nullptr, idx, nullptr, knnws,
                                       p.knn_ws, stream));
-        PU3_TRYT(PROF_EDGECONV, pu3_edgeconv_f32(t, n, K, h, 24LL * n, idx, K + 1, 1, w->ec_w[blk][0], w->ec_b[blk][0], w->ec_w[blk][1],
+        PU3_TRYT(PROF_EDGECONV, (saved ? pu3_edgeconv_ffma_f32 : pu3_edgeconv_f32)(t, n, K, h, 24LL * n, idx, K + 1, 1, w->ec_w[blk][0], w->ec_b[blk][0], w->ec_w[blk][1],
                                  w->ec_b[blk][1], w->ec_w[blk][2], w->ec_b[blk][2], feat + (size_t)(lo - 60) * n, fs, stream));
         lo -= 60;
     }

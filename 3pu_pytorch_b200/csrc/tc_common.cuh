@@ -83,9 +83,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// round to tf32 (10 mantissa bits).  .rn (ties to even) is ONE instruction on sm_100 (F2FP.TF32.F32.PACK_B); the older .rna form
+// compiles to FSETP + IMAD + LOP3.  For the hi / lo splits the tie rule is irrelevant: lo = v - hi is exact either way.
 __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
 

@@ -106,13 +106,14 @@ def pointwise_conv(x, weight, bias, relu=False):
     return out.reshape(shape[0], weight.shape[0], *shape[2:])
 
 
-def edgeconv_into(x, idx32, idx_off, k, weights, biases, out):
-    """out (B,60,N) slice <- fused DenseEdgeConv of x (B,24,N) slice with neighbours idx32[..., idx_off:idx_off+k]."""
+def edgeconv_into(x, idx32, idx_off, k, weights, biases, out, ffma=False):
+    """out (B,60,N) slice <- fused DenseEdgeConv of x (B,24,N) slice with neighbours idx32[..., idx_off:idx_off+k].
+    ffma=True: the FFMA kernels only (the arithmetic the backward kernel recomputes) -- for forwards that will be differentiated."""
     B, C, N = x.shape
     assert C == 24 and out.shape[1] == 60 and idx32.dtype == torch.int32 and idx32.is_contiguous()
     assert x.stride(2) == 1 and x.stride(1) == N and out.stride(2) == 1 and out.stride(1) == N
     w = [wi.reshape(wi.shape[0], wi.shape[1]).contiguous() for wi in weights]
-    _lib.launch("pu3_edgeconv_f32", x, B, N, k, x.data_ptr(), x.stride(0) if B > 1 else C * N, idx32.data_ptr(),
+    _lib.launch("pu3_edgeconv_ffma_f32" if ffma else "pu3_edgeconv_f32", x, B, N, k, x.data_ptr(), x.stride(0) if B > 1 else C * N, idx32.data_ptr(),
                                                idx32.shape[2], idx_off, w[0].data_ptr(), biases[0].data_ptr(),
                                                w[1].data_ptr(), biases[1].data_ptr(), w[2].data_ptr(),
                                                biases[2].data_ptr(), out.data_ptr(),
@@ -133,7 +134,7 @@ class DenseEdgeConvFunction(torch.autograd.Function):
     def forward(ctx, x, idx32, k, w0, b0, w1, b1, w2, b2):
         B, C, N = x.shape
         out = torch.empty(B, 60, N, dtype=torch.float32, device=x.device)
-        edgeconv_into(x, idx32, 0, k, [w0, w1, w2], [b0, b1, b2], out)
+        edgeconv_into(x, idx32, 0, k, [w0, w1, w2], [b0, b1, b2], out, ffma=True)
         ctx.k = k
         ctx.save_for_backward(x, idx32, w0, b0, w1, b1, w2, b2)
         return out

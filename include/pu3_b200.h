@@ -241,6 +241,11 @@ void pu3_head_tc_set_mode(int mode);   /* A/B hook: 2 (default) = CTA pairs (tcg
 int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx, int idx_stride,
                      int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
                      const float *w2, const float *b2, float *y, long long y_bstride, pu3_stream_t stream);
+/* The same function on the FFMA kernels only -- the arithmetic pu3_edgeconv_bwd_f32 recomputes.  The train-mode forward uses it so that
+ * it returns exactly the function its backward differentiates (ReLU masks and arg-max edges included). */
+int pu3_edgeconv_ffma_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx, int idx_stride,
+                          int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
+                          const float *w2, const float *b2, float *y, long long y_bstride, pu3_stream_t stream);
 void pu3_edgeconv_set_tc(int on);   /* test / A-B hook: 1 (default) = for k == 32 the two per-edge layers run on the tensor cores (tcgen05, 3xTF32; edgeconv_tc.cu), 0 = FFMA kernels only; results agree to 1e-5 */
 
 /*

@@ -237,8 +237,13 @@ def test_model_optimize_accumulates_into_the_flat_gradient_buffer(pu3, cuda):
                 model.optimizer.step()
         res.append({k: p.detach().clone() for k, p in net.named_parameters()})
         assert lt.accumulate_into_param_grads is False
-    for k in res[0]:      # atomics order differs run to run: a gradient entry near zero may change Adam's +-lr step for one weight
-        torch.testing.assert_close(res[0][k], res[1][k], rtol=1e-3, atol=1e-5)
+    # atomics order differs run to run: a gradient entry that is zero up to rounding noise gets Adam's full +-lr step with the sign of
+    # the noise.  So: every entry within rtol 1e-3 / atol 1e-5, except at most 2 per tensor, and those within 2 steps x 2 lr.
+    for k in res[0]:
+        a, b = res[0][k], res[1][k]
+        off = (a - b).abs() > 1e-5 + 1e-3 * b.abs()
+        assert int(off.sum()) <= 2 and float((a - b).abs().max()) <= 2 * 2 * 5e-4, \
+            f"{k}: {int(off.sum())} entries differ, max |diff| {float((a - b).abs().max()):.3e}"
 
 
 def test_graphed_train_step_equals_the_eager_one(pu3, cuda):

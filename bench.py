@@ -64,15 +64,19 @@ NCU_METRICS = {
                    "source": "profiles/r2/ncu_fps_skip_raw.csv"},
     "knn_feat_kernel": {"ms": 0.666, "issue_active_pct": 67.4, "fma_pipe_pct": 32.2, "alu_pipe_pct": 59.5, "bound": "fp32/int issue (selection)",
                         "source": "profiles/r1g/ncu_summary.md"},
-    "edgeconv_fast_kernel": {"ms": 0.504, "issue_active_pct": 48.7, "fma_pipe_pct": 38.2, "lsu_pct": 43.0, "bound": "issue + shared-memory gathers",
-                             "source": "profiles/r1g/ncu_summary.md"},
+    "edgeconv_tc_kernel": {"ms": 0.394, "ms_under_ncu": 0.330, "tensor_pipe_pct": 20.0, "issue_active_pct": 61.9,
+                           "smem_pipe_pct": {"lsu": 49.6, "tensor_core": 21.5}, "warp_instructions_per_point": 520,
+                           "bound": "shared-memory pipe (71 %: operand images, neighbour-row gathers) + issue (36 redux.sync.max per point at ~5 cycles each per scheduler)",
+                           "source": "profiles/r2/ncu_edgeconv_tc_raw.csv"},
+    "edgeconv_fast_kernel": {"ms": 0.550, "issue_active_pct": 48.7, "fma_pipe_pct": 38.2, "lsu_pct": 43.0,
+                             "bound": "FFMA kernel, now only k != 32 and the train-mode forward: issue + shared-memory gathers", "source": "profiles/r1g/ncu_summary.md"},
     "skip_fuse_fixed_kernel": {"ms": 0.945, "issue_active_pct": 52.2, "warps_active_pct": 35.1, "dram_mb": 1362.8,
                                "long_scoreboard_per_issue": 5.0, "bound": "L2 gather latency", "source": "profiles/r2/ncu_fps_skip_raw.csv"},
     "knn_thread_kernel<5>": {"ms": 0.691, "issue_active_pct": 79.0, "bound": "fp32 issue", "source": "profiles/r2/ncu_skip_knnthread_raw.csv"},
-    "head_ts2_kernel": {"ms": 0.352, "ms_under_ncu": 0.382, "tensor_pipe_pct": 55.5, "issue_active_pct": 38.9, "dram_mb": 438.3,
-                        "smem_pipe_pct": {"lsu": 13.6, "tensor_core": 13.3},
-                        "bound": "tensor pipe at 55 %: per-instruction cost of the K = 8 tf32 MMA with A from TMEM, L2 -> SM weight delivery in the up1 phase",
-                        "source": "profiles/r2/ncu_head_ts2_raw.csv"},
+    "head_ts2_kernel": {"ms": 0.327, "ms_under_ncu": 0.354, "tensor_pipe_pct": 60.2, "issue_active_pct": 32.8, "dram_mb": 438.9,
+                        "smem_pipe_pct": {"lsu": 14.9, "tensor_core": 14.4},
+                        "bound": "tensor pipe at 60 %: per-instruction cost of the K = 8 tf32 MMA with A from TMEM, L2 -> SM weight delivery in the up1 phase",
+                        "source": "profiles/r2/ncu_head_ts2_cvt_rn_raw.csv"},
     "conv_tc_kernel": {"ms": [0.255, 0.218, 0.135], "tensor_pipe_pct": [34.8, 28.3, 29.5], "dram_pct": [33.5, 33.2, 37.0],
                        "bound": "three-kernel head (now only the train-mode forward): HBM round trips of the 128-channel activations, pipeline depth",
                        "source": "profiles/r1g/ncu_summary.md"},

@@ -456,11 +456,15 @@ using namespace pu3;
 // Test hook: force the generic kernel.
 static int g_ec_force_generic = 0;
 extern "C" void pu3_edgeconv_force_generic(int on) { g_ec_force_generic = on; }
-// A/B hook: 1 (default) = k == 32 runs the per-edge layers on the tensor cores (edgeconv_tc.cu), 0 = FFMA kernels only
-static int g_ec_tc = 1;
+// A/B hook: k == 32 runs the per-edge layers on the tensor cores -- 2 = every operand in tensor memory (edgeconv_ts.cu), 1 = layer-1
+// operand images in shared memory (edgeconv_tc.cu), 0 = FFMA kernels only
+static int g_ec_tc = 2;
 extern "C" void pu3_edgeconv_set_tc(int on) { g_ec_tc = on; }
 namespace pu3 {
 bool edgeconv_tc_launch(int b, int n, const float *x, long long x_bstride, const int32_t *idx, int idx_stride, int idx_off,
+                        const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
+                        float *y, long long y_bstride, cudaStream_t s, int *status);
+bool edgeconv_ts_launch(int b, int n, const float *x, long long x_bstride, const int32_t *idx, int idx_stride, int idx_off,
                         const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
                         float *y, long long y_bstride, cudaStream_t s, int *status);
 }
@@ -491,7 +495,8 @@ static int edgeconv_forward(bool allow_tc, int b, int n, int k, const float *x, 
     cudaStream_t s = as_stream(stream);
     int st;
     if (k == 32 && allow_tc && g_ec_tc && !g_ec_force_generic) {
-        if (edgeconv_tc_launch(b, n, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, s, &st)) {
+        if ((g_ec_tc >= 2 && edgeconv_ts_launch(b, n, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, s, &st)) ||
+            edgeconv_tc_launch(b, n, x, x_bstride, idx, idx_stride, idx_off, w0, b0, w1, b1, w2, b2, y, y_bstride, s, &st)) {
             if (st) return st;
             PU3_LAUNCH_CHECK("edgeconv_tc_kernel");
             return PU3_OK;

@@ -41,12 +41,12 @@ for b, n in [(2, 45), (5, 100), (3, 312), (32, 312), (160, 312), (640, 312), (12
     x = torch.randn(b, 24, n, generator=g).to(dev)
     idx = torch.randint(0, n, (b, n, k), generator=g).to(dev)
     outs = []
-    for tc in (1, 0):
+    for tc in (2, 0):
         lib.pu3_edgeconv_set_tc(tc)
         with torch.no_grad():
             outs.append(F.dense_edge_conv(x, ws, bs, k, idx=idx)[0].clone())
     torch.cuda.synchronize()
-    lib.pu3_edgeconv_set_tc(1)
+    lib.pu3_edgeconv_set_tc(2)
     with torch.no_grad():
         same = all(torch.equal(F.dense_edge_conv(x, ws, bs, k, idx=idx)[0], outs[0]) for _ in range(6))
     if not same:
@@ -61,7 +61,7 @@ for b, n in [(2, 45), (5, 100), (3, 312), (32, 312), (160, 312), (640, 312), (12
     bad = int((d > tol).sum())
     per = [float(d[:, a:a + 12].max()) for a in (0, 12, 24)] + [float(d[:, 36:].max())]
     t = []
-    for tc in (1, 0):
+    for tc in (2, 0):
         lib.pu3_edgeconv_set_tc(tc)
         with torch.no_grad():
             t.append(timed(lambda: F.dense_edge_conv(x, ws, bs, k, idx=idx)))
@@ -69,5 +69,5 @@ for b, n in [(2, 45), (5, 100), (3, 312), (32, 312), (160, 312), (640, 312), (12
         tot[0] += t[0]; tot[1] += t[1]
     print(f"b={b:5d} n={n}: max|tc - ffma| h2/h1/h0/centre = {per[0]:.2e} {per[1]:.2e} {per[2]:.2e} {per[3]:.1e}, outside 1e-5: {bad} of {d.numel()};"
           f"  tensor-core {t[0]:.4f} ms, FFMA {t[1]:.4f} ms ({t[1] / t[0]:.2f}x)", flush=True)
-lib.pu3_edgeconv_set_tc(1)
+lib.pu3_edgeconv_set_tc(2)
 print(f"sum over the four level shapes: tensor-core {tot[0]:.3f} ms, FFMA {tot[1]:.3f} ms (x4 blocks per level in the step)")

@@ -1,4 +1,4 @@
-"""DenseEdgeConv forward on the tensor cores (csrc/edgeconv_tc.cu, tcgen05 3xTF32) -- network/layers.py:22-64 of the reference.
+"""DenseEdgeConv forward on the tensor cores (csrc/edgeconv_ts.cu and its first version csrc/edgeconv_tc.cu, tcgen05 3xTF32) -- network/layers.py:22-64 of the reference.
 Checked against a float64 restatement of the reference's graph (edge feature [c, n - c], three 1x1 layers with dense
 concatenation, max over k) at 1e-5, against the FFMA kernel, for bit-reproducibility, and on ragged shapes (points per cloud that
 do not fill the 16-point blocks / 128-point prolog tiles, few and many clouds)."""
@@ -36,24 +36,27 @@ def test_tensor_core_edgeconv_against_float64_and_ffma(pu3, cuda, b, n):
     idx = torch.randint(0, n, (b, n, K), generator=g).to(cuda)
     outs = []
     try:
-        for tc in (1, 0):
+        for tc in (2, 1, 0):          # operands in tensor memory (shipped) / layer-1 operand images in shared memory / FFMA
             lib.pu3_edgeconv_set_tc(tc)
             with torch.no_grad():
                 outs.append(pu3.fused.dense_edge_conv(x, ws, bs, K, idx=idx)[0].clone())
-        lib.pu3_edgeconv_set_tc(1)
+        lib.pu3_edgeconv_set_tc(2)
         with torch.no_grad():
             again = pu3.fused.dense_edge_conv(x, ws, bs, K, idx=idx)[0]
     finally:
-        lib.pu3_edgeconv_set_tc(1)
+        lib.pu3_edgeconv_set_tc(2)
     assert torch.equal(again, outs[0]), "the tensor-core kernel is not bit-reproducible"
-    assert torch.equal(outs[0][:, 36:], x), "pass-through channels must be copies"
+    names = ("tensor-core (TS)", "tensor-core (SS + TS)", "FFMA")
+    for name, o in zip(names, outs):
+        assert torch.equal(o[:, 36:], x), f"{name}: pass-through channels must be copies"
     if b * n <= 4096:
         ref = _reference64(x, idx, ws, bs)
-        for name, o in (("tensor-core", outs[0]), ("FFMA", outs[1])):
+        for name, o in zip(names, outs):
             err = (o.double() - ref).abs()
             assert bool((err <= 1e-5 + 1e-5 * ref.abs()).all()), f"{name} kernel vs float64: max err {float(err.max()):.2e}"
-    err = (outs[0] - outs[1]).abs()
-    assert bool((err <= 1e-5 + 1e-5 * outs[1].abs()).all()), f"tensor-core vs FFMA: max diff {float(err.max()):.2e}"
+    for name, o in zip(names[:2], outs[:2]):
+        err = (o - outs[2]).abs()
+        assert bool((err <= 1e-5 + 1e-5 * outs[2].abs()).all()), f"{name} vs FFMA: max diff {float(err.max()):.2e}"
 
 
 def test_tensor_core_edgeconv_through_the_level_layout(pu3, cuda):
@@ -86,5 +89,5 @@ def test_train_mode_forward_stays_on_the_ffma_kernels(pu3, cuda):
         with torch.no_grad():
             y_ffma = pu3.fused.dense_edge_conv(x, ws, bs, K, idx=idx)[0]
     finally:
-        lib.pu3_edgeconv_set_tc(1)
+        lib.pu3_edgeconv_set_tc(2)
     assert y_train.requires_grad and torch.equal(y_train.detach(), y_ffma)

@@ -64,9 +64,13 @@ NCU_METRICS = {
                    "source": "profiles/r2/ncu_fps_skip_raw.csv"},
     "knn_feat_kernel": {"ms": 0.666, "issue_active_pct": 67.4, "fma_pipe_pct": 32.2, "alu_pipe_pct": 59.5, "bound": "fp32/int issue (selection)",
                         "source": "profiles/r1g/ncu_summary.md"},
+    "edgeconv_ts_kernel": {"ms": 0.351, "ms_under_ncu": 0.289, "tensor_pipe_pct": 18.1, "issue_active_pct": 66.1, "alu_pipe_pct": 54.2,
+                           "smem_pipe_pct": {"lsu": 33.9, "tensor_core": 8.5}, "warp_instructions_per_point": 466,
+                           "bound": "issue: 36 redux.sync.max per point (~5 cycles each per scheduler) + their moves out of uniform registers, hi/lo splits, waits",
+                           "source": "profiles/r2/ncu_edgeconv_ts_raw.csv"},
     "edgeconv_tc_kernel": {"ms": 0.394, "ms_under_ncu": 0.330, "tensor_pipe_pct": 20.0, "issue_active_pct": 61.9,
                            "smem_pipe_pct": {"lsu": 49.6, "tensor_core": 21.5}, "warp_instructions_per_point": 520,
-                           "bound": "shared-memory pipe (71 %: operand images, neighbour-row gathers) + issue (36 redux.sync.max per point at ~5 cycles each per scheduler)",
+                           "bound": "first tensor-core version (layer-1 operand images in shared memory; A/B hook pu3_edgeconv_set_tc(1)): shared-memory pipe 71 %",
                            "source": "profiles/r2/ncu_edgeconv_tc_raw.csv"},
     "edgeconv_fast_kernel": {"ms": 0.550, "issue_active_pct": 48.7, "fma_pipe_pct": 38.2, "lsu_pct": 43.0,
                              "bound": "FFMA kernel, now only k != 32 and the train-mode forward: issue + shared-memory gathers", "source": "profiles/r1g/ncu_summary.md"},

@@ -246,7 +246,7 @@ int pu3_edgeconv_f32(int b, int n, int k, const float *x, long long x_bstride, c
 int pu3_edgeconv_ffma_f32(int b, int n, int k, const float *x, long long x_bstride, const int32_t *idx, int idx_stride,
                           int idx_off, const float *w0, const float *b0, const float *w1, const float *b1,
                           const float *w2, const float *b2, float *y, long long y_bstride, pu3_stream_t stream);
-void pu3_edgeconv_set_tc(int on);   /* test / A-B hook: 1 (default) = for k == 32 the two per-edge layers run on the tensor cores (tcgen05, 3xTF32; edgeconv_tc.cu), 0 = FFMA kernels only; results agree to 1e-5 */
+void pu3_edgeconv_set_tc(int on);   /* test / A-B hook: 2 (default) = for k == 32 the two per-edge layers run on the tensor cores with every operand in tensor memory (tcgen05 TS form, 3xTF32; edgeconv_ts.cu), 1 = first version with layer-1 operand images in shared memory (edgeconv_tc.cu), 0 = FFMA kernels only; results agree to 1e-5 */
 
 /*
  * Inter-level skip connection, fused (network/upsampler.py:317-347 and exponential_distance :232-250):

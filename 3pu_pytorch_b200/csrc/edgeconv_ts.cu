@@ -468,12 +468,9 @@ bool edgeconv_ts_launch(int b, int n, const float *x, long long x_bstride, const
     const int splits = (n + pts - 1) / pts;
     const size_t smem = eu_smem_bytes(n, pts);
     if (smem > 113 * 1024 || n < 48) return false;
-    static bool attr_done = false;
-    if (!attr_done) {
-        *status = cuda_status(cudaFuncSetAttribute(edgeconv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024), "edgeconv_ts: smem attr");
-        if (*status) return true;
-        attr_done = true;
-    }
+    // per launch, not once per process: the attribute belongs to the device the caller has made current
+    *status = cuda_status(cudaFuncSetAttribute(edgeconv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024), "edgeconv_ts: smem attr");
+    if (*status) return true;
     EuWeights W{w0, b0, w1, b1, w2, b2};
     const long long items = (long long)splits * b;
     const int grid = (int)(items < 2LL * sms ? items : 2LL * sms);

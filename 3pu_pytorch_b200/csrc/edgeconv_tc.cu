@@ -7,14 +7,19 @@
 //     h2 = W2[:, :12] h1 + W2[:, 12:24] h0 + A2_i   12 x 24
 // and y = [max_k h2, max_k h1, max_k h0, c].  The FFMA kernel spends 432 MAC per edge in FFMA2 at 48 % issue efficiency;
 // here the two small layers are GEMMs over the EDGES: a tile is 128 edges = 4 points x 32 neighbours (one warp per point,
-// one lane per edge = one row of the MMA = one lane of tensor memory), K = 12 padded to 16, and
-//     stage 1:  [h1 | h2 part] (128 x 64) = h0_hi . [W1a_hi | W1a_lo | W2b_hi | W2b_lo]^T ,  (128 x 32) = h0_lo . [W1a_hi | W2b_hi]^T
-//     stage 2:  h2 (128 x 32, accumulating) += h1_hi . [W2a_hi | W2a_lo]^T ,  (128 x 16) += h1_lo . W2a_hi^T
-// i.e. 8 small tcgen05.mma per tile (3xTF32: hi.hi in a main accumulator, hi.lo + lo.hi in correction columns, summed in
-// the epilogue -- profiles/r1g: the accuracy of the FFMA kernel).  The threads only add the centre terms, apply ReLU, split
-// hi/lo, write the next operand image (K-major, no swizzle) and take the maximum over the 32 edges of a point with
-// redux.sync.max.f32 (the 32 edges of a point are the 32 lanes of a warp).  A CTA is two warpgroups working on their own
-// tiles; two CTAs per SM (2 x 256 tensor-memory columns), so four tiles per SM are in flight and hide each other's MMA waits.
+// one lane per edge = one row of the MMA = one lane of tensor memory).  An operand row is [hi(12) | lo(12)] (K = 24 = three
+// K = 8 steps, nothing padded), the weight images pair it with [W_hi | W_lo] against the hi half and [0 | W_hi] against the lo half:
+//     stage 1:  [h1 | h1 corr | h2a | h2a corr] (128 x 64) = [h0_hi | h0_lo] . B1^T       (operand image in shared memory, 3 MMAs)
+//     stage 2:  [h2 | h2 corr] (128 x 32, accumulating)   += [h1_hi | h1_lo] . B2^T       (operand in TENSOR MEMORY, written by
+//               tcgen05.st over the dead h1 columns: TS form, 3 MMAs)
+// (3xTF32: hi.hi in a main accumulator, hi.lo + lo.hi in correction columns, summed in the epilogue -- profiles/r1g: the accuracy
+// of the FFMA kernel).  The edge threads only add the centre terms, apply ReLU, split hi/lo, write the next operand and take the
+// maximum over the 32 edges of a point with redux.sync.max.f32 (the 32 edges of a point are the 32 lanes of a warp).
+// Warp-specialised: two warpgroups of edge threads + one MMA-issuing warp each, hand-over by mbarriers (128 arrivals /
+// tcgen05.commit), two tiles in flight per warpgroup (64 tensor-memory columns each), two CTAs per SM; persistent CTAs over
+// (cloud, part) work items; the prolog [P | A0 A1 A2] = x . Wp^T of a cloud is a tcgen05 GEMM too.
+// This is the FIRST tensor-core version, kept behind pu3_edgeconv_set_tc(1) and for 32 <= n < 48; edgeconv_ts.cu (every operand
+// in tensor memory) is the one that ships.  History and measurements: profiles/r2/ncu_summary.md.
 #include "tc_common.cuh"
 
 namespace pu3 {

@@ -320,7 +320,9 @@ def run_product(args):
                 "traffic": NCU_TRAFFIC_PER_LAUNCH.get(dom_name),
                 "peak_source": peak_src, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "alg_bytes_per_launch": int(alg) if alg else None,
-                "share_of_step": round(dom_ms / ms_prof, 4),
+                # against the graph-replayed step the line reports: the profiled pass launches eagerly and its wall time carries
+                # one-off allocator work of the first eager step (profiled_ms_per_step varies run to run, the kernel times do not)
+                "share_of_step": round((dom_ms / prof_steps) / (ms_res / args.steps), 4),
                 "note": "\"hbm\" is the contract's category for a non-GEMM kernel; what bounds it is latency / FP32 issue (serial FPS "
                         "exchanges, all-pairs kNN, per-edge MLP): the HBM fraction is small by construction -- see ncu_metrics "
                         "for the measured limiter of every kernel family and DESIGN.md section 5"}
